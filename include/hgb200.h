@@ -1,0 +1,185 @@
+/*
+ * hgb200.h -- C ABI of libhgb200.so, the B200 (sm_100a) implementation of the
+ * stacked-hourglass heatmap path of MindlessBoid/single-person-pose-estimation.
+ *
+ * The reference has no FFI: its boundary is the Python call surface.  Each entry
+ * point below names the reference function (file:line, relative to the reference
+ * tree) whose arithmetic it replaces; the Python shim in
+ * single-person-pose-estimation_b200/ binds these over ctypes and keeps the
+ * reference's Python signatures (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (HGB_ERR_*); the message is
+ *     available from hgb_last_error() (thread-local).
+ *   - all data pointers are DEVICE pointers owned by the caller; the library never
+ *     allocates per call.  `stream` is a cudaStream_t passed as void* (NULL = default).
+ *   - calls are asynchronous on `stream`.
+ *   - tensors are NHWC, C innermost, densely packed unless a pitch is given.
+ */
+#ifndef HGB200_H
+#define HGB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGB_OK               0
+#define HGB_ERR_INVALID     -1   /* bad argument / unsupported shape */
+#define HGB_ERR_CUDA        -2   /* CUDA runtime / driver error */
+#define HGB_ERR_STATE       -3   /* call out of order (e.g. buffers not bound) */
+
+#define HGB_F32   0
+#define HGB_BF16  1
+
+/* loss kinds: trainer.py:224-245 string table */
+#define HGB_LOSS_WEIGHTED_MSE           0   /* loss.py:2-21 */
+#define HGB_LOSS_MSE                    1   /* tf.keras.losses.mean_squared_error, trainer.py:231 */
+#define HGB_LOSS_IOU                    2   /* loss.py:23-28 */
+#define HGB_LOSS_WEIGHTED_KEYPOINT_MSE  3   /* loss.py:30-36 */
+
+const char* hgb_last_error(void);
+int         hgb_version(void);
+/* debug/tuning knobs (key, value); unknown keys -> HGB_ERR_INVALID */
+int         hgb_debug_set(int key, int value);
+
+/* ------------------------------------------------------------------------- */
+/* Heatmap path                                                              */
+/* ------------------------------------------------------------------------- */
+
+/* dataset_builder.py:220-235 (np_gen_heatmaps) + utilities/data_utils.py:187-211 (gaussian).
+ * kps_x, kps_y: (B,K) float32 heatmap-pixel coordinates; kps_v: (B,K) int32 visibility.
+ * out: (B,H,W,K) float32, fully written (zeros + 7x7 sigma=1 stamps). */
+int hgb_render_targets(const float* kps_x, const float* kps_y, const int32_t* kps_v,
+                       int B, int H, int W, int K, float* out, void* stream);
+
+/* bytes of scratch hgb_loss_fwd_bwd needs for (B,K) */
+int64_t hgb_loss_workspace_bytes(int B, int K);
+
+/* One Keras output's loss and gradient (loss.py:2-36; reduction = mean over everything the
+ * loss fn returns).  y_true f32 (B,H,W,K); y_pred / grad in pred_dtype /
+ * grad_dtype.  inv_count = 1/(B_global*H*W*K) for the MSE family, 1/(B_global*K) for IoU, so
+ * a batch shard produces its share of the global mean.  loss_acc: device double, ADDED to
+ * (caller zeroes).  grad may be NULL (loss only). */
+int hgb_loss_fwd_bwd(int kind, const float* y_true, const void* y_pred, int pred_dtype,
+                     int B, int H, int W, int K, double inv_count,
+                     double* loss_acc, void* grad, int grad_dtype,
+                     void* workspace, void* stream);
+
+/* The tensor the reference loss functions return: (B,H,W) f32 for the MSE family
+ * (loss.py:21,36), (B,) f32 for IoU (loss.py:28). */
+int hgb_loss_map(int kind, const float* y_true, const float* y_pred,
+                 int B, int H, int W, int K, float* out, void* workspace, void* stream);
+
+/* utilities/data_utils.py:100-132 (version 1) and :135-183 (version 2).
+ * heatmaps (B,H,W,K) in `dtype`, H == W required (data_utils.py:122 divides by height).
+ * out_idx (B,K,4) int32 = [argmax index, x, y, patch argmax index]; out_kpts (B,K,3) f32 =
+ * [x + dx, y + dy, conf] or zeros when conf <= conf_threshold (compared in double). The
+ * input is NOT modified; the (1,1) element of the clipped 3x3 window is read as 0. */
+int hgb_decode(const void* heatmaps, int dtype, int B, int H, int W, int K,
+               double conf_threshold, int version, int32_t* out_idx, float* out_kpts, void* stream);
+
+/* eval.py:62-88: per-joint PCK counters.  All (N,K) double except vs (N,K) int32 and
+ * bbox_wh (N,2) double (original COCO bbox width,height).  counts: int32[2*K] =
+ * correct[K] then visible[K], ADDED to (caller zeroes). */
+int hgb_pck_reduce(const double* xs_pred, const double* ys_pred, const double* xs_gt, const double* ys_gt,
+                   const int32_t* vs, const double* bbox_wh, int N, int K, double pck_threshold,
+                   int32_t* counts, void* stream);
+
+/* COCO object-keypoint-similarity of each prediction with its own annotation (the arithmetic
+ * eval.py:39-49 delegates to pycocotools COCOeval.computeOks).  bbox_xywh (N,4), area (N,),
+ * oks_out (N,) double. K <= 17. */
+int hgb_oks_similarity(const double* xs_pred, const double* ys_pred, const double* xs_gt, const double* ys_gt,
+                       const int32_t* vs, const double* area, const double* bbox_xywh, int N, int K,
+                       double* oks_out, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Hourglass network  (model/hourglass.py:5-206)                             */
+/* ------------------------------------------------------------------------- */
+
+typedef struct hgb_model hgb_model;
+
+typedef struct {
+  int num_classes;    /* 17 */
+  int num_stacks;     /* model/hourglass.py:21 */
+  int num_channels;   /* 256; must be a multiple of 128 */
+  int in_h, in_w;     /* 256, 256 (multiples of 64) */
+  int activation;     /* predict_activation: 0 linear, 1 sigmoid */
+  int batch;          /* per-device batch the execution plan is built for */
+  int training;       /* 1: plan keeps activations and allocates the backward pass */
+} hgb_model_config;
+
+/* buffers the caller allocates and binds */
+#define HGB_BUF_PARAMS   0   /* fp32: trainable scalars first, then BN moving statistics */
+#define HGB_BUF_GRADS    1   /* fp32, trainable count */
+#define HGB_BUF_ADAM_M   2
+#define HGB_BUF_ADAM_V   3
+#define HGB_BUF_ARENA    4   /* activations, bf16 weight shadows, scratch */
+
+int     hgb_model_create(const hgb_model_config* cfg, int device, hgb_model** out);
+int     hgb_model_destroy(hgb_model* m);
+int64_t hgb_model_param_count(const hgb_model* m, int trainable_only);
+int64_t hgb_model_buffer_bytes(const hgb_model* m, int which);
+int     hgb_model_bind(hgb_model* m, int which, void* ptr, int64_t bytes);
+
+/* parameter table: names are the Keras layer names of model/hourglass.py plus
+ * /kernel /bias /gamma /beta /moving_mean /moving_variance; kernel dims are HWIO. */
+int     hgb_model_num_tensors(const hgb_model* m);
+int     hgb_model_tensor_info(const hgb_model* m, int index, const char** name, int* rank,
+                              int64_t dims[4], int64_t* offset, int* trainable);
+int     hgb_model_num_convs(const hgb_model* m);
+/* per-conv FLOPs (2*MAC) of one forward pass at the plan's batch, and its class */
+int     hgb_model_conv_info(const hgb_model* m, int index, const char** name, int* k, int* cin, int* cout,
+                            int* h, int* w, double* flops);
+
+/* re-derive the bf16 GEMM-layout weights from the fp32 parameters (after load / Adam) */
+int hgb_model_sync_weights(hgb_model* m, void* stream);
+
+/* forward.  images: (B,in_h,in_w,3) f32.  training=1 uses batch statistics and updates
+ * the moving averages (Keras fit); 0 uses moving statistics (predict / evaluate).
+ * heatmaps_out: array of num_stacks device pointers (B,H/4,W/4,num_classes) f32, entries may be
+ * NULL to skip that stack's output copy. */
+int hgb_model_forward(hgb_model* m, const float* images, int training, float* const* heatmaps_out, void* stream);
+
+/* losses of all stacks + gradient wrt each stack's pre-activation output; y_true f32
+ * (B,h,w,classes) shared by every stack (Keras compile with one loss fn, trainer.py:35).
+ * loss_acc: device double[num_stacks], added to.  Needs a preceding training forward. */
+int hgb_model_loss(hgb_model* m, int kind, const float* y_true, double inv_count, double* loss_acc, void* stream);
+
+/* backward over segments [seg_lo, seg_hi): segment 0 = front module, 1+i = stack i.
+ * Must be called from the highest segment down.  Gradients are written (not accumulated). */
+int hgb_model_num_segments(const hgb_model* m);
+int hgb_model_backward(hgb_model* m, int seg_lo, int seg_hi, void* stream);
+/* contiguous range of the gradient buffer that segment `seg` owns (for bucketed allreduce) */
+int hgb_model_segment_grads(const hgb_model* m, int seg, int64_t* offset, int64_t* count);
+
+/* Keras legacy Adam (trainer.py:31): w -= lr_t*m/(sqrt(v)+eps) with
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); grads are multiplied by grad_scale first (1/world_size).
+ * Also refreshes the bf16 GEMM weights. */
+int hgb_model_adam_step(hgb_model* m, double lr, double beta1, double beta2, double eps, int64_t t,
+                        double grad_scale, void* stream);
+
+/* number of kernels this handle has launched since creation (bench "gpu_launches") */
+int64_t hgb_model_launch_count(const hgb_model* m);
+
+/* ------------------------------------------------------------------------- */
+/* Stand-alone convolution GEMM entry points (unit tests / kernel benchmarks) */
+/* ------------------------------------------------------------------------- */
+
+/* out[M,Cout] = act(conv_kxk(in[N,H,W,Cin], w) + bias) (+res1 +res2), bf16 NHWC, fp32 accumulate.
+ * w: bf16 [Cout][k*k*Cin] (tap-major, channel-minor).  k in {1,3}; Cin % 64 == 0; Cout % 16 == 0, <= 256.
+ * ldc: row pitch of out/res in elements.  stats: optional float[2*Cout] (sum, sum of squares of the
+ * stored values), ADDED to. tap_sign = +1 forward, -1 for dgrad (taps mirrored). */
+int hgb_conv_gemm(const void* in, const void* w, const float* bias, const void* res1, const void* res2,
+                  void* out, float* stats, int N, int H, int W, int Cin, int Cout, int ksize,
+                  int relu, int ldc, int tap_sign, void* stream);
+
+/* dw[Cout][k*k*Cin] (fp32, ADDED to) = sum_pixels dy[p][Cout]^T x_tap[p][Cin]  (weight gradient) */
+int hgb_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
+                   int ksize, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGB200_H */

@@ -1,0 +1,18 @@
+"""B200-native stacked-hourglass heatmap path (drop-in for the reference's Python API).
+
+The package mirrors the reference layout for the hot path only:
+    model/hourglass.py   create_hourglass_model(...)
+    loss.py              weighted_mse / IOU / weighed_keypoint_mse / mean_squared_error
+    trainer.py           Trainer.train() / resume_training()
+    utilities/data_utils.py  heatmaps_to_keypoints_v1/_v2
+    eval.py              predict_ds / eval_PCK / eval_OKS
+Everything numerical runs in libhgb200.so (hand-written sm_100a CUDA) through ctypes;
+torch tensors only hold device memory.  There is no CPU fallback: importing works
+without a GPU (so the ABI can be inspected), calling an op without one raises.
+"""
+from . import _lib  # noqa: F401  (loads libhgb200.so; raises if it is missing)
+
+__all__ = ["_lib"]
+from . import ops  # noqa: E402,F401
+
+__all__ += ["ops"]

@@ -1,0 +1,548 @@
+// Convolutions of the hourglass as implicit GEMMs on the 5th-generation tensor cores.
+//
+//   forward / dgrad : out[pixel][cout] = sum_tap sum_cin  x[pixel + tap][cin] * w[cout][tap][cin]
+//                     (model/hourglass.py:193-200 -- Conv2D 1x1 / 3x3 'same', bias, ReLU)
+//   wgrad           : dw[cout][tap][cin] += sum_pixel dy[pixel][cout] * x[pixel + tap][cin]
+//
+// One CTA = one 128-pixel tile.  A warp-specialised pipeline:
+//   warp 0   TMA producer: a 4-D tensor map over the NHWC activation tensor delivers the 128 pixels
+//            of the tile shifted by the filter tap; out-of-image pixels are zero-filled by TMA,
+//            which is exactly TF 'same' padding.  Weights arrive through a 2-D map.
+//   warp 1   owns TMEM and issues tcgen05.mma (one elected lane); accumulators live in TMEM.
+//   warps 2-5 epilogue: tcgen05.ld -> bias / ReLU / residuals -> bf16 NHWC store, plus the
+//            per-channel sum and sum-of-squares the following BatchNorm needs (warp butterfly).
+// Operands sit in shared memory in the canonical 128-byte-swizzled layout that both TMA and the
+// tensor-core descriptors understand; nothing is staged through registers.
+#include "conv_gemm.cuh"
+#include "sm100_ptx.cuh"
+
+namespace hgb {
+
+using namespace ptx;
+
+constexpr int kBlockM = 128;
+constexpr int kABytes = kBlockM * 128;  // 128 pixels x 64 bf16
+constexpr int kThreads = 192;
+
+struct GemmKernelParams {
+  int M_total, H, W, HW;
+  int cblk;      // Cin / 64
+  int nkb;       // taps * cblk
+  int tap3;      // 1 when 3x3
+  int tap_sign;
+  int Cout, ldc, relu;
+  const float* bias;
+  const __nv_bfloat16* res1;
+  const __nv_bfloat16* res2;
+  __nv_bfloat16* out;
+  float* stats;
+};
+
+template <int OFF>
+__device__ __forceinline__ void bfly_step(float (&x)[32], int lane) {
+  const bool hi = (lane & OFF) != 0;
+#pragma unroll
+  for (int i = 0; i < OFF; ++i) {
+    const float send = hi ? x[i] : x[i + OFF];
+    const float keep = hi ? x[i + OFF] : x[i];
+    x[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+  }
+}
+// x[j] = value of column j in this lane's row.  Afterwards x[0] of lane L = sum over the 32 rows of column L.
+__device__ __forceinline__ float warp_column_sums(float (&x)[32], int lane) {
+  bfly_step<16>(x, lane);
+  bfly_step<8>(x, lane);
+  bfly_step<4>(x, lane);
+  bfly_step<2>(x, lane);
+  bfly_step<1>(x, lane);
+  return x[0];
+}
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB,
+                                                             const GemmKernelParams p) {
+  constexpr int kBBytes = BLOCK_N * 128;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // 128-byte swizzle atoms need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bar0 = base + STAGES * kStageBytes;  // full[STAGES] | empty[STAGES] | tmem_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * kStageBytes + (2 * STAGES + 1) * 8);
+  float* s_stats = reinterpret_cast<float*>(smem + STAGES * kStageBytes + (2 * STAGES + 1) * 8 + 16);  // [2*BLOCK_N]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < 2 * STAGES + 1; ++s) mbar_init(bar0 + 8 * s, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), BLOCK_N);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kThreads) s_stats[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int p0 = tile_m * kBlockM;
+  const uint32_t full0 = bar0, empty0 = bar0 + 8 * STAGES, tfull = bar0 + 16 * STAGES;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int n0 = p0 / p.HW;
+      const int y0 = (p0 - n0 * p.HW) / p.W;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const int tap = kb / p.cblk, cb = kb - tap * p.cblk;
+        int dy = 0, dx = 0;
+        if (p.tap3) {
+          dy = (tap / 3 - 1) * p.tap_sign;
+          dx = (tap % 3 - 1) * p.tap_sign;
+        }
+        const uint32_t sa = base + s * kStageBytes;
+        mbar_expect_tx(full0 + 8 * s, kStageBytes);
+        tma_load_4d(sa, &tmA, full0 + 8 * s, cb * 64, dx, y0 + dy, n0);
+        tma_load_2d(sa + kABytes, &tmB, full0 + 8 * s, kb * 64, tile_n * BLOCK_N);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * kStageBytes;
+        const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(sa + kABytes, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // 4 x (K = 16) per 64-channel block: +32 bytes inside the swizzle atom
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        umma_commit(empty0 + 8 * s);  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    // ---------------- epilogue: TMEM lane quarter = warp % 4
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int pix = p0 + row;
+    const bool row_ok = pix < p.M_total;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      const int n0c = tile_n * BLOCK_N + c * 32;
+      if (n0c >= p.Cout) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (p.bias) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0c) + j4);
+          f[4 * j4] += b.x; f[4 * j4 + 1] += b.y; f[4 * j4 + 2] += b.z; f[4 * j4 + 3] += b.w;
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      const size_t off = (size_t)pix * p.ldc + n0c;
+      if (p.res1 && row_ok) {
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          float r[8];
+          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.res1 + off) + j8), r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[8 * j8 + j] += r[j];
+        }
+      }
+      if (p.res2 && row_ok) {
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          float r[8];
+          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.res2 + off) + j8), r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[8 * j8 + j] += r[j];
+        }
+      }
+      uint32_t w[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      if (row_ok) {
+        uint4* o = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) o[j4] = make_uint4(w[4 * j4], w[4 * j4 + 1], w[4 * j4 + 2], w[4 * j4 + 3]);
+      }
+      if (p.stats) {
+        // statistics of the values as stored (bf16-rounded); rows past the end contribute 0
+        float g[32], g2[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float lo = row_ok ? __uint_as_float(w[j] << 16) : 0.f;
+          const float hi = row_ok ? __uint_as_float(w[j] & 0xffff0000u) : 0.f;
+          g[2 * j] = lo; g[2 * j + 1] = hi;
+          g2[2 * j] = lo * lo; g2[2 * j + 1] = hi * hi;
+        }
+        const float s1 = warp_column_sums(g, lane);
+        const float s2 = warp_column_sums(g2, lane);
+        atomicAdd(&s_stats[c * 32 + lane], s1);
+        atomicAdd(&s_stats[BLOCK_N + c * 32 + lane], s2);
+      }
+    }
+    if (p.stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+      const int t = threadIdx.x - 64;
+      for (int i = t; i < 2 * BLOCK_N; i += 128) {
+        const int stat = i / BLOCK_N, col = i - stat * BLOCK_N;
+        const int n = tile_n * BLOCK_N + col;
+        if (n < p.Cout) atomicAdd(p.stats + (size_t)stat * p.Cout + n, s_stats[i]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BLOCK_N);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight gradient.  D[cout 128][cin BLOCK_N] accumulates over the CTA's share of the pixel tiles;
+// both operands are "MN-major" (the reduction axis -- pixels -- is the strided one), which the
+// tensor core reads directly from the same swizzled [pixel][64 channel] boxes TMA delivers.
+// ------------------------------------------------------------------------------------------
+struct WgradKernelParams {
+  int M_tiles, H, W, HW;
+  int Cin, Cout, Ktot;
+  int cin_tiles;
+  int tap3;
+  int tiles_per_split;
+  int swap_lbo_sbo;  // debug knob
+  float* dw;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY,
+                                                              const __grid_constant__ CUtensorMap tmX,
+                                                              const WgradKernelParams p) {
+  constexpr int kBBytes = (BLOCK_N / 64) * kABytes;
+  constexpr int kStageBytes = 2 * kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bar0 = base + STAGES * kStageBytes;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * kStageBytes + (2 * STAGES + 1) * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x;
+  const int tap = blockIdx.y / p.cin_tiles, cin_tile = blockIdx.y - tap * p.cin_tiles;
+  const int cout_tile = blockIdx.z;
+  const int t_begin = split * p.tiles_per_split;
+  int t_end = t_begin + p.tiles_per_split;
+  if (t_end > p.M_tiles) t_end = p.M_tiles;
+  const int nkb = t_end - t_begin;  // may be <= 0 for trailing splits
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmDY);
+    prefetch_tmap(&tmX);
+    for (int s = 0; s < 2 * STAGES + 1; ++s) mbar_init(bar0 + 8 * s, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), BLOCK_N < 32 ? 32 : BLOCK_N);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t full0 = bar0, empty0 = bar0 + 8 * STAGES, tfull = bar0 + 16 * STAGES;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int dy = 0, dx = 0;
+        if (p.tap3) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (kb / STAGES) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          const int p0 = (t_begin + kb) * kBlockM;
+          const int n0 = p0 / p.HW;
+          const int y0 = (p0 - n0 * p.HW) / p.W;
+          const uint32_t sa = base + s * kStageBytes;
+          mbar_expect_tx(full0 + 8 * s, kStageBytes);
+          tma_load_4d(sa, &tmDY, full0 + 8 * s, cout_tile * 128, 0, y0, n0);
+          tma_load_4d(sa + kABytes, &tmDY, full0 + 8 * s, cout_tile * 128 + 64, 0, y0, n0);
+#pragma unroll
+          for (int i = 0; i < BLOCK_N / 64; ++i)
+            tma_load_4d(sa + (2 + i) * kABytes, &tmX, full0 + 8 * s, cin_tile * BLOCK_N + i * 64, dx, y0 + dy, n0);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+        // MN-major, 128-byte swizzle: 64 channels contiguous (one 128-byte row per pixel), groups of
+        // 8 pixels every 1024 bytes (SBO), the next 64-channel chunk one whole box later (LBO).
+        const uint32_t lbo = p.swap_lbo_sbo ? 1024u : (uint32_t)kABytes;
+        const uint32_t sbo = p.swap_lbo_sbo ? (uint32_t)kABytes : 1024u;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (kb / STAGES) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = base + s * kStageBytes;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // 16 pixels per MMA
+            const uint64_t adesc = make_smem_desc_sw128(sa + k * 2048, lbo, sbo);
+            const uint64_t bdesc = make_smem_desc_sw128(sa + 2 * kABytes + k * 2048, lbo, sbo);
+            umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(tfull);
+      }
+    } else {
+      const int q = warp & 3;
+      const int row = cout_tile * 128 + q * 32 + lane;  // output channel
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        if (row < p.Cout) {
+          float* d = p.dw + (size_t)row * p.Ktot + (size_t)tap * p.Cin + cin_tile * BLOCK_N + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(d + j, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BLOCK_N < 32 ? 32 : BLOCK_N);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int act_box(int H, int W, ActBox* box) {
+  HGB_CHECK_ARG(W > 0 && H > 0 && (W & (W - 1)) == 0 && (H & (H - 1)) == 0 && W <= 128,
+                "conv: H and W must be powers of two, W <= 128 (got %dx%d)", H, W);
+  box->wb = W;
+  box->hb = H < 128 / W ? H : 128 / W;
+  box->nb = 128 / (box->wb * box->hb);
+  return HGB_OK;
+}
+
+int make_tmap_act(CUtensorMap* out, const void* ptr, int N, int H, int W, int C) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)"); return HGB_ERR_CUDA; }
+  HGB_CHECK_ARG(C % 8 == 0 && ((uintptr_t)ptr & 15) == 0, "activation tensor: C %% 8 and 16-byte alignment required");
+  ActBox b;
+  int rc = act_box(H, W, &b);
+  if (rc) return rc;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)b.wb, (cuuint32_t)b.hb, (cuuint32_t)b.nb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation %dx%dx%dx%d) failed: %d", N, H, W, C, (int)r); return HGB_ERR_CUDA; }
+  return HGB_OK;
+}
+
+int make_tmap_mat(CUtensorMap* out, const void* ptr, int rows, int cols, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)"); return HGB_ERR_CUDA; }
+  HGB_CHECK_ARG(cols % 8 == 0 && ((uintptr_t)ptr & 15) == 0 && box_rows <= 256, "weight matrix: bad shape/alignment");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(matrix %dx%d) failed: %d", rows, cols, (int)r); return HGB_ERR_CUDA; }
+  return HGB_OK;
+}
+
+int conv_gemm_block_n(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256); }
+
+template <int BLOCK_N, int STAGES>
+static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKernelParams& kp, int tiles_m, int tiles_n,
+                         cudaStream_t st) {
+  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + (2 * STAGES + 1) * 8 + 16 + 2 * BLOCK_N * 4 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    HGB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  conv_gemm_kernel<BLOCK_N, STAGES><<<dim3(tiles_m, tiles_n), kThreads, smem, st>>>(tmA, tmB, kp);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmArgs& a, cudaStream_t st) {
+  HGB_CHECK_ARG(a.ksize == 1 || a.ksize == 3, "conv_gemm: kernel size must be 1 or 3");
+  HGB_CHECK_ARG(a.Cin % 64 == 0 && a.Cin > 0, "conv_gemm: Cin must be a multiple of 64 (got %d)", a.Cin);
+  HGB_CHECK_ARG(a.Cout % 32 == 0 && a.Cout > 0, "conv_gemm: Cout must be a multiple of 32 (got %d)", a.Cout);
+  HGB_CHECK_ARG(a.ldc % 8 == 0 && a.ldc >= a.Cout, "conv_gemm: bad output pitch");
+  HGB_CHECK_ARG(a.tap_sign == 1 || a.tap_sign == -1, "conv_gemm: tap_sign must be +-1");
+  ActBox b;
+  int rc = act_box(a.H, a.W, &b);
+  if (rc) return rc;
+  GemmKernelParams kp;
+  kp.M_total = a.N * a.H * a.W;
+  kp.H = a.H; kp.W = a.W; kp.HW = a.H * a.W;
+  kp.cblk = a.Cin / 64;
+  kp.tap3 = a.ksize == 3;
+  kp.nkb = kp.cblk * (kp.tap3 ? 9 : 1);
+  kp.tap_sign = a.tap_sign;
+  kp.Cout = a.Cout; kp.ldc = a.ldc; kp.relu = a.relu;
+  kp.bias = a.bias; kp.res1 = a.res1; kp.res2 = a.res2; kp.out = a.out; kp.stats = a.stats;
+  if (kp.M_total == 0) return HGB_OK;
+  const int tiles_m = cdiv(kp.M_total, kBlockM);
+  const int bn = conv_gemm_block_n(a.Cout);
+  const int tiles_n = cdiv(a.Cout, bn);
+  switch (bn) {
+    case 64: return launch_gemm_t<64, 4>(tmA, tmB, kp, tiles_m, tiles_n, st);
+    case 128: return launch_gemm_t<128, 3>(tmA, tmB, kp, tiles_m, tiles_n, st);
+    default: return launch_gemm_t<256, 2>(tmA, tmB, kp, tiles_m, tiles_n, st);
+  }
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_wgrad_t(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradKernelParams& kp, dim3 grid, cudaStream_t st) {
+  constexpr int smem = STAGES * (2 + BLOCK_N / 64) * kABytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    HGB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  conv_wgrad_kernel<BLOCK_N, STAGES><<<grid, kThreads, smem, st>>>(tmDY, tmX, kp);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+int launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradArgs& a, cudaStream_t st) {
+  HGB_CHECK_ARG(a.ksize == 1 || a.ksize == 3, "conv_wgrad: kernel size must be 1 or 3");
+  HGB_CHECK_ARG(a.Cin % 64 == 0 && a.Cin > 0, "conv_wgrad: Cin must be a multiple of 64 (got %d)", a.Cin);
+  HGB_CHECK_ARG(a.Cout % 32 == 0 && a.Cout > 0, "conv_wgrad: Cout must be a multiple of 32 (got %d)", a.Cout);
+  ActBox b;
+  int rc = act_box(a.H, a.W, &b);
+  if (rc) return rc;
+  WgradKernelParams kp;
+  const int M_total = a.N * a.H * a.W;
+  if (M_total == 0) return HGB_OK;
+  kp.M_tiles = cdiv(M_total, kBlockM);
+  kp.H = a.H; kp.W = a.W; kp.HW = a.H * a.W;
+  kp.Cin = a.Cin; kp.Cout = a.Cout;
+  const int taps = a.ksize == 3 ? 9 : 1;
+  kp.Ktot = taps * a.Cin;
+  kp.tap3 = a.ksize == 3;
+  const int bn = (a.Cin % 128 == 0) ? 128 : 64;
+  kp.cin_tiles = a.Cin / bn;
+  const int cout_tiles = cdiv(a.Cout, 128);
+  const int groups = taps * kp.cin_tiles * cout_tiles;
+  int splits = cdiv(2 * 148, groups);
+  if (splits > kp.M_tiles) splits = kp.M_tiles;
+  if (splits < 1) splits = 1;
+  kp.tiles_per_split = cdiv(kp.M_tiles, splits);
+  splits = cdiv(kp.M_tiles, kp.tiles_per_split);
+  kp.swap_lbo_sbo = g_debug[1];
+  kp.dw = a.dw;
+  dim3 grid(splits, taps * kp.cin_tiles, cout_tiles);
+  if (bn == 128) return launch_wgrad_t<128, 3>(tmDY, tmX, kp, grid, st);
+  return launch_wgrad_t<64, 4>(tmDY, tmX, kp, grid, st);
+}
+
+}  // namespace hgb
+
+// ------------------------------------------------------------------------------------------
+// Stand-alone C entry points (tensor maps are built per call; the model caches them)
+// ------------------------------------------------------------------------------------------
+using namespace hgb;
+
+extern "C" int hgb_conv_gemm(const void* in, const void* w, const float* bias, const void* res1, const void* res2, void* out,
+                             float* stats, int N, int H, int W, int Cin, int Cout, int ksize, int relu, int ldc,
+                             int tap_sign, void* stream) {
+  HGB_CHECK_ARG(in && w && out, "hgb_conv_gemm: null pointer");
+  HGB_CHECK_ARG(N > 0, "hgb_conv_gemm: empty batch");
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_act(&tmA, in, N, H, W, Cin);
+  if (rc) return rc;
+  const int bn = conv_gemm_block_n(Cout);
+  rc = make_tmap_mat(&tmB, w, Cout, ksize * ksize * Cin, bn);
+  if (rc) return rc;
+  ConvGemmArgs a;
+  a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.tap_sign = tap_sign; a.relu = relu; a.ldc = ldc;
+  a.bias = bias; a.res1 = (const __nv_bfloat16*)res1; a.res2 = (const __nv_bfloat16*)res2; a.out = (__nv_bfloat16*)out;
+  a.stats = stats;
+  return launch_conv_gemm(tmA, tmB, a, (cudaStream_t)stream);
+}
+
+extern "C" int hgb_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int ksize,
+                              void* stream) {
+  HGB_CHECK_ARG(x && dy && dw, "hgb_conv_wgrad: null pointer");
+  HGB_CHECK_ARG(N > 0, "hgb_conv_wgrad: empty batch");
+  CUtensorMap tmDY, tmX;
+  int rc = make_tmap_act(&tmDY, dy, N, H, W, Cout);
+  if (rc) return rc;
+  rc = make_tmap_act(&tmX, x, N, H, W, Cin);
+  if (rc) return rc;
+  WgradArgs a;
+  a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.dw = dw;
+  return launch_conv_wgrad(tmDY, tmX, a, (cudaStream_t)stream);
+}

@@ -1,0 +1,43 @@
+// Host-side interface of the tcgen05 convolution kernels (conv_gemm.cu).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace hgb {
+
+// geometry of the 128-pixel TMA box of an NHWC activation tensor
+struct ActBox {
+  int wb, hb, nb;  // box extent along W, H, N (wb*hb*nb == 128)
+};
+int act_box(int H, int W, ActBox* box);
+
+// 4-D map over an NHWC bf16 tensor: dims (C, W, H, N), box (64, wb, hb, nb), 128-byte swizzle.
+int make_tmap_act(CUtensorMap* out, const void* ptr, int N, int H, int W, int C);
+// 2-D map over a row-major bf16 matrix [rows][cols]; box (64 cols, box_rows rows), 128-byte swizzle.
+int make_tmap_mat(CUtensorMap* out, const void* ptr, int rows, int cols, int box_rows);
+
+struct ConvGemmArgs {
+  int N, H, W, Cin, Cout;   // Cout = channels actually stored (multiple of 32)
+  int ksize;                // 1 or 3
+  int tap_sign;             // +1 forward, -1 mirrored taps (dgrad)
+  int relu;
+  int ldc;                  // pitch (elements) of out / res1 / res2
+  const float* bias;        // [Cout] or null
+  const __nv_bfloat16* res1;
+  const __nv_bfloat16* res2;
+  __nv_bfloat16* out;
+  float* stats;             // [2*Cout] (sum, sumsq), added to; or null
+};
+// tmA: activation map of the input; tmB: weight matrix [>=Cout rows][ksize^2*Cin], box rows = block_n
+int conv_gemm_block_n(int Cout);
+int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmArgs& a, cudaStream_t st);
+
+struct WgradArgs {
+  int N, H, W, Cin, Cout;
+  int ksize;
+  float* dw;                // [Cout][ksize^2*Cin] fp32, added to
+};
+// tmDY: activation map of dy (C = Cout); tmX: activation map of x (C = Cin)
+int launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradArgs& a, cudaStream_t st);
+
+}  // namespace hgb

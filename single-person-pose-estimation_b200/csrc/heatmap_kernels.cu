@@ -1,0 +1,635 @@
+// Heatmap-path kernels: target rendering, one-pass losses, decode, PCK / OKS.
+// All are HBM- or latency-bound byte/float streaming kernels: 16-byte coalesced
+// accesses, per-joint state kept in registers by making the per-thread element stride a
+// multiple of the joint count (so a thread always sees the same joints), warp-shuffle
+// reductions, no tensor cores.
+//
+// Reference arithmetic (relative to the reference tree):
+//   render  : dataset_builder.py:220-235, utilities/data_utils.py:187-211
+//   losses  : loss.py:2-36, trainer.py:231-233
+//   decode  : utilities/data_utils.py:100-183
+//   PCK     : eval.py:62-88 ; OKS: public COCO keypoint similarity (pycocotools computeOks)
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace hgb {
+
+// ------------------------------------------------------------------------------------
+// Target rendering
+// ------------------------------------------------------------------------------------
+// float32(exp(-d2/2)) for d2 = dx^2+dy^2, |dx|,|dy| <= 3 -- bit patterns of the values numpy
+// produces (float64 exp, rounded on assignment into the float32 map; data_utils.py:202,209).
+__constant__ uint32_t c_gauss_lut[19] = {
+    0x3f800000u /*0*/, 0x3f1b4598u /*1*/, 0x3ebc5ab2u /*2*/, 0u, 0x3e0a9555u /*4*/, 0x3da81c2eu /*5*/, 0u, 0u,
+    0x3c960aaeu /*8*/, 0x3c360282u /*9*/, 0x3bdcc9ffu /*10*/, 0u, 0u, 0x3ac50f0cu /*13*/, 0u, 0u, 0u, 0u,
+    0x39016791u /*18*/};
+
+__global__ void __launch_bounds__(256) render_targets_kernel(const float* __restrict__ kx, const float* __restrict__ ky,
+                                                             const int32_t* __restrict__ kv, int H, int W, int K,
+                                                             int vec_per_sample, float* __restrict__ out) {
+  // grid: (chunks, B).  One sample's K joints are staged in smem as integer centres.
+  extern __shared__ int s_joint[];  // [K][2]: cx, cy  (cx = INT_MIN/2 when the joint is not drawn)
+  const int b = blockIdx.y;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float fx = kx[(size_t)b * K + k], fy = ky[(size_t)b * K + k];
+    const int x = (int)fx, y = (int)fy;  // Python int(): truncate toward zero (dataset_builder.py:229-230)
+    const bool ok = (0 < x) && (x < W) && (0 < y) && (y < H) && (kv[(size_t)b * K + k] > 0);
+    s_joint[2 * k] = ok ? x : -(1 << 28);
+    s_joint[2 * k + 1] = y;
+  }
+  __syncthreads();
+  float4* o4 = reinterpret_cast<float4*>(out + (size_t)b * H * W * K);
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < vec_per_sample; v += gridDim.x * blockDim.x) {
+    const int e0 = v * 4;
+    int pix = e0 / K;
+    int k = e0 - pix * K;
+    int py = pix / W, px = pix - py * W;
+    float r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int dx = px - s_joint[2 * k], dy = py - s_joint[2 * k + 1];
+      const int adx = dx < 0 ? -dx : dx, ady = dy < 0 ? -dy : dy;
+      float val = 0.f;
+      if (adx <= 3 && ady <= 3) val = __uint_as_float(c_gauss_lut[adx * adx + ady * ady]);
+      r[j] = val;
+      if (++k == K) {
+        k = 0;
+        if (++px == W) { px = 0; ++py; }
+      }
+    }
+    __stcs(o4 + v, make_float4(r[0], r[1], r[2], r[3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Losses
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+struct Vec4 {};
+template <>
+struct Vec4<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&r)[4]) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&r)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+};
+template <>
+struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&r)[4]) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+    r[0] = __low2float(a); r[1] = __high2float(a); r[2] = __low2float(b); r[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&r)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(r[0], r[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(r[2], r[3]);
+    uint2 v;
+    v.x = *reinterpret_cast<uint32_t*>(&a);
+    v.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = v;
+  }
+};
+
+// Per-(b,k) sums.  Block = 16*K threads, one block per sample; thread t always owns joints
+// (4t + j) % K because the vector stride 4*blockDim is a multiple of K.
+//   mode 0: s0 = sum t                        (weighted_keypoint_mse, loss.py:32)
+//   mode 1: s0 = sum t*p, s1 = sum t*t, s2 = sum p*p   (IOU, loss.py:25-26)
+template <typename TP, int MODE>
+__global__ void bk_sums_kernel(const float* __restrict__ yt, const TP* __restrict__ yp, int HWK, int K,
+                               float* __restrict__ ws /* [B][K][4] */) {
+  extern __shared__ float s_part[];  // [3][S*4]
+  const int b = blockIdx.x, t = threadIdx.x, S = 16 * K;  // blockDim = S rounded up to a warp multiple
+  const float* tb = yt + (size_t)b * HWK;
+  const TP* pb = yp + (size_t)b * HWK;
+  float a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+  for (int v = t; v < HWK / 4 && t < S; v += S) {
+    float tv[4], pv[4];
+    Vec4<float>::load(tb + 4 * (size_t)v, tv);
+    if (MODE == 1) Vec4<TP>::load(pb + 4 * (size_t)v, pv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (MODE == 0) {
+        a0[j] += tv[j];
+      } else {
+        a0[j] += tv[j] * pv[j];
+        a1[j] += tv[j] * tv[j];
+        a2[j] += pv[j] * pv[j];
+      }
+    }
+  }
+  if (t < S) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s_part[0 * 4 * S + 4 * t + j] = a0[j];
+      if (MODE == 1) {
+        s_part[1 * 4 * S + 4 * t + j] = a1[j];
+        s_part[2 * 4 * S + 4 * t + j] = a2[j];
+      }
+    }
+  }
+  __syncthreads();
+  // candidate c = 4t+j belongs to joint c % K; 64 candidates per joint
+  const int warp = t >> 5, lane = t & 31, nwarp = blockDim.x >> 5;
+  for (int k = warp; k < K; k += nwarp) {
+    double r0 = 0, r1 = 0, r2 = 0;
+    for (int m = lane; m < 64; m += 32) {
+      const int c = k + K * m;
+      r0 += (double)s_part[c];
+      if (MODE == 1) {
+        r1 += (double)s_part[4 * S + c];
+        r2 += (double)s_part[8 * S + c];
+      }
+    }
+    r0 = warp_sum_d(r0);
+    if (MODE == 1) { r1 = warp_sum_d(r1); r2 = warp_sum_d(r2); }
+    if (lane == 0) {
+      float* o = ws + ((size_t)b * K + k) * 4;
+      if (MODE == 0) {
+        o[0] = (float)r0;
+      } else {
+        // IoU pieces: a = 1/(U+eps), c = (I+eps)/(U+eps)^2, iou
+        const double eps = 1e-7;
+        const double U = r1 + r2 - r0;
+        const double a = 1.0 / (U + eps);
+        const double iou = (r0 + eps) * a;
+        o[0] = (float)a;
+        o[1] = (float)(iou * a);
+        o[2] = (float)iou;
+      }
+    }
+  }
+}
+
+// One pass: loss partial sums + gradient.  kind 0 weighted_mse, 1 mse, 2 iou, 3 keypoint mse.
+template <typename TP, typename TG, int KIND>
+__global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ yt, const TP* __restrict__ yp,
+                                                        TG* __restrict__ grad, const float* __restrict__ ws,
+                                                        int64_t nvec, int HWK, int K, double inv_count,
+                                                        double* __restrict__ loss_acc) {
+  const float gscale = (float)(2.0 * inv_count);
+  const float iou_gscale = (float)inv_count;
+  double part = 0.0;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    float tv[4], pv[4], gv[4];
+    Vec4<float>::load(yt + 4 * v, tv);
+    Vec4<TP>::load(yp + 4 * v, pv);
+    int b = 0, k = 0;
+    if (KIND >= 2) {
+      const int64_t e0 = 4 * v;
+      b = (int)(e0 / HWK);
+      k = (int)((e0 - (int64_t)b * HWK) % K);
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float d = pv[j] - tv[j];
+      if (KIND == 0) {
+        const float w = tv[j] > 0.f ? 82.f : 1.f;  // loss.py:14
+        acc += w * d * d;
+        gv[j] = gscale * w * d;
+      } else if (KIND == 1) {
+        acc += d * d;
+        gv[j] = gscale * d;
+      } else if (KIND == 3) {
+        const float kw = ws[((size_t)b * K + k) * 4] == 0.f ? 0.f : 1.f;  // loss.py:34
+        acc += kw * d * d;
+        gv[j] = gscale * kw * d;
+      } else {  // IoU: d iou/dp = t*a - c*(2p - t); loss = sum(1 - iou)/(B*K)
+        const float* c = ws + ((size_t)b * K + k) * 4;
+        gv[j] = -iou_gscale * (tv[j] * c[0] - c[1] * (2.f * pv[j] - tv[j]));
+      }
+      if (KIND >= 2) {
+        if (++k == K) k = 0;  // HWK % 4 == 0 so a vector never crosses a sample
+      }
+    }
+    part += (double)acc;
+    if (grad) Vec4<TG>::store(grad + 4 * v, gv);
+  }
+  if (KIND == 2) return;  // IoU loss scalar is summed by iou_loss_sum_kernel
+  part = warp_sum_d(part);
+  __shared__ double s_w[8];
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += s_w[i];
+    atomicAdd(loss_acc, s * inv_count);
+  }
+}
+
+__global__ void iou_loss_sum_kernel(const float* __restrict__ ws, int BK, double inv_count, double* loss_acc) {
+  double part = 0;
+  for (int i = threadIdx.x; i < BK; i += blockDim.x) part += 1.0 - (double)ws[(size_t)i * 4 + 2];
+  part = warp_sum_d(part);
+  __shared__ double s_w[32];
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += s_w[i];
+    atomicAdd(loss_acc, s * inv_count);
+  }
+}
+
+// (B,H,W) map the reference loss functions return (mean over the joint axis).
+template <int KIND>
+__global__ void loss_map_kernel(const float* __restrict__ yt, const float* __restrict__ yp, const float* __restrict__ ws,
+                                int64_t npix, int HW, int K, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const int b = (int)(i / HW);
+  const float* t = yt + i * K;
+  const float* p = yp + i * K;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float d = t[k] - p[k];
+    float w = 1.f;
+    if (KIND == 0) w = t[k] > 0.f ? 82.f : 1.f;
+    if (KIND == 3) w = ws[((size_t)b * K + k) * 4] == 0.f ? 0.f : 1.f;
+    acc += d * d * w;
+  }
+  out[i] = acc / (float)K;
+}
+
+__global__ void iou_vec_kernel(const float* __restrict__ ws, int B, int K, float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) s += ws[((size_t)b * K + k) * 4 + 2];
+  out[b] = 1.f - s / (float)K;
+}
+
+// ------------------------------------------------------------------------------------
+// Decode
+// ------------------------------------------------------------------------------------
+// numpy argmax order: a NaN beats everything, then larger value, then lower flat index.
+__device__ __forceinline__ bool better(float a, int ia, float b, int ib) {
+  const bool an = a != a, bn = b != b;
+  if (an || bn) return an && (!bn || ia < ib);
+  return a > b || (a == b && ia < ib);
+}
+
+template <typename T, int VEC>
+struct DecLoad {};
+template <>
+struct DecLoad<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, float (&r)[4]) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(p));
+    r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+  }
+};
+template <>
+struct DecLoad<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&r)[8]) {
+    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      r[2 * i] = __uint_as_float(w[i] << 16);
+      r[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// One block (16*K threads) per sample.  The vector stride VEC*blockDim is a multiple of K, so
+// slot j of thread t always carries joint (VEC*t + j) % K: VEC running (value,index) pairs in
+// registers, no dynamic indexing.  UNROLL independent 16-byte loads are in flight per thread.
+template <typename T, int VEC>
+__global__ void decode_kernel(const T* __restrict__ hm, int H, int W, int K, double thr, int version,
+                              int32_t* __restrict__ out_idx, float* __restrict__ out_kp) {
+  extern __shared__ unsigned char s_raw[];
+  const int S = 16 * K, t = threadIdx.x, b = blockIdx.x;  // blockDim = S rounded up to a warp multiple
+  float* s_val = reinterpret_cast<float*>(s_raw);         // [S*VEC]
+  int* s_idx = reinterpret_cast<int*>(s_raw) + S * VEC;   // [S*VEC]
+  const int HWK = H * W * K;
+  const int nvec = HWK / VEC;
+  const T* base = hm + (size_t)b * HWK;
+
+  float bv[VEC];
+  int bi[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { bv[j] = -CUDART_INF_F; bi[j] = 0x7fffffff; }
+
+  constexpr int UNROLL = 4;
+  int v = t < S ? t : nvec;  // the padding threads of the last warp only help in the reduction
+  for (; v + (UNROLL - 1) * S < nvec; v += UNROLL * S) {
+    float r[UNROLL][VEC];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) DecLoad<T, VEC>::load(base + (size_t)(v + u * S) * VEC, r[u]);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int e = (v + u * S) * VEC + j;
+        if (better(r[u][j], e, bv[j], bi[j])) { bv[j] = r[u][j]; bi[j] = e; }
+      }
+  }
+  for (; v < nvec; v += S) {
+    float r[VEC];
+    DecLoad<T, VEC>::load(base + (size_t)v * VEC, r);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int e = v * VEC + j;
+      if (better(r[j], e, bv[j], bi[j])) { bv[j] = r[j]; bi[j] = e; }
+    }
+  }
+  if (t < S) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      s_val[t * VEC + j] = bv[j];
+      s_idx[t * VEC + j] = bi[j];
+    }
+  }
+  __syncthreads();
+
+  const int warp = t >> 5, lane = t & 31, nwarp = blockDim.x >> 5;
+  const int ncand = 16 * VEC;  // candidates per joint: c = k + K*m
+  for (int k = warp; k < K; k += nwarp) {
+    float cv = -CUDART_INF_F;
+    int ci = 0x7fffffff;
+    for (int m = lane; m < ncand; m += 32) {
+      const float a = s_val[k + K * m];
+      const int ia = s_idx[k + K * m];
+      if (better(a, ia, cv, ci)) { cv = a; ci = ia; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+      if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
+    }
+    if (lane == 0) {
+      const int index = ci / K;  // flat pixel index (row-major)
+      const int x = index % W;   // data_utils.py:121
+      const int y = index / H;   // data_utils.py:122 (height; square maps only)
+      const float conf = cv;
+      int pidx = 0;
+      if (version == 2) {        // data_utils.py:160-169
+        const int x1 = max(x - 1, 0), x2 = min(x + 2, W), y1 = max(y - 1, 0), y2 = min(y + 2, H);
+        const int pw = x2 - x1, ph = y2 - y1;
+        float pb = 0.f;
+        int pbi = 0x7fffffff;
+        for (int r = 0; r < ph; ++r)
+          for (int c = 0; c < pw; ++c) {
+            float a = (r == 1 && c == 1) ? 0.f : to_f32<T>(base[((size_t)(y1 + r) * W + (x1 + c)) * K + k]);
+            const int ia = r * pw + c;
+            if (pbi == 0x7fffffff || better(a, ia, pb, pbi)) { pb = a; pbi = ia; }
+          }
+        pidx = pbi;
+      }
+      const int px = pidx % 3, py = pidx / 3;  // always 3 (data_utils.py:168-169)
+      int32_t* oi = out_idx + ((size_t)b * K + k) * 4;
+      oi[0] = index; oi[1] = x; oi[2] = y; oi[3] = pidx;
+      float* ok = out_kp + ((size_t)b * K + k) * 3;
+      if ((double)conf > thr) {
+        ok[0] = (float)x + 0.25f * (float)px;
+        ok[1] = (float)y + 0.25f * (float)py;
+        ok[2] = conf;
+      } else {
+        ok[0] = 0.f; ok[1] = 0.f; ok[2] = 0.f;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// PCK / OKS
+// ------------------------------------------------------------------------------------
+__global__ void pck_kernel(const double* __restrict__ xp, const double* __restrict__ yp, const double* __restrict__ xg,
+                           const double* __restrict__ yg, const int32_t* __restrict__ vs,
+                           const double* __restrict__ bbox_wh, int N, int K, double pck_thr, int32_t* counts) {
+  extern __shared__ int s_cnt[];  // [2K]
+  for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * K; i += gridDim.x * blockDim.x) {
+    const int n = i / K, k = i - n * K;
+    if (vs[i] > 0) {
+      const double bw = bbox_wh[2 * n], bh = bbox_wh[2 * n + 1];
+      const double diam = sqrt(__dadd_rn(__dmul_rn(bw, bw), __dmul_rn(bh, bh)));  // eval.py:70
+      const double th = __dmul_rn(pck_thr, diam);                                  // eval.py:71
+      const double dx = __dsub_rn(xg[i], xp[i]), dy = __dsub_rn(yg[i], yp[i]);
+      const double dist = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));  // eval.py:85
+      atomicAdd(&s_cnt[K + k], 1);
+      if (dist <= th) atomicAdd(&s_cnt[k], 1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * K; i += blockDim.x)
+    if (s_cnt[i]) atomicAdd(&counts[i], s_cnt[i]);
+}
+
+__constant__ double c_coco_sigmas[17] = {.026, .025, .025, .035, .035, .079, .079, .072, .072,
+                                         .062, .062, .107, .107, .087, .087, .089, .089};
+
+__global__ void oks_kernel(const double* __restrict__ xp, const double* __restrict__ yp, const double* __restrict__ xg,
+                           const double* __restrict__ yg, const int32_t* __restrict__ vs, const double* __restrict__ area,
+                           const double* __restrict__ bb, int N, int K, double* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int k1 = 0;
+  for (int k = 0; k < K; ++k) k1 += vs[(size_t)n * K + k] > 0;
+  const double a = area[n] + 2.220446049250313e-16;  // np.spacing(1)
+  double s = 0;
+  int cnt = 0;
+  for (int k = 0; k < K; ++k) {
+    const size_t i = (size_t)n * K + k;
+    double dx, dy;
+    if (k1 > 0) {
+      if (!(vs[i] > 0)) continue;
+      dx = xp[i] - xg[i];
+      dy = yp[i] - yg[i];
+    } else {
+      const double x0 = bb[4 * n] - bb[4 * n + 2], x1 = bb[4 * n] + bb[4 * n + 2] * 2;
+      const double y0 = bb[4 * n + 1] - bb[4 * n + 3], y1 = bb[4 * n + 1] + bb[4 * n + 3] * 2;
+      dx = fmax(0.0, x0 - xp[i]) + fmax(0.0, xp[i] - x1);
+      dy = fmax(0.0, y0 - yp[i]) + fmax(0.0, yp[i] - y1);
+    }
+    const double sg = c_coco_sigmas[k] * 2;
+    const double e = (dx * dx + dy * dy) / (sg * sg) / a / 2;
+    s += exp(-e);
+    ++cnt;
+  }
+  out[n] = cnt ? s / cnt : 0.0;
+}
+
+}  // namespace hgb
+
+// ------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------
+using namespace hgb;
+
+extern "C" int hgb_render_targets(const float* kps_x, const float* kps_y, const int32_t* kps_v, int B, int H, int W,
+                                  int K, float* out, void* stream) {
+  HGB_CHECK_ARG(kps_x && kps_y && kps_v && out, "hgb_render_targets: null pointer");
+  HGB_CHECK_ARG(B >= 0 && H > 0 && W > 0 && K > 0 && K <= 1024, "hgb_render_targets: bad shape");
+  HGB_CHECK_ARG(((int64_t)H * W * K) % 4 == 0, "hgb_render_targets: H*W*K must be a multiple of 4");
+  if (B == 0) return HGB_OK;
+  const int vec = H * W * K / 4;
+  int chunks = cdiv(vec, 256 * 4);
+  const int want = cdiv(148 * 8, B);
+  if (chunks > want) chunks = want < 1 ? 1 : want;
+  dim3 grid(chunks, B);
+  render_targets_kernel<<<grid, 256, 2 * K * sizeof(int), (cudaStream_t)stream>>>(kps_x, kps_y, kps_v, H, W, K, vec, out);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+extern "C" int64_t hgb_loss_workspace_bytes(int B, int K) { return (int64_t)B * K * 4 * sizeof(float) + 256; }
+
+template <typename TP>
+static int launch_bk_sums(int kind, const float* yt, const TP* yp, int B, int HWK, int K, float* ws, cudaStream_t st) {
+  const int threads = (16 * K + 31) / 32 * 32;
+  const size_t smem = 3 * 4 * (16 * K) * sizeof(float);
+  if (kind == HGB_LOSS_IOU)
+    bk_sums_kernel<TP, 1><<<B, threads, smem, st>>>(yt, yp, HWK, K, ws);
+  else
+    bk_sums_kernel<TP, 0><<<B, threads, smem, st>>>(yt, yp, HWK, K, ws);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+template <typename TP, typename TG>
+static int launch_loss(int kind, const float* yt, const TP* yp, TG* grad, const float* ws, int64_t nvec, int HWK, int K,
+                       double inv_count, double* loss_acc, cudaStream_t st) {
+  int blocks = (int)((nvec + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  switch (kind) {
+    case 0: loss_grad_kernel<TP, TG, 0><<<blocks, 256, 0, st>>>(yt, yp, grad, ws, nvec, HWK, K, inv_count, loss_acc); break;
+    case 1: loss_grad_kernel<TP, TG, 1><<<blocks, 256, 0, st>>>(yt, yp, grad, ws, nvec, HWK, K, inv_count, loss_acc); break;
+    case 2: loss_grad_kernel<TP, TG, 2><<<blocks, 256, 0, st>>>(yt, yp, grad, ws, nvec, HWK, K, inv_count, loss_acc); break;
+    default: loss_grad_kernel<TP, TG, 3><<<blocks, 256, 0, st>>>(yt, yp, grad, ws, nvec, HWK, K, inv_count, loss_acc); break;
+  }
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+extern "C" int hgb_loss_fwd_bwd(int kind, const float* y_true, const void* y_pred, int pred_dtype, int B, int H, int W,
+                                int K, double inv_count, double* loss_acc, void* grad, int grad_dtype, void* workspace,
+                                void* stream) {
+  HGB_CHECK_ARG(kind >= 0 && kind <= 3, "hgb_loss_fwd_bwd: unknown loss kind %d", kind);
+  HGB_CHECK_ARG(y_true && y_pred && loss_acc, "hgb_loss_fwd_bwd: null pointer");
+  HGB_CHECK_ARG(B >= 0 && H > 0 && W > 0 && K > 0 && K <= 64, "hgb_loss_fwd_bwd: bad shape");
+  HGB_CHECK_ARG(((int64_t)H * W * K) % 4 == 0, "hgb_loss_fwd_bwd: H*W*K must be a multiple of 4");
+  HGB_CHECK_ARG(pred_dtype == HGB_F32 || pred_dtype == HGB_BF16, "hgb_loss_fwd_bwd: bad pred dtype");
+  HGB_CHECK_ARG(grad_dtype == HGB_F32 || grad_dtype == HGB_BF16, "hgb_loss_fwd_bwd: bad grad dtype");
+  HGB_CHECK_ARG(kind < 2 || workspace, "hgb_loss_fwd_bwd: this loss needs a workspace");
+  if (B == 0) return HGB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HWK = H * W * K;
+  const int64_t nvec = (int64_t)B * HWK / 4;
+  float* ws = (float*)workspace;
+  int rc = HGB_OK;
+  if (kind >= 2) {
+    rc = pred_dtype == HGB_F32 ? launch_bk_sums<float>(kind, y_true, (const float*)y_pred, B, HWK, K, ws, st)
+                               : launch_bk_sums<__nv_bfloat16>(kind, y_true, (const __nv_bfloat16*)y_pred, B, HWK, K, ws, st);
+    if (rc) return rc;
+    if (kind == HGB_LOSS_IOU) {
+      iou_loss_sum_kernel<<<1, 1024, 0, st>>>(ws, B * K, inv_count, loss_acc);
+      HGB_LAUNCH_CHECK();
+      if (!grad) return HGB_OK;
+    }
+  }
+  if (pred_dtype == HGB_F32) {
+    if (grad_dtype == HGB_F32)
+      rc = launch_loss<float, float>(kind, y_true, (const float*)y_pred, (float*)grad, ws, nvec, HWK, K, inv_count, loss_acc, st);
+    else
+      rc = launch_loss<float, __nv_bfloat16>(kind, y_true, (const float*)y_pred, (__nv_bfloat16*)grad, ws, nvec, HWK, K, inv_count, loss_acc, st);
+  } else {
+    if (grad_dtype == HGB_F32)
+      rc = launch_loss<__nv_bfloat16, float>(kind, y_true, (const __nv_bfloat16*)y_pred, (float*)grad, ws, nvec, HWK, K, inv_count, loss_acc, st);
+    else
+      rc = launch_loss<__nv_bfloat16, __nv_bfloat16>(kind, y_true, (const __nv_bfloat16*)y_pred, (__nv_bfloat16*)grad, ws, nvec, HWK, K, inv_count, loss_acc, st);
+  }
+  return rc;
+}
+
+extern "C" int hgb_loss_map(int kind, const float* y_true, const float* y_pred, int B, int H, int W, int K, float* out,
+                            void* workspace, void* stream) {
+  HGB_CHECK_ARG(kind >= 0 && kind <= 3, "hgb_loss_map: unknown loss kind %d", kind);
+  HGB_CHECK_ARG(y_true && y_pred && out, "hgb_loss_map: null pointer");
+  HGB_CHECK_ARG(B >= 0 && H > 0 && W > 0 && K > 0 && K <= 64, "hgb_loss_map: bad shape");
+  HGB_CHECK_ARG(kind < 2 || (workspace && ((int64_t)H * W * K) % 4 == 0), "hgb_loss_map: workspace / shape");
+  if (B == 0) return HGB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HWK = H * W * K;
+  float* ws = (float*)workspace;
+  if (kind >= 2) {
+    int rc = launch_bk_sums<float>(kind, y_true, y_pred, B, HWK, K, ws, st);
+    if (rc) return rc;
+  }
+  const int64_t npix = (int64_t)B * H * W;
+  const int blocks = (int)((npix + 255) / 256);
+  switch (kind) {
+    case 0: loss_map_kernel<0><<<blocks, 256, 0, st>>>(y_true, y_pred, ws, npix, H * W, K, out); break;
+    case 1: loss_map_kernel<1><<<blocks, 256, 0, st>>>(y_true, y_pred, ws, npix, H * W, K, out); break;
+    case 3: loss_map_kernel<3><<<blocks, 256, 0, st>>>(y_true, y_pred, ws, npix, H * W, K, out); break;
+    default: iou_vec_kernel<<<(B + 127) / 128, 128, 0, st>>>(ws, B, K, out); break;
+  }
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+extern "C" int hgb_decode(const void* heatmaps, int dtype, int B, int H, int W, int K, double conf_threshold,
+                          int version, int32_t* out_idx, float* out_kpts, void* stream) {
+  HGB_CHECK_ARG(heatmaps && out_idx && out_kpts, "hgb_decode: null pointer");
+  HGB_CHECK_ARG(version == 1 || version == 2, "hgb_decode: version must be 1 or 2");
+  HGB_CHECK_ARG(H == W, "hgb_decode: reference divides the flat index by height (data_utils.py:122); H must equal W");
+  HGB_CHECK_ARG(B >= 0 && H >= 2 && K > 0 && K <= 64, "hgb_decode: bad shape");
+  HGB_CHECK_ARG(dtype == HGB_F32 || dtype == HGB_BF16, "hgb_decode: bad dtype");
+  const int vec = dtype == HGB_F32 ? 4 : 8;
+  HGB_CHECK_ARG(((int64_t)H * W * K) % vec == 0, "hgb_decode: H*W*K must be a multiple of %d", vec);
+  HGB_CHECK_ARG((int64_t)H * W * K < (1ll << 31), "hgb_decode: map too large");
+  if (B == 0) return HGB_OK;
+  const int threads = (16 * K + 31) / 32 * 32;
+  const size_t smem = (size_t)(16 * K) * vec * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == HGB_F32)
+    decode_kernel<float, 4><<<B, threads, smem, st>>>((const float*)heatmaps, H, W, K, conf_threshold, version, out_idx, out_kpts);
+  else
+    decode_kernel<__nv_bfloat16, 8><<<B, threads, smem, st>>>((const __nv_bfloat16*)heatmaps, H, W, K, conf_threshold, version, out_idx, out_kpts);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+extern "C" int hgb_pck_reduce(const double* xs_pred, const double* ys_pred, const double* xs_gt, const double* ys_gt,
+                              const int32_t* vs, const double* bbox_wh, int N, int K, double pck_threshold,
+                              int32_t* counts, void* stream) {
+  HGB_CHECK_ARG(xs_pred && ys_pred && xs_gt && ys_gt && vs && bbox_wh && counts, "hgb_pck_reduce: null pointer");
+  HGB_CHECK_ARG(N >= 0 && K > 0 && K <= 1024, "hgb_pck_reduce: bad shape");
+  if (N == 0) return HGB_OK;
+  int blocks = cdiv((int64_t)N * K, 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  pck_kernel<<<blocks, 256, 2 * K * sizeof(int), (cudaStream_t)stream>>>(xs_pred, ys_pred, xs_gt, ys_gt, vs, bbox_wh, N, K,
+                                                                         pck_threshold, counts);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+extern "C" int hgb_oks_similarity(const double* xs_pred, const double* ys_pred, const double* xs_gt, const double* ys_gt,
+                                  const int32_t* vs, const double* area, const double* bbox_xywh, int N, int K,
+                                  double* oks_out, void* stream) {
+  HGB_CHECK_ARG(xs_pred && ys_pred && xs_gt && ys_gt && vs && area && bbox_xywh && oks_out, "hgb_oks_similarity: null pointer");
+  HGB_CHECK_ARG(N >= 0 && K > 0 && K <= 17, "hgb_oks_similarity: K must be in [1,17] (COCO sigmas)");
+  if (N == 0) return HGB_OK;
+  oks_kernel<<<cdiv(N, 128), 128, 0, (cudaStream_t)stream>>>(xs_pred, ys_pred, xs_gt, ys_gt, vs, area, bbox_xywh, N, K, oks_out);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
