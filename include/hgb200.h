@@ -75,7 +75,7 @@ int hgb_loss_map(int kind, const float* y_true, const float* y_pred,
 /* utilities/data_utils.py:100-132 (version 1) and :135-183 (version 2).
  * heatmaps (B,H,W,K) in `dtype`, H == W required (data_utils.py:122 divides by height).
  * out_idx (B,K,4) int32 = [argmax index, x, y, patch argmax index]; out_kpts (B,K,3) f32 =
- * [x + dx, y + dy, conf] or zeros when conf <= conf_threshold (compared in double). The
+ * [x + dx, y + dy, conf] or zeros when conf <= float32(conf_threshold) (numpy >= 2 semantics). The
  * input is NOT modified; the (1,1) element of the clipped 3x3 window is read as 0. */
 int hgb_decode(const void* heatmaps, int dtype, int B, int H, int W, int K,
                double conf_threshold, int version, int32_t* out_idx, float* out_kpts, void* stream);
@@ -159,6 +159,10 @@ int hgb_model_segment_grads(const hgb_model* m, int seg, int64_t* offset, int64_
  * Also refreshes the bf16 GEMM weights. */
 int hgb_model_adam_step(hgb_model* m, double lr, double beta1, double beta2, double eps, int64_t t,
                         double grad_scale, void* stream);
+
+/* debugging / layer-wise parity: where conv `index` wrote its (bias+activation) output, bf16 NHWC,
+ * dims = {N,H,W,C_padded}, as a byte offset into the bound arena */
+int hgb_model_conv_output(const hgb_model* m, int index, int64_t* arena_offset, int dims[4]);
 
 /* number of kernels this handle has launched since creation (bench "gpu_launches") */
 int64_t hgb_model_launch_count(const hgb_model* m);

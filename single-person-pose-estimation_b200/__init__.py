@@ -16,3 +16,8 @@ __all__ = ["_lib"]
 from . import ops  # noqa: E402,F401
 
 __all__ += ["ops"]
+from . import loss, parallel  # noqa: E402,F401
+from .model import hourglass  # noqa: E402,F401
+from .model.hourglass import Adam, HourglassModel, create_hourglass_model  # noqa: E402,F401
+
+__all__ += ["loss", "parallel", "hourglass", "Adam", "HourglassModel", "create_hourglass_model"]

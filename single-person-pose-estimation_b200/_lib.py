@@ -56,6 +56,7 @@ PROTOTYPES = {
     "hgb_model_backward": (i32, [vp, i32, i32, vp]),
     "hgb_model_segment_grads": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i64)]),
     "hgb_model_adam_step": (i32, [vp, f64, f64, f64, f64, i64, f64, vp]),
+    "hgb_model_conv_output": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i32 * 4)]),
     "hgb_model_launch_count": (i64, [vp]),
 }
 

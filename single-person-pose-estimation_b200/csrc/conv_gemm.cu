@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
 // ------------------------------------------------------------------------------------------
 struct WgradKernelParams {
   int M_tiles, H, W, HW;
-  int Cin, Cout, Ktot;
+  int Cin_valid, Cout, ldw;  // valid input channels, valid output channels, row pitch of dw
   int cin_tiles;
   int tap3;
   int tiles_per_split;
@@ -341,10 +341,17 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
         tmem_ld_wait();
-        if (row < p.Cout) {
-          float* d = p.dw + (size_t)row * p.Ktot + (size_t)tap * p.Cin + cin_tile * BLOCK_N + c * 32;
+        const int col0 = cin_tile * BLOCK_N + c * 32;
+        if (row < p.Cout && col0 < p.Cin_valid) {
+          float* d = p.dw + (size_t)row * p.ldw + (size_t)tap * p.Cin_valid + col0;
+          if (col0 + 32 <= p.Cin_valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(d + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j) atomicAdd(d + j, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.Cin_valid) atomicAdd(d + j, __uint_as_float(v[j]));
+          }
         }
       }
     }
@@ -488,9 +495,10 @@ int launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const Wgr
   if (M_total == 0) return HGB_OK;
   kp.M_tiles = cdiv(M_total, kBlockM);
   kp.H = a.H; kp.W = a.W; kp.HW = a.H * a.W;
-  kp.Cin = a.Cin; kp.Cout = a.Cout;
   const int taps = a.ksize == 3 ? 9 : 1;
-  kp.Ktot = taps * a.Cin;
+  kp.Cin_valid = a.Cin_valid > 0 ? a.Cin_valid : a.Cin;
+  kp.Cout = a.Cout_valid > 0 ? a.Cout_valid : a.Cout;
+  kp.ldw = taps * kp.Cin_valid;
   kp.tap3 = a.ksize == 3;
   const int bn = (a.Cin % 128 == 0) ? 128 : 64;
   kp.cin_tiles = a.Cin / bn;
@@ -544,5 +552,6 @@ extern "C" int hgb_conv_wgrad(const void* x, const void* dy, float* dw, int N, i
   if (rc) return rc;
   WgradArgs a;
   a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.dw = dw;
+  a.Cin_valid = 0; a.Cout_valid = 0;
   return launch_conv_wgrad(tmDY, tmX, a, (cudaStream_t)stream);
 }

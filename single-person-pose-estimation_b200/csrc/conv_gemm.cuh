@@ -35,7 +35,8 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvG
 struct WgradArgs {
   int N, H, W, Cin, Cout;
   int ksize;
-  float* dw;                // [Cout][ksize^2*Cin] fp32, added to
+  int Cin_valid, Cout_valid; // 0 = all; otherwise only dw[:Cout_valid][tap][:Cin_valid] is written (padded tensors)
+  float* dw;                // [Cout_valid][ksize^2*Cin_valid] fp32, added to
 };
 // tmDY: activation map of dy (C = Cout); tmX: activation map of x (C = Cin)
 int launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradArgs& a, cudaStream_t st);

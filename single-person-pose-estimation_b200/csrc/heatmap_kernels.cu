@@ -398,7 +398,9 @@ __global__ void decode_kernel(const T* __restrict__ hm, int H, int W, int K, dou
       int32_t* oi = out_idx + ((size_t)b * K + k) * 4;
       oi[0] = index; oi[1] = x; oi[2] = y; oi[3] = pidx;
       float* ok = out_kp + ((size_t)b * K + k) * 3;
-      if ((double)conf > thr) {
+      // numpy >= 2 (NEP 50) compares the float32 confidence with float32(threshold); numpy 1.x
+      // promoted to float64.  They differ only when conf == float32(thr) rounds above thr.
+      if (conf > (float)thr) {
         ok[0] = (float)x + 0.25f * (float)px;
         ok[1] = (float)y + 0.25f * (float)py;
         ok[2] = conf;

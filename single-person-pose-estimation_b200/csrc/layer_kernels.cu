@@ -1,0 +1,564 @@
+// Non-GEMM layers of the hourglass: BatchNorm apply / backward, max-pool, nearest-upsample+add,
+// prediction-head activation, 7x7 stem patch extraction, Adam and the fp32 -> bf16 weight refresh.
+// All are HBM-bound streaming kernels: one thread owns 8 consecutive channels (one 16-byte access)
+// of a row; per-channel reductions are accumulated in registers over the thread's rows, combined in
+// shared memory and flushed with one atomic per channel per block.
+#include "layer_kernels.cuh"
+
+namespace hgb {
+
+static constexpr float kBnEps = 1e-3f;        // Keras BatchNormalization default
+static constexpr float kBnMomentum = 0.99f;   // Keras BatchNormalization default
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ uint4 ld16(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void st16(bf16* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+static inline int row_blocks(int M, int C, int rows_per_thread = 4) {
+  const int R = 256 / (C / 8);
+  int b = cdiv(M, R * rows_per_thread);
+  if (b > 148 * 8) b = 148 * 8;
+  return b < 1 ? 1 : b;
+}
+
+// ---------------------------------------------------------------------------------- BN forward
+__global__ void __launch_bounds__(256) bn_apply_fwd_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res,
+                                                           bf16* __restrict__ out, const float* __restrict__ sums,
+                                                           float* __restrict__ saved, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* __restrict__ mm,
+                                                           float* __restrict__ mv, int M, int C, int training) {
+  const int G = C >> 3, R = 256 / G;
+  const int g = threadIdx.x % G, r0 = threadIdx.x / G;
+  float sc[8], sh[8];
+  const float invM = 1.f / (float)M;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    float mean, var;
+    if (training) {
+      mean = sums[c] * invM;
+      var = fmaxf(sums[C + c] * invM - mean * mean, 0.f);
+    } else {
+      mean = mm[c];
+      var = mv[c];
+    }
+    const float rstd = rsqrtf(var + kBnEps);
+    sc[j] = gamma[c] * rstd;
+    sh[j] = beta[c] - mean * sc[j];
+    if (training && blockIdx.x == 0 && r0 == 0) {
+      saved[c] = mean;
+      saved[C + c] = rstd;
+      const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
+      mm[c] = mm[c] * kBnMomentum + mean * (1.f - kBnMomentum);
+      mv[c] = mv[c] * kBnMomentum + unbiased * (1.f - kBnMomentum);
+    }
+  }
+  for (int r = blockIdx.x * R + r0; r < M; r += gridDim.x * R) {
+    const size_t off = (size_t)r * C + g * 8;
+    float f[8];
+    unpack8(ld16(y + off), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = f[j] * sc[j] + sh[j];
+    if (res) {
+      float q[8];
+      unpack8(ld16(res + off), q);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += q[j];
+    }
+    st16(out + off, pack8(f));
+  }
+}
+
+int bn_apply_fwd(const bf16* y, const bf16* res, bf16* out, const float* sums, float* saved, const float* gamma,
+                 const float* beta, float* moving_mean, float* moving_var, int M, int C, int training, cudaStream_t st) {
+  HGB_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "bn_apply: unsupported channel count %d", C);
+  if (M == 0) return HGB_OK;
+  // In inference the moving statistics are read-only, in training block 0 rewrites them after reading.
+  bn_apply_fwd_kernel<<<row_blocks(M, C), 256, 0, st>>>(y, res, out, sums, saved, gamma, beta, moving_mean, moving_var, M, C,
+                                                        training);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+// ---------------------------------------------------------------------------------- max-pool
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int64_t total,
+                                                          int h, int w, int G) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    int64_t pix = i / G;
+    const int ox = (int)(pix % w);
+    pix /= w;
+    const int oy = (int)(pix % h);
+    const int n = (int)(pix / h);
+    const size_t C = (size_t)G * 8;
+    const size_t base = (((size_t)n * 2 * h + 2 * oy) * 2 * w + 2 * ox) * C + g * 8;
+    float a[8], b[8], c[8], d[8], o[8];
+    unpack8(ld16(x + base), a);
+    unpack8(ld16(x + base + C), b);
+    unpack8(ld16(x + base + 2 * w * C), c);
+    unpack8(ld16(x + base + 2 * w * C + C), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaxf(a[j], b[j]), fmaxf(c[j], d[j]));
+    st16(out + (size_t)i * 8, pack8(o));
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                          bf16* __restrict__ dx, int64_t total, int h, int w, int G,
+                                                          int accumulate) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    int64_t pix = i / G;
+    const int ox = (int)(pix % w);
+    pix /= w;
+    const int oy = (int)(pix % h);
+    const int n = (int)(pix / h);
+    const size_t C = (size_t)G * 8;
+    const size_t base = (((size_t)n * 2 * h + 2 * oy) * 2 * w + 2 * ox) * C + g * 8;
+    const size_t offs[4] = {base, base + C, base + 2 * w * C, base + 2 * w * C + C};
+    float v[4][8], gy[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) unpack8(ld16(x + offs[q]), v[q]);
+    unpack8(ld16(dy + (size_t)i * 8), gy);
+    float o[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int best = 0;
+      float bv = v[0][j];
+#pragma unroll
+      for (int q = 1; q < 4; ++q)
+        if (v[q][j] > bv) { bv = v[q][j]; best = q; }  // strict: first maximum wins
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q][j] = (q == best) ? gy[j] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (accumulate) {
+        float old[8];
+        unpack8(*reinterpret_cast<const uint4*>(dx + offs[q]), old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[q][j] += old[j];
+      }
+      st16(dx + offs[q], pack8(o[q]));
+    }
+  }
+}
+
+static inline int flat_blocks(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  return b < 1 ? 1 : (int)b;
+}
+
+int maxpool_fwd(const bf16* x, bf16* out, int N, int h, int w, int C, cudaStream_t st) {
+  HGB_CHECK_ARG(C % 8 == 0, "maxpool: C %% 8");
+  const int64_t total = (int64_t)N * h * w * (C / 8);
+  if (total == 0) return HGB_OK;
+  maxpool_fwd_kernel<<<flat_blocks(total), 256, 0, st>>>(x, out, total, h, w, C / 8);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+int maxpool_bwd(const bf16* x, const bf16* dy, bf16* dx, int N, int h, int w, int C, int accumulate, cudaStream_t st) {
+  HGB_CHECK_ARG(C % 8 == 0, "maxpool: C %% 8");
+  const int64_t total = (int64_t)N * h * w * (C / 8);
+  if (total == 0) return HGB_OK;
+  maxpool_bwd_kernel<<<flat_blocks(total), 256, 0, st>>>(x, dy, dx, total, h, w, C / 8, accumulate);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+// ---------------------------------------------------------------------------------- upsample + add
+__global__ void __launch_bounds__(256) upsample_add_fwd_kernel(const bf16* __restrict__ skip, const bf16* __restrict__ low,
+                                                               bf16* __restrict__ out, int64_t total, int h, int w, int G) {
+  // one thread per (low-res pixel, channel group): reads 1 low + 4 skip vectors, writes 4
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    int64_t pix = i / G;
+    const int ox = (int)(pix % w);
+    pix /= w;
+    const int oy = (int)(pix % h);
+    const int n = (int)(pix / h);
+    const size_t C = (size_t)G * 8;
+    const size_t base = (((size_t)n * 2 * h + 2 * oy) * 2 * w + 2 * ox) * C + g * 8;
+    const size_t offs[4] = {base, base + C, base + 2 * w * C, base + 2 * w * C + C};
+    float l[8];
+    unpack8(ld16(low + (size_t)i * 8), l);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float s[8];
+      unpack8(ld16(skip + offs[q]), s);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += l[j];
+      st16(out + offs[q], pack8(s));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) upsample_add_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dlow,
+                                                               int64_t total, int h, int w, int G) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    int64_t pix = i / G;
+    const int ox = (int)(pix % w);
+    pix /= w;
+    const int oy = (int)(pix % h);
+    const int n = (int)(pix / h);
+    const size_t C = (size_t)G * 8;
+    const size_t base = (((size_t)n * 2 * h + 2 * oy) * 2 * w + 2 * ox) * C + g * 8;
+    float a[8], b[8], c[8], d[8];
+    unpack8(ld16(dout + base), a);
+    unpack8(ld16(dout + base + C), b);
+    unpack8(ld16(dout + base + 2 * w * C), c);
+    unpack8(ld16(dout + base + 2 * w * C + C), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = (a[j] + b[j]) + (c[j] + d[j]);
+    st16(dlow + (size_t)i * 8, pack8(a));
+  }
+}
+
+int upsample_add_fwd(const bf16* skip, const bf16* low, bf16* out, int N, int h, int w, int C, cudaStream_t st) {
+  HGB_CHECK_ARG(C % 8 == 0, "upsample_add: C %% 8");
+  const int64_t total = (int64_t)N * h * w * (C / 8);
+  if (total == 0) return HGB_OK;
+  upsample_add_fwd_kernel<<<flat_blocks(total), 256, 0, st>>>(skip, low, out, total, h, w, C / 8);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+int upsample_add_bwd(const bf16* dout, bf16* dlow, int N, int h, int w, int C, cudaStream_t st) {
+  HGB_CHECK_ARG(C % 8 == 0, "upsample_add: C %% 8");
+  const int64_t total = (int64_t)N * h * w * (C / 8);
+  if (total == 0) return HGB_OK;
+  upsample_add_bwd_kernel<<<flat_blocks(total), 256, 0, st>>>(dout, dlow, total, h, w, C / 8);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+// ---------------------------------------------------------------------------------- BN backward
+// Block-level combine of per-thread 8-channel partials: threads with the same channel group add into smem.
+template <int NSTAT>
+__device__ __forceinline__ void block_channel_flush(float (&acc)[NSTAT][8], float* s_acc /*[NSTAT*C]*/, float* const* dst,
+                                                    int C, int g, int c_valid) {
+  for (int i = threadIdx.x; i < NSTAT * C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < NSTAT; ++s)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[s * C + g * 8 + j], acc[s][j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < NSTAT * C; i += blockDim.x) {
+    const int s = i / C, c = i - s * C;
+    if (dst[s] && c < c_valid) atomicAdd(dst[s] + c, s_acc[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y,
+                                                            float* __restrict__ bsums, int M, int C) {
+  extern __shared__ float s_acc[];
+  const int G = C >> 3, R = 256 / G;
+  const int g = threadIdx.x % G, r0 = threadIdx.x / G;
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  for (int r = blockIdx.x * R + r0; r < M; r += gridDim.x * R) {
+    const size_t off = (size_t)r * C + g * 8;
+    float a[8], b[8];
+    unpack8(ld16(dz + off), a);
+    unpack8(ld16(y + off), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[0][j] += a[j]; acc[1][j] += a[j] * b[j]; }
+  }
+  float* dst[2] = {bsums, bsums + C};
+  block_channel_flush<2>(acc, s_acc, dst, C, g, C);
+}
+
+int bn_bwd_reduce(const bf16* dz, const bf16* y, float* bsums, int M, int C, cudaStream_t st) {
+  HGB_CHECK_ARG(C % 8 == 0 && 256 % (C / 8) == 0, "bn_bwd_reduce: unsupported channel count %d", C);
+  if (M == 0) return HGB_OK;
+  bn_bwd_reduce_kernel<<<row_blocks(M, C, 16), 256, 2 * C * sizeof(float), st>>>(dz, y, bsums, M, C);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y,
+                                                           bf16* __restrict__ dp, const float* __restrict__ bsums,
+                                                           const float* __restrict__ saved, const float* __restrict__ gamma,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           float* __restrict__ dbias, int M, int C) {
+  extern __shared__ float s_acc[];
+  const int G = C >> 3, R = 256 / G;
+  const int g = threadIdx.x % G, r0 = threadIdx.x / G;
+  const float invM = 1.f / (float)M;
+  float mean[8], rstd[8], a[8], mdz[8], mdzx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    mean[j] = saved[c];
+    rstd[j] = saved[C + c];
+    const float sdz = bsums[c];
+    const float sdzx = rstd[j] * (bsums[C + c] - mean[j] * sdz);  // sum dz * xhat
+    a[j] = gamma[c] * rstd[j];
+    mdz[j] = sdz * invM;
+    mdzx[j] = sdzx * invM;
+    if (blockIdx.x == 0 && r0 == 0) {
+      dgamma[c] = sdzx;
+      dbeta[c] = sdz;
+    }
+  }
+  float acc[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+  for (int r = blockIdx.x * R + r0; r < M; r += gridDim.x * R) {
+    const size_t off = (size_t)r * C + g * 8;
+    float d[8], v[8], o[8];
+    unpack8(ld16(dz + off), d);
+    unpack8(ld16(y + off), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (v[j] - mean[j]) * rstd[j];
+      const float t = a[j] * (d[j] - mdz[j] - xh * mdzx[j]);
+      o[j] = v[j] > 0.f ? t : 0.f;   // ReLU sits between the conv and the BN (hourglass.py:196-201)
+    }
+    const uint4 packed = pack8(o);
+    st16(dp + off, packed);
+    float rr[8];
+    unpack8(packed, rr);              // bias gradient of the values the GEMMs will actually read
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] += rr[j];
+  }
+  float* dst[1] = {dbias};
+  block_channel_flush<1>(acc, s_acc, dst, C, g, C);
+}
+
+int bn_bwd_apply(const bf16* dz, const bf16* y, bf16* dp, const float* bsums, const float* saved, const float* gamma,
+                 float* dgamma, float* dbeta, float* dbias, int M, int C, cudaStream_t st) {
+  HGB_CHECK_ARG(C % 8 == 0 && 256 % (C / 8) == 0, "bn_bwd_apply: unsupported channel count %d", C);
+  if (M == 0) return HGB_OK;
+  bn_bwd_apply_kernel<<<row_blocks(M, C, 16), 256, C * sizeof(float), st>>>(dz, y, dp, bsums, saved, gamma, dgamma, dbeta,
+                                                                           dbias, M, C);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+__global__ void __launch_bounds__(256) relu_mask_colsum_kernel(const bf16* __restrict__ gsrc, const bf16* __restrict__ y,
+                                                               bf16* __restrict__ dp, float* __restrict__ dbias, int M, int C,
+                                                               int c_valid, int relu) {
+  extern __shared__ float s_acc[];
+  const int G = C >> 3, R = 256 / G;
+  const int g = threadIdx.x % G, r0 = threadIdx.x / G;
+  float acc[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+  for (int r = blockIdx.x * R + r0; r < M; r += gridDim.x * R) {
+    const size_t off = (size_t)r * C + g * 8;
+    float d[8];
+    unpack8(*reinterpret_cast<const uint4*>(gsrc + off), d);
+    if (relu) {
+      float v[8];
+      unpack8(ld16(y + off), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = v[j] > 0.f ? d[j] : 0.f;
+      st16(dp + off, pack8(d));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] += d[j];
+  }
+  float* dst[1] = {dbias};
+  block_channel_flush<1>(acc, s_acc, dst, C, g, c_valid);
+}
+
+int relu_mask_colsum(const bf16* g, const bf16* y, bf16* dp, float* dbias, int M, int C, int c_valid, int relu,
+                     cudaStream_t st) {
+  HGB_CHECK_ARG(C % 8 == 0 && 256 % (C / 8) == 0, "relu_mask_colsum: unsupported channel count %d", C);
+  if (M == 0) return HGB_OK;
+  relu_mask_colsum_kernel<<<row_blocks(M, C, 16), 256, C * sizeof(float), st>>>(g, y, dp, dbias, M, C, c_valid, relu);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+// ---------------------------------------------------------------------------------- prediction head
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+__global__ void __launch_bounds__(256) head_act_fwd_kernel(const bf16* __restrict__ logits, int ldl, float* __restrict__ heat,
+                                                           bf16* __restrict__ pbf, int M, int K, int sigmoid) {
+  // thread = (pixel, 8-channel group of the 64-wide padded row)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)M * 8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i & 7);
+    const int64_t r = i >> 3;
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (g * 8 < K) {
+      unpack8(ld16(logits + r * ldl + g * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        if (c < K) {
+          f[j] = sigmoid ? sigmoidf_(f[j]) : f[j];
+          heat[r * K + c] = f[j];
+        } else {
+          f[j] = 0.f;
+        }
+      }
+    }
+    st16(pbf + r * 64 + g * 8, pack8(f));
+  }
+}
+
+int head_act_fwd(const bf16* logits, int ldl, float* heat, bf16* pbf, int M, int K, int sigmoid, cudaStream_t st) {
+  HGB_CHECK_ARG(K > 0 && K <= 64 && ldl % 8 == 0, "head_act: K must be <= 64");
+  if (M == 0) return HGB_OK;
+  head_act_fwd_kernel<<<flat_blocks((int64_t)M * 8), 256, 0, st>>>(logits, ldl, heat, pbf, M, K, sigmoid);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+__global__ void __launch_bounds__(256) head_act_bwd_kernel(const float* __restrict__ dLdp, const bf16* __restrict__ g_p,
+                                                           const float* __restrict__ heat, bf16* __restrict__ dlogits, int M,
+                                                           int K, int sigmoid) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)M * 8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i & 7);
+    const int64_t r = i >> 3;
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (g * 8 < K) {
+      float gp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (g_p) unpack8(ld16(g_p + r * 64 + g * 8), gp);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        if (c < K) {
+          const float p = heat[r * K + c];
+          const float d = dLdp[r * K + c] + gp[j];
+          f[j] = sigmoid ? d * p * (1.f - p) : d;
+        }
+      }
+    }
+    st16(dlogits + r * 64 + g * 8, pack8(f));
+  }
+}
+
+int head_act_bwd(const float* dLdp, const bf16* g_p, const float* heat, bf16* dlogits, int M, int K, int sigmoid,
+                 cudaStream_t st) {
+  HGB_CHECK_ARG(K > 0 && K <= 64, "head_act: K must be <= 64");
+  if (M == 0) return HGB_OK;
+  head_act_bwd_kernel<<<flat_blocks((int64_t)M * 8), 256, 0, st>>>(dLdp, g_p, heat, dlogits, M, K, sigmoid);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+// ---------------------------------------------------------------------------------- stem patches
+__global__ void __launch_bounds__(256) im2col_7x7s2_kernel(const float* __restrict__ img, bf16* __restrict__ col, int64_t total,
+                                                           int H, int W) {
+  // thread = (output pixel, group of 8 K-elements); 24 groups per pixel (192 = 147 + padding)
+  const int oh = H / 2, ow = W / 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % 24);
+    int64_t pix = i / 24;
+    const int ox = (int)(pix % ow);
+    pix /= ow;
+    const int oy = (int)(pix % oh);
+    const int n = (int)(pix / oh);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kk = g * 8 + j;
+      float v = 0.f;
+      if (kk < 147) {
+        const int ky = kk / 21, rem = kk - ky * 21, kx = rem / 3, c = rem - kx * 3;
+        const int iy = oy * 2 + ky - 2, ix = ox * 2 + kx - 2;  // TF 'same', stride 2, k 7: pad 2 before / 3 after
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + (((size_t)n * H + iy) * W + ix) * 3 + c);
+      }
+      f[j] = v;
+    }
+    st16(col + (size_t)i * 8, pack8(f));
+  }
+}
+
+int im2col_7x7s2(const float* img, bf16* col, int N, int H, int W, cudaStream_t st) {
+  HGB_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "im2col: even image size required");
+  const int64_t total = (int64_t)N * (H / 2) * (W / 2) * 24;
+  if (total == 0) return HGB_OK;
+  im2col_7x7s2_kernel<<<flat_blocks(total), 256, 0, st>>>(img, col, total, H, W);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+// ---------------------------------------------------------------------------------- Adam
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n4, float lr_t, float b1, float b2,
+                                                   float eps, float gs) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 W = reinterpret_cast<float4*>(w)[i];
+    const float4 G = reinterpret_cast<const float4*>(g)[i];
+    float4 Mv = reinterpret_cast<float4*>(m)[i];
+    float4 Vv = reinterpret_cast<float4*>(v)[i];
+    float* pw = &W.x; const float* pg = &G.x; float* pm = &Mv.x; float* pv = &Vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = pg[j] * gs;
+      pm[j] = b1 * pm[j] + (1.f - b1) * gr;
+      pv[j] = b2 * pv[j] + (1.f - b2) * gr * gr;
+      pw[j] -= lr_t * pm[j] / (sqrtf(pv[j]) + eps);   // epsilon outside the bias correction (Keras)
+    }
+    reinterpret_cast<float4*>(w)[i] = W;
+    reinterpret_cast<float4*>(m)[i] = Mv;
+    reinterpret_cast<float4*>(v)[i] = Vv;
+  }
+}
+
+int adam_step(float* w, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps,
+              float grad_scale, cudaStream_t st) {
+  HGB_CHECK_ARG(n % 4 == 0, "adam: element count must be a multiple of 4");
+  if (n == 0) return HGB_OK;
+  adam_kernel<<<flat_blocks(n / 4), 256, 0, st>>>(w, g, m, v, n / 4, lr_t, b1, b2, eps, grad_scale);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+// ---------------------------------------------------------------------------------- weight refresh
+__global__ void __launch_bounds__(256) weight_sync_kernel(const WeightSyncEntry* __restrict__ entries) {
+  const WeightSyncEntry e = entries[blockIdx.y];
+  const int kf = e.taps * e.cin_pad;
+  const int nf = e.cout_pad * kf;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += gridDim.x * blockDim.x) {
+    const int co = i / kf, r = i - co * kf, t = r / e.cin_pad, ci = r - t * e.cin_pad;
+    float v = 0.f;
+    if (co < e.cout && ci < e.cin) v = e.w[((size_t)co * e.taps + t) * e.cin + ci];
+    e.wf[i] = __float2bfloat16_rn(v);
+  }
+  if (e.wd) {
+    const int kd = e.taps * e.cout_pad;
+    const int nd = e.cin_pad * kd;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nd; i += gridDim.x * blockDim.x) {
+      const int ci = i / kd, r = i - ci * kd, t = r / e.cout_pad, co = r - t * e.cout_pad;
+      float v = 0.f;
+      if (co < e.cout && ci < e.cin) v = e.w[((size_t)co * e.taps + t) * e.cin + ci];
+      e.wd[i] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+int weight_sync(const WeightSyncEntry* entries_dev, int n_entries, int max_elems, cudaStream_t st) {
+  if (n_entries == 0) return HGB_OK;
+  int bx = cdiv(max_elems, 256 * 4);
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  weight_sync_kernel<<<dim3(bx, n_entries), 256, 0, st>>>(entries_dev);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+}  // namespace hgb

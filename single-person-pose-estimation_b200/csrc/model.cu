@@ -1,0 +1,840 @@
+// The stacked-hourglass network (model/hourglass.py:5-206) as a static execution plan.
+//
+// hgb_model_create() walks the same construction code path as the reference (front module,
+// num_stacks hourglass modules, heads) and records
+//   * the parameter table (Keras layer names, creation order; kernels stored OHWI so they are
+//     the K-major GEMM operand directly),
+//   * every activation tensor (bf16 NHWC) with its offset in one caller-owned arena,
+//   * a forward op list and, per segment (front, stack 0..S-1), a backward op list.
+// Nothing is allocated or traced at run time; forward/backward replay the lists on a stream.
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "conv_gemm.cuh"
+#include "layer_kernels.cuh"
+
+using namespace hgb;
+
+namespace {
+
+constexpr size_t kAlign = 1024;
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Act {
+  int n, h, w, c;
+  size_t off;  // bytes into the arena
+  CUtensorMap tmap;
+  bool has_tmap = false;
+};
+
+struct ConvL {
+  std::string name;
+  int ksize;            // GEMM view: 1 or 3 (the 7x7 stem runs as a 1x1 over extracted patches)
+  int taps;             // ksize^2
+  int cin, cout;        // valid channels of the GEMM view (stem: 147)
+  int cin_pad, cout_pad;
+  int real_k, real_cin; // Keras kernel shape (stem: 7, 3)
+  int relu;
+  int h, w;             // spatial size the GEMM runs at
+  int64_t w_off, b_off; // float offsets into the parameter buffer
+  size_t wf_off, wd_off;
+  bool has_wd;
+  CUtensorMap tm_wf, tm_wd;
+  double flops;
+  int seg;
+  int y_act = -1;
+};
+
+struct BNL {
+  std::string name;
+  int c;
+  int64_t gamma_off, beta_off, mm_off, mv_off;  // float offsets into the parameter buffer
+  size_t sums_off, bsums_off, saved_off;        // byte offsets into the arena
+};
+
+struct ParamT {
+  std::string name;
+  int rank;
+  int64_t dims[4];
+  int64_t off;
+  int trainable;
+};
+
+enum OpType {
+  F_IM2COL, F_CONV, F_BN, F_POOL, F_UPADD, F_HEAD,
+  B_BN_REDUCE, B_BN_APPLY, B_WGRAD, B_DGRAD, B_RELU_MASK, B_COLSUM, B_POOL, B_UPADD, B_HEAD
+};
+
+struct Op {
+  OpType type;
+  int conv = -1, bn = -1;
+  int a0 = -1, a1 = -1, a2 = -1, a3 = -1;
+  int flag = 0;
+};
+
+struct BneckRec {
+  int x, out;
+  int skip_conv, s_act;  // -1 when identity
+  int c1, c2, c3, bn1, bn2, bn3;
+  int y1, z1, y2, z2, y3;
+};
+
+struct StackRec {
+  BneckRec down[4], bottom[3], shortb[4], merged[4];
+  int pool_in[4], pool_out[4];   // pools after f1,f2,f4 and the bottom pool after f8
+  int up_a[4];                   // upsample+add outputs (f8,f4,f2,f1 order)
+  int up_low[4];                 // the lower-resolution input of each merge
+  int conv_h, bn_h, y_h, z_h, conv_p, logits, pbf, conv2, conv3, t1, x_in, next;
+};
+
+}  // namespace
+
+struct hgb_model {
+  hgb_model_config cfg;
+  int device;
+  int S, C, K, B;
+  int hm_h, hm_w;
+
+  std::vector<Act> acts;
+  std::vector<ConvL> convs;
+  std::vector<BNL> bns;
+  std::vector<ParamT> params;
+  std::vector<std::vector<Op>> fwd_ops, bwd_ops;  // per segment
+  std::vector<int64_t> seg_begin, seg_end;        // trainable float ranges
+
+  int64_t n_train = 0, n_nontrain = 0;            // exact scalar counts
+  int64_t train_floats = 0, nontrain_floats = 0;  // padded region sizes
+  size_t arena_bytes = 0;
+  size_t zero_off = 0, zero_bytes = 0;
+  std::vector<size_t> heat_off, dldp_off;
+  size_t lossws_off = 0, sync_off = 0;
+  int sync_max_elems = 0;
+  int col_act = -1;
+
+  float* p_params = nullptr;
+  float* p_grads = nullptr;
+  float* p_m = nullptr;
+  float* p_v = nullptr;
+  uint8_t* p_arena = nullptr;
+  bool maps_ready = false;
+  bool fwd_training_done = false;
+  int64_t launches = 0;
+
+  // ---- build-time state
+  size_t arena_cur = 0;
+  int bn_counter = 0;
+  int cur_seg = 0;
+  size_t scratch_off[3] = {0, 0, 0}, scratch_bytes[3] = {0, 0, 0};
+  size_t grad_base = 0, grad_cur = 0, grad_max = 0;
+  bool sizing_pass = true;
+
+  size_t arena_alloc(size_t bytes) {
+    const size_t off = arena_cur;
+    arena_cur += align_up(bytes, kAlign);
+    return off;
+  }
+  int new_act(int n, int h, int w, int c) {
+    Act a;
+    a.n = n; a.h = h; a.w = w; a.c = c;
+    a.off = arena_alloc((size_t)n * h * w * c * 2);
+    acts.push_back(a);
+    return (int)acts.size() - 1;
+  }
+  int alias_act(int n, int h, int w, int c, size_t off) {
+    Act a;
+    a.n = n; a.h = h; a.w = w; a.c = c; a.off = off;
+    acts.push_back(a);
+    return (int)acts.size() - 1;
+  }
+  int64_t add_param(const std::string& name, int rank, const int64_t* dims, int trainable) {
+    ParamT p;
+    p.name = name; p.rank = rank; p.trainable = trainable;
+    int64_t n = 1;
+    for (int i = 0; i < 4; ++i) { p.dims[i] = i < rank ? dims[i] : 1; if (i < rank) n *= dims[i]; }
+    if (trainable) {
+      p.off = train_floats;
+      train_floats += (n + 3) / 4 * 4;
+      n_train += n;
+    } else {
+      p.off = nontrain_floats;  // relocated behind the trainable region in finalize()
+      nontrain_floats += (n + 3) / 4 * 4;
+      n_nontrain += n;
+    }
+    params.push_back(p);
+    return p.off;
+  }
+
+  int add_conv(const std::string& name, int in_act, int real_k, int real_cin, int cout, int relu, bool need_dgrad) {
+    const Act& in = acts[in_act];
+    ConvL c;
+    c.name = name;
+    c.real_k = real_k; c.real_cin = real_cin;
+    if (real_k == 7) { c.ksize = 1; c.taps = 1; c.cin = 147; c.cin_pad = 192; }
+    else { c.ksize = real_k; c.taps = real_k * real_k; c.cin = real_cin; c.cin_pad = (real_cin + 63) / 64 * 64; }
+    c.cout = cout;
+    c.cout_pad = (cout + 63) / 64 * 64;
+    c.relu = relu;
+    c.h = in.h; c.w = in.w;
+    const int64_t kd[4] = {real_k, real_k, real_cin, cout};
+    c.w_off = add_param(name + "/kernel", 4, kd, 1);
+    const int64_t bd[1] = {cout};
+    c.b_off = add_param(name + "/bias", 1, bd, 1);
+    c.wf_off = arena_alloc((size_t)c.cout_pad * c.taps * c.cin_pad * 2);
+    c.has_wd = need_dgrad;
+    c.wd_off = need_dgrad ? arena_alloc((size_t)c.cin_pad * c.taps * c.cout_pad * 2) : 0;
+    c.flops = 2.0 * (double)in.n * in.h * in.w * (double)real_k * real_k * real_cin * cout;
+    c.seg = cur_seg;
+    sync_max_elems = std::max(sync_max_elems, c.cout_pad * c.taps * c.cin_pad);
+    convs.push_back(c);
+    return (int)convs.size() - 1;
+  }
+  int add_bn(int c) {
+    BNL b;
+    b.name = bn_counter == 0 ? "batch_normalization" : "batch_normalization_" + std::to_string(bn_counter);
+    ++bn_counter;
+    b.c = c;
+    const int64_t d[1] = {c};
+    b.gamma_off = add_param(b.name + "/gamma", 1, d, 1);
+    b.beta_off = add_param(b.name + "/beta", 1, d, 1);
+    b.mm_off = add_param(b.name + "/moving_mean", 1, d, 0);
+    b.mv_off = add_param(b.name + "/moving_variance", 1, d, 0);
+    b.sums_off = b.bsums_off = b.saved_off = 0;  // assigned in finalize()
+    bns.push_back(b);
+    return (int)bns.size() - 1;
+  }
+  void emit_f(const Op& o) { fwd_ops[cur_seg].push_back(o); }
+  void emit_b(const Op& o) { bwd_ops[cur_seg].push_back(o); }
+
+  // conv (+ReLU) [+ BN] -> returns the tensor the next layer consumes; y/z report both stages
+  int conv_unit(const std::string& name, int in_act, int real_k, int real_cin, int cout, int relu, bool bn, bool need_dgrad,
+                int bn_res, int* conv_idx, int* bn_idx, int* y_act, int res1 = -1, int res2 = -1) {
+    const int ci = add_conv(name, in_act, real_k, real_cin, cout, relu, need_dgrad);
+    const Act in = acts[in_act];
+    const int y = new_act(in.n, in.h, in.w, convs[ci].cout_pad);
+    Op o;
+    o.type = F_CONV; o.conv = ci; o.a0 = in_act; o.a1 = y; o.a2 = res1; o.a3 = res2; o.flag = bn ? 1 : 0;
+    int bi = -1, out = y;
+    if (bn) { bi = add_bn(cout); o.bn = bi; }
+    emit_f(o);
+    convs[ci].y_act = y;
+    if (bn) {
+      out = new_act(in.n, in.h, in.w, cout);
+      Op b;
+      b.type = F_BN; b.bn = bi; b.a0 = y; b.a1 = bn_res; b.a2 = out;
+      emit_f(b);
+    }
+    if (conv_idx) *conv_idx = ci;
+    if (bn_idx) *bn_idx = bi;
+    if (y_act) *y_act = y;
+    return out;
+  }
+
+  // model/hourglass.py:184-206
+  BneckRec bottleneck(int x, int cout, const std::string& name) {
+    BneckRec r;
+    const int cin = acts[x].c;
+    r.x = x;
+    r.skip_conv = -1; r.s_act = -1;
+    int skip = x;
+    if (cin != cout) {
+      skip = conv_unit(name + "_skip", x, 1, cin, cout, 1, false, true, -1, &r.skip_conv, nullptr, nullptr);
+      r.s_act = skip;
+    }
+    r.z1 = conv_unit(name + "_conv_1x1_1", x, 1, cin, cout / 2, 1, true, true, -1, &r.c1, &r.bn1, &r.y1);
+    r.z2 = conv_unit(name + "_conv_3x3_2", r.z1, 3, cout / 2, cout / 2, 1, true, true, -1, &r.c2, &r.bn2, &r.y2);
+    r.out = conv_unit(name + "_conv_1x1_3", r.z2, 1, cout / 2, cout, 1, true, true, skip, &r.c3, &r.bn3, &r.y3);
+    return r;
+  }
+  int pool(int x) {
+    const Act a = acts[x];
+    const int o = new_act(a.n, a.h / 2, a.w / 2, a.c);
+    Op p;
+    p.type = F_POOL; p.a0 = x; p.a1 = o;
+    emit_f(p);
+    return o;
+  }
+
+  // ---------------- backward emission
+  void need_scratch(int which, size_t bytes) { scratch_bytes[which] = std::max(scratch_bytes[which], bytes); }
+  int scratch_act(int which, int n, int h, int w, int c) {
+    need_scratch(which, (size_t)n * h * w * c * 2);
+    return alias_act(n, h, w, c, scratch_off[which]);
+  }
+  int grad_act(int n, int h, int w, int c) {
+    const size_t bytes = align_up((size_t)n * h * w * c * 2, kAlign);
+    const size_t off = grad_base + grad_cur;
+    grad_cur += bytes;
+    grad_max = std::max(grad_max, grad_cur);
+    return alias_act(n, h, w, c, off);
+  }
+  void bn_conv_bwd(int bn, int conv, int dz, int y, int dp, int x_in, int dgrad_out, int res1, int res2) {
+    Op o;
+    o = Op(); o.type = B_BN_REDUCE; o.bn = bn; o.a0 = dz; o.a1 = y; emit_b(o);
+    o = Op(); o.type = B_BN_APPLY; o.bn = bn; o.conv = conv; o.a0 = dz; o.a1 = y; o.a2 = dp; emit_b(o);
+    o = Op(); o.type = B_WGRAD; o.conv = conv; o.a0 = dp; o.a1 = x_in; emit_b(o);
+    if (dgrad_out >= 0) {
+      o = Op(); o.type = B_DGRAD; o.conv = conv; o.a0 = dp; o.a1 = dgrad_out; o.a2 = res1; o.a3 = res2; emit_b(o);
+    }
+  }
+  // g_out: gradient wrt the block output (read; masked in place when the skip is a conv);
+  // g_x: gradient wrt the block input (written); extra: one more tensor summed into g_x.
+  void bottleneck_bwd(const BneckRec& r, int g_out, int g_x, int extra) {
+    const Act o = acts[r.out];
+    const int cmid = convs[r.c1].cout;
+    const int dp3 = scratch_act(0, o.n, o.h, o.w, o.c);
+    const int dzm = scratch_act(1, o.n, o.h, o.w, cmid);
+    const int dpm = scratch_act(2, o.n, o.h, o.w, cmid);
+    bn_conv_bwd(r.bn3, r.c3, g_out, r.y3, dp3, r.z2, dzm, -1, -1);
+    bn_conv_bwd(r.bn2, r.c2, dzm, r.y2, dpm, r.z1, dzm, -1, -1);
+    if (r.skip_conv >= 0) {
+      bn_conv_bwd(r.bn1, r.c1, dzm, r.y1, dpm, r.x, -1, -1, -1);
+      Op m;
+      m.type = B_RELU_MASK; m.conv = r.skip_conv; m.a0 = g_out; m.a1 = r.s_act; m.flag = 1; emit_b(m);
+      m = Op(); m.type = B_WGRAD; m.conv = r.skip_conv; m.a0 = g_out; m.a1 = r.x; emit_b(m);
+      if (g_x >= 0) {
+        m = Op(); m.type = B_DGRAD; m.conv = r.skip_conv; m.a0 = g_out; m.a1 = g_x; m.a2 = extra; emit_b(m);
+        m = Op(); m.type = B_DGRAD; m.conv = r.c1; m.a0 = dpm; m.a1 = g_x; m.a2 = g_x; emit_b(m);
+      }
+    } else {
+      bn_conv_bwd(r.bn1, r.c1, dzm, r.y1, dpm, r.x, g_x, g_out, extra);
+    }
+  }
+  void linear_conv_bwd(int conv, int dp, int x_in, int dgrad_out, int res1) {
+    Op o;
+    o.type = B_COLSUM; o.conv = conv; o.a0 = dp; emit_b(o);
+    o = Op(); o.type = B_WGRAD; o.conv = conv; o.a0 = dp; o.a1 = x_in; emit_b(o);
+    if (dgrad_out >= 0) {
+      o = Op(); o.type = B_DGRAD; o.conv = conv; o.a0 = dp; o.a1 = dgrad_out; o.a2 = res1; emit_b(o);
+    }
+  }
+};
+
+namespace {
+
+int build(hgb_model* m) {
+  const hgb_model_config& cfg = m->cfg;
+  const int B = cfg.batch, C = cfg.num_channels, S = cfg.num_stacks;
+  m->fwd_ops.assign(S + 1, {});
+  m->bwd_ops.assign(S + 1, {});
+  m->seg_begin.assign(S + 1, 0);
+  m->seg_end.assign(S + 1, 0);
+
+  // ---------------- front module (hourglass.py:54-68)
+  m->cur_seg = 0;
+  m->col_act = m->new_act(B, cfg.in_h / 2, cfg.in_w / 2, 192);
+  { Op o; o.type = F_IM2COL; o.a0 = m->col_act; m->emit_f(o); }
+  int conv0, bn0, y0;
+  const int z0 = m->conv_unit("front_conv_1x1_1", m->col_act, 7, 3, 64, 1, true, false, -1, &conv0, &bn0, &y0);
+  BneckRec fb1 = m->bottleneck(z0, C / 2, "front_bottleneck_1");
+  const int fpool = m->pool(fb1.out);
+  BneckRec fb2 = m->bottleneck(fpool, C / 2, "front_bottleneck_2");
+  BneckRec fb3 = m->bottleneck(fb2.out, C, "front_bottleneck_3");
+  m->seg_end[0] = m->train_floats;
+
+  // ---------------- stacks (hourglass.py:35-52, 71-181)
+  std::vector<StackRec> stacks(S);
+  int x = fb3.out;
+  static const char* fnames[4] = {"f1", "f2", "f4", "f8"};
+  for (int s = 0; s < S; ++s) {
+    m->cur_seg = 1 + s;
+    m->seg_begin[1 + s] = m->train_floats;
+    StackRec& r = stacks[s];
+    const std::string hg = "hg" + std::to_string(s);
+    r.x_in = x;
+    int cur = x;
+    for (int l = 0; l < 4; ++l) {  // create_downsample_blocks
+      r.down[l] = m->bottleneck(cur, C, hg + "_downsample_" + fnames[l]);
+      r.pool_in[l] = r.down[l].out;
+      if (l < 3) { r.pool_out[l] = m->pool(r.down[l].out); cur = r.pool_out[l]; }
+    }
+    r.pool_out[3] = m->pool(r.down[3].out);  // bottom_block
+    cur = r.pool_out[3];
+    for (int i = 0; i < 3; ++i) {
+      r.bottom[i] = m->bottleneck(cur, C, hg + "_downsample_f8_" + std::to_string(i + 1));
+      cur = r.bottom[i].out;
+    }
+    for (int u = 0; u < 4; ++u) {  // connect_downsample_upsample for f8, f4, f2, f1
+      const int l = 3 - u;
+      const std::string nm = hg + "_upsample_" + fnames[l];
+      r.shortb[u] = m->bottleneck(r.down[l].out, C, nm + "_short");
+      const Act sa = m->acts[r.shortb[u].out];
+      r.up_low[u] = cur;
+      r.up_a[u] = m->new_act(sa.n, sa.h, sa.w, sa.c);
+      Op o; o.type = F_UPADD; o.a0 = r.shortb[u].out; o.a1 = cur; o.a2 = r.up_a[u]; m->emit_f(o);
+      r.merged[u] = m->bottleneck(r.up_a[u], C, nm + "_merged");
+      cur = r.merged[u].out;
+    }
+    // create_heads
+    r.z_h = m->conv_unit(hg + "_conv_1x1_1", cur, 1, C, C, 1, true, true, -1, &r.conv_h, &r.bn_h, &r.y_h);
+    r.logits = m->conv_unit(hg + "_conv_1x1_predict", r.z_h, 1, C, cfg.num_classes, 0, false, true, -1, &r.conv_p, nullptr, nullptr);
+    const Act la = m->acts[r.logits];
+    r.pbf = m->new_act(la.n, la.h, la.w, 64);
+    { Op o; o.type = F_HEAD; o.flag = s; o.a0 = r.logits; o.a1 = r.pbf; m->emit_f(o); }
+    r.conv2 = r.conv3 = r.t1 = r.next = -1;
+    if (s + 1 < S) {  // the last stack's re-injection branch is pruned by Keras (not on a path to an output)
+      r.t1 = m->conv_unit(hg + "_conv_1x1_2", r.z_h, 1, C, C, 0, false, true, -1, &r.conv2, nullptr, nullptr, r.x_in);
+      r.next = m->conv_unit(hg + "_conv_1x1_3", r.pbf, 1, cfg.num_classes, C, 0, false, true, -1, &r.conv3, nullptr, nullptr, r.t1);
+      x = r.next;
+    }
+    m->seg_end[1 + s] = m->train_floats;
+  }
+  m->seg_begin[0] = 0;
+
+  // ---------------- per-step float state (zeroed each training step) + saved BN statistics
+  size_t zf = 0;
+  for (auto& b : m->bns) { zf += 4 * (size_t)b.c; }
+  m->zero_bytes = align_up(zf * sizeof(float), kAlign);
+  m->zero_off = m->arena_alloc(m->zero_bytes);
+  size_t saved_off = m->arena_alloc(align_up(zf / 2 * sizeof(float), kAlign));
+  size_t zcur = m->zero_off;
+  for (auto& b : m->bns) {
+    b.sums_off = zcur; zcur += 2 * (size_t)b.c * sizeof(float);
+    b.bsums_off = zcur; zcur += 2 * (size_t)b.c * sizeof(float);
+    b.saved_off = saved_off; saved_off += 2 * (size_t)b.c * sizeof(float);
+  }
+  // heat maps (f32) and loss gradients per stack
+  const int hh = cfg.in_h / 4, hw = cfg.in_w / 4;
+  m->hm_h = hh; m->hm_w = hw;
+  m->heat_off.resize(S);
+  m->dldp_off.resize(S);
+  for (int s = 0; s < S; ++s) m->heat_off[s] = m->arena_alloc((size_t)B * hh * hw * cfg.num_classes * 4);
+  m->sync_off = m->arena_alloc(m->convs.size() * sizeof(WeightSyncEntry));
+
+  if (cfg.training) {
+    for (int s = 0; s < S; ++s) m->dldp_off[s] = m->arena_alloc((size_t)B * hh * hw * cfg.num_classes * 4);
+    m->lossws_off = m->arena_alloc((size_t)hgb_loss_workspace_bytes(B, cfg.num_classes));
+    // stack-input gradients ping-pong; everything else of a stack's backward lives in a region reused by all stacks
+    const Act xa = m->acts[fb3.out];
+    int gx[2];
+    gx[0] = m->new_act(xa.n, xa.h, xa.w, xa.c);
+    gx[1] = m->new_act(xa.n, xa.h, xa.w, xa.c);
+    // Two passes over the backward emission: the first only sizes the scratch / gradient regions.
+    const size_t acts_mark = m->acts.size();
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1) {
+        m->acts.resize(acts_mark);
+        for (auto& v : m->bwd_ops) v.clear();
+        for (int i = 0; i < 3; ++i) m->scratch_off[i] = m->arena_alloc(m->scratch_bytes[i]);
+        m->grad_base = m->arena_alloc(m->grad_max);
+      }
+      for (int s = S - 1; s >= 0; --s) {
+        m->cur_seg = 1 + s;
+        m->grad_cur = 0;
+        const StackRec& r = stacks[s];
+        const bool last = (s + 1 == S);
+        const int g_next = last ? -1 : gx[(s + 1) & 1];
+        const Act ha = m->acts[r.z_h];
+        const int g_zh = m->grad_act(ha.n, ha.h, ha.w, ha.c);
+        const int g_logits = m->grad_act(ha.n, ha.h, ha.w, 64);
+        int g_p = -1;
+        if (!last) {
+          g_p = m->grad_act(ha.n, ha.h, ha.w, 64);
+          m->linear_conv_bwd(r.conv3, g_next, r.pbf, g_p, -1);
+          m->linear_conv_bwd(r.conv2, g_next, r.z_h, g_zh, -1);
+        }
+        { Op o; o.type = B_HEAD; o.flag = s; o.a0 = g_p; o.a1 = g_logits; m->emit_b(o); }
+        m->linear_conv_bwd(r.conv_p, g_logits, r.z_h, g_zh, last ? -1 : g_zh);
+        int g_cur = m->grad_act(ha.n, ha.h, ha.w, ha.c);  // gradient wrt the last merged block's output
+        {
+          const int dp_h = m->scratch_act(0, ha.n, ha.h, ha.w, ha.c);
+          m->bn_conv_bwd(r.bn_h, r.conv_h, g_zh, r.y_h, dp_h, r.merged[3].out, g_cur, -1, -1);
+        }
+        int g_f[4];  // gradients wrt the down-path features f1,f2,f4,f8
+        for (int u = 3; u >= 0; --u) {
+          const int l = 3 - u;
+          const Act aa = m->acts[r.up_a[u]];
+          const int g_a = m->grad_act(aa.n, aa.h, aa.w, aa.c);
+          m->bottleneck_bwd(r.merged[u], g_cur, g_a, -1);
+          const Act lo = m->acts[r.up_low[u]];
+          const int g_low = m->grad_act(lo.n, lo.h, lo.w, lo.c);
+          { Op o; o.type = B_UPADD; o.a0 = g_a; o.a1 = g_low; m->emit_b(o); }
+          g_f[l] = m->grad_act(aa.n, aa.h, aa.w, aa.c);
+          m->bottleneck_bwd(r.shortb[u], g_a, g_f[l], -1);
+          g_cur = g_low;
+        }
+        for (int i = 2; i >= 0; --i) {
+          const Act ba = m->acts[r.bottom[i].x];
+          const int g_in = m->grad_act(ba.n, ba.h, ba.w, ba.c);
+          m->bottleneck_bwd(r.bottom[i], g_cur, g_in, -1);
+          g_cur = g_in;
+        }
+        // g_cur = gradient wrt the bottom pool's output
+        for (int l = 3; l >= 0; --l) {
+          { Op o; o.type = B_POOL; o.a0 = r.pool_in[l]; o.a1 = g_cur; o.a2 = g_f[l]; o.flag = 1; m->emit_b(o); }
+          if (l > 0) {
+            const Act pa = m->acts[r.down[l].x];
+            const int g_in = m->grad_act(pa.n, pa.h, pa.w, pa.c);
+            m->bottleneck_bwd(r.down[l], g_f[l], g_in, -1);
+            g_cur = g_in;
+          } else {
+            m->bottleneck_bwd(r.down[0], g_f[0], gx[s & 1], g_next);
+          }
+        }
+      }
+      // front module
+      m->cur_seg = 0;
+      m->grad_cur = 0;
+      {
+        const Act a2 = m->acts[fb3.x];
+        const int g_b2 = m->grad_act(a2.n, a2.h, a2.w, a2.c);
+        m->bottleneck_bwd(fb3, gx[0], g_b2, -1);
+        const Act ap = m->acts[fb2.x];
+        const int g_pool = m->grad_act(ap.n, ap.h, ap.w, ap.c);
+        m->bottleneck_bwd(fb2, g_b2, g_pool, -1);
+        const Act a1 = m->acts[fb1.out];
+        const int g_b1 = m->grad_act(a1.n, a1.h, a1.w, a1.c);
+        { Op o; o.type = B_POOL; o.a0 = fb1.out; o.a1 = g_pool; o.a2 = g_b1; o.flag = 0; m->emit_b(o); }
+        const Act az = m->acts[z0];
+        const int g_z0 = m->grad_act(az.n, az.h, az.w, az.c);
+        m->bottleneck_bwd(fb1, g_b1, g_z0, -1);
+        const int dp0 = m->scratch_act(0, az.n, az.h, az.w, az.c);
+        m->bn_conv_bwd(bn0, conv0, g_z0, y0, dp0, m->col_act, -1, -1, -1);
+      }
+    }
+  }
+  // relocate the non-trainable parameters behind the trainable region
+  for (auto& p : m->params)
+    if (!p.trainable) p.off += m->train_floats;
+  for (auto& b : m->bns) { b.mm_off += m->train_floats; b.mv_off += m->train_floats; }
+  m->arena_bytes = m->arena_cur + kAlign;
+  return HGB_OK;
+}
+
+inline bf16* act_ptr(const hgb_model* m, int a) { return a < 0 ? nullptr : reinterpret_cast<bf16*>(m->p_arena + m->acts[a].off); }
+inline float* arena_f(const hgb_model* m, size_t off) { return reinterpret_cast<float*>(m->p_arena + off); }
+
+int build_maps(hgb_model* m) {
+  for (auto& a : m->acts) {
+    a.has_tmap = false;
+    if (a.c % 64 != 0 || a.w > 128) continue;
+    int rc = make_tmap_act(&a.tmap, m->p_arena + a.off, a.n, a.h, a.w, a.c);
+    if (rc) return rc;
+    a.has_tmap = true;
+  }
+  for (auto& c : m->convs) {
+    int rc = make_tmap_mat(&c.tm_wf, m->p_arena + c.wf_off, c.cout_pad, c.taps * c.cin_pad, conv_gemm_block_n(c.cout_pad));
+    if (rc) return rc;
+    if (c.has_wd) {
+      rc = make_tmap_mat(&c.tm_wd, m->p_arena + c.wd_off, c.cin_pad, c.taps * c.cout_pad, conv_gemm_block_n(c.cin_pad));
+      if (rc) return rc;
+    }
+  }
+  // weight-refresh table
+  std::vector<WeightSyncEntry> tab(m->convs.size());
+  for (size_t i = 0; i < m->convs.size(); ++i) {
+    const ConvL& c = m->convs[i];
+    tab[i].w = m->p_params + c.w_off;
+    tab[i].wf = reinterpret_cast<bf16*>(m->p_arena + c.wf_off);
+    tab[i].wd = c.has_wd ? reinterpret_cast<bf16*>(m->p_arena + c.wd_off) : nullptr;
+    tab[i].taps = c.taps; tab[i].cin = c.cin; tab[i].cout = c.cout; tab[i].cin_pad = c.cin_pad; tab[i].cout_pad = c.cout_pad;
+  }
+  HGB_CUDA(cudaMemcpy(m->p_arena + m->sync_off, tab.data(), tab.size() * sizeof(WeightSyncEntry), cudaMemcpyHostToDevice));
+  m->maps_ready = true;
+  return HGB_OK;
+}
+
+int run_op(hgb_model* m, const Op& o, const float* images, int training, cudaStream_t st) {
+  int rc = HGB_OK;
+  switch (o.type) {
+    case F_IM2COL: {
+      rc = im2col_7x7s2(images, act_ptr(m, o.a0), m->B, m->cfg.in_h, m->cfg.in_w, st);
+      break;
+    }
+    case F_CONV: {
+      const ConvL& c = m->convs[o.conv];
+      const Act& in = m->acts[o.a0];
+      const Act& out = m->acts[o.a1];
+      ConvGemmArgs a;
+      a.N = in.n; a.H = in.h; a.W = in.w; a.Cin = c.cin_pad; a.Cout = c.cout_pad; a.ksize = c.ksize; a.tap_sign = 1;
+      a.relu = c.relu; a.ldc = out.c;
+      a.bias = m->p_params + c.b_off;
+      a.res1 = act_ptr(m, o.a2); a.res2 = act_ptr(m, o.a3); a.out = act_ptr(m, o.a1);
+      a.stats = (o.bn >= 0 && training) ? arena_f(m, m->bns[o.bn].sums_off) : nullptr;
+      rc = launch_conv_gemm(in.tmap, c.tm_wf, a, st);
+      break;
+    }
+    case F_BN: {
+      const BNL& b = m->bns[o.bn];
+      const Act& y = m->acts[o.a0];
+      rc = bn_apply_fwd(act_ptr(m, o.a0), act_ptr(m, o.a1), act_ptr(m, o.a2), arena_f(m, b.sums_off), arena_f(m, b.saved_off),
+                        m->p_params + b.gamma_off, m->p_params + b.beta_off, m->p_params + b.mm_off, m->p_params + b.mv_off,
+                        y.n * y.h * y.w, b.c, training, st);
+      break;
+    }
+    case F_POOL: {
+      const Act& out = m->acts[o.a1];
+      rc = maxpool_fwd(act_ptr(m, o.a0), act_ptr(m, o.a1), out.n, out.h, out.w, out.c, st);
+      break;
+    }
+    case F_UPADD: {
+      const Act& lo = m->acts[o.a1];
+      rc = upsample_add_fwd(act_ptr(m, o.a0), act_ptr(m, o.a1), act_ptr(m, o.a2), lo.n, lo.h, lo.w, lo.c, st);
+      break;
+    }
+    case F_HEAD: {
+      const Act& l = m->acts[o.a0];
+      rc = head_act_fwd(act_ptr(m, o.a0), l.c, arena_f(m, m->heat_off[o.flag]), act_ptr(m, o.a1), l.n * l.h * l.w, m->K,
+                        m->cfg.activation, st);
+      break;
+    }
+    case B_BN_REDUCE: {
+      const BNL& b = m->bns[o.bn];
+      const Act& y = m->acts[o.a1];
+      rc = bn_bwd_reduce(act_ptr(m, o.a0), act_ptr(m, o.a1), arena_f(m, b.bsums_off), y.n * y.h * y.w, b.c, st);
+      break;
+    }
+    case B_BN_APPLY: {
+      const BNL& b = m->bns[o.bn];
+      const ConvL& c = m->convs[o.conv];
+      const Act& y = m->acts[o.a1];
+      rc = bn_bwd_apply(act_ptr(m, o.a0), act_ptr(m, o.a1), act_ptr(m, o.a2), arena_f(m, b.bsums_off), arena_f(m, b.saved_off),
+                        m->p_params + b.gamma_off, m->p_grads + b.gamma_off, m->p_grads + b.beta_off, m->p_grads + c.b_off,
+                        y.n * y.h * y.w, b.c, st);
+      break;
+    }
+    case B_WGRAD: {
+      const ConvL& c = m->convs[o.conv];
+      const Act& dp = m->acts[o.a0];
+      const Act& x = m->acts[o.a1];
+      WgradArgs a;
+      a.N = x.n; a.H = x.h; a.W = x.w; a.Cin = c.cin_pad; a.Cout = c.cout_pad; a.ksize = c.ksize;
+      a.Cin_valid = c.cin; a.Cout_valid = c.cout;
+      a.dw = m->p_grads + c.w_off;
+      rc = launch_conv_wgrad(dp.tmap, x.tmap, a, st);
+      break;
+    }
+    case B_DGRAD: {
+      const ConvL& c = m->convs[o.conv];
+      const Act& dp = m->acts[o.a0];
+      const Act& out = m->acts[o.a1];
+      ConvGemmArgs a;
+      a.N = dp.n; a.H = dp.h; a.W = dp.w; a.Cin = c.cout_pad; a.Cout = c.cin_pad; a.ksize = c.ksize; a.tap_sign = -1;
+      a.relu = 0; a.ldc = out.c; a.bias = nullptr;
+      a.res1 = act_ptr(m, o.a2); a.res2 = act_ptr(m, o.a3); a.out = act_ptr(m, o.a1); a.stats = nullptr;
+      rc = launch_conv_gemm(dp.tmap, c.tm_wd, a, st);
+      break;
+    }
+    case B_RELU_MASK: {
+      const ConvL& c = m->convs[o.conv];
+      const Act& g = m->acts[o.a0];
+      rc = relu_mask_colsum(act_ptr(m, o.a0), act_ptr(m, o.a1), act_ptr(m, o.a0), m->p_grads + c.b_off, g.n * g.h * g.w, g.c,
+                            c.cout, 1, st);
+      break;
+    }
+    case B_COLSUM: {
+      const ConvL& c = m->convs[o.conv];
+      const Act& g = m->acts[o.a0];
+      rc = relu_mask_colsum(act_ptr(m, o.a0), nullptr, nullptr, m->p_grads + c.b_off, g.n * g.h * g.w, g.c, c.cout, 0, st);
+      break;
+    }
+    case B_POOL: {
+      const Act& gy = m->acts[o.a1];
+      rc = maxpool_bwd(act_ptr(m, o.a0), act_ptr(m, o.a1), act_ptr(m, o.a2), gy.n, gy.h, gy.w, gy.c, o.flag, st);
+      break;
+    }
+    case B_UPADD: {
+      const Act& lo = m->acts[o.a1];
+      rc = upsample_add_bwd(act_ptr(m, o.a0), act_ptr(m, o.a1), lo.n, lo.h, lo.w, lo.c, st);
+      break;
+    }
+    case B_HEAD: {
+      const Act& gl = m->acts[o.a1];
+      rc = head_act_bwd(arena_f(m, m->dldp_off[o.flag]), act_ptr(m, o.a0), arena_f(m, m->heat_off[o.flag]), act_ptr(m, o.a1),
+                        gl.n * gl.h * gl.w, m->K, m->cfg.activation, st);
+      break;
+    }
+  }
+  if (rc == HGB_OK) ++m->launches;
+  return rc;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------- C ABI
+extern "C" int hgb_model_create(const hgb_model_config* cfg, int device, hgb_model** out) {
+  HGB_CHECK_ARG(cfg && out, "hgb_model_create: null pointer");
+  HGB_CHECK_ARG(cfg->num_stacks >= 1 && cfg->num_stacks <= 64, "hgb_model_create: num_stacks out of range");
+  HGB_CHECK_ARG(cfg->num_channels >= 128 && cfg->num_channels % 128 == 0 && cfg->num_channels <= 256,
+                "hgb_model_create: num_channels must be 128 or 256 (got %d)", cfg->num_channels);
+  HGB_CHECK_ARG(cfg->num_classes >= 1 && cfg->num_classes <= 64, "hgb_model_create: num_classes must be in [1,64]");
+  HGB_CHECK_ARG(cfg->in_h == cfg->in_w && cfg->in_h >= 64 && cfg->in_h <= 256 && (cfg->in_h & (cfg->in_h - 1)) == 0,
+                "hgb_model_create: input must be square, a power of two in [64,256] (got %dx%d)", cfg->in_h, cfg->in_w);
+  HGB_CHECK_ARG(cfg->activation == 0 || cfg->activation == 1, "hgb_model_create: activation must be 0 (linear) or 1 (sigmoid)");
+  HGB_CHECK_ARG(cfg->batch >= 1, "hgb_model_create: batch must be >= 1");
+  HGB_CHECK_ARG(((int64_t)cfg->in_h / 4) * (cfg->in_w / 4) * cfg->num_classes % 4 == 0, "hgb_model_create: heat map size");
+  hgb_model* m = new hgb_model();
+  m->cfg = *cfg;
+  m->device = device;
+  m->S = cfg->num_stacks; m->C = cfg->num_channels; m->K = cfg->num_classes; m->B = cfg->batch;
+  int rc = build(m);
+  if (rc) { delete m; return rc; }
+  *out = m;
+  return HGB_OK;
+}
+
+extern "C" int hgb_model_destroy(hgb_model* m) {
+  delete m;
+  return HGB_OK;
+}
+
+extern "C" int64_t hgb_model_param_count(const hgb_model* m, int trainable_only) {
+  return trainable_only ? m->n_train : m->n_train + m->n_nontrain;
+}
+
+extern "C" int64_t hgb_model_buffer_bytes(const hgb_model* m, int which) {
+  switch (which) {
+    case HGB_BUF_PARAMS: return (m->train_floats + m->nontrain_floats + 256) * 4;
+    case HGB_BUF_GRADS:
+    case HGB_BUF_ADAM_M:
+    case HGB_BUF_ADAM_V: return (m->train_floats + 256) * 4;
+    case HGB_BUF_ARENA: return (int64_t)m->arena_bytes;
+  }
+  set_error("hgb_model_buffer_bytes: unknown buffer %d", which);
+  return HGB_ERR_INVALID;
+}
+
+extern "C" int hgb_model_bind(hgb_model* m, int which, void* ptr, int64_t bytes) {
+  HGB_CHECK_ARG(m && ptr, "hgb_model_bind: null pointer");
+  HGB_CHECK_ARG(bytes >= hgb_model_buffer_bytes(m, which), "hgb_model_bind: buffer %d too small (%lld < %lld)", which,
+                (long long)bytes, (long long)hgb_model_buffer_bytes(m, which));
+  HGB_CHECK_ARG(((uintptr_t)ptr & 255) == 0, "hgb_model_bind: buffers must be 256-byte aligned");
+  switch (which) {
+    case HGB_BUF_PARAMS: m->p_params = (float*)ptr; break;
+    case HGB_BUF_GRADS: m->p_grads = (float*)ptr; break;
+    case HGB_BUF_ADAM_M: m->p_m = (float*)ptr; break;
+    case HGB_BUF_ADAM_V: m->p_v = (float*)ptr; break;
+    case HGB_BUF_ARENA: m->p_arena = (uint8_t*)ptr; break;
+    default: set_error("hgb_model_bind: unknown buffer %d", which); return HGB_ERR_INVALID;
+  }
+  m->maps_ready = false;
+  if (m->p_params && m->p_arena) return build_maps(m);
+  return HGB_OK;
+}
+
+extern "C" int hgb_model_num_tensors(const hgb_model* m) { return (int)m->params.size(); }
+
+extern "C" int hgb_model_tensor_info(const hgb_model* m, int index, const char** name, int* rank, int64_t dims[4], int64_t* offset,
+                                     int* trainable) {
+  HGB_CHECK_ARG(index >= 0 && index < (int)m->params.size(), "hgb_model_tensor_info: index out of range");
+  const ParamT& p = m->params[index];
+  if (name) *name = p.name.c_str();
+  if (rank) *rank = p.rank;
+  if (dims) for (int i = 0; i < 4; ++i) dims[i] = p.dims[i];
+  if (offset) *offset = p.off;
+  if (trainable) *trainable = p.trainable;
+  return HGB_OK;
+}
+
+extern "C" int hgb_model_num_convs(const hgb_model* m) { return (int)m->convs.size(); }
+
+extern "C" int hgb_model_conv_info(const hgb_model* m, int index, const char** name, int* k, int* cin, int* cout, int* h, int* w,
+                                   double* flops) {
+  HGB_CHECK_ARG(index >= 0 && index < (int)m->convs.size(), "hgb_model_conv_info: index out of range");
+  const ConvL& c = m->convs[index];
+  if (name) *name = c.name.c_str();
+  if (k) *k = c.real_k;
+  if (cin) *cin = c.real_cin;
+  if (cout) *cout = c.cout;
+  if (h) *h = c.h;
+  if (w) *w = c.w;
+  if (flops) *flops = c.flops;
+  return HGB_OK;
+}
+
+#define HGB_REQUIRE_READY(m)                                                                   \
+  do {                                                                                         \
+    if (!(m) || !(m)->maps_ready) {                                                            \
+      set_error("model buffers are not bound (bind HGB_BUF_PARAMS and HGB_BUF_ARENA first)");  \
+      return HGB_ERR_STATE;                                                                    \
+    }                                                                                          \
+  } while (0)
+
+extern "C" int hgb_model_sync_weights(hgb_model* m, void* stream) {
+  HGB_REQUIRE_READY(m);
+  int rc = weight_sync(reinterpret_cast<const WeightSyncEntry*>(m->p_arena + m->sync_off), (int)m->convs.size(),
+                       m->sync_max_elems, (cudaStream_t)stream);
+  if (rc == HGB_OK) ++m->launches;
+  return rc;
+}
+
+extern "C" int hgb_model_forward(hgb_model* m, const float* images, int training, float* const* heatmaps_out, void* stream) {
+  HGB_REQUIRE_READY(m);
+  HGB_CHECK_ARG(images, "hgb_model_forward: null images");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (training) {
+    if (!m->cfg.training || !m->p_grads) { set_error("hgb_model_forward: model was not created/bound for training"); return HGB_ERR_STATE; }
+    HGB_CUDA(cudaMemsetAsync(m->p_arena + m->zero_off, 0, m->zero_bytes, st));
+    HGB_CUDA(cudaMemsetAsync(m->p_grads, 0, (size_t)m->train_floats * 4, st));
+  }
+  for (int seg = 0; seg <= m->S; ++seg)
+    for (const Op& o : m->fwd_ops[seg]) {
+      int rc = run_op(m, o, images, training, st);
+      if (rc) return rc;
+    }
+  if (heatmaps_out) {
+    const size_t bytes = (size_t)m->B * m->hm_h * m->hm_w * m->K * 4;
+    for (int s = 0; s < m->S; ++s)
+      if (heatmaps_out[s]) HGB_CUDA(cudaMemcpyAsync(heatmaps_out[s], m->p_arena + m->heat_off[s], bytes, cudaMemcpyDeviceToDevice, st));
+  }
+  m->fwd_training_done = training != 0;
+  return HGB_OK;
+}
+
+extern "C" int hgb_model_loss(hgb_model* m, int kind, const float* y_true, double inv_count, double* loss_acc, void* stream) {
+  HGB_REQUIRE_READY(m);
+  HGB_CHECK_ARG(y_true && loss_acc, "hgb_model_loss: null pointer");
+  if (!m->cfg.training) { set_error("hgb_model_loss: model was not created for training"); return HGB_ERR_STATE; }
+  for (int s = 0; s < m->S; ++s) {
+    int rc = hgb_loss_fwd_bwd(kind, y_true, arena_f(m, m->heat_off[s]), HGB_F32, m->B, m->hm_h, m->hm_w, m->K, inv_count,
+                              loss_acc + s, arena_f(m, m->dldp_off[s]), HGB_F32, m->p_arena + m->lossws_off, stream);
+    if (rc) return rc;
+    m->launches += kind >= 2 ? 2 : 1;
+  }
+  return HGB_OK;
+}
+
+extern "C" int hgb_model_num_segments(const hgb_model* m) { return m->S + 1; }
+
+extern "C" int hgb_model_backward(hgb_model* m, int seg_lo, int seg_hi, void* stream) {
+  HGB_REQUIRE_READY(m);
+  HGB_CHECK_ARG(seg_lo >= 0 && seg_hi <= m->S + 1 && seg_lo < seg_hi, "hgb_model_backward: bad segment range");
+  if (!m->cfg.training || !m->fwd_training_done) { set_error("hgb_model_backward: needs a training forward pass first"); return HGB_ERR_STATE; }
+  for (int seg = seg_hi - 1; seg >= seg_lo; --seg)
+    for (const Op& o : m->bwd_ops[seg]) {
+      int rc = run_op(m, o, nullptr, 1, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+  return HGB_OK;
+}
+
+extern "C" int hgb_model_segment_grads(const hgb_model* m, int seg, int64_t* offset, int64_t* count) {
+  HGB_CHECK_ARG(seg >= 0 && seg <= m->S, "hgb_model_segment_grads: bad segment");
+  if (offset) *offset = m->seg_begin[seg];
+  if (count) *count = m->seg_end[seg] - m->seg_begin[seg];
+  return HGB_OK;
+}
+
+extern "C" int hgb_model_adam_step(hgb_model* m, double lr, double beta1, double beta2, double eps, int64_t t, double grad_scale,
+                                   void* stream) {
+  HGB_REQUIRE_READY(m);
+  HGB_CHECK_ARG(t >= 1, "hgb_model_adam_step: t starts at 1");
+  if (!m->p_grads || !m->p_m || !m->p_v) { set_error("hgb_model_adam_step: optimizer buffers are not bound"); return HGB_ERR_STATE; }
+  const double lr_t = lr * std::sqrt(1.0 - std::pow(beta2, (double)t)) / (1.0 - std::pow(beta1, (double)t));
+  int rc = adam_step(m->p_params, m->p_grads, m->p_m, m->p_v, m->train_floats, (float)lr_t, (float)beta1, (float)beta2, (float)eps,
+                     (float)grad_scale, (cudaStream_t)stream);
+  if (rc) return rc;
+  ++m->launches;
+  return hgb_model_sync_weights(m, stream);
+}
+
+extern "C" int hgb_model_conv_output(const hgb_model* m, int index, int64_t* arena_offset, int dims[4]) {
+  HGB_CHECK_ARG(index >= 0 && index < (int)m->convs.size(), "hgb_model_conv_output: index out of range");
+  const Act& a = m->acts[m->convs[index].y_act];
+  if (arena_offset) *arena_offset = (int64_t)a.off;
+  if (dims) { dims[0] = a.n; dims[1] = a.h; dims[2] = a.w; dims[3] = a.c; }
+  return HGB_OK;
+}
+
+extern "C" int64_t hgb_model_launch_count(const hgb_model* m) { return m->launches; }

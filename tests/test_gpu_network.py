@@ -1,0 +1,186 @@
+"""End-to-end parity of the CUDA hourglass (bf16 NHWC, fp32 accumulate) with the fp32 oracle
+(oracle/network_oracle.py) on identical synthetic inputs and identical random-init weights.
+
+Gates (BASELINE.json north_star): forward heatmaps and loss within a relative tolerance of 2e-2,
+per-layer gradient cosine > 0.999, targets bit-exact (covered in test_gpu_heatmap.py).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import heatmap_oracle as horc
+from oracle import network_oracle as norc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hgb():
+    import hgb200
+    return hgb200
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    return torch
+
+
+def _inputs(B, seed_img=0, seed_kp=1):
+    """SURVEY section 8(d) config 1 inputs."""
+    images = np.random.default_rng(seed_img).random((B, 256, 256, 3), dtype=np.float32)
+    rng = np.random.default_rng(seed_kp)
+    kx = rng.uniform(-4, 68, (B, 17)).astype(np.float32)
+    ky = rng.uniform(-4, 68, (B, 17)).astype(np.float32)
+    kv = rng.choice([0, 1, 2], p=[.2, .3, .5], size=(B, 17))
+    return images, horc.render_targets(kx, ky, kv, 64, 64)
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+def _cos(a, b):
+    a = a.astype(np.float64).ravel()
+    b = b.astype(np.float64).ravel()
+    na, nb = np.linalg.norm(a), np.linalg.norm(b)
+    if na == 0 and nb == 0:
+        return 1.0
+    return float(a @ b / max(na * nb, 1e-300))
+
+
+def _conv_outputs(hgb, model, plan):
+    """name -> fp32 numpy NHWC of every conv's (bias+activation) output, read from the arena."""
+    lib = hgb._lib.lib
+    out = {}
+    off, dims = C.c_int64(), (C.c_int * 4)()
+    for i, c in enumerate(model.conv_table()):
+        hgb._lib.check(lib.hgb_model_conv_output(plan.handle, i, C.byref(off), C.byref(dims)))
+        n = dims[0] * dims[1] * dims[2] * dims[3]
+        t = plan.arena[off.value:off.value + 2 * n].view(hgb._lib.require_cuda().bfloat16)
+        out[c["name"]] = t.float().reshape(dims[0], dims[1], dims[2], dims[3])[..., :c["cout"]].cpu().numpy()
+    return out
+
+
+def _run_train_case(hgb, torch, S, B, kind, perturb=True, layerwise=True):
+    images, targets = _inputs(B)
+    spec = norc.param_spec(17, S, 256)
+    weights = norc.init_params(spec, seed=2, perturb_bn=perturb)
+    model = hgb.HourglassModel(17, S, 256, (256, 256, 3), "sigmoid")
+    model.set_weights_dict(weights)
+    model.compile(optimizer=hgb.Adam(1e-3), loss=kind)
+
+    lib, chk = hgb._lib.lib, hgb._lib.check
+    plan = model._plan(B, True)
+    x = torch.as_tensor(images, device="cuda")
+    t = torch.as_tensor(targets, device="cuda")
+    outs = model.forward_device(x, training=True, plan=plan)
+    losses = torch.zeros(S, dtype=torch.float64, device="cuda")
+    chk(lib.hgb_model_loss(plan.handle, model._loss_kind, hgb._lib.ptr(t), 1.0 / (B * (17 if kind == "iou" else 64 * 64 * 17)),
+                           hgb._lib.ptr(losses), hgb._lib.stream_ptr()))
+    chk(lib.hgb_model_backward(plan.handle, 0, S + 1, hgb._lib.stream_ptr()))
+    torch.cuda.synchronize()
+
+    o_outs, o_losses, o_grads = norc.loss_and_grads(weights, images, targets, kind, 17, S, 256)
+
+    report = []
+    if layerwise:
+        _, _, taps = norc.forward(weights, images, 17, S, 256, training=True, return_taps=True)
+        dev = _conv_outputs(hgb, model, plan)
+        for name, ref in taps.items():
+            r = ref.detach().permute(0, 2, 3, 1).numpy()
+            report.append((name, _rel(dev[name], r)))
+        worst = sorted(report, key=lambda v: -v[1])[:8]
+        print("layer-wise forward max-rel-err (worst 8):", worst)
+
+    for s in range(S):
+        got = outs[s].cpu().numpy()
+        err = _rel(got, o_outs[s])
+        print(f"stack {s}: heatmap max-rel-err {err:.4g}, loss {losses[s].item():.6g} vs {o_losses[s]:.6g}")
+        assert err <= 2e-2, f"stack {s} heatmaps differ: {err}"
+        assert abs(losses[s].item() - o_losses[s]) <= 2e-2 * abs(o_losses[s]), "loss differs"
+
+    grads = model._unpack(np.concatenate([model._grads.cpu().numpy(), np.zeros(model._param_floats - model._train_floats, np.float32)]))
+    cos = [(name, _cos(grads[name], g)) for name, g in o_grads.items()]
+    bad = sorted(cos, key=lambda v: v[1])[:10]
+    print("lowest gradient cosines:", bad)
+    for name, c in cos:
+        assert c > 0.999, f"gradient cosine of {name} = {c}"
+    # magnitudes too: ratio of norms within 2 %
+    for name, g in o_grads.items():
+        n0, n1 = np.linalg.norm(g), np.linalg.norm(grads[name])
+        if n0 > 1e-12:
+            assert abs(n1 / n0 - 1) < 2e-2, f"gradient norm of {name}: {n1} vs {n0}"
+    return model, plan, grads
+
+
+def test_config1_one_stack_weighted_mse(hgb, torch):
+    """BASELINE config 1: 1-stack, 256 ch, batch 8, training forward + weighted_MSE backward."""
+    _run_train_case(hgb, torch, S=1, B=8, kind="weighted_mse", perturb=False)
+
+
+def test_two_stack_reinjection_and_perturbed_bn(hgb, torch):
+    """Covers the inter-stack re-injection convs (hourglass.py:87-91) and non-trivial gamma/beta."""
+    _run_train_case(hgb, torch, S=2, B=2, kind="weighted_mse", perturb=True)
+
+
+def test_iou_loss_backward(hgb, torch):
+    _run_train_case(hgb, torch, S=1, B=2, kind="iou", perturb=True, layerwise=False)
+
+
+def test_inference_mode_uses_moving_statistics(hgb, torch):
+    images, _ = _inputs(3)
+    spec = norc.param_spec(17, 2, 256)
+    weights = norc.init_params(spec, seed=5, perturb_bn=True)
+    model = hgb.HourglassModel(17, 2, 256, (256, 256, 3), "sigmoid")
+    model.set_weights_dict(weights)
+    got = model.predict(images, batch_size=2)            # 2 + padded tail of 1
+    ref, _ = norc.forward(weights, images, 17, 2, 256, training=False)
+    assert isinstance(got, list) and len(got) == 2 and got[0].shape == (3, 64, 64, 17)
+    for s in range(2):
+        assert _rel(got[s], ref[s].detach().numpy()) <= 2e-2
+
+
+def test_moving_statistics_update(hgb, torch):
+    images, targets = _inputs(4)
+    spec = norc.param_spec(17, 1, 256)
+    weights = norc.init_params(spec, seed=6, perturb_bn=True)
+    model = hgb.HourglassModel(17, 1, 256, (256, 256, 3), "sigmoid")
+    model.set_weights_dict(weights)
+    model.forward_device(torch.as_tensor(images, device="cuda"), training=True, plan=model._plan(4, True))
+    new = model.get_weights_dict()
+    _, params = norc.forward(weights, images, 17, 1, 256, training=True, update_moving=True)
+    for name in ("batch_normalization", "batch_normalization_7", "batch_normalization_55"):
+        for s in ("moving_mean", "moving_variance"):
+            ref = params[f"{name}/{s}"].detach().numpy()
+            np.testing.assert_allclose(new[f"{name}/{s}"], ref, rtol=2e-2, atol=2e-3)
+
+
+def test_adam_step_matches_keras_formula(hgb, torch):
+    model, plan, grads = _run_train_case(hgb, torch, S=1, B=2, kind="mse", perturb=True, layerwise=False)
+    before = model.get_weights_dict()
+    lib = hgb._lib.lib
+    for t in (1, 2):
+        hgb._lib.check(lib.hgb_model_adam_step(plan.handle, 1e-3, 0.9, 0.999, 1e-7, t, 1.0, hgb._lib.stream_ptr()))
+    after = model.get_weights_dict()
+    for name in ("front_conv_1x1_1/kernel", "hg0_conv_1x1_predict/bias", "batch_normalization_20/gamma",
+                 "hg0_upsample_f2_merged_conv_3x3_2/kernel"):
+        w = before[name].astype(np.float32).copy()
+        m = np.zeros_like(w)
+        v = np.zeros_like(w)
+        for t in (1, 2):
+            norc.adam_step(w, grads[name], m, v, t)
+        np.testing.assert_allclose(after[name], w, rtol=1e-5, atol=1e-7)
+
+
+def test_training_reduces_loss(hgb, torch):
+    """A few optimizer steps on one batch must lower the summed loss (whole-pipeline sanity)."""
+    images, targets = _inputs(4)
+    model = hgb.HourglassModel(17, 2, 256, (256, 256, 3), "sigmoid", seed=3)
+    model.compile(optimizer=hgb.Adam(1e-3), loss=hgb.loss.weighted_mse)
+    first = model.train_on_batch(images, targets)
+    for _ in range(6):
+        last = model.train_on_batch(images, targets)
+    assert len(first) == 3 and abs(first[0] - (first[1] + first[2])) < 1e-9
+    assert last[0] < first[0]
