@@ -28,35 +28,46 @@ BN_MOMENTUM = 0.99
 class _Builder:
     """Walks model/hourglass.py once; in 'spec' mode it records parameter names/shapes, in 'run' mode it computes."""
 
-    def __init__(self, params=None, training=True, update_moving=False):
+    def __init__(self, params=None, training=True, update_moving=False, emulate_bf16=False):
         self.params = params
         self.training = training
         self.update_moving = update_moving
+        # emulate_bf16: round to bfloat16 at exactly the points where the CUDA pipeline stores bf16
+        # (conv operands, conv outputs, BN(+residual) outputs, merges); straight-through in backward.
+        self.emulate = emulate_bf16
         self.spec = OrderedDict()
         self.bn_count = 0
         self.taps = {}
 
+    def q(self, t):
+        if not self.emulate:
+            return t
+        return t + (t.to(torch.bfloat16).to(torch.float32) - t).detach()
+
     # ---- layers
-    def conv(self, x, name, k, cin, cout, activation, stride=1):
+    def conv(self, x, name, k, cin, cout, activation, stride=1, residual=None):
         if self.params is None:
             self.spec[name + "/kernel"] = (k, k, cin, cout)
             self.spec[name + "/bias"] = (cout,)
             return x
-        w = self.params[name + "/kernel"].permute(3, 2, 0, 1)  # HWIO -> OIHW
+        w = self.q(self.params[name + "/kernel"]).permute(3, 2, 0, 1)  # HWIO -> OIHW
         b = self.params[name + "/bias"]
         if stride == 2:  # TF 'same': total pad = k - stride, extra pixel after (hourglass.py:59)
             x = F.pad(x, (2, 3, 2, 3))
             y = F.conv2d(x, w, b, stride=2)
         else:
             y = F.conv2d(x, w, b, padding=k // 2)
+        if residual is not None:
+            y = y + residual
         if activation == "relu":
             y = torch.relu(y)
-        elif activation == "sigmoid":
-            y = torch.sigmoid(y)
+        y = self.q(y)                      # the conv epilogue stores bf16 (logits included)
+        if activation == "sigmoid":
+            y = torch.sigmoid(y)           # fp32 heat map computed from the stored logits
         self.taps[name] = y
         return y
 
-    def bn(self, x, c):
+    def bn(self, x, c, residual=None):
         name = "batch_normalization" if self.bn_count == 0 else f"batch_normalization_{self.bn_count}"
         self.bn_count += 1
         if self.params is None:
@@ -65,20 +76,30 @@ class _Builder:
             return x
         g = self.params[name + "/gamma"].view(1, -1, 1, 1)
         b = self.params[name + "/beta"].view(1, -1, 1, 1)
-        if self.training:
+        if self.training and self.emulate:  # same algebra as the kernels: E[y^2] - E[y]^2, scale/shift form
+            mean = x.mean(dim=(0, 2, 3), keepdim=True)
+            var = ((x * x).mean(dim=(0, 2, 3), keepdim=True) - mean * mean).clamp_min(0)
+        elif self.training:
             mean = x.mean(dim=(0, 2, 3), keepdim=True)
             var = x.var(dim=(0, 2, 3), unbiased=False, keepdim=True)
-            if self.update_moving:
-                n = x.numel() / x.shape[1]
-                with torch.no_grad():
-                    mm = self.params[name + "/moving_mean"]
-                    mv = self.params[name + "/moving_variance"]
-                    mm.mul_(BN_MOMENTUM).add_(mean.flatten() * (1 - BN_MOMENTUM))
-                    mv.mul_(BN_MOMENTUM).add_(var.flatten() * (n / max(n - 1, 1)) * (1 - BN_MOMENTUM))
         else:
             mean = self.params[name + "/moving_mean"].view(1, -1, 1, 1)
             var = self.params[name + "/moving_variance"].view(1, -1, 1, 1)
-        return (x - mean) / torch.sqrt(var + BN_EPS) * g + b
+        if self.training and self.update_moving:  # TF fused BN feeds the unbiased variance to the moving average
+            n = x.numel() / x.shape[1]
+            with torch.no_grad():
+                mm = self.params[name + "/moving_mean"]
+                mv = self.params[name + "/moving_variance"]
+                mm.mul_(BN_MOMENTUM).add_(mean.flatten() * (1 - BN_MOMENTUM))
+                mv.mul_(BN_MOMENTUM).add_(var.flatten() * (n / max(n - 1, 1)) * (1 - BN_MOMENTUM))
+        if self.emulate:
+            sc = g * torch.rsqrt(var + BN_EPS)
+            z = x * sc + (b - mean * sc)
+        else:
+            z = (x - mean) / torch.sqrt(var + BN_EPS) * g + b
+        if residual is not None:
+            z = z + residual
+        return self.q(z)
 
     def pool(self, x):
         return x if self.params is None else F.max_pool2d(x, 2, 2)
@@ -96,10 +117,12 @@ class _Builder:
         y = self.conv(y, name + "_conv_3x3_2", 3, cout // 2, cout // 2, "relu")
         y = self.bn(y, cout // 2)
         y = self.conv(y, name + "_conv_1x1_3", 1, cout // 2, cout, "relu")
-        y = self.bn(y, cout)
-        return skip + y if self.params is not None else x
+        y = self.bn(y, cout, residual=skip if self.params is not None else None)  # Add (hourglass.py:204)
+        return y if self.params is not None else x
 
     def front(self, x, C):
+        if self.params is not None:
+            x = self.q(x)                  # the stem reads bf16 patches of the f32 image
         x = self.conv(x, "front_conv_1x1_1", 7, 3, 64, "relu", stride=2)
         x = self.bn(x, 64)
         x = self.bottleneck(x, 64, C // 2, "front_bottleneck_1")
@@ -120,16 +143,17 @@ class _Builder:
         cur = b
         for f, nm in ((f8, "f8"), (f4, "f4"), (f2, "f2"), (f1, "f1")):
             s = self.bottleneck(f, C, C, f"{hg}_upsample_{nm}_short")
-            a = s + self.up(cur) if self.params is not None else s
+            a = self.q(s + self.up(cur)) if self.params is not None else s
             cur = self.bottleneck(a, C, C, f"{hg}_upsample_{nm}_merged")
         head = self.conv(cur, hg + "_conv_1x1_1", 1, C, C, "relu")
         head = self.bn(head, C)
         predict = self.conv(head, hg + "_conv_1x1_predict", 1, C, K, activation)
         nxt = None
         if not last:  # Keras prunes the last stack's re-injection branch (not on a path to an output)
-            h2 = self.conv(head, hg + "_conv_1x1_2", 1, C, C, "linear")
-            h3 = self.conv(predict, hg + "_conv_1x1_3", 1, K, C, "linear")
-            nxt = h2 + h3 + x if self.params is not None else x
+            # Add()([head, head_m, x]) (hourglass.py:91), evaluated as two GEMM epilogues with residuals
+            h2 = self.conv(head, hg + "_conv_1x1_2", 1, C, C, "linear", residual=x)
+            pin = self.q(predict) if self.params is not None else predict
+            nxt = self.conv(pin, hg + "_conv_1x1_3", 1, K, C, "linear", residual=h2)
         return nxt, predict
 
     def model(self, x, K, S, C, activation):
@@ -180,12 +204,12 @@ def init_params(spec, seed=2, perturb_bn=False):
 
 
 def forward(params_np, images_nhwc, num_classes, num_stacks, num_channels, activation="sigmoid", training=True,
-            requires_grad=False, update_moving=False, return_taps=False):
+            requires_grad=False, update_moving=False, return_taps=False, emulate_bf16=False):
     """images (B,H,W,3) f32 -> list of S tensors (B,h,w,K) f32 (NHWC).  Returns (outputs, torch params)."""
     params = OrderedDict((k, torch.tensor(v, dtype=torch.float32, requires_grad=requires_grad and "moving_" not in k))
                          for k, v in params_np.items())
     x = torch.as_tensor(np.asarray(images_nhwc), dtype=torch.float32).permute(0, 3, 1, 2)
-    b = _Builder(params, training=training, update_moving=update_moving)
+    b = _Builder(params, training=training, update_moving=update_moving, emulate_bf16=emulate_bf16)
     outs = b.model(x, num_classes, num_stacks, num_channels, activation)
     outs = [o.permute(0, 2, 3, 1) for o in outs]
     if return_taps:
@@ -212,10 +236,11 @@ def torch_loss(kind, y_true, y_pred):
     raise ValueError(kind)
 
 
-def loss_and_grads(params_np, images, y_true, kind, num_classes, num_stacks, num_channels, activation="sigmoid"):
+def loss_and_grads(params_np, images, y_true, kind, num_classes, num_stacks, num_channels, activation="sigmoid",
+                   emulate_bf16=False):
     """Training-mode forward, sum of per-stack losses (Keras compile with one loss fn), backward."""
     outs, params = forward(params_np, images, num_classes, num_stacks, num_channels, activation, training=True,
-                           requires_grad=True)
+                           requires_grad=True, emulate_bf16=emulate_bf16)
     t = torch.as_tensor(np.asarray(y_true), dtype=torch.float32)
     losses = [torch_loss(kind, t, o) for o in outs]
     total = sum(losses)

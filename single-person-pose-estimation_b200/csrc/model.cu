@@ -44,7 +44,7 @@ struct ConvL {
   CUtensorMap tm_wf, tm_wd;
   double flops;
   int seg;
-  int y_act = -1;
+  int y_act = -1, in_act = -1, z_act = -1;
 };
 
 struct BNL {
@@ -219,11 +219,13 @@ struct hgb_model {
     if (bn) { bi = add_bn(cout); o.bn = bi; }
     emit_f(o);
     convs[ci].y_act = y;
+    convs[ci].in_act = in_act;
     if (bn) {
       out = new_act(in.n, in.h, in.w, cout);
       Op b;
       b.type = F_BN; b.bn = bi; b.a0 = y; b.a1 = bn_res; b.a2 = out;
       emit_f(b);
+      convs[ci].z_act = out;
     }
     if (conv_idx) *conv_idx = ci;
     if (bn_idx) *bn_idx = bi;
@@ -831,7 +833,11 @@ extern "C" int hgb_model_adam_step(hgb_model* m, double lr, double beta1, double
 
 extern "C" int hgb_model_conv_output(const hgb_model* m, int index, int64_t* arena_offset, int dims[4]) {
   HGB_CHECK_ARG(index >= 0 && index < (int)m->convs.size(), "hgb_model_conv_output: index out of range");
-  const Act& a = m->acts[m->convs[index].y_act];
+  const int which = hgb::g_debug[2];  // 0: conv output, 1: conv input, 2: BN output (if any)
+  const ConvL& c = m->convs[index];
+  const int ai = which == 1 ? c.in_act : (which == 2 ? c.z_act : c.y_act);
+  HGB_CHECK_ARG(ai >= 0, "hgb_model_conv_output: conv %d has no such tensor", index);
+  const Act& a = m->acts[ai];
   if (arena_offset) *arena_offset = (int64_t)a.off;
   if (dims) { dims[0] = a.n; dims[1] = a.h; dims[2] = a.w; dims[3] = a.c; }
   return HGB_OK;

@@ -99,6 +99,10 @@ def decode_batch(heatmaps, conf_threshold: float = 1e-6, version: int = 2):
     B, H, W, K = hm.shape
     idx = torch.empty((B, K, 4), dtype=torch.int32, device="cuda")
     kp = torch.empty((B, K, 3), dtype=torch.float32, device="cuda")
+    if version not in (1, 2) or H != W:
+        raise ValueError("decode: version must be 1 or 2 and maps must be square (data_utils.py:122)")
+    if B == 0:
+        return idx, kp
     check(lib.hgb_decode(ptr(hm), _tdtype(hm), B, H, W, K, float(conf_threshold), int(version), ptr(idx), ptr(kp),
                          stream_ptr()))
     return idx, kp
