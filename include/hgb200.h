@@ -164,6 +164,18 @@ int hgb_model_adam_step(hgb_model* m, double lr, double beta1, double beta2, dou
  * dims = {N,H,W,C_padded}, as a byte offset into the bound arena */
 int hgb_model_conv_output(const hgb_model* m, int index, int64_t* arena_offset, int dims[4]);
 
+/* plan introspection and single-op stepping: lets a test replay EVERY op of the real execution plan
+ * (forward and backward) against an fp32 reference computed from the device's own input tensors.
+ * op info = {type, conv, bn, a0, a1, a2, a3, flag}; see csrc/model.cu (OpType) for the roles. */
+int hgb_model_num_ops(const hgb_model* m, int seg, int backward);
+int hgb_model_op_info(const hgb_model* m, int seg, int backward, int index, int info[8]);
+int hgb_model_act_info(const hgb_model* m, int act, int64_t* arena_offset, int dims[4]);
+int hgb_model_run_op(hgb_model* m, int seg, int backward, int index, const float* images, int training, void* stream);
+int hgb_model_conv_detail(const hgb_model* m, int conv, int info[8], int64_t offs[2]);
+int hgb_model_bn_detail(const hgb_model* m, int bn, int64_t offs[8]);
+int hgb_model_head_buffers(const hgb_model* m, int stack, int64_t offs[2]);
+int hgb_model_begin_step(hgb_model* m, void* stream);
+
 /* number of kernels this handle has launched since creation (bench "gpu_launches") */
 int64_t hgb_model_launch_count(const hgb_model* m);
 

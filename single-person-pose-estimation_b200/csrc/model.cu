@@ -799,6 +799,16 @@ extern "C" int hgb_model_loss(hgb_model* m, int kind, const float* y_true, doubl
 
 extern "C" int hgb_model_num_segments(const hgb_model* m) { return m->S + 1; }
 
+// zero the per-step accumulators (BN sums, gradients); hgb_model_forward(training=1) does this itself
+extern "C" int hgb_model_begin_step(hgb_model* m, void* stream) {
+  HGB_REQUIRE_READY(m);
+  if (!m->cfg.training || !m->p_grads) { set_error("hgb_model_begin_step: model was not created/bound for training"); return HGB_ERR_STATE; }
+  HGB_CUDA(cudaMemsetAsync(m->p_arena + m->zero_off, 0, m->zero_bytes, (cudaStream_t)stream));
+  HGB_CUDA(cudaMemsetAsync(m->p_grads, 0, (size_t)m->train_floats * 4, (cudaStream_t)stream));
+  m->fwd_training_done = true;
+  return HGB_OK;
+}
+
 extern "C" int hgb_model_backward(hgb_model* m, int seg_lo, int seg_hi, void* stream) {
   HGB_REQUIRE_READY(m);
   HGB_CHECK_ARG(seg_lo >= 0 && seg_hi <= m->S + 1 && seg_lo < seg_hi, "hgb_model_backward: bad segment range");
@@ -840,6 +850,59 @@ extern "C" int hgb_model_conv_output(const hgb_model* m, int index, int64_t* are
   const Act& a = m->acts[ai];
   if (arena_offset) *arena_offset = (int64_t)a.off;
   if (dims) { dims[0] = a.n; dims[1] = a.h; dims[2] = a.w; dims[3] = a.c; }
+  return HGB_OK;
+}
+
+// ---- plan introspection / single-op stepping (tests replay every op against fp32 torch)
+extern "C" int hgb_model_num_ops(const hgb_model* m, int seg, int backward) {
+  if (seg < 0 || seg > m->S) return 0;
+  return (int)(backward ? m->bwd_ops[seg].size() : m->fwd_ops[seg].size());
+}
+extern "C" int hgb_model_op_info(const hgb_model* m, int seg, int backward, int index, int info[8]) {
+  HGB_CHECK_ARG(seg >= 0 && seg <= m->S, "hgb_model_op_info: bad segment");
+  const std::vector<Op>& v = backward ? m->bwd_ops[seg] : m->fwd_ops[seg];
+  HGB_CHECK_ARG(index >= 0 && index < (int)v.size(), "hgb_model_op_info: index out of range");
+  const Op& o = v[index];
+  info[0] = (int)o.type; info[1] = o.conv; info[2] = o.bn; info[3] = o.a0; info[4] = o.a1; info[5] = o.a2; info[6] = o.a3;
+  info[7] = o.flag;
+  return HGB_OK;
+}
+extern "C" int hgb_model_act_info(const hgb_model* m, int act, int64_t* arena_offset, int dims[4]) {
+  HGB_CHECK_ARG(act >= 0 && act < (int)m->acts.size(), "hgb_model_act_info: index out of range");
+  const Act& a = m->acts[act];
+  if (arena_offset) *arena_offset = (int64_t)a.off;
+  if (dims) { dims[0] = a.n; dims[1] = a.h; dims[2] = a.w; dims[3] = a.c; }
+  return HGB_OK;
+}
+extern "C" int hgb_model_run_op(hgb_model* m, int seg, int backward, int index, const float* images, int training, void* stream) {
+  HGB_REQUIRE_READY(m);
+  HGB_CHECK_ARG(seg >= 0 && seg <= m->S, "hgb_model_run_op: bad segment");
+  const std::vector<Op>& v = backward ? m->bwd_ops[seg] : m->fwd_ops[seg];
+  HGB_CHECK_ARG(index >= 0 && index < (int)v.size(), "hgb_model_run_op: index out of range");
+  return run_op(m, v[index], images, training, (cudaStream_t)stream);
+}
+// info: ksize, taps, cin, cout, cin_pad, cout_pad, relu, has_dgrad; offs: kernel, bias (floats into params/grads)
+extern "C" int hgb_model_conv_detail(const hgb_model* m, int conv, int info[8], int64_t offs[2]) {
+  HGB_CHECK_ARG(conv >= 0 && conv < (int)m->convs.size(), "hgb_model_conv_detail: index out of range");
+  const ConvL& c = m->convs[conv];
+  info[0] = c.ksize; info[1] = c.taps; info[2] = c.cin; info[3] = c.cout; info[4] = c.cin_pad; info[5] = c.cout_pad;
+  info[6] = c.relu; info[7] = c.has_wd;
+  offs[0] = c.w_off; offs[1] = c.b_off;
+  return HGB_OK;
+}
+// offs: channels, gamma, beta, moving_mean, moving_var (floats into params), sums, bsums, saved (bytes into arena)
+extern "C" int hgb_model_bn_detail(const hgb_model* m, int bn, int64_t offs[8]) {
+  HGB_CHECK_ARG(bn >= 0 && bn < (int)m->bns.size(), "hgb_model_bn_detail: index out of range");
+  const BNL& b = m->bns[bn];
+  offs[0] = b.c; offs[1] = b.gamma_off; offs[2] = b.beta_off; offs[3] = b.mm_off; offs[4] = b.mv_off;
+  offs[5] = (int64_t)b.sums_off; offs[6] = (int64_t)b.bsums_off; offs[7] = (int64_t)b.saved_off;
+  return HGB_OK;
+}
+// byte offsets into the arena of stack s's fp32 heat map and loss gradient
+extern "C" int hgb_model_head_buffers(const hgb_model* m, int stack, int64_t offs[2]) {
+  HGB_CHECK_ARG(stack >= 0 && stack < m->S, "hgb_model_head_buffers: bad stack");
+  offs[0] = (int64_t)m->heat_off[stack];
+  offs[1] = m->cfg.training ? (int64_t)m->dldp_off[stack] : -1;
   return HGB_OK;
 }
 

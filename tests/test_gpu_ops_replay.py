@@ -1,0 +1,317 @@
+"""Replay of EVERY op of the real execution plan (forward and backward, 2 stacks) against an fp32
+torch reference computed from the device's own input tensors, one op at a time
+(hgb_model_run_op).  This is the parity proof that does not depend on how the network amplifies
+noise: each convolution (forward, dgrad, wgrad -- incl. the padded 17-channel and 7x7-stem cases and
+fused residuals), BatchNorm forward/backward, pool, upsample-add and head op must match the fp32
+arithmetic of model/hourglass.py to bf16 output rounding; integer-like ops must match exactly.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import network_oracle as norc
+from tests.test_gpu_network import _inputs
+
+pytestmark = pytest.mark.gpu
+
+(F_IM2COL, F_CONV, F_BN, F_POOL, F_UPADD, F_HEAD, B_BN_REDUCE, B_BN_APPLY, B_WGRAD, B_DGRAD, B_RELU_MASK, B_COLSUM,
+ B_POOL, B_UPADD, B_HEAD) = range(15)
+NAMES = ["F_IM2COL", "F_CONV", "F_BN", "F_POOL", "F_UPADD", "F_HEAD", "B_BN_REDUCE", "B_BN_APPLY", "B_WGRAD", "B_DGRAD",
+         "B_RELU_MASK", "B_COLSUM", "B_POOL", "B_UPADD", "B_HEAD"]
+
+
+class Replay:
+    def __init__(self, hgb, torch, S, B, kind="weighted_mse"):
+        self.hgb, self.torch, self.S, self.B = hgb, torch, S, B
+        self.lib, self.chk = hgb._lib.lib, hgb._lib.check
+        images, targets = _inputs(B)
+        weights = norc.init_params(norc.param_spec(17, S, 256), seed=7, perturb_bn=True)
+        self.model = hgb.HourglassModel(17, S, 256, (256, 256, 3), "sigmoid")
+        self.model.set_weights_dict(weights)
+        self.model.compile(optimizer=hgb.Adam(1e-3), loss=kind)
+        self.plan = self.model._plan(B, True)
+        self.h = self.plan.handle
+        self.images = torch.as_tensor(images, device="cuda")
+        self.targets = torch.as_tensor(targets, device="cuda")
+        self.params, self.grads, self.arena = self.model._params, self.model._grads, self.plan.arena
+        self.worst = {}
+
+    # ---- views
+    def act(self, a):
+        if a < 0:
+            return None
+        off, dims = C.c_int64(), (C.c_int * 4)()
+        self.chk(self.lib.hgb_model_act_info(self.h, a, C.byref(off), C.byref(dims)))
+        n = dims[0] * dims[1] * dims[2] * dims[3]
+        return self.arena[off.value:off.value + 2 * n].view(self.torch.bfloat16).view(*dims)
+
+    def arena_f32(self, off, n):
+        return self.arena[off:off + 4 * n].view(self.torch.float32)
+
+    def conv(self, ci):
+        info, offs = (C.c_int * 8)(), (C.c_int64 * 2)()
+        self.chk(self.lib.hgb_model_conv_detail(self.h, ci, C.byref(info), C.byref(offs)))
+        d = dict(zip(("ksize", "taps", "cin", "cout", "cin_pad", "cout_pad", "relu", "has_dgrad"), info))
+        d["w_off"], d["b_off"] = offs[0], offs[1]
+        return d
+
+    def bn(self, bi):
+        offs = (C.c_int64 * 8)()
+        self.chk(self.lib.hgb_model_bn_detail(self.h, bi, C.byref(offs)))
+        return dict(zip(("c", "gamma", "beta", "mm", "mv", "sums", "bsums", "saved"), offs))
+
+    def weight_oihw(self, c, src=None):
+        """bf16-rounded kernel as the GEMM sees it, OIHW fp32."""
+        t = self.torch
+        src = self.params if src is None else src
+        n = c["cout"] * c["taps"] * c["cin"]
+        w = src[c["w_off"]:c["w_off"] + n].view(c["cout"], c["ksize"], c["ksize"], c["cin"])
+        return w.to(t.bfloat16).float().permute(0, 3, 1, 2).contiguous()
+
+    def note(self, op_type, err):
+        k = NAMES[op_type]
+        self.worst[k] = max(self.worst.get(k, 0.0), float(err))
+
+    @staticmethod
+    def rel(a, b):
+        return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
+
+    def ops(self, seg, backward):
+        n = self.lib.hgb_model_num_ops(self.h, seg, backward)
+        for i in range(n):
+            info = (C.c_int * 8)()
+            self.chk(self.lib.hgb_model_op_info(self.h, seg, backward, i, C.byref(info)))
+            yield i, tuple(info)
+
+    def run(self, seg, backward, i):
+        self.chk(self.lib.hgb_model_run_op(self.h, seg, backward, i, self.hgb._lib.ptr(self.images), 1, self.hgb._lib.stream_ptr()))
+        self.torch.cuda.synchronize()
+
+
+def _first_max_mask(torch, v):
+    """v: (..., 4, C) window values in row-major order -> one-hot mask of the first maximum."""
+    mx = v.max(dim=-2, keepdim=True).values
+    eq = (v == mx)
+    return eq & (eq.int().cumsum(dim=-2) == 1)
+
+
+def _windows(x):
+    """(N,2h,2w,C) -> (N,h,w,4,C), window order (0,0),(0,1),(1,0),(1,1)."""
+    N, H, W, Cc = x.shape
+    return x.view(N, H // 2, 2, W // 2, 2, Cc).permute(0, 1, 3, 2, 4, 5).reshape(N, H // 2, W // 2, 4, Cc)
+
+
+def _unwindows(v, N, H, W, Cc):
+    return v.view(N, H // 2, W // 2, 2, 2, Cc).permute(0, 1, 3, 2, 4, 5).reshape(N, H, W, Cc)
+
+
+def test_replay_every_op(request):
+    import hgb200 as hgb
+    import torch
+    import torch.nn.functional as F
+    S, B = 2, 3
+    R = Replay(hgb, torch, S, B)
+    lib, chk, ptr, sp = R.lib, R.chk, hgb._lib.ptr, hgb._lib.stream_ptr
+    chk(lib.hgb_model_begin_step(R.h, sp()))
+    torch.cuda.synchronize()
+    bf = torch.bfloat16
+
+    # ------------------------------------------------------------------ forward
+    for seg in range(S + 1):
+        for i, (ty, ci, bi, a0, a1, a2, a3, flag) in R.ops(seg, 0):
+            if ty == F_IM2COL:
+                R.run(seg, 0, i)
+                col = R.act(a0).float()
+                x = R.images.to(bf).float().permute(0, 3, 1, 2)
+                u = F.unfold(F.pad(x, (2, 3, 2, 3)), kernel_size=7, stride=2)            # (B, 3*49, L), (c,ky,kx) major
+                u = u.view(B, 3, 7, 7, 128, 128).permute(0, 4, 5, 2, 3, 1).reshape(B, 128, 128, 147)
+                assert torch.equal(col[..., :147], u) and col[..., 147:].abs().max().item() == 0
+            elif ty == F_CONV:
+                c = R.conv(ci)
+                bnd = R.bn(bi) if bi >= 0 else None
+                s0 = R.arena_f32(bnd["sums"], 2 * bnd["c"]).clone() if bnd else None
+                x = R.act(a0).float()[..., :c["cin"]]
+                res = sum(R.act(a).float().clone() for a in (a2, a3) if a >= 0) if (a2 >= 0 or a3 >= 0) else None
+                R.run(seg, 0, i)
+                y = R.act(a1).float()
+                bias = R.params[c["b_off"]:c["b_off"] + c["cout"]]
+                ref = F.conv2d(x.permute(0, 3, 1, 2), R.weight_oihw(c), bias, padding=c["ksize"] // 2).permute(0, 2, 3, 1)
+                if res is not None:
+                    ref = ref + res[..., :c["cout"]]
+                if c["relu"]:
+                    ref = torch.relu(ref)
+                e = R.rel(y[..., :c["cout"]], ref)
+                R.note(ty, e)
+                assert e <= 1e-2, f"conv {ci}: {e}"
+                if bnd:
+                    s1 = R.arena_f32(bnd["sums"], 2 * bnd["c"]) - s0
+                    yy = y.reshape(-1, y.shape[-1])
+                    torch.testing.assert_close(s1[:bnd["c"]], yy.sum(0), rtol=2e-3, atol=1e-2)
+                    torch.testing.assert_close(s1[bnd["c"]:], (yy * yy).sum(0), rtol=2e-3, atol=1e-2)
+            elif ty == F_BN:
+                b = R.bn(bi)
+                Cc = b["c"]
+                y = R.act(a0).float()
+                res = R.act(a1).float() if a1 >= 0 else 0.0
+                mm0 = R.params[b["mm"]:b["mm"] + Cc].clone()
+                mv0 = R.params[b["mv"]:b["mv"] + Cc].clone()
+                R.run(seg, 0, i)
+                out = R.act(a2).float()
+                mean = y.mean(dim=(0, 1, 2))
+                var = y.var(dim=(0, 1, 2), unbiased=False)
+                g, be = R.params[b["gamma"]:b["gamma"] + Cc], R.params[b["beta"]:b["beta"] + Cc]
+                ref = (y - mean) / torch.sqrt(var + 1e-3) * g + be + res
+                e = R.rel(out, ref)
+                R.note(ty, e)
+                assert e <= 1e-2, f"bn {bi}: {e}"
+                saved = R.arena_f32(b["saved"], 2 * Cc)
+                torch.testing.assert_close(saved[:Cc], mean, rtol=1e-3, atol=1e-4)
+                torch.testing.assert_close(saved[Cc:], torch.rsqrt(var + 1e-3), rtol=2e-3, atol=1e-4)
+                M = y.numel() // Cc
+                torch.testing.assert_close(R.params[b["mm"]:b["mm"] + Cc], 0.99 * mm0 + 0.01 * mean, rtol=1e-4, atol=1e-5)
+                torch.testing.assert_close(R.params[b["mv"]:b["mv"] + Cc], 0.99 * mv0 + 0.01 * var * M / (M - 1), rtol=1e-3, atol=1e-5)
+            elif ty == F_POOL:
+                R.run(seg, 0, i)
+                x, out = R.act(a0), R.act(a1)
+                assert torch.equal(out, _windows(x.float()).max(dim=-2).values.to(bf))
+            elif ty == F_UPADD:
+                R.run(seg, 0, i)
+                s, lo, out = R.act(a0).float(), R.act(a1).float(), R.act(a2)
+                up = lo.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+                assert torch.equal(out, (s + up).to(bf))
+            elif ty == F_HEAD:
+                R.run(seg, 0, i)
+                offs = (C.c_int64 * 2)()
+                chk(lib.hgb_model_head_buffers(R.h, flag, C.byref(offs)))
+                logits = R.act(a0).float()[..., :17]
+                heat = R.arena_f32(offs[0], B * 64 * 64 * 17).view(B, 64, 64, 17)
+                torch.testing.assert_close(heat, torch.sigmoid(logits), rtol=1e-4, atol=1e-6)
+                pbf = R.act(a1).float()
+                assert pbf[..., 17:].abs().max().item() == 0
+                assert R.rel(pbf[..., :17], heat) <= 4e-3
+            else:
+                raise AssertionError(f"unexpected forward op {ty}")
+
+    # ------------------------------------------------------------------ loss, then backward op by op
+    losses = torch.zeros(S, dtype=torch.float64, device="cuda")
+    chk(lib.hgb_model_loss(R.h, R.model._loss_kind, ptr(R.targets), 1.0 / (B * 64 * 64 * 17), ptr(losses), sp()))
+    torch.cuda.synchronize()
+    for seg in range(S, -1, -1):
+        for i, (ty, ci, bi, a0, a1, a2, a3, flag) in R.ops(seg, 1):
+            if ty == B_BN_REDUCE:
+                b = R.bn(bi)
+                Cc = b["c"]
+                s0 = R.arena_f32(b["bsums"], 2 * Cc).clone()
+                R.run(seg, 1, i)
+                dz, y = R.act(a0).float().reshape(-1, Cc), R.act(a1).float().reshape(-1, Cc)
+                s1 = R.arena_f32(b["bsums"], 2 * Cc) - s0
+                sc = max(dz.abs().sum(0).max().item(), 1e-20)
+                assert (s1[:Cc] - dz.sum(0)).abs().max().item() <= 2e-3 * sc
+                sc = max((dz * y).abs().sum(0).max().item(), 1e-20)
+                assert (s1[Cc:] - (dz * y).sum(0)).abs().max().item() <= 2e-3 * sc
+            elif ty == B_BN_APPLY:
+                b, c = R.bn(bi), R.conv(ci)
+                Cc = b["c"]
+                dz, y = R.act(a0).float().reshape(-1, Cc).clone(), R.act(a1).float().reshape(-1, Cc)
+                db0 = R.grads[c["b_off"]:c["b_off"] + Cc].clone()
+                R.run(seg, 1, i)
+                dp = R.act(a2).float().reshape(-1, Cc)
+                saved = R.arena_f32(b["saved"], 2 * Cc)
+                mean, rstd = saved[:Cc], saved[Cc:]
+                g = R.params[b["gamma"]:b["gamma"] + Cc]
+                xh = (y - mean) * rstd
+                M = y.shape[0]
+                sdz, sdzx = dz.sum(0), (dz * xh).sum(0)
+                ref = torch.where(y > 0, g * rstd * (dz - sdz / M - xh * sdzx / M), torch.zeros_like(y))
+                e = R.rel(dp, ref)
+                R.note(ty, e)
+                assert e <= 1.5e-2, f"bn_bwd {bi}: {e}"
+                scale = max(sdzx.abs().max().item(), sdz.abs().max().item(), 1e-20)
+                assert (R.grads[b["gamma"]:b["gamma"] + Cc] - sdzx).abs().max().item() <= 5e-3 * max(scale, (dz * xh).abs().sum(0).max().item())
+                assert (R.grads[b["beta"]:b["beta"] + Cc] - sdz).abs().max().item() <= 5e-3 * max(scale, dz.abs().sum(0).max().item())
+                dbias = R.grads[c["b_off"]:c["b_off"] + Cc] - db0
+                assert (dbias - dp.sum(0)).abs().max().item() <= 2e-3 * max(dp.abs().sum(0).max().item(), 1e-20)
+            elif ty == B_WGRAD:
+                c = R.conv(ci)
+                n = c["cout"] * c["taps"] * c["cin"]
+                g0 = R.grads[c["w_off"]:c["w_off"] + n].clone()
+                R.run(seg, 1, i)
+                dp = R.act(a0).float()[..., :c["cout"]]
+                x = R.act(a1).float()[..., :c["cin"]]
+                w = torch.zeros((c["cout"], c["cin"], c["ksize"], c["ksize"]), device="cuda", requires_grad=True)
+                F.conv2d(x.permute(0, 3, 1, 2), w, padding=c["ksize"] // 2).backward(dp.permute(0, 3, 1, 2))
+                ref = w.grad.permute(0, 2, 3, 1).reshape(-1)
+                got = R.grads[c["w_off"]:c["w_off"] + n] - g0
+                e = R.rel(got, ref)
+                R.note(ty, e)
+                assert e <= 3e-3, f"wgrad conv {ci}: {e}"
+            elif ty == B_DGRAD:
+                c = R.conv(ci)
+                dp = R.act(a0).float()[..., :c["cout"]].clone()
+                res = [R.act(a).float().clone() for a in (a2, a3) if a >= 0]
+                R.run(seg, 1, i)
+                out = R.act(a1).float()
+                xz = torch.zeros((dp.shape[0], c["cin"], dp.shape[1], dp.shape[2]), device="cuda", requires_grad=True)
+                F.conv2d(xz, R.weight_oihw(c), padding=c["ksize"] // 2).backward(dp.permute(0, 3, 1, 2))
+                ref = xz.grad.permute(0, 2, 3, 1)
+                for r in res:
+                    ref = ref + r[..., :c["cin"]]
+                e = R.rel(out[..., :c["cin"]], ref)
+                R.note(ty, e)
+                assert e <= 1e-2, f"dgrad conv {ci}: {e}"
+                if out.shape[-1] > c["cin"] and not res:
+                    assert out[..., c["cin"]:].abs().max().item() == 0
+            elif ty in (B_RELU_MASK, B_COLSUM):
+                c = R.conv(ci)
+                g0 = R.act(a0).clone()
+                db0 = R.grads[c["b_off"]:c["b_off"] + c["cout"]].clone()
+                R.run(seg, 1, i)
+                g1 = R.act(a0)
+                if ty == B_RELU_MASK:
+                    y = R.act(a1)
+                    assert torch.equal(g1, torch.where(y > 0, g0, torch.zeros_like(g0)))
+                else:
+                    assert torch.equal(g1, g0)
+                col = g1.float().reshape(-1, g1.shape[-1]).sum(0)[:c["cout"]]
+                dbias = R.grads[c["b_off"]:c["b_off"] + c["cout"]] - db0
+                denom = max(g1.float().abs().reshape(-1, g1.shape[-1]).sum(0).max().item(), 1e-20)
+                assert (dbias - col).abs().max().item() <= 2e-3 * denom
+            elif ty == B_POOL:
+                x, gy = R.act(a0).float(), R.act(a1).float()
+                old = R.act(a2).float().clone()
+                R.run(seg, 1, i)
+                N, H, W, Cc = x.shape
+                mask = _first_max_mask(torch, _windows(x))
+                routed = _unwindows((mask * gy.unsqueeze(-2)).reshape(N, H // 2, W // 2, 4 * Cc), N, H, W, Cc)
+                ref = (routed + old) if flag else routed
+                assert torch.equal(R.act(a2), ref.to(bf))
+            elif ty == B_UPADD:
+                R.run(seg, 1, i)
+                wv = _windows(R.act(a0).float())
+                ref = (wv[..., 0, :] + wv[..., 1, :]) + (wv[..., 2, :] + wv[..., 3, :])
+                assert torch.equal(R.act(a1), ref.to(bf))
+            elif ty == B_HEAD:
+                offs = (C.c_int64 * 2)()
+                chk(lib.hgb_model_head_buffers(R.h, flag, C.byref(offs)))
+                heat = R.arena_f32(offs[0], B * 64 * 64 * 17).view(B, 64, 64, 17)
+                dldp = R.arena_f32(offs[1], B * 64 * 64 * 17).view(B, 64, 64, 17)
+                gp = R.act(a0).float()[..., :17] if a0 >= 0 else 0.0
+                R.run(seg, 1, i)
+                out = R.act(a1).float()
+                ref = (dldp + gp) * heat * (1 - heat)
+                e = R.rel(out[..., :17], ref)
+                R.note(ty, e)
+                assert e <= 1e-2 and out[..., 17:].abs().max().item() == 0
+            else:
+                raise AssertionError(f"unexpected backward op {ty}")
+    print("worst relative error per op type:", {k: round(v, 5) for k, v in R.worst.items()})
+
+    # the stepped run must have produced the same gradients as one whole training step
+    stepped = R.grads.clone()
+    R.model.forward_device(R.images, training=True, plan=R.plan)   # NB: moving stats advance again; grads do not depend on them
+    chk(lib.hgb_model_loss(R.h, R.model._loss_kind, ptr(R.targets), 1.0 / (B * 64 * 64 * 17), ptr(losses), sp()))
+    chk(lib.hgb_model_backward(R.h, 0, S + 1, sp()))
+    torch.cuda.synchronize()
+    cos = torch.nn.functional.cosine_similarity(stepped.double(), R.grads.double(), dim=0).item()
+    assert cos > 0.999999, cos
