@@ -176,6 +176,13 @@ int hgb_model_bn_detail(const hgb_model* m, int bn, int64_t offs[8]);
 int hgb_model_head_buffers(const hgb_model* m, int stack, int64_t offs[2]);
 int hgb_model_begin_step(hgb_model* m, void* stream);
 
+/* live timing of one convolution class inside a running step (bench.py roofline): CUDA event pairs
+ * are recorded on the launching stream around every matching launch.  op_type: 1 forward, 8 wgrad,
+ * 9 dgrad; (k, cin, cout, h) select the layer class by its Keras shape.  Read after a stream sync:
+ * total milliseconds, number of launches, and their algorithmic FLOPs (2*MAC, forward count). */
+int hgb_model_profile_conv(hgb_model* m, int enable, int op_type, int k, int cin, int cout, int h);
+int hgb_model_profile_read(hgb_model* m, double* total_ms, int* launches, double* flops);
+
 /* number of kernels this handle has launched since creation (bench "gpu_launches") */
 int64_t hgb_model_launch_count(const hgb_model* m);
 

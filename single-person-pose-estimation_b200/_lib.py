@@ -65,6 +65,8 @@ PROTOTYPES = {
     "hgb_model_bn_detail": (i32, [vp, i32, C.POINTER(i64 * 8)]),
     "hgb_model_head_buffers": (i32, [vp, i32, C.POINTER(i64 * 2)]),
     "hgb_model_begin_step": (i32, [vp, vp]),
+    "hgb_model_profile_conv": (i32, [vp, i32, i32, i32, i32, i32, i32]),
+    "hgb_model_profile_read": (i32, [vp, C.POINTER(f64), C.POINTER(i32), C.POINTER(f64)]),
     "hgb_model_launch_count": (i64, [vp]),
 }
 

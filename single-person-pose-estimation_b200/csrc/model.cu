@@ -121,6 +121,11 @@ struct hgb_model {
   bool maps_ready = false;
   bool fwd_training_done = false;
   int64_t launches = 0;
+  // live timing of one conv class (bench.py roofline): CUDA event pairs around matching launches
+  int prof_on = 0, prof_type = -1, prof_k = 0, prof_cin = 0, prof_cout = 0, prof_h = 0;
+  std::vector<cudaEvent_t> prof_ev;
+  size_t prof_used = 0;
+  double prof_flops = 0;
 
   // ---- build-time state
   size_t arena_cur = 0;
@@ -537,7 +542,22 @@ int build_maps(hgb_model* m) {
   return HGB_OK;
 }
 
+int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cudaStream_t st);
+
 int run_op(hgb_model* m, const Op& o, const float* images, int training, cudaStream_t st) {
+  bool timed = false;
+  if (m->prof_on && (int)o.type == m->prof_type && o.conv >= 0) {
+    const ConvL& c = m->convs[o.conv];
+    timed = c.real_k == m->prof_k && c.real_cin == m->prof_cin && c.cout == m->prof_cout && c.h == m->prof_h &&
+            m->prof_used + 2 <= m->prof_ev.size();
+    if (timed) { cudaEventRecord(m->prof_ev[m->prof_used], st); m->prof_flops += c.flops; }
+  }
+  const int rc = run_op_impl(m, o, images, training, st);
+  if (timed) { cudaEventRecord(m->prof_ev[m->prof_used + 1], st); m->prof_used += 2; }
+  return rc;
+}
+
+int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cudaStream_t st) {
   int rc = HGB_OK;
   switch (o.type) {
     case F_IM2COL: {
@@ -677,6 +697,7 @@ extern "C" int hgb_model_create(const hgb_model_config* cfg, int device, hgb_mod
 }
 
 extern "C" int hgb_model_destroy(hgb_model* m) {
+  if (m) for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
   delete m;
   return HGB_OK;
 }
@@ -903,6 +924,33 @@ extern "C" int hgb_model_head_buffers(const hgb_model* m, int stack, int64_t off
   HGB_CHECK_ARG(stack >= 0 && stack < m->S, "hgb_model_head_buffers: bad stack");
   offs[0] = (int64_t)m->heat_off[stack];
   offs[1] = m->cfg.training ? (int64_t)m->dldp_off[stack] : -1;
+  return HGB_OK;
+}
+
+// time every launch of one conv class with CUDA event pairs on the launching stream.
+// op_type: 1 forward conv, 8 wgrad, 9 dgrad (OpType).  enable=0 stops; read after a stream sync.
+extern "C" int hgb_model_profile_conv(hgb_model* m, int enable, int op_type, int k, int cin, int cout, int h) {
+  HGB_CHECK_ARG(m, "hgb_model_profile_conv: null model");
+  m->prof_on = enable; m->prof_type = op_type; m->prof_k = k; m->prof_cin = cin; m->prof_cout = cout; m->prof_h = h;
+  if (enable) {
+    m->prof_used = 0; m->prof_flops = 0;
+    while (m->prof_ev.size() < 16384) {
+      cudaEvent_t e;
+      HGB_CUDA(cudaEventCreate(&e));
+      m->prof_ev.push_back(e);
+    }
+  }
+  return HGB_OK;
+}
+extern "C" int hgb_model_profile_read(hgb_model* m, double* total_ms, int* launches, double* flops) {
+  HGB_CHECK_ARG(m && total_ms && launches && flops, "hgb_model_profile_read: null pointer");
+  double tot = 0;
+  for (size_t i = 0; i + 1 < m->prof_used; i += 2) {
+    float ms = 0;
+    HGB_CUDA(cudaEventElapsedTime(&ms, m->prof_ev[i], m->prof_ev[i + 1]));
+    tot += ms;
+  }
+  *total_ms = tot; *launches = (int)(m->prof_used / 2); *flops = m->prof_flops;
   return HGB_OK;
 }
 

@@ -432,6 +432,21 @@ class HourglassModel:
             per = ar.sum_host(per)
         return [float(per.sum())] + [float(v) for v in per]
 
+    def train_on_keypoints(self, images, kps_x, kps_y, kps_v):
+        """One optimizer step from (images, keypoints): the Gaussian targets are rendered on the device
+        (hgb_render_targets) instead of travelling over PCIe -- BASELINE.json config 2."""
+        from .. import ops
+        from ..parallel import current_allreduce
+        ar = current_allreduce()
+        x = self._to_device_images(images)
+        h, w, _k = self.heatmap_shape
+        y = ops.render_targets(kps_x, kps_y, kps_v, h, w)
+        gb = x.shape[0] * (ar.world_size if ar else 1)
+        per = self.train_step_device(x, y, global_batch=gb, allreduce=ar).cpu().numpy()
+        if ar:
+            per = ar.sum_host(per)
+        return [float(per.sum())] + [float(v) for v in per]
+
     def test_on_batch(self, x, y):
         from .. import ops
         x = self._to_device_images(x.numpy() if hasattr(x, "numpy") and not isinstance(x, np.ndarray) and not hasattr(x, "is_cuda") else x)

@@ -1,0 +1,120 @@
+"""The reference-facing Python surface on a GPU: per-sample decode functions (incl. the caller's-array
+mutation of v2), loss callables, predict_ds / eval_PCK JSON schema, Trainer.train() + resume_training()
+with the reference's checkpoint/log file protocol."""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+
+from oracle import heatmap_oracle as horc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hgb():
+    import hgb200
+    return hgb200
+
+
+def test_per_sample_decode_functions_match_reference(hgb, golden_dir):
+    g = np.load(os.path.join(golden_dir, "decode_golden.npz"))
+    hm = g["heatmaps"]
+    mut_ref = hm.copy()
+    mut_ref[tuple(g["v2_mut_idx"])] = g["v2_mut_val"]
+    for n in range(hm.shape[0]):
+        v1 = hgb.heatmaps_to_keypoints_v1(hm[n].copy(), 1e-6)
+        work = hm[n].copy()
+        v2 = hgb.heatmaps_to_keypoints_v2(work, 1e-6)
+        assert v1.dtype == np.float32 and v1.shape == (17, 3)
+        np.testing.assert_array_equal(v1.view(np.uint32), g["v1_thr0"][n].view(np.uint32))
+        np.testing.assert_array_equal(v2.view(np.uint32), g["v2_thr0"][n].view(np.uint32))
+        np.testing.assert_array_equal(work.view(np.uint32), mut_ref[n].view(np.uint32))     # data_utils.py:166 side effect
+    np.testing.assert_array_equal(hgb.heatmaps_to_keypoints_v2(hm[1].copy(), conf_threshold=0.1).view(np.uint32),
+                                  g["v2_thr1"][1].view(np.uint32))
+
+
+def test_loss_callables_return_reference_shapes(hgb):
+    rng = np.random.default_rng(0)
+    t = horc.render_targets(rng.uniform(0, 64, (3, 17)), rng.uniform(0, 64, (3, 17)), rng.integers(0, 3, (3, 17)), 64, 64)
+    p = rng.random(t.shape, dtype=np.float32)
+    assert hgb.loss.weighted_mse(t, p).shape == (3, 64, 64)
+    assert hgb.loss.mean_squared_error(t, p).shape == (3, 64, 64)
+    assert hgb.loss.weighed_keypoint_mse(t, p).shape == (3, 64, 64)
+    assert hgb.loss.IOU(t, p).shape == (3,)
+    np.testing.assert_allclose(hgb.loss.weighted_mse(t, p), horc.weighted_mse_map(t, p), rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(hgb.dataset_builder.np_gen_heatmaps(np.full(17, 10.7), np.full(17, 20.2), np.ones(17)),
+                               horc.render_targets(np.full((1, 17), 10.7), np.full((1, 17), 20.2), np.ones((1, 17)), 64, 64)[0])
+
+
+def _fake_prediction_ds(n, batch, rng):
+    for i in range(0, n, batch):
+        m = min(batch, n - i)
+        meta = {"keypoints/vis": rng.integers(0, 3, (m, 17)), "bbox_w": rng.integers(80, 200, m), "bbox_h": rng.integers(80, 200, m),
+                "bbox_x": rng.uniform(0, 50, m), "bbox_y": rng.uniform(0, 50, m), "keypoints/x": rng.uniform(0, 80, (m, 17)),
+                "keypoints/y": rng.uniform(0, 80, (m, 17)), "image_id": np.arange(i, i + m), "ann_id": np.arange(i, i + m) + 1000,
+                "original_bbox": rng.uniform(10, 100, (m, 4))}
+        meta["keypoints/vis"][:, 0] = 2
+        yield rng.random((m, 256, 256, 3), dtype=np.float32), meta
+
+
+def test_predict_ds_and_pck(hgb, tmp_path):
+    model = hgb.create_hourglass_model(17, 1, 256, (256, 256, 3), "sigmoid")
+    path = str(tmp_path / "result.json")
+    preds = hgb.eval.predict_ds(model, _fake_prediction_ds(7, 4, np.random.default_rng(3)), 7, 4, hgb.heatmaps_to_keypoints_v2,
+                                save_path=path, conf_threshold=1e-6)
+    assert len(preds) == 7
+    assert set(preds[0]) == {"xs/pred", "ys/pred", "xs/gt", "ys/gt", "vs", "confs", "image_id", "ann_id", "original_bbox"}
+    assert json.load(open(path)) == preds
+    # the slow path (arbitrary callable, host decode loop of eval.py:108-112) gives the same predictions
+    calls = []
+
+    def spy(hms, conf_threshold=1e-6):
+        calls.append(1)
+        return hgb.heatmaps_to_keypoints_v2(hms, conf_threshold)
+    preds2 = hgb.eval.predict_ds(model, _fake_prediction_ds(7, 4, np.random.default_rng(3)), 7, 4, spy, save_path=path)
+    assert len(calls) == 7 and preds2 == preds
+    labels = hgb.default_config.COCO_KEYPOINT_LABELS
+    stats = hgb.eval.eval_PCK(path, labels, 0.5)
+    c, v = horc.pck_counts(*[np.array([p[k] for p in preds]) for k in ("xs/pred", "ys/pred", "xs/gt", "ys/gt", "vs")],
+                           np.array([p["original_bbox"] for p in preds])[:, 2:4], 0.5)
+    np.testing.assert_array_equal(np.array(stats), c / v)
+
+
+def test_trainer_train_and_resume(hgb, tmp_path, capsys):
+    cfg = types.SimpleNamespace(**{k: getattr(hgb.default_config, k) for k in dir(hgb.default_config) if k.isupper()})
+    cfg.BATCH_SIZE = 2
+    cfg.CHECKPOINTS_PATH = str(tmp_path / "checkpoints")
+    cfg.LOGS_PATH = str(tmp_path / "logs")
+    builder = hgb.dataset_builder.SyntheticDatasetBuilder(cfg, num_train_examples=4, num_valid_examples=2)
+    model = hgb.create_hourglass_model(17, 2, 256, (256, 256, 3), "sigmoid")
+    tr = hgb.Trainer(model, builder, epochs=2, learning_rate=1e-3, loss_str="weighted_mse", config=cfg)
+    assert (tr.steps_per_epoch, tr.valid_steps) == (2, 1)
+    H = tr.train()
+    assert set(H.history) == {"loss", "hg0_conv_1x1_predict_loss", "hg1_conv_1x1_predict_loss", "val_loss",
+                              "val_hg0_conv_1x1_predict_loss", "val_hg1_conv_1x1_predict_loss"}        # Train.ipynb cell 20
+    assert len(H.history["loss"]) == 2
+    assert abs(H.history["loss"][0] - H.history["hg0_conv_1x1_predict_loss"][0] - H.history["hg1_conv_1x1_predict_loss"][0]) < 1e-6
+    files = sorted(os.listdir(cfg.CHECKPOINTS_PATH))
+    assert "best_val_loss_weights.ckpt.index" in files and "best_val_loss_weights.ckpt.data-00000-of-00001" in files
+    assert any(f.startswith("E2_") and f.endswith("_cont.ckpt.index") for f in files)
+    assert os.listdir(cfg.LOGS_PATH) == ["log_E2_lr0.001.csv"]
+    out = capsys.readouterr().out
+    assert "First training with:" in out and "Learning rate for epoch 1 is" in out
+
+    # resume on a NEW instance (trainer.py:74-75): epochs add up, Adam state and step are restored, LR is forced
+    model2 = hgb.create_hourglass_model(17, 2, 256, (256, 256, 3), "sigmoid")
+    tr2 = hgb.Trainer(model2, builder, epochs=1, learning_rate=5e-4, loss_str="weighted_mse", config=cfg)
+    H2 = tr2.resume_train()
+    assert tr2.epochs == 3 and len(H2.history["loss"]) == 1
+    assert model2.optimizer.iterations == 2 * 2 + 2 and float(model2.optimizer.lr.numpy()) == pytest.approx(5e-4)
+    files = sorted(os.listdir(cfg.CHECKPOINTS_PATH))
+    assert any(f.startswith("E3_") for f in files) and not any(f.startswith("temp.ckpt") for f in files)
+    assert sorted(os.listdir(cfg.LOGS_PATH)) == ["log_E2_lr0.001.csv", "log_E3_lr0.0005.csv"]
+    w_saved = model2.get_weights_dict()
+    best = tr2.get_best_weights_model().get_weights_dict()
+    assert set(best) == set(w_saved)
+    latest = hgb.Trainer(hgb.create_hourglass_model(17, 2, 256, (256, 256, 3), "sigmoid"), builder, 1, 1e-3, "mse", cfg).get_lattest_weights_model()
+    np.testing.assert_array_equal(latest.get_weights_dict()["hg1_conv_1x1_predict/kernel"], w_saved["hg1_conv_1x1_predict/kernel"])
