@@ -182,6 +182,10 @@ int hgb_model_begin_step(hgb_model* m, void* stream);
  * total milliseconds, number of launches, and their algorithmic FLOPs (2*MAC, forward count). */
 int hgb_model_profile_conv(hgb_model* m, int enable, int op_type, int k, int cin, int cout, int h);
 int hgb_model_profile_read(hgb_model* m, double* total_ms, int* launches, double* flops);
+/* time EVERY op (event pair per op) of the steps that follow; read back per op after a stream sync */
+int hgb_model_profile_all(hgb_model* m, int enable);
+int hgb_model_profile_count(const hgb_model* m);
+int hgb_model_profile_op(hgb_model* m, int i, int info[8], double* ms);
 
 /* number of kernels this handle has launched since creation (bench "gpu_launches") */
 int64_t hgb_model_launch_count(const hgb_model* m);

@@ -67,6 +67,9 @@ PROTOTYPES = {
     "hgb_model_begin_step": (i32, [vp, vp]),
     "hgb_model_profile_conv": (i32, [vp, i32, i32, i32, i32, i32, i32]),
     "hgb_model_profile_read": (i32, [vp, C.POINTER(f64), C.POINTER(i32), C.POINTER(f64)]),
+    "hgb_model_profile_all": (i32, [vp, i32]),
+    "hgb_model_profile_count": (i32, [vp]),
+    "hgb_model_profile_op": (i32, [vp, i32, C.POINTER(i32 * 8), C.POINTER(f64)]),
     "hgb_model_launch_count": (i64, [vp]),
 }
 

@@ -22,7 +22,9 @@ using namespace ptx;
 
 constexpr int kBlockM = 128;
 constexpr int kABytes = kBlockM * 128;  // 128 pixels x 64 bf16
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;       // wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
+constexpr int kGemmThreads = 320;   // forward/dgrad kernel: TMA warp, MMA warp, 8 epilogue warps
+constexpr int kEpiThreads = 256;
 
 struct GemmKernelParams {
   int M_total, H, W, HW;
@@ -67,162 +69,220 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
   }
 }
 
+// Persistent: grid = min(#tiles, #SMs); CTA i handles tiles i, i+grid, ...  The TMA producer runs ahead
+// across tile boundaries; two TMEM accumulator stages let the MMA of the next tile overlap the epilogue
+// of the current one; the output tile is staged in swizzled smem and written with TMA bulk stores.
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                             const __grid_constant__ CUtensorMap tmB,
-                                                             const GemmKernelParams p) {
+__global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const __grid_constant__ CUtensorMap tmC,
+                                                                const GemmKernelParams p) {
   constexpr int kBBytes = BLOCK_N * 128;
   constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kOutBytes = (BLOCK_N / 64) * kABytes;
+  constexpr int kNumBars = 2 * STAGES + 4;  // full[S] | empty[S] | tmem_full[2] | tmem_empty[2]
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // 128-byte swizzle atoms need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t bar0 = base + STAGES * kStageBytes;  // full[STAGES] | empty[STAGES] | tmem_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * kStageBytes + (2 * STAGES + 1) * 8);
-  float* s_stats = reinterpret_cast<float*>(smem + STAGES * kStageBytes + (2 * STAGES + 1) * 8 + 16);  // [2*BLOCK_N]
+  const uint32_t out0 = base + STAGES * kStageBytes;          // epilogue staging (1024-aligned)
+  const uint32_t bar0 = out0 + kOutBytes;
+  uint8_t* tail = smem + STAGES * kStageBytes + kOutBytes + kNumBars * 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail);
+  float* s_bias = reinterpret_cast<float*>(tail + 16);        // [BLOCK_N]
+  float* s_stats = s_bias + BLOCK_N;                          // [2*BLOCK_N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  const int num_tiles = (p.M_total + kBlockM - 1) / kBlockM;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    for (int s = 0; s < 2 * STAGES + 1; ++s) mbar_init(bar0 + 8 * s, 1);
+    prefetch_tmap(&tmC);
+    for (int s = 0; s < 2 * STAGES + 2; ++s) mbar_init(bar0 + 8 * s, 1);
+    mbar_init(bar0 + 8 * (2 * STAGES + 2), 8);  // tmem_empty: one arrival per epilogue warp
+    mbar_init(bar0 + 8 * (2 * STAGES + 3), 8);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), BLOCK_N);
+    tmem_alloc(smem_u32(tmem_slot), 2 * BLOCK_N);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kThreads) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < BLOCK_N; i += kGemmThreads) s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kGemmThreads) s_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  const int p0 = tile_m * kBlockM;
-  const uint32_t full0 = bar0, empty0 = bar0 + 8 * STAGES, tfull = bar0 + 16 * STAGES;
+  const uint32_t full0 = bar0, empty0 = bar0 + 8 * STAGES, tfull0 = bar0 + 16 * STAGES, tempty0 = tfull0 + 16;
 
   if (warp == 0) {
     if (lane == 0) {
-      const int n0 = p0 / p.HW;
-      const int y0 = (p0 - n0 * p.HW) / p.W;
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(empty0 + 8 * s, ph ^ 1);
-        const int tap = kb / p.cblk, cb = kb - tap * p.cblk;
-        int dy = 0, dx = 0;
-        if (p.tap3) {
-          dy = (tap / 3 - 1) * p.tap_sign;
-          dx = (tap % 3 - 1) * p.tap_sign;
+      int kbt = 0;  // running k-block counter: the smem ring continues across tiles
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int p0 = tile * kBlockM;
+        const int n0 = p0 / p.HW;
+        const int y0 = (p0 - n0 * p.HW) / p.W;
+        for (int kb = 0; kb < p.nkb; ++kb, ++kbt) {
+          const int s = kbt % STAGES;
+          const uint32_t ph = (kbt / STAGES) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          const int tap = kb / p.cblk, cb = kb - tap * p.cblk;
+          int dy = 0, dx = 0;
+          if (p.tap3) {
+            dy = (tap / 3 - 1) * p.tap_sign;
+            dx = (tap % 3 - 1) * p.tap_sign;
+          }
+          const uint32_t sa = base + s * kStageBytes;
+          mbar_expect_tx(full0 + 8 * s, kStageBytes);
+          tma_load_4d(sa, &tmA, full0 + 8 * s, cb * 64, dx, y0 + dy, n0);
+          tma_load_2d(sa + kABytes, &tmB, full0 + 8 * s, kb * 64, 0);
         }
-        const uint32_t sa = base + s * kStageBytes;
-        mbar_expect_tx(full0 + 8 * s, kStageBytes);
-        tma_load_4d(sa, &tmA, full0 + 8 * s, cb * 64, dx, y0 + dy, n0);
-        tma_load_2d(sa + kABytes, &tmB, full0 + 8 * s, kb * 64, tile_n * BLOCK_N);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(full0 + 8 * s, ph);
+      int kbt = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        const uint32_t aph = (lt >> 1) & 1;
+        mbar_wait(tempty0 + 8 * acc, aph ^ 1);  // the epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t sa = base + s * kStageBytes;
-        const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
-        const uint64_t bdesc = make_smem_desc_sw128(sa + kABytes, 16, 1024);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < p.nkb; ++kb, ++kbt) {
+          const int s = kbt % STAGES;
+          const uint32_t ph = (kbt / STAGES) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = base + s * kStageBytes;
+          const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + kABytes, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // 4 x (K = 16) per 64-channel block: +32 bytes inside the swizzle atom
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-        umma_commit(empty0 + 8 * s);  // frees the smem stage once these MMAs have read it
+          for (int k = 0; k < 4; ++k)  // 4 x (K = 16) per 64-channel block: +32 bytes inside the swizzle atom
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(empty0 + 8 * s);  // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(tfull0 + 8 * acc);
       }
-      umma_commit(tfull);
     }
   } else {
-    // ---------------- epilogue: TMEM lane quarter = warp % 4
+    // ---------------- epilogue: 8 warps; TMEM lane quarter = warp % 4, the two warps of a quarter split
+    // every 64-channel box into its two 32-column halves
     const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const int pix = p0 + row;
-    const bool row_ok = pix < p.M_total;
-    mbar_wait(tfull, 0);
-    tc_fence_after();
+    const int et = threadIdx.x - 64;                 // 0..255
+    // BN statistics: thread -> (column pair, row group) of the staged tile
+    constexpr int kPairs = BLOCK_N / 2;
+    constexpr int kRowsPer = kBlockM / (kEpiThreads / kPairs);
+    const int cp = et % kPairs, rg = et / kPairs;
+    const uint32_t st_box = out0 + (uint32_t)(cp >> 5) * kABytes;
+    const uint32_t st_chunk = (uint32_t)((cp & 31) >> 2), st_word = (uint32_t)(cp & 3) * 4u;
+    float a_lo = 0.f, a_hi = 0.f, q_lo = 0.f, q_hi = 0.f;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int acc = lt & 1;
+      const uint32_t aph = (lt >> 1) & 1;
+      const int p0 = tile * kBlockM;
+      const int pix = p0 + row;
+      const bool row_ok = pix < p.M_total;
+      mbar_wait(tfull0 + 8 * acc, aph);
+      tc_fence_after();
+      // the previous tile's bulk store (and statistics pass) must be done with the staging buffer
+      if (et == 0) tma_store_wait_read();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
-      const int n0c = tile_n * BLOCK_N + c * 32;
-      if (n0c >= p.Cout) break;  // warp-uniform
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      tmem_ld_wait();
-      float f[32];
+      for (int g = 0; g < BLOCK_N / 64; ++g) {
+        const int n0c = g * 64 + hsel * 32;
+        if (g * 64 >= p.Cout) break;  // warp-uniform (Cout is a multiple of 64: whole boxes)
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + n0c), v);
+        tmem_ld_wait();
+        float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      if (p.bias) {
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + s_bias[n0c + j];
+        if (p.relu) {
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0c) + j4);
-          f[4 * j4] += b.x; f[4 * j4 + 1] += b.y; f[4 * j4 + 2] += b.z; f[4 * j4 + 3] += b.w;
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        const size_t off = (size_t)pix * p.ldc + n0c;
+        if (p.res1 && row_ok) {
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            float r[8];
+            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.res1 + off) + j8), r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[8 * j8 + j] += r[j];
+          }
+        }
+        if (p.res2 && row_ok) {
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            float r[8];
+            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.res2 + off) + j8), r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[8 * j8 + j] += r[j];
+          }
+        }
+        // stage as 128-pixel x 64-channel boxes in the 128-byte-swizzled layout TMA expects:
+        // 16-byte chunk index XOR (row mod 8)
+        const uint32_t box = out0 + (uint32_t)g * kABytes + (uint32_t)row * 128u;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[8 * j4 + 2 * j], f[8 * j4 + 2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          const uint32_t dst = box + ((((uint32_t)hsel * 4u + j4) ^ ((uint32_t)row & 7u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                       : "memory");
         }
       }
-      if (p.relu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+      // accumulator stage fully read: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      fence_proxy_async();                            // generic-proxy smem writes -> visible to the TMA engine
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps: tile fully staged
+      if (et == 0) {
+        const int n0 = p0 / p.HW;
+        const int y0 = (p0 - n0 * p.HW) / p.W;
+        for (int g = 0; g < BLOCK_N / 64; ++g)
+          if (g * 64 < p.Cout) tma_store_4d(&tmC, out0 + (uint32_t)g * kABytes, g * 64, 0, y0, n0);
+        tma_store_commit();
       }
-      const size_t off = (size_t)pix * p.ldc + n0c;
-      if (p.res1 && row_ok) {
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          float r[8];
-          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.res1 + off) + j8), r);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[8 * j8 + j] += r[j];
+      if (p.stats && 2 * cp < p.Cout) {
+        // per-channel sum / sum of squares of the values as stored (bf16), read back from the staged tile:
+        // a warp reads the 32 words of one pixel row (the swizzle only permutes them) -> conflict-free
+        int rows = p.M_total - p0;
+        if (rows > kBlockM) rows = kBlockM;
+        const int r1 = min(rows, (rg + 1) * kRowsPer);
+#pragma unroll 4
+        for (int r = rg * kRowsPer; r < r1; ++r) {
+          uint32_t wv;
+          const uint32_t src = st_box + (uint32_t)r * 128u + ((st_chunk ^ ((uint32_t)r & 7u)) << 4) + st_word;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(src));
+          const float lo = __uint_as_float(wv << 16), hi = __uint_as_float(wv & 0xffff0000u);
+          a_lo += lo; a_hi += hi;
+          q_lo = fmaf(lo, lo, q_lo); q_hi = fmaf(hi, hi, q_hi);
         }
-      }
-      if (p.res2 && row_ok) {
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          float r[8];
-          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.res2 + off) + j8), r);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[8 * j8 + j] += r[j];
-        }
-      }
-      uint32_t w[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-        w[j] = *reinterpret_cast<uint32_t*>(&h);
-      }
-      if (row_ok) {
-        uint4* o = reinterpret_cast<uint4*>(p.out + off);
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) o[j4] = make_uint4(w[4 * j4], w[4 * j4 + 1], w[4 * j4 + 2], w[4 * j4 + 3]);
-      }
-      if (p.stats) {
-        // statistics of the values as stored (bf16-rounded); rows past the end contribute 0
-        float g[32], g2[32];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float lo = row_ok ? __uint_as_float(w[j] << 16) : 0.f;
-          const float hi = row_ok ? __uint_as_float(w[j] & 0xffff0000u) : 0.f;
-          g[2 * j] = lo; g[2 * j + 1] = hi;
-          g2[2 * j] = lo * lo; g2[2 * j + 1] = hi * hi;
-        }
-        const float s1 = warp_column_sums(g, lane);
-        const float s2 = warp_column_sums(g2, lane);
-        atomicAdd(&s_stats[c * 32 + lane], s1);
-        atomicAdd(&s_stats[BLOCK_N + c * 32 + lane], s2);
       }
     }
+    if (et == 0) tma_store_wait_read();               // smem must stay valid until the last bulk store has read it
     if (p.stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
-      const int t = threadIdx.x - 64;
-      for (int i = t; i < 2 * BLOCK_N; i += 128) {
+      if (2 * cp < p.Cout) {
+        atomicAdd(&s_stats[2 * cp], a_lo);
+        atomicAdd(&s_stats[2 * cp + 1], a_hi);
+        atomicAdd(&s_stats[BLOCK_N + 2 * cp], q_lo);
+        atomicAdd(&s_stats[BLOCK_N + 2 * cp + 1], q_hi);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = et; i < 2 * BLOCK_N; i += kEpiThreads) {  // one atomic per channel per CTA for the whole layer
         const int stat = i / BLOCK_N, col = i - stat * BLOCK_N;
-        const int n = tile_n * BLOCK_N + col;
-        if (n < p.Cout) atomicAdd(p.stats + (size_t)stat * p.Cout + n, s_stats[i]);
+        if (col < p.Cout) atomicAdd(p.stats + (size_t)stat * p.Cout + col, s_stats[i]);
       }
     }
   }
@@ -230,7 +290,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BLOCK_N);
+    tmem_dealloc(tmem_base, 2 * BLOCK_N);
   }
 }
 
@@ -427,24 +487,35 @@ int make_tmap_mat(CUtensorMap* out, const void* ptr, int rows, int cols, int box
 
 int conv_gemm_block_n(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256); }
 
+static int g_num_sms = 0;
+
 template <int BLOCK_N, int STAGES>
-static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKernelParams& kp, int tiles_m, int tiles_n,
-                         cudaStream_t st) {
-  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + (2 * STAGES + 1) * 8 + 16 + 2 * BLOCK_N * 4 + 1024;
+static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmKernelParams& kp,
+                         int tiles_m, cudaStream_t st) {
+  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + (BLOCK_N / 64) * kABytes + (2 * STAGES + 4) * 8 + 16 +
+                       3 * BLOCK_N * 4 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
     HGB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
-  conv_gemm_kernel<BLOCK_N, STAGES><<<dim3(tiles_m, tiles_n), kThreads, smem, st>>>(tmA, tmB, kp);
+  if (!g_num_sms) {
+    int dev = 0;
+    HGB_CUDA(cudaGetDevice(&dev));
+    HGB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = tiles_m < g_num_sms ? tiles_m : g_num_sms;
+  conv_gemm_kernel<BLOCK_N, STAGES><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, tmC, kp);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
 
-int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmArgs& a, cudaStream_t st) {
+int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvGemmArgs& a,
+                     cudaStream_t st) {
   HGB_CHECK_ARG(a.ksize == 1 || a.ksize == 3, "conv_gemm: kernel size must be 1 or 3");
   HGB_CHECK_ARG(a.Cin % 64 == 0 && a.Cin > 0, "conv_gemm: Cin must be a multiple of 64 (got %d)", a.Cin);
-  HGB_CHECK_ARG(a.Cout % 32 == 0 && a.Cout > 0, "conv_gemm: Cout must be a multiple of 32 (got %d)", a.Cout);
+  HGB_CHECK_ARG(a.Cout % 64 == 0 && a.Cout > 0, "conv_gemm: Cout must be a multiple of 64 (got %d)", a.Cout);
   HGB_CHECK_ARG(a.ldc % 8 == 0 && a.ldc >= a.Cout, "conv_gemm: bad output pitch");
   HGB_CHECK_ARG(a.tap_sign == 1 || a.tap_sign == -1, "conv_gemm: tap_sign must be +-1");
   ActBox b;
@@ -460,13 +531,12 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvG
   kp.Cout = a.Cout; kp.ldc = a.ldc; kp.relu = a.relu;
   kp.bias = a.bias; kp.res1 = a.res1; kp.res2 = a.res2; kp.out = a.out; kp.stats = a.stats;
   if (kp.M_total == 0) return HGB_OK;
+  HGB_CHECK_ARG(a.Cout <= 256, "conv_gemm: Cout must be <= 256 (one N tile per CTA), got %d", a.Cout);
   const int tiles_m = cdiv(kp.M_total, kBlockM);
-  const int bn = conv_gemm_block_n(a.Cout);
-  const int tiles_n = cdiv(a.Cout, bn);
-  switch (bn) {
-    case 64: return launch_gemm_t<64, 4>(tmA, tmB, kp, tiles_m, tiles_n, st);
-    case 128: return launch_gemm_t<128, 3>(tmA, tmB, kp, tiles_m, tiles_n, st);
-    default: return launch_gemm_t<256, 2>(tmA, tmB, kp, tiles_m, tiles_n, st);
+  switch (conv_gemm_block_n(a.Cout)) {
+    case 64: return launch_gemm_t<64, 6>(tmA, tmB, tmC, kp, tiles_m, st);
+    case 128: return launch_gemm_t<128, 5>(tmA, tmB, tmC, kp, tiles_m, st);
+    default: return launch_gemm_t<256, 3>(tmA, tmB, tmC, kp, tiles_m, st);
   }
 }
 
@@ -528,8 +598,10 @@ extern "C" int hgb_conv_gemm(const void* in, const void* w, const float* bias, c
                              int tap_sign, void* stream) {
   HGB_CHECK_ARG(in && w && out, "hgb_conv_gemm: null pointer");
   HGB_CHECK_ARG(N > 0, "hgb_conv_gemm: empty batch");
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   int rc = make_tmap_act(&tmA, in, N, H, W, Cin);
+  if (rc) return rc;
+  rc = make_tmap_act(&tmC, out, N, H, W, ldc);
   if (rc) return rc;
   const int bn = conv_gemm_block_n(Cout);
   rc = make_tmap_mat(&tmB, w, Cout, ksize * ksize * Cin, bn);
@@ -538,7 +610,7 @@ extern "C" int hgb_conv_gemm(const void* in, const void* w, const float* bias, c
   a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.tap_sign = tap_sign; a.relu = relu; a.ldc = ldc;
   a.bias = bias; a.res1 = (const __nv_bfloat16*)res1; a.res2 = (const __nv_bfloat16*)res2; a.out = (__nv_bfloat16*)out;
   a.stats = stats;
-  return launch_conv_gemm(tmA, tmB, a, (cudaStream_t)stream);
+  return launch_conv_gemm(tmA, tmB, tmC, a, (cudaStream_t)stream);
 }
 
 extern "C" int hgb_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int ksize,

@@ -30,7 +30,9 @@ struct ConvGemmArgs {
 };
 // tmA: activation map of the input; tmB: weight matrix [>=Cout rows][ksize^2*Cin], box rows = block_n
 int conv_gemm_block_n(int Cout);
-int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmArgs& a, cudaStream_t st);
+// tmC: activation map of the output tensor (the epilogue writes the tile with TMA bulk stores)
+int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvGemmArgs& a,
+                     cudaStream_t st);
 
 struct WgradArgs {
   int N, H, W, Cin, Cout;

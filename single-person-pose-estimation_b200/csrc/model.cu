@@ -126,6 +126,8 @@ struct hgb_model {
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
   double prof_flops = 0;
+  int prof_all = 0;
+  std::vector<Op> prof_ops;
 
   // ---- build-time state
   size_t arena_cur = 0;
@@ -546,7 +548,10 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
 
 int run_op(hgb_model* m, const Op& o, const float* images, int training, cudaStream_t st) {
   bool timed = false;
-  if (m->prof_on && (int)o.type == m->prof_type && o.conv >= 0) {
+  if (m->prof_all) {
+    timed = m->prof_used + 2 <= m->prof_ev.size();
+    if (timed) { cudaEventRecord(m->prof_ev[m->prof_used], st); m->prof_ops.push_back(o); }
+  } else if (m->prof_on && (int)o.type == m->prof_type && o.conv >= 0) {
     const ConvL& c = m->convs[o.conv];
     timed = c.real_k == m->prof_k && c.real_cin == m->prof_cin && c.cout == m->prof_cout && c.h == m->prof_h &&
             m->prof_used + 2 <= m->prof_ev.size();
@@ -574,7 +579,7 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
       a.bias = m->p_params + c.b_off;
       a.res1 = act_ptr(m, o.a2); a.res2 = act_ptr(m, o.a3); a.out = act_ptr(m, o.a1);
       a.stats = (o.bn >= 0 && training) ? arena_f(m, m->bns[o.bn].sums_off) : nullptr;
-      rc = launch_conv_gemm(in.tmap, c.tm_wf, a, st);
+      rc = launch_conv_gemm(in.tmap, c.tm_wf, out.tmap, a, st);
       break;
     }
     case F_BN: {
@@ -635,7 +640,7 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
       a.N = dp.n; a.H = dp.h; a.W = dp.w; a.Cin = c.cout_pad; a.Cout = c.cin_pad; a.ksize = c.ksize; a.tap_sign = -1;
       a.relu = 0; a.ldc = out.c; a.bias = nullptr;
       a.res1 = act_ptr(m, o.a2); a.res2 = act_ptr(m, o.a3); a.out = act_ptr(m, o.a1); a.stats = nullptr;
-      rc = launch_conv_gemm(dp.tmap, c.tm_wd, a, st);
+      rc = launch_conv_gemm(dp.tmap, c.tm_wd, out.tmap, a, st);
       break;
     }
     case B_RELU_MASK: {
@@ -942,6 +947,32 @@ extern "C" int hgb_model_profile_conv(hgb_model* m, int enable, int op_type, int
   }
   return HGB_OK;
 }
+// time EVERY op of the following steps (event pair per op); dump with hgb_model_profile_op after a sync
+extern "C" int hgb_model_profile_all(hgb_model* m, int enable) {
+  HGB_CHECK_ARG(m, "hgb_model_profile_all: null model");
+  m->prof_all = enable; m->prof_on = 0;
+  if (enable) {
+    m->prof_used = 0; m->prof_ops.clear();
+    while (m->prof_ev.size() < 16384) {
+      cudaEvent_t e;
+      HGB_CUDA(cudaEventCreate(&e));
+      m->prof_ev.push_back(e);
+    }
+  }
+  return HGB_OK;
+}
+extern "C" int hgb_model_profile_count(const hgb_model* m) { return (int)m->prof_ops.size(); }
+extern "C" int hgb_model_profile_op(hgb_model* m, int i, int info[8], double* ms) {
+  HGB_CHECK_ARG(i >= 0 && i < (int)m->prof_ops.size() && (size_t)(2 * i + 1) < m->prof_used + 0 + 1, "hgb_model_profile_op: index");
+  const Op& o = m->prof_ops[i];
+  info[0] = (int)o.type; info[1] = o.conv; info[2] = o.bn; info[3] = o.a0; info[4] = o.a1; info[5] = o.a2; info[6] = o.a3;
+  info[7] = o.flag;
+  float t = 0;
+  HGB_CUDA(cudaEventElapsedTime(&t, m->prof_ev[2 * i], m->prof_ev[2 * i + 1]));
+  *ms = t;
+  return HGB_OK;
+}
+
 extern "C" int hgb_model_profile_read(hgb_model* m, double* total_ms, int* launches, double* flops) {
   HGB_CHECK_ARG(m && total_ms && launches && flops, "hgb_model_profile_read: null pointer");
   double tot = 0;
