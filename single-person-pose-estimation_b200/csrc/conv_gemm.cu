@@ -38,6 +38,8 @@ struct GemmKernelParams {
   const __nv_bfloat16* res2;
   __nv_bfloat16* out;
   float* stats;
+  const __nv_bfloat16* bn_y;  // non-null: second statistic is sum(out * bn_y) (BatchNorm backward) instead of sum(out^2)
+  int res1_tma;               // res1 is fetched by TMA (tmR) into the staging buffer
 };
 
 template <int OFF>
@@ -76,11 +78,12 @@ template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ CUtensorMap tmC,
+                                                                const __grid_constant__ CUtensorMap tmR,
                                                                 const GemmKernelParams p) {
   constexpr int kBBytes = BLOCK_N * 128;
   constexpr int kStageBytes = kABytes + kBBytes;
   constexpr int kOutBytes = (BLOCK_N / 64) * kABytes;
-  constexpr int kNumBars = 2 * STAGES + 4;  // full[S] | empty[S] | tmem_full[2] | tmem_empty[2]
+  constexpr int kNumBars = 2 * STAGES + 5;  // full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | residual
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // 128-byte swizzle atoms need 1024-byte alignment
@@ -99,9 +102,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmC);
+    if (p.res1_tma) prefetch_tmap(&tmR);
     for (int s = 0; s < 2 * STAGES + 2; ++s) mbar_init(bar0 + 8 * s, 1);
     mbar_init(bar0 + 8 * (2 * STAGES + 2), 8);  // tmem_empty: one arrival per epilogue warp
     mbar_init(bar0 + 8 * (2 * STAGES + 3), 8);
+    mbar_init(bar0 + 8 * (2 * STAGES + 4), 1);  // residual tile landed in the staging buffer
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -115,6 +120,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t full0 = bar0, empty0 = bar0 + 8 * STAGES, tfull0 = bar0 + 16 * STAGES, tempty0 = tfull0 + 16;
+  const uint32_t resbar = tempty0 + 16;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -173,13 +179,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     const int hsel = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;                 // 0..255
-    // BN statistics: thread -> (column pair, row group) of the staged tile
-    constexpr int kPairs = BLOCK_N / 2;
-    constexpr int kRowsPer = kBlockM / (kEpiThreads / kPairs);
-    const int cp = et % kPairs, rg = et / kPairs;
-    const uint32_t st_box = out0 + (uint32_t)(cp >> 5) * kABytes;
-    const uint32_t st_chunk = (uint32_t)((cp & 31) >> 2), st_word = (uint32_t)(cp & 3) * 4u;
-    float a_lo = 0.f, a_hi = 0.f, q_lo = 0.f, q_hi = 0.f;
+    // BN statistics: thread -> (16-byte chunk = 8 channels, group of kRowsPer pixel rows) of the staged tile
+    constexpr int kChunks = BLOCK_N / 8;
+    constexpr int kRowsPer = kBlockM / (kEpiThreads / kChunks);   // 16 / 8 / 4 rows for N = 256 / 128 / 64
+    const int sch = et % kChunks, rg = et / kChunks;
+    const uint32_t st_box = out0 + (uint32_t)(sch >> 3) * kABytes;
+    const uint32_t st_chunk = (uint32_t)(sch & 7);
+    float sa[8], sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sa[j] = 0.f; sq[j] = 0.f; }
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int acc = lt & 1;
@@ -187,11 +195,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       const int p0 = tile * kBlockM;
       const int pix = p0 + row;
       const bool row_ok = pix < p.M_total;
-      mbar_wait(tfull0 + 8 * acc, aph);
-      tc_fence_after();
-      // the previous tile's bulk store (and statistics pass) must be done with the staging buffer
+      // the previous tile's bulk store (and statistics pass) must be done with the staging buffer;
+      // then the residual tile (if any) is fetched into it while this tile's MMAs may still be running
       if (et == 0) tma_store_wait_read();
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (p.res1_tma) {
+        if (et == 0) {
+          const int n0 = p0 / p.HW;
+          const int y0 = (p0 - n0 * p.HW) / p.W;
+          int nbox = 0;
+          for (int g = 0; g < BLOCK_N / 64; ++g) nbox += (g * 64 < p.Cout);
+          mbar_expect_tx(resbar, nbox * kABytes);
+          for (int g = 0; g < BLOCK_N / 64; ++g)
+            if (g * 64 < p.Cout) tma_load_4d(out0 + (uint32_t)g * kABytes, &tmR, resbar, g * 64, 0, y0, n0);
+        }
+      }
+      mbar_wait(tfull0 + 8 * acc, aph);
+      tc_fence_after();
+      if (p.res1_tma) mbar_wait(resbar, lt & 1);
 #pragma unroll 1
       for (int g = 0; g < BLOCK_N / 64; ++g) {
         const int n0c = g * 64 + hsel * 32;
@@ -207,7 +228,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
         const size_t off = (size_t)pix * p.ldc + n0c;
-        if (p.res1 && row_ok) {
+        // staging: 128-pixel x 64-channel boxes in the 128-byte-swizzled layout TMA expects
+        // (16-byte chunk index XOR (row mod 8)); a TMA-fetched residual sits at the very same addresses
+        const uint32_t box = out0 + (uint32_t)g * kABytes + (uint32_t)row * 128u;
+        if (p.res1_tma) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const uint32_t src = box + ((((uint32_t)hsel * 4u + j4) ^ ((uint32_t)row & 7u)) << 4);
+            uint4 u;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(src));
+            float r[8];
+            unpack_bf16x8(u, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[8 * j4 + j] += r[j];
+          }
+        } else if (p.res1 && row_ok) {
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             float r[8];
@@ -225,9 +260,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             for (int j = 0; j < 8; ++j) f[8 * j8 + j] += r[j];
           }
         }
-        // stage as 128-pixel x 64-channel boxes in the 128-byte-swizzled layout TMA expects:
-        // 16-byte chunk index XOR (row mod 8)
-        const uint32_t box = out0 + (uint32_t)g * kABytes + (uint32_t)row * 128u;
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           uint32_t w[4];
@@ -254,30 +286,55 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
           if (g * 64 < p.Cout) tma_store_4d(&tmC, out0 + (uint32_t)g * kABytes, g * 64, 0, y0, n0);
         tma_store_commit();
       }
-      if (p.stats && 2 * cp < p.Cout) {
-        // per-channel sum / sum of squares of the values as stored (bf16), read back from the staged tile:
-        // a warp reads the 32 words of one pixel row (the swizzle only permutes them) -> conflict-free
+      if (p.stats && sch * 8 < p.Cout) {
+        // per-channel sums of the values as stored (bf16), read back from the staged tile with one 16-byte
+        // shared load per pixel row (a warp covers whole rows: conflict-free); second statistic is either
+        // sum(v^2) (BatchNorm forward) or sum(v * y) with y streamed from global memory (BatchNorm backward).
+        // All rows of a thread are issued before they are consumed -> the whole y tile is in flight.
         int rows = p.M_total - p0;
         if (rows > kBlockM) rows = kBlockM;
-        const int r1 = min(rows, (rg + 1) * kRowsPer);
-#pragma unroll 4
-        for (int r = rg * kRowsPer; r < r1; ++r) {
-          uint32_t wv;
-          const uint32_t src = st_box + (uint32_t)r * 128u + ((st_chunk ^ ((uint32_t)r & 7u)) << 4) + st_word;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(src));
-          const float lo = __uint_as_float(wv << 16), hi = __uint_as_float(wv & 0xffff0000u);
-          a_lo += lo; a_hi += hi;
-          q_lo = fmaf(lo, lo, q_lo); q_hi = fmaf(hi, hi, q_hi);
+        constexpr int kBatch = kRowsPer < 8 ? kRowsPer : 8;   // rows in flight per thread (bounds register use)
+#pragma unroll 1
+        for (int rb = rg * kRowsPer; rb < (rg + 1) * kRowsPer; rb += kBatch) {
+          uint4 vv[kBatch], yy[kBatch];
+#pragma unroll
+          for (int i = 0; i < kBatch; ++i) {
+            const int r = rb + i;
+            yy[i] = make_uint4(0, 0, 0, 0);
+            if (p.bn_y && r < rows) yy[i] = __ldg(reinterpret_cast<const uint4*>(p.bn_y + (size_t)(p0 + r) * p.ldc) + sch);
+          }
+#pragma unroll
+          for (int i = 0; i < kBatch; ++i) {
+            const int r = rb + i;
+            const uint32_t src = st_box + (uint32_t)r * 128u + ((st_chunk ^ ((uint32_t)r & 7u)) << 4);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(vv[i].x), "=r"(vv[i].y), "=r"(vv[i].z), "=r"(vv[i].w) : "r"(src));
+          }
+#pragma unroll
+          for (int i = 0; i < kBatch; ++i) {
+            if (rb + i < rows) {
+              float v8[8], y8[8];
+              unpack_bf16x8(vv[i], v8);
+              if (p.bn_y) {
+                unpack_bf16x8(yy[i], y8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { sa[j] += v8[j]; sq[j] = fmaf(v8[j], y8[j], sq[j]); }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { sa[j] += v8[j]; sq[j] = fmaf(v8[j], v8[j], sq[j]); }
+              }
+            }
+          }
         }
       }
     }
     if (et == 0) tma_store_wait_read();               // smem must stay valid until the last bulk store has read it
     if (p.stats) {
-      if (2 * cp < p.Cout) {
-        atomicAdd(&s_stats[2 * cp], a_lo);
-        atomicAdd(&s_stats[2 * cp + 1], a_hi);
-        atomicAdd(&s_stats[BLOCK_N + 2 * cp], q_lo);
-        atomicAdd(&s_stats[BLOCK_N + 2 * cp + 1], q_hi);
+      if (sch * 8 < p.Cout) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          atomicAdd(&s_stats[sch * 8 + j], sa[j]);
+          atomicAdd(&s_stats[BLOCK_N + sch * 8 + j], sq[j]);
+        }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int i = et; i < 2 * BLOCK_N; i += kEpiThreads) {  // one atomic per channel per CTA for the whole layer
@@ -306,6 +363,7 @@ struct WgradKernelParams {
   int tap3;
   int tiles_per_split;
   int swap_lbo_sbo;  // debug knob
+  int vec4;          // dw rows are 16-byte aligned: vector reductions allowed
   float* dw;
 };
 
@@ -404,7 +462,13 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
         const int col0 = cin_tile * BLOCK_N + c * 32;
         if (row < p.Cout && col0 < p.Cin_valid) {
           float* d = p.dw + (size_t)row * p.ldw + (size_t)tap * p.Cin_valid + col0;
-          if (col0 + 32 <= p.Cin_valid) {
+          if (col0 + 32 <= p.Cin_valid && p.vec4) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)   // 16-byte vector reductions: a quarter of the atomic instructions
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4 * j), "f"(__uint_as_float(v[4 * j])),
+                           "f"(__uint_as_float(v[4 * j + 1])), "f"(__uint_as_float(v[4 * j + 2])),
+                           "f"(__uint_as_float(v[4 * j + 3])) : "memory");
+          } else if (col0 + 32 <= p.Cin_valid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) atomicAdd(d + j, __uint_as_float(v[j]));
           } else {
@@ -490,9 +554,9 @@ int conv_gemm_block_n(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 
 static int g_num_sms = 0;
 
 template <int BLOCK_N, int STAGES>
-static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmKernelParams& kp,
-                         int tiles_m, cudaStream_t st) {
-  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + (BLOCK_N / 64) * kABytes + (2 * STAGES + 4) * 8 + 16 +
+static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                         const GemmKernelParams& kp, int tiles_m, cudaStream_t st) {
+  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + (BLOCK_N / 64) * kABytes + (2 * STAGES + 5) * 8 + 16 +
                        3 * BLOCK_N * 4 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
@@ -506,13 +570,13 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     HGB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = tiles_m < g_num_sms ? tiles_m : g_num_sms;
-  conv_gemm_kernel<BLOCK_N, STAGES><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, tmC, kp);
+  conv_gemm_kernel<BLOCK_N, STAGES><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, tmC, tmR, kp);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
 
-int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvGemmArgs& a,
-                     cudaStream_t st) {
+int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap* tmR,
+                     const ConvGemmArgs& a, cudaStream_t st) {
   HGB_CHECK_ARG(a.ksize == 1 || a.ksize == 3, "conv_gemm: kernel size must be 1 or 3");
   HGB_CHECK_ARG(a.Cin % 64 == 0 && a.Cin > 0, "conv_gemm: Cin must be a multiple of 64 (got %d)", a.Cin);
   HGB_CHECK_ARG(a.Cout % 64 == 0 && a.Cout > 0, "conv_gemm: Cout must be a multiple of 64 (got %d)", a.Cout);
@@ -530,13 +594,16 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   kp.tap_sign = a.tap_sign;
   kp.Cout = a.Cout; kp.ldc = a.ldc; kp.relu = a.relu;
   kp.bias = a.bias; kp.res1 = a.res1; kp.res2 = a.res2; kp.out = a.out; kp.stats = a.stats;
+  kp.bn_y = a.bn_y;
+  kp.res1_tma = (a.res1 != nullptr && tmR != nullptr && !g_debug[3]) ? 1 : 0;
+  const CUtensorMap& tmRr = kp.res1_tma ? *tmR : tmC;
   if (kp.M_total == 0) return HGB_OK;
   HGB_CHECK_ARG(a.Cout <= 256, "conv_gemm: Cout must be <= 256 (one N tile per CTA), got %d", a.Cout);
   const int tiles_m = cdiv(kp.M_total, kBlockM);
   switch (conv_gemm_block_n(a.Cout)) {
-    case 64: return launch_gemm_t<64, 6>(tmA, tmB, tmC, kp, tiles_m, st);
-    case 128: return launch_gemm_t<128, 5>(tmA, tmB, tmC, kp, tiles_m, st);
-    default: return launch_gemm_t<256, 3>(tmA, tmB, tmC, kp, tiles_m, st);
+    case 64: return launch_gemm_t<64, 6>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);
+    case 128: return launch_gemm_t<128, 5>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);
+    default: return launch_gemm_t<256, 3>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);
   }
 }
 
@@ -574,12 +641,15 @@ int launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const Wgr
   kp.cin_tiles = a.Cin / bn;
   const int cout_tiles = cdiv(a.Cout, 128);
   const int groups = taps * kp.cin_tiles * cout_tiles;
+  // split-K over pixel tiles: enough CTAs to fill the chip, but at least 8 tiles per CTA so the fp32
+  // atomic epilogue (a full 128 x N tile per CTA) is amortised -- it dominated the low-resolution levels
   int splits = cdiv(2 * 148, groups);
-  if (splits > kp.M_tiles) splits = kp.M_tiles;
+  if (splits > kp.M_tiles / 8) splits = kp.M_tiles / 8;
   if (splits < 1) splits = 1;
   kp.tiles_per_split = cdiv(kp.M_tiles, splits);
   splits = cdiv(kp.M_tiles, kp.tiles_per_split);
   kp.swap_lbo_sbo = g_debug[1];
+  kp.vec4 = (kp.ldw % 4 == 0) && (kp.Cin_valid % 4 == 0) && (((uintptr_t)a.dw & 15) == 0);
   kp.dw = a.dw;
   dim3 grid(splits, taps * kp.cin_tiles, cout_tiles);
   if (bn == 128) return launch_wgrad_t<128, 3>(tmDY, tmX, kp, grid, st);
@@ -610,7 +680,13 @@ extern "C" int hgb_conv_gemm(const void* in, const void* w, const float* bias, c
   a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.tap_sign = tap_sign; a.relu = relu; a.ldc = ldc;
   a.bias = bias; a.res1 = (const __nv_bfloat16*)res1; a.res2 = (const __nv_bfloat16*)res2; a.out = (__nv_bfloat16*)out;
   a.stats = stats;
-  return launch_conv_gemm(tmA, tmB, tmC, a, (cudaStream_t)stream);
+  a.bn_y = nullptr;
+  CUtensorMap tmR;
+  if (res1) {
+    rc = make_tmap_act(&tmR, res1, N, H, W, ldc);
+    if (rc) return rc;
+  }
+  return launch_conv_gemm(tmA, tmB, tmC, res1 ? &tmR : nullptr, a, (cudaStream_t)stream);
 }
 
 extern "C" int hgb_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int ksize,

@@ -27,12 +27,14 @@ struct ConvGemmArgs {
   const __nv_bfloat16* res2;
   __nv_bfloat16* out;
   float* stats;             // [2*Cout] (sum, sumsq), added to; or null
+  const __nv_bfloat16* bn_y; // non-null: stats = (sum out, sum out*bn_y) -- fused BatchNorm-backward reduction
 };
 // tmA: activation map of the input; tmB: weight matrix [>=Cout rows][ksize^2*Cin], box rows = block_n
 int conv_gemm_block_n(int Cout);
 // tmC: activation map of the output tensor (the epilogue writes the tile with TMA bulk stores)
-int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvGemmArgs& a,
-                     cudaStream_t st);
+// tmR: activation map of res1 (or null): the residual tile is then fetched by TMA into the staging buffer
+int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap* tmR,
+                     const ConvGemmArgs& a, cudaStream_t st);
 
 struct WgradArgs {
   int N, H, W, Cin, Cout;

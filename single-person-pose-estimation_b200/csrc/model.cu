@@ -503,6 +503,31 @@ int build(hgb_model* m) {
       }
     }
   }
+  // fuse each BatchNorm-backward reduction into the dgrad GEMM that produced its dz, when that GEMM is the
+  // most recent writer of the tensor (pool / upsample gradients keep the stand-alone reduction)
+  if (cfg.training && !hgb::g_debug[4]) {
+    for (auto& ops : m->bwd_ops) {
+      std::vector<Op> out;
+      for (const Op& o : ops) {
+        if (o.type == B_BN_REDUCE) {
+          int w = -1;
+          for (int i = (int)out.size() - 1; i >= 0 && w < 0; --i) {
+            const Op& q = out[i];
+            const int written = q.type == B_DGRAD ? q.a1 : q.type == B_POOL ? q.a2 : q.type == B_UPADD ? q.a1
+                              : q.type == B_BN_APPLY ? q.a2 : q.type == B_RELU_MASK ? q.a0 : q.type == B_HEAD ? q.a1 : -1;
+            if (written >= 0 && (written == o.a0 || m->acts[written].off == m->acts[o.a0].off)) w = i;
+          }
+          if (w >= 0 && out[w].type == B_DGRAD && out[w].a1 == o.a0 && out[w].bn < 0) {
+            out[w].bn = o.bn;
+            out[w].flag = o.a1 + 1;   // y act (+1 so that 0 means none)
+            continue;                 // the stand-alone reduction disappears
+          }
+        }
+        out.push_back(o);
+      }
+      ops.swap(out);
+    }
+  }
   // relocate the non-trainable parameters behind the trainable region
   for (auto& p : m->params)
     if (!p.trainable) p.off += m->train_floats;
@@ -579,7 +604,8 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
       a.bias = m->p_params + c.b_off;
       a.res1 = act_ptr(m, o.a2); a.res2 = act_ptr(m, o.a3); a.out = act_ptr(m, o.a1);
       a.stats = (o.bn >= 0 && training) ? arena_f(m, m->bns[o.bn].sums_off) : nullptr;
-      rc = launch_conv_gemm(in.tmap, c.tm_wf, out.tmap, a, st);
+      a.bn_y = nullptr;
+      rc = launch_conv_gemm(in.tmap, c.tm_wf, out.tmap, o.a2 >= 0 ? &m->acts[o.a2].tmap : nullptr, a, st);
       break;
     }
     case F_BN: {
@@ -639,8 +665,11 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
       ConvGemmArgs a;
       a.N = dp.n; a.H = dp.h; a.W = dp.w; a.Cin = c.cout_pad; a.Cout = c.cin_pad; a.ksize = c.ksize; a.tap_sign = -1;
       a.relu = 0; a.ldc = out.c; a.bias = nullptr;
-      a.res1 = act_ptr(m, o.a2); a.res2 = act_ptr(m, o.a3); a.out = act_ptr(m, o.a1); a.stats = nullptr;
-      rc = launch_conv_gemm(dp.tmap, c.tm_wd, out.tmap, a, st);
+      a.res1 = act_ptr(m, o.a2); a.res2 = act_ptr(m, o.a3); a.out = act_ptr(m, o.a1);
+      // fused BatchNorm-backward reduction of the BN that consumes this gradient (o.bn, y = act o.flag - 1)
+      a.stats = o.bn >= 0 ? arena_f(m, m->bns[o.bn].bsums_off) : nullptr;
+      a.bn_y = o.bn >= 0 ? act_ptr(m, o.flag - 1) : nullptr;
+      rc = launch_conv_gemm(dp.tmap, c.tm_wd, out.tmap, o.a2 >= 0 ? &m->acts[o.a2].tmap : nullptr, a, st);
       break;
     }
     case B_RELU_MASK: {

@@ -197,6 +197,7 @@ def test_replay_every_op(request):
     losses = torch.zeros(S, dtype=torch.float64, device="cuda")
     chk(lib.hgb_model_loss(R.h, R.model._loss_kind, ptr(R.targets), 1.0 / (B * 64 * 64 * 17), ptr(losses), sp()))
     torch.cuda.synchronize()
+    fused_reduces = [0]
     for seg in range(S, -1, -1):
         for i, (ty, ci, bi, a0, a1, a2, a3, flag) in R.ops(seg, 1):
             if ty == B_BN_REDUCE:
@@ -250,8 +251,18 @@ def test_replay_every_op(request):
                 c = R.conv(ci)
                 dp = R.act(a0).float()[..., :c["cout"]].clone()
                 res = [R.act(a).float().clone() for a in (a2, a3) if a >= 0]
+                bnd = R.bn(bi) if bi >= 0 else None      # fused BatchNorm-backward reduction of the consumer BN
+                s0 = R.arena_f32(bnd["bsums"], 2 * bnd["c"]).clone() if bnd else None
                 R.run(seg, 1, i)
                 out = R.act(a1).float()
+                if bnd:
+                    Cc = bnd["c"]
+                    dzf, yf = out.reshape(-1, Cc), R.act(flag - 1).float().reshape(-1, Cc)
+                    s1 = R.arena_f32(bnd["bsums"], 2 * Cc) - s0
+                    assert (s1[:Cc] - dzf.sum(0)).abs().max().item() <= 2e-3 * max(dzf.abs().sum(0).max().item(), 1e-20)
+                    assert (s1[Cc:] - (dzf * yf).sum(0)).abs().max().item() <= 2e-3 * max((dzf * yf).abs().sum(0).max().item(), 1e-20)
+                    R.note(B_BN_REDUCE, 0.0)
+                    fused_reduces[0] += 1
                 xz = torch.zeros((dp.shape[0], c["cin"], dp.shape[1], dp.shape[2]), device="cuda", requires_grad=True)
                 F.conv2d(xz, R.weight_oihw(c), padding=c["ksize"] // 2).backward(dp.permute(0, 3, 1, 2))
                 ref = xz.grad.permute(0, 2, 3, 1)
@@ -305,7 +316,9 @@ def test_replay_every_op(request):
                 assert e <= 1e-2 and out[..., 17:].abs().max().item() == 0
             else:
                 raise AssertionError(f"unexpected backward op {ty}")
-    print("worst relative error per op type:", {k: round(v, 5) for k, v in R.worst.items()})
+    print("worst relative error per op type:", {k: round(v, 5) for k, v in R.worst.items()},
+          "fused BN-backward reductions checked:", fused_reduces[0])
+    assert fused_reduces[0] > 20
 
     # the stepped run and one whole training step see the same loss (gradients are not compared end to
     # end: fp32 atomics ordering differs between two runs and a random-init hourglass in training mode
