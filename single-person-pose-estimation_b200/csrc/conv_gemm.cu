@@ -71,17 +71,23 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
   }
 }
 
-// Persistent: grid = min(#tiles, #SMs); CTA i handles tiles i, i+grid, ...  The TMA producer runs ahead
-// across tile boundaries; two TMEM accumulator stages let the MMA of the next tile overlap the epilogue
-// of the current one; the output tile is staged in swizzled smem and written with TMA bulk stores.
-template <int BLOCK_N, int STAGES>
+// Persistent: grid = min(#tile groups, #SMs); CTA i handles groups i, i+grid, ...  The TMA producer runs
+// ahead across group boundaries; the output tile is staged in swizzled smem and written with TMA bulk stores.
+//   TILES == 1: one 128-pixel tile per group, two TMEM accumulator stages (the MMAs of the next tile overlap
+//               the epilogue of the current one) -- the memory-bound 1x1 convolutions.
+//   TILES == 4: weight-stationary: every weight box feeds four pixel tiles (four TMEM accumulators), which
+//               cuts the shared-memory fill per MAC by 37 % -- the 3x3 convolutions, whose MMA rate is
+//               bounded by the bytes that fit in flight (ncu: tensor pipe 40 % with TILES == 1).
+template <int BLOCK_N, int STAGES, int TILES>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ CUtensorMap tmC,
                                                                 const __grid_constant__ CUtensorMap tmR,
                                                                 const GemmKernelParams p) {
   constexpr int kBBytes = BLOCK_N * 128;
-  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kStageBytes = TILES * kABytes + kBBytes;
+  constexpr int kAccStages = TILES == 1 ? 2 : 1;
+  static_assert(kAccStages * TILES * BLOCK_N <= 512, "TMEM columns");
   constexpr int kOutBytes = (BLOCK_N / 64) * kABytes;
   constexpr int kNumBars = 2 * STAGES + 5;  // full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | residual
   extern __shared__ uint8_t smem_raw[];
@@ -97,6 +103,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (p.M_total + kBlockM - 1) / kBlockM;
+  const int num_groups = (num_tiles + TILES - 1) / TILES;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -110,7 +117,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), 2 * BLOCK_N);
+    tmem_alloc(smem_u32(tmem_slot), kAccStages * TILES * BLOCK_N);
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < BLOCK_N; i += kGemmThreads) s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
@@ -125,10 +132,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   if (warp == 0) {
     if (lane == 0) {
       int kbt = 0;  // running k-block counter: the smem ring continues across tiles
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int p0 = tile * kBlockM;
-        const int n0 = p0 / p.HW;
-        const int y0 = (p0 - n0 * p.HW) / p.W;
+      for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
+        int n0[TILES], y0[TILES];
+#pragma unroll
+        for (int t = 0; t < TILES; ++t) {   // tiles past the end address images >= N: TMA zero-fills them
+          const int p0 = (grp * TILES + t) * kBlockM;
+          n0[t] = p0 / p.HW;
+          y0[t] = (p0 - n0[t] * p.HW) / p.W;
+        }
         for (int kb = 0; kb < p.nkb; ++kb, ++kbt) {
           const int s = kbt % STAGES;
           const uint32_t ph = (kbt / STAGES) & 1;
@@ -141,8 +152,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
           }
           const uint32_t sa = base + s * kStageBytes;
           mbar_expect_tx(full0 + 8 * s, kStageBytes);
-          tma_load_4d(sa, &tmA, full0 + 8 * s, cb * 64, dx, y0 + dy, n0);
-          tma_load_2d(sa + kABytes, &tmB, full0 + 8 * s, kb * 64, 0);
+          tma_load_2d(sa + TILES * kABytes, &tmB, full0 + 8 * s, kb * 64, 0);
+#pragma unroll
+          for (int t = 0; t < TILES; ++t)
+            tma_load_4d(sa + t * kABytes, &tmA, full0 + 8 * s, cb * 64, dx, y0[t] + dy, n0[t]);
         }
       }
     }
@@ -150,23 +163,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
       int kbt = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-        const int acc = lt & 1;
-        const uint32_t aph = (lt >> 1) & 1;
+      for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x, ++lt) {
+        const int acc = lt % kAccStages;
+        const uint32_t aph = (lt / kAccStages) & 1;
         mbar_wait(tempty0 + 8 * acc, aph ^ 1);  // the epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TILES * BLOCK_N);
         for (int kb = 0; kb < p.nkb; ++kb, ++kbt) {
           const int s = kbt % STAGES;
           const uint32_t ph = (kbt / STAGES) & 1;
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
           const uint32_t sa = base + s * kStageBytes;
-          const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(sa + kABytes, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + TILES * kABytes, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 4 x (K = 16) per 64-channel block: +32 bytes inside the swizzle atom
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int t = 0; t < TILES; ++t) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + t * kABytes, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)  // 4 x (K = 16) per 64-channel block: +32 bytes inside the swizzle atom
+              umma_bf16(d_tmem + (uint32_t)(t * BLOCK_N), adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
           umma_commit(empty0 + 8 * s);  // frees the smem stage once these MMAs have read it
         }
         umma_commit(tfull0 + 8 * acc);
@@ -188,10 +204,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     float sa[8], sq[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sa[j] = 0.f; sq[j] = 0.f; }
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int acc = lt & 1;
-      const uint32_t aph = (lt >> 1) & 1;
+    int lt = 0, rt = 0;   // groups / residual tiles processed by this CTA
+    for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x, ++lt) {
+      const int acc = lt % kAccStages;
+      const uint32_t aph = (lt / kAccStages) & 1;
+#pragma unroll 1
+      for (int t = 0; t < TILES; ++t) {
+      const int tile = grp * TILES + t;
+      if (tile >= num_tiles) break;      // uniform over the CTA
+      const uint32_t acc_col = (uint32_t)((acc * TILES + t) * BLOCK_N);
       const int p0 = tile * kBlockM;
       const int pix = p0 + row;
       const bool row_ok = pix < p.M_total;
@@ -212,13 +233,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       }
       mbar_wait(tfull0 + 8 * acc, aph);
       tc_fence_after();
-      if (p.res1_tma) mbar_wait(resbar, lt & 1);
+      if (p.res1_tma) { mbar_wait(resbar, rt & 1); ++rt; }
 #pragma unroll 1
       for (int g = 0; g < BLOCK_N / 64; ++g) {
         const int n0c = g * 64 + hsel * 32;
         if (g * 64 >= p.Cout) break;  // warp-uniform (Cout is a multiple of 64: whole boxes)
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + n0c), v);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)n0c, v);
         tmem_ld_wait();
         float f[32];
 #pragma unroll
@@ -273,10 +294,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                        : "memory");
         }
       }
-      // accumulator stage fully read: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      // last tile of the group: the accumulator stage is fully read, hand it back to the MMA warp
+      if (t == TILES - 1 || tile + 1 >= num_tiles) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      }
       fence_proxy_async();                            // generic-proxy smem writes -> visible to the TMA engine
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps: tile fully staged
       if (et == 0) {
@@ -326,6 +349,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
           }
         }
       }
+      }  // tiles of the group
     }
     if (et == 0) tma_store_wait_read();               // smem must stay valid until the last bulk store has read it
     if (p.stats) {
@@ -347,7 +371,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BLOCK_N);
+    tmem_dealloc(tmem_base, kAccStages * TILES * BLOCK_N);
   }
 }
 
@@ -553,15 +577,15 @@ int conv_gemm_block_n(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 
 
 static int g_num_sms = 0;
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int TILES>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                          const GemmKernelParams& kp, int tiles_m, cudaStream_t st) {
-  constexpr int smem = STAGES * (kABytes + BLOCK_N * 128) + (BLOCK_N / 64) * kABytes + (2 * STAGES + 5) * 8 + 16 +
+  constexpr int smem = STAGES * (TILES * kABytes + BLOCK_N * 128) + (BLOCK_N / 64) * kABytes + (2 * STAGES + 5) * 8 + 16 +
                        3 * BLOCK_N * 4 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    HGB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HGB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES, TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
   if (!g_num_sms) {
@@ -569,8 +593,9 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     HGB_CUDA(cudaGetDevice(&dev));
     HGB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int grid = tiles_m < g_num_sms ? tiles_m : g_num_sms;
-  conv_gemm_kernel<BLOCK_N, STAGES><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, tmC, tmR, kp);
+  const int groups = (tiles_m + TILES - 1) / TILES;
+  const int grid = groups < g_num_sms ? groups : g_num_sms;
+  conv_gemm_kernel<BLOCK_N, STAGES, TILES><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, tmC, tmR, kp);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -600,10 +625,19 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   if (kp.M_total == 0) return HGB_OK;
   HGB_CHECK_ARG(a.Cout <= 256, "conv_gemm: Cout must be <= 256 (one N tile per CTA), got %d", a.Cout);
   const int tiles_m = cdiv(kp.M_total, kBlockM);
+  if (!g_num_sms) {
+    int dev = 0;
+    HGB_CUDA(cudaGetDevice(&dev));
+    HGB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // weight-stationary 4-tile groups for the 3x3 convolutions when there are enough groups to fill the chip
+  const bool ws = kp.tap3 && !g_debug[5] && tiles_m >= 8 * g_num_sms;
   switch (conv_gemm_block_n(a.Cout)) {
-    case 64: return launch_gemm_t<64, 6>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);
-    case 128: return launch_gemm_t<128, 5>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);
-    default: return launch_gemm_t<256, 3>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);
+    case 64: return ws ? launch_gemm_t<64, 2, 4>(tmA, tmB, tmC, tmRr, kp, tiles_m, st)
+                       : launch_gemm_t<64, 6, 1>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);
+    case 128: return ws ? launch_gemm_t<128, 2, 4>(tmA, tmB, tmC, tmRr, kp, tiles_m, st)
+                        : launch_gemm_t<128, 5, 1>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);
+    default: return launch_gemm_t<256, 3, 1>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);
   }
 }
 

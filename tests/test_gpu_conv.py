@@ -50,6 +50,10 @@ CASES = [
     (1, 128, 64, 128, 1),
     (2, 64, 64, 256, 1),
     (1, 64, 192, 64, 1),
+    # >= 8*148 pixel tiles: the weight-stationary 4-tile path of the 3x3 kernel (incl. a group tail: 1186 tiles)
+    (40, 64, 128, 128, 3),
+    (593, 16, 128, 128, 3),
+    (10, 128, 64, 64, 3),
 ]
 
 
@@ -85,13 +89,14 @@ def test_conv_linear_residuals_and_pitch(ops, torch):
     assert (y2.float() - ref2).abs().max().item() <= 3e-2 * max(1.0, ref2.abs().max().item())
 
 
-@pytest.mark.parametrize("N,H,C", [(2, 64, 128), (3, 8, 128), (2, 4, 128)])
+@pytest.mark.parametrize("N,H,C", [(2, 64, 128), (3, 8, 128), (2, 4, 128), (38, 64, 128)])
 def test_conv_dgrad_mirrored_taps(ops, torch, N, H, C):
     """tap_sign=-1 with the same tap-major weights == correlation with the flipped kernel."""
     dy = _rand(torch, (N, H, H, C), 7)
     w = _rand(torch, (C, 9 * C), 8, scale=(9 * C) ** -0.5)
-    y = ops.conv_gemm(dy, w, ksize=3, relu=False, tap_sign=-1)
-    ref = _ref_conv(torch, dy, w, None, 3, False, flip=True)
+    res = _rand(torch, (N, H, H, C), 11)
+    y = ops.conv_gemm(dy, w, ksize=3, relu=False, tap_sign=-1, res1=res)
+    ref = _ref_conv(torch, dy, w, None, 3, False, flip=True) + res.float()
     assert (y.float() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
 
 
