@@ -33,7 +33,7 @@ __device__ __forceinline__ void st16(bf16* p, const uint4& v) { *reinterpret_cas
 static inline int row_blocks(int M, int C, int rows_per_thread = 4) {
   const int R = 256 / (C / 8);
   int b = cdiv(M, R * rows_per_thread);
-  if (b > 148 * 8) b = 148 * 8;
+  if (b > 148 * 8) b = 148 * 8;   // 8 resident 256-thread blocks per SM
   return b < 1 ? 1 : b;
 }
 
@@ -69,19 +69,36 @@ __global__ void __launch_bounds__(256) bn_apply_fwd_kernel(const bf16* __restric
       mv[c] = mv[c] * kBnMomentum + unbiased * (1.f - kBnMomentum);
     }
   }
-  for (int r = blockIdx.x * R + r0; r < M; r += gridDim.x * R) {
-    const size_t off = (size_t)r * C + g * 8;
-    float f[8];
-    unpack8(ld16(y + off), f);
+  // 4 rows per iteration: 4 (8 with a residual) independent 16-byte loads in flight per thread
+  const int stride = gridDim.x * R;
+  for (int rb = blockIdx.x * R + r0; rb < M; rb += 4 * stride) {
+    uint4 vy[4], vr[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = f[j] * sc[j] + sh[j];
-    if (res) {
-      float q[8];
-      unpack8(ld16(res + off), q);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += q[j];
+    for (int u = 0; u < 4; ++u) {
+      const int r = rb + u * stride;
+      if (r < M) {
+        const size_t off = (size_t)r * C + g * 8;
+        vy[u] = ld16(y + off);
+        if (res) vr[u] = ld16(res + off);
+      }
     }
-    st16(out + off, pack8(f));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = rb + u * stride;
+      if (r < M) {
+        float f[8];
+        unpack8(vy[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = f[j] * sc[j] + sh[j];
+        if (res) {
+          float q[8];
+          unpack8(vr[u], q);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += q[j];
+        }
+        st16(out + (size_t)r * C + g * 8, pack8(f));
+      }
+    }
   }
 }
 
@@ -275,13 +292,28 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
-  for (int r = blockIdx.x * R + r0; r < M; r += gridDim.x * R) {
-    const size_t off = (size_t)r * C + g * 8;
-    float a[8], b[8];
-    unpack8(ld16(dz + off), a);
-    unpack8(ld16(y + off), b);
+  const int stride = gridDim.x * R;
+  for (int rb = blockIdx.x * R + r0; rb < M; rb += 4 * stride) {
+    uint4 va[4], vb[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[0][j] += a[j]; acc[1][j] += a[j] * b[j]; }
+    for (int u = 0; u < 4; ++u) {
+      const int r = rb + u * stride;
+      if (r < M) {
+        const size_t off = (size_t)r * C + g * 8;
+        va[u] = ld16(dz + off);
+        vb[u] = ld16(y + off);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (rb + u * stride < M) {
+        float a[8], b[8];
+        unpack8(va[u], a);
+        unpack8(vb[u], b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[0][j] += a[j]; acc[1][j] += a[j] * b[j]; }
+      }
+    }
   }
   float* dst[2] = {bsums, bsums + C};
   block_channel_flush<2>(acc, s_acc, dst, C, g, C);
@@ -323,23 +355,39 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
   float acc[1][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
-  for (int r = blockIdx.x * R + r0; r < M; r += gridDim.x * R) {
-    const size_t off = (size_t)r * C + g * 8;
-    float d[8], v[8], o[8];
-    unpack8(ld16(dz + off), d);
-    unpack8(ld16(y + off), v);
+  const int stride = gridDim.x * R;
+  for (int rb = blockIdx.x * R + r0; rb < M; rb += 4 * stride) {   // 8 independent 16-byte loads in flight
+    uint4 vd[4], vy[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (v[j] - mean[j]) * rstd[j];
-      const float t = a[j] * (d[j] - mdz[j] - xh * mdzx[j]);
-      o[j] = v[j] > 0.f ? t : 0.f;   // ReLU sits between the conv and the BN (hourglass.py:196-201)
+    for (int u = 0; u < 4; ++u) {
+      const int r = rb + u * stride;
+      if (r < M) {
+        const size_t off = (size_t)r * C + g * 8;
+        vd[u] = ld16(dz + off);
+        vy[u] = ld16(y + off);
+      }
     }
-    const uint4 packed = pack8(o);
-    st16(dp + off, packed);
-    float rr[8];
-    unpack8(packed, rr);              // bias gradient of the values the GEMMs will actually read
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[0][j] += rr[j];
+    for (int u = 0; u < 4; ++u) {
+      const int r = rb + u * stride;
+      if (r < M) {
+        float d[8], v[8], o[8];
+        unpack8(vd[u], d);
+        unpack8(vy[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (v[j] - mean[j]) * rstd[j];
+          const float t = a[j] * (d[j] - mdz[j] - xh * mdzx[j]);
+          o[j] = v[j] > 0.f ? t : 0.f;   // ReLU sits between the conv and the BN (hourglass.py:196-201)
+        }
+        const uint4 packed = pack8(o);
+        st16(dp + (size_t)r * C + g * 8, packed);
+        float rr[8];
+        unpack8(packed, rr);              // bias gradient of the values the GEMMs will actually read
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[0][j] += rr[j];
+      }
+    }
   }
   float* dst[1] = {dbias};
   block_channel_flush<1>(acc, s_acc, dst, C, g, C);
