@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (p.M_total + kBlockM - 1) / kBlockM;
   const int num_groups = (num_tiles + TILES - 1) / TILES;
+  pdl_trigger();   // the next kernel may start its own setup; it blocks in pdl_wait() until this grid completes
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -120,8 +121,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     tmem_alloc(smem_u32(tmem_slot), kAccStages * TILES * BLOCK_N);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < BLOCK_N; i += kGemmThreads) s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
   for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kGemmThreads) s_stats[i] = 0.f;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
+  for (int i = threadIdx.x; i < BLOCK_N; i += kGemmThreads) s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -412,6 +414,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
   int t_end = t_begin + p.tiles_per_split;
   if (t_end > p.M_tiles) t_end = p.M_tiles;
   const int nkb = t_end - t_begin;  // may be <= 0 for trailing splits
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmDY);
@@ -423,6 +426,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
     tmem_alloc(smem_u32(tmem_slot), BLOCK_N < 32 ? 32 : BLOCK_N);
     tmem_relinquish();
   }
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -595,7 +599,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   }
   const int groups = (tiles_m + TILES - 1) / TILES;
   const int grid = groups < g_num_sms ? groups : g_num_sms;
-  conv_gemm_kernel<BLOCK_N, STAGES, TILES><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, tmC, tmR, kp);
+  HGB_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N, STAGES, TILES>, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, tmC, tmR, kp));
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -649,7 +653,7 @@ static int launch_wgrad_t(const CUtensorMap& tmDY, const CUtensorMap& tmX, const
     HGB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
-  conv_wgrad_kernel<BLOCK_N, STAGES><<<grid, kThreads, smem, st>>>(tmDY, tmX, kp);
+  HGB_CUDA(launch_pdl(conv_wgrad_kernel<BLOCK_N, STAGES>, grid, dim3(kThreads), smem, st, tmDY, tmX, kp));
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }

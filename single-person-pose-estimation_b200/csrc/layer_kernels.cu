@@ -43,6 +43,8 @@ __global__ void __launch_bounds__(256) bn_apply_fwd_kernel(const bf16* __restric
                                                            float* __restrict__ saved, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float* __restrict__ mm,
                                                            float* __restrict__ mv, int M, int C, int training) {
+  pdl_trigger();
+  pdl_wait();
   const int G = C >> 3, R = 256 / G;
   const int g = threadIdx.x % G, r0 = threadIdx.x / G;
   float sc[8], sh[8];
@@ -107,7 +109,7 @@ int bn_apply_fwd(const bf16* y, const bf16* res, bf16* out, const float* sums, f
   HGB_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "bn_apply: unsupported channel count %d", C);
   if (M == 0) return HGB_OK;
   // In inference the moving statistics are read-only, in training block 0 rewrites them after reading.
-  bn_apply_fwd_kernel<<<row_blocks(M, C), 256, 0, st>>>(y, res, out, sums, saved, gamma, beta, moving_mean, moving_var, M, C,
+  launch_pdl(bn_apply_fwd_kernel, dim3(row_blocks(M, C)), dim3(256), 0, st, y, res, out, sums, saved, gamma, beta, moving_mean, moving_var, M, C,
                                                         training);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
@@ -116,6 +118,8 @@ int bn_apply_fwd(const bf16* y, const bf16* res, bf16* out, const float* sums, f
 // ---------------------------------------------------------------------------------- max-pool
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int64_t total,
                                                           int h, int w, int G) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(i % G);
     int64_t pix = i / G;
@@ -139,6 +143,8 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const bf16* __restrict
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
                                                           bf16* __restrict__ dx, int64_t total, int h, int w, int G,
                                                           int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(i % G);
     int64_t pix = i / G;
@@ -187,7 +193,7 @@ int maxpool_fwd(const bf16* x, bf16* out, int N, int h, int w, int C, cudaStream
   HGB_CHECK_ARG(C % 8 == 0, "maxpool: C %% 8");
   const int64_t total = (int64_t)N * h * w * (C / 8);
   if (total == 0) return HGB_OK;
-  maxpool_fwd_kernel<<<flat_blocks(total), 256, 0, st>>>(x, out, total, h, w, C / 8);
+  launch_pdl(maxpool_fwd_kernel, dim3(flat_blocks(total)), dim3(256), 0, st, x, out, total, h, w, C / 8);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -195,7 +201,7 @@ int maxpool_bwd(const bf16* x, const bf16* dy, bf16* dx, int N, int h, int w, in
   HGB_CHECK_ARG(C % 8 == 0, "maxpool: C %% 8");
   const int64_t total = (int64_t)N * h * w * (C / 8);
   if (total == 0) return HGB_OK;
-  maxpool_bwd_kernel<<<flat_blocks(total), 256, 0, st>>>(x, dy, dx, total, h, w, C / 8, accumulate);
+  launch_pdl(maxpool_bwd_kernel, dim3(flat_blocks(total)), dim3(256), 0, st, x, dy, dx, total, h, w, C / 8, accumulate);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -203,6 +209,8 @@ int maxpool_bwd(const bf16* x, const bf16* dy, bf16* dx, int N, int h, int w, in
 // ---------------------------------------------------------------------------------- upsample + add
 __global__ void __launch_bounds__(256) upsample_add_fwd_kernel(const bf16* __restrict__ skip, const bf16* __restrict__ low,
                                                                bf16* __restrict__ out, int64_t total, int h, int w, int G) {
+  pdl_trigger();
+  pdl_wait();
   // one thread per (low-res pixel, channel group): reads 1 low + 4 skip vectors, writes 4
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(i % G);
@@ -229,6 +237,8 @@ __global__ void __launch_bounds__(256) upsample_add_fwd_kernel(const bf16* __res
 
 __global__ void __launch_bounds__(256) upsample_add_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dlow,
                                                                int64_t total, int h, int w, int G) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(i % G);
     int64_t pix = i / G;
@@ -253,7 +263,7 @@ int upsample_add_fwd(const bf16* skip, const bf16* low, bf16* out, int N, int h,
   HGB_CHECK_ARG(C % 8 == 0, "upsample_add: C %% 8");
   const int64_t total = (int64_t)N * h * w * (C / 8);
   if (total == 0) return HGB_OK;
-  upsample_add_fwd_kernel<<<flat_blocks(total), 256, 0, st>>>(skip, low, out, total, h, w, C / 8);
+  launch_pdl(upsample_add_fwd_kernel, dim3(flat_blocks(total)), dim3(256), 0, st, skip, low, out, total, h, w, C / 8);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -261,7 +271,7 @@ int upsample_add_bwd(const bf16* dout, bf16* dlow, int N, int h, int w, int C, c
   HGB_CHECK_ARG(C % 8 == 0, "upsample_add: C %% 8");
   const int64_t total = (int64_t)N * h * w * (C / 8);
   if (total == 0) return HGB_OK;
-  upsample_add_bwd_kernel<<<flat_blocks(total), 256, 0, st>>>(dout, dlow, total, h, w, C / 8);
+  launch_pdl(upsample_add_bwd_kernel, dim3(flat_blocks(total)), dim3(256), 0, st, dout, dlow, total, h, w, C / 8);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -286,6 +296,8 @@ __device__ __forceinline__ void block_channel_flush(float (&acc)[NSTAT][8], floa
 
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y,
                                                             float* __restrict__ bsums, int M, int C) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_acc[];
   const int G = C >> 3, R = 256 / G;
   const int g = threadIdx.x % G, r0 = threadIdx.x / G;
@@ -322,7 +334,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
 int bn_bwd_reduce(const bf16* dz, const bf16* y, float* bsums, int M, int C, cudaStream_t st) {
   HGB_CHECK_ARG(C % 8 == 0 && 256 % (C / 8) == 0, "bn_bwd_reduce: unsupported channel count %d", C);
   if (M == 0) return HGB_OK;
-  bn_bwd_reduce_kernel<<<row_blocks(M, C, 16), 256, 2 * C * sizeof(float), st>>>(dz, y, bsums, M, C);
+  launch_pdl(bn_bwd_reduce_kernel, dim3(row_blocks(M, C, 16)), dim3(256), 2 * C * sizeof(float), st, dz, y, bsums, M, C);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -332,6 +344,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
                                                            const float* __restrict__ saved, const float* __restrict__ gamma,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                            float* __restrict__ dbias, int M, int C) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_acc[];
   const int G = C >> 3, R = 256 / G;
   const int g = threadIdx.x % G, r0 = threadIdx.x / G;
@@ -397,7 +411,7 @@ int bn_bwd_apply(const bf16* dz, const bf16* y, bf16* dp, const float* bsums, co
                  float* dgamma, float* dbeta, float* dbias, int M, int C, cudaStream_t st) {
   HGB_CHECK_ARG(C % 8 == 0 && 256 % (C / 8) == 0, "bn_bwd_apply: unsupported channel count %d", C);
   if (M == 0) return HGB_OK;
-  bn_bwd_apply_kernel<<<row_blocks(M, C, 16), 256, C * sizeof(float), st>>>(dz, y, dp, bsums, saved, gamma, dgamma, dbeta,
+  launch_pdl(bn_bwd_apply_kernel, dim3(row_blocks(M, C, 16)), dim3(256), C * sizeof(float), st, dz, y, dp, bsums, saved, gamma, dgamma, dbeta,
                                                                            dbias, M, C);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
@@ -406,6 +420,8 @@ int bn_bwd_apply(const bf16* dz, const bf16* y, bf16* dp, const float* bsums, co
 __global__ void __launch_bounds__(256) relu_mask_colsum_kernel(const bf16* __restrict__ gsrc, const bf16* __restrict__ y,
                                                                bf16* __restrict__ dp, float* __restrict__ dbias, int M, int C,
                                                                int c_valid, int relu) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_acc[];
   const int G = C >> 3, R = 256 / G;
   const int g = threadIdx.x % G, r0 = threadIdx.x / G;
@@ -434,7 +450,7 @@ int relu_mask_colsum(const bf16* g, const bf16* y, bf16* dp, float* dbias, int M
                      cudaStream_t st) {
   HGB_CHECK_ARG(C % 8 == 0 && 256 % (C / 8) == 0, "relu_mask_colsum: unsupported channel count %d", C);
   if (M == 0) return HGB_OK;
-  relu_mask_colsum_kernel<<<row_blocks(M, C, 16), 256, C * sizeof(float), st>>>(g, y, dp, dbias, M, C, c_valid, relu);
+  launch_pdl(relu_mask_colsum_kernel, dim3(row_blocks(M, C, 16)), dim3(256), C * sizeof(float), st, g, y, dp, dbias, M, C, c_valid, relu);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -444,6 +460,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf
 
 __global__ void __launch_bounds__(256) head_act_fwd_kernel(const bf16* __restrict__ logits, int ldl, float* __restrict__ heat,
                                                            bf16* __restrict__ pbf, int M, int K, int sigmoid) {
+  pdl_trigger();
+  pdl_wait();
   // thread = (pixel, 8-channel group of the 64-wide padded row)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)M * 8; i += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(i & 7);
@@ -469,7 +487,7 @@ __global__ void __launch_bounds__(256) head_act_fwd_kernel(const bf16* __restric
 int head_act_fwd(const bf16* logits, int ldl, float* heat, bf16* pbf, int M, int K, int sigmoid, cudaStream_t st) {
   HGB_CHECK_ARG(K > 0 && K <= 64 && ldl % 8 == 0, "head_act: K must be <= 64");
   if (M == 0) return HGB_OK;
-  head_act_fwd_kernel<<<flat_blocks((int64_t)M * 8), 256, 0, st>>>(logits, ldl, heat, pbf, M, K, sigmoid);
+  launch_pdl(head_act_fwd_kernel, dim3(flat_blocks((int64_t)M * 8)), dim3(256), 0, st, logits, ldl, heat, pbf, M, K, sigmoid);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -477,6 +495,8 @@ int head_act_fwd(const bf16* logits, int ldl, float* heat, bf16* pbf, int M, int
 __global__ void __launch_bounds__(256) head_act_bwd_kernel(const float* __restrict__ dLdp, const bf16* __restrict__ g_p,
                                                            const float* __restrict__ heat, bf16* __restrict__ dlogits, int M,
                                                            int K, int sigmoid) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)M * 8; i += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(i & 7);
     const int64_t r = i >> 3;
@@ -502,7 +522,7 @@ int head_act_bwd(const float* dLdp, const bf16* g_p, const float* heat, bf16* dl
                  cudaStream_t st) {
   HGB_CHECK_ARG(K > 0 && K <= 64, "head_act: K must be <= 64");
   if (M == 0) return HGB_OK;
-  head_act_bwd_kernel<<<flat_blocks((int64_t)M * 8), 256, 0, st>>>(dLdp, g_p, heat, dlogits, M, K, sigmoid);
+  launch_pdl(head_act_bwd_kernel, dim3(flat_blocks((int64_t)M * 8)), dim3(256), 0, st, dLdp, g_p, heat, dlogits, M, K, sigmoid);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -510,6 +530,8 @@ int head_act_bwd(const float* dLdp, const bf16* g_p, const float* heat, bf16* dl
 // ---------------------------------------------------------------------------------- stem patches
 __global__ void __launch_bounds__(256) im2col_7x7s2_kernel(const float* __restrict__ img, bf16* __restrict__ col, int64_t total,
                                                            int H, int W) {
+  pdl_trigger();
+  pdl_wait();
   // thread = (output pixel, group of 8 K-elements); 24 groups per pixel (192 = 147 + padding)
   const int oh = H / 2, ow = W / 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -539,7 +561,7 @@ int im2col_7x7s2(const float* img, bf16* col, int N, int H, int W, cudaStream_t 
   HGB_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "im2col: even image size required");
   const int64_t total = (int64_t)N * (H / 2) * (W / 2) * 24;
   if (total == 0) return HGB_OK;
-  im2col_7x7s2_kernel<<<flat_blocks(total), 256, 0, st>>>(img, col, total, H, W);
+  launch_pdl(im2col_7x7s2_kernel, dim3(flat_blocks(total)), dim3(256), 0, st, img, col, total, H, W);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -548,6 +570,8 @@ int im2col_7x7s2(const float* img, bf16* col, int N, int H, int W, cudaStream_t 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n4, float lr_t, float b1, float b2,
                                                    float eps, float gs) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 W = reinterpret_cast<float4*>(w)[i];
     const float4 G = reinterpret_cast<const float4*>(g)[i];
@@ -571,13 +595,15 @@ int adam_step(float* w, const float* g, float* m, float* v, int64_t n, float lr_
               float grad_scale, cudaStream_t st) {
   HGB_CHECK_ARG(n % 4 == 0, "adam: element count must be a multiple of 4");
   if (n == 0) return HGB_OK;
-  adam_kernel<<<flat_blocks(n / 4), 256, 0, st>>>(w, g, m, v, n / 4, lr_t, b1, b2, eps, grad_scale);
+  launch_pdl(adam_kernel, dim3(flat_blocks(n / 4)), dim3(256), 0, st, w, g, m, v, n / 4, lr_t, b1, b2, eps, grad_scale);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
 
 // ---------------------------------------------------------------------------------- weight refresh
 __global__ void __launch_bounds__(256) weight_sync_kernel(const WeightSyncEntry* __restrict__ entries) {
+  pdl_trigger();
+  pdl_wait();
   const WeightSyncEntry e = entries[blockIdx.y];
   const int kf = e.taps * e.cin_pad;
   const int nf = e.cout_pad * kf;
@@ -604,7 +630,7 @@ int weight_sync(const WeightSyncEntry* entries_dev, int n_entries, int max_elems
   int bx = cdiv(max_elems, 256 * 4);
   if (bx > 64) bx = 64;
   if (bx < 1) bx = 1;
-  weight_sync_kernel<<<dim3(bx, n_entries), 256, 0, st>>>(entries_dev);
+  launch_pdl(weight_sync_kernel, dim3(bx, n_entries), dim3(256), 0, st, entries_dev);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
