@@ -78,7 +78,7 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
 //   TILES == 4: weight-stationary: every weight box feeds four pixel tiles (four TMEM accumulators), which
 //               cuts the shared-memory fill per MAC by 37 % -- the 3x3 convolutions, whose MMA rate is
 //               bounded by the bytes that fit in flight (ncu: tensor pipe 40 % with TILES == 1).
-template <int BLOCK_N, int STAGES, int TILES>
+template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ CUtensorMap tmC,
@@ -94,12 +94,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // 128-byte swizzle atoms need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t out0 = base + STAGES * kStageBytes;          // epilogue staging (1024-aligned)
-  const uint32_t bar0 = out0 + kOutBytes;
-  uint8_t* tail = smem + STAGES * kStageBytes + kOutBytes + kNumBars * 8;
+  const uint32_t outbase = base + STAGES * kStageBytes;       // OUT_BUFS epilogue staging buffers (1024-aligned)
+  const uint32_t bar0 = outbase + OUT_BUFS * kOutBytes;
+  uint8_t* tail = smem + STAGES * kStageBytes + OUT_BUFS * kOutBytes + kNumBars * 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail);
   float* s_bias = reinterpret_cast<float*>(tail + 16);        // [BLOCK_N]
-  float* s_stats = s_bias + BLOCK_N;                          // [2*BLOCK_N]
+  float* s_stats = reinterpret_cast<float*>(smem);            // [2*BLOCK_N], aliases pipeline stage 0: used only after the last tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (p.M_total + kBlockM - 1) / kBlockM;
@@ -121,7 +121,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     tmem_alloc(smem_u32(tmem_slot), kAccStages * TILES * BLOCK_N);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kGemmThreads) s_stats[i] = 0.f;
   pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
   for (int i = threadIdx.x; i < BLOCK_N; i += kGemmThreads) s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
   tc_fence_before();
@@ -201,12 +200,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     constexpr int kChunks = BLOCK_N / 8;
     constexpr int kRowsPer = kBlockM / (kEpiThreads / kChunks);   // 16 / 8 / 4 rows for N = 256 / 128 / 64
     const int sch = et % kChunks, rg = et / kChunks;
-    const uint32_t st_box = out0 + (uint32_t)(sch >> 3) * kABytes;
+    const uint32_t st_boxoff = (uint32_t)(sch >> 3) * kABytes;
     const uint32_t st_chunk = (uint32_t)(sch & 7);
     float sa[8], sq[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sa[j] = 0.f; sq[j] = 0.f; }
-    int lt = 0, rt = 0;   // groups / residual tiles processed by this CTA
+    int lt = 0, rt = 0, nt = 0;   // groups / residual tiles / tiles processed by this CTA
     for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x, ++lt) {
       const int acc = lt % kAccStages;
       const uint32_t aph = (lt / kAccStages) & 1;
@@ -215,12 +214,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       const int tile = grp * TILES + t;
       if (tile >= num_tiles) break;      // uniform over the CTA
       const uint32_t acc_col = (uint32_t)((acc * TILES + t) * BLOCK_N);
+      const uint32_t out0 = outbase + (uint32_t)(nt & (OUT_BUFS - 1)) * kOutBytes;   // staging buffers alternate tile by tile
+      const uint32_t st_box = out0 + st_boxoff;
+      ++nt;
       const int p0 = tile * kBlockM;
       const int pix = p0 + row;
       const bool row_ok = pix < p.M_total;
-      // the previous tile's bulk store (and statistics pass) must be done with the staging buffer;
-      // then the residual tile (if any) is fetched into it while this tile's MMAs may still be running
-      if (et == 0) tma_store_wait_read();
+      // the bulk store issued two tiles ago must be done reading this staging buffer (the previous tile's
+      // store may still be draining from the other one); then the residual tile (if any) is fetched into
+      // it while this tile's MMAs may still be running
+      if (et == 0) { if (OUT_BUFS == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (p.res1_tma) {
         if (et == 0) {
@@ -355,6 +358,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     }
     if (et == 0) tma_store_wait_read();               // smem must stay valid until the last bulk store has read it
     if (p.stats) {
+      // the pipeline stages are idle now: stage 0 doubles as the cross-thread reduction scratch
+      for (int i = et; i < 2 * BLOCK_N; i += kEpiThreads) s_stats[i] = 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (sch * 8 < p.Cout) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -581,15 +587,16 @@ int conv_gemm_block_n(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 
 
 static int g_num_sms = 0;
 
-template <int BLOCK_N, int STAGES, int TILES>
+template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                          const GemmKernelParams& kp, int tiles_m, cudaStream_t st) {
-  constexpr int smem = STAGES * (TILES * kABytes + BLOCK_N * 128) + (BLOCK_N / 64) * kABytes + (2 * STAGES + 5) * 8 + 16 +
-                       3 * BLOCK_N * 4 + 1024;
+  constexpr int smem = STAGES * (TILES * kABytes + BLOCK_N * 128) + OUT_BUFS * (BLOCK_N / 64) * kABytes + (2 * STAGES + 5) * 8 + 16 +
+                       BLOCK_N * 4 + 1024;
+  static_assert(STAGES * (TILES * kABytes + BLOCK_N * 128) >= 2 * BLOCK_N * 4, "stats scratch aliases stage 0");
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    HGB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES, TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HGB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
   if (!g_num_sms) {
@@ -599,7 +606,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   }
   const int groups = (tiles_m + TILES - 1) / TILES;
   const int grid = groups < g_num_sms ? groups : g_num_sms;
-  HGB_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N, STAGES, TILES>, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, tmC, tmR, kp));
+  HGB_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS>, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, tmC, tmR, kp));
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -637,11 +644,11 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   // weight-stationary 4-tile groups for the 3x3 convolutions when there are enough groups to fill the chip
   const bool ws = kp.tap3 && !g_debug[5] && tiles_m >= 8 * g_num_sms;
   switch (conv_gemm_block_n(a.Cout)) {
-    case 64: return ws ? launch_gemm_t<64, 2, 4>(tmA, tmB, tmC, tmRr, kp, tiles_m, st)
-                       : launch_gemm_t<64, 6, 1>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);
-    case 128: return ws ? launch_gemm_t<128, 2, 4>(tmA, tmB, tmC, tmRr, kp, tiles_m, st)
-                        : launch_gemm_t<128, 5, 1>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);
-    default: return launch_gemm_t<256, 3, 1>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);
+    case 64: return ws ? launch_gemm_t<64, 2, 4, 2>(tmA, tmB, tmC, tmRr, kp, tiles_m, st)
+                       : launch_gemm_t<64, 6, 1, 2>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);
+    case 128: return ws ? launch_gemm_t<128, 2, 4, 2>(tmA, tmB, tmC, tmRr, kp, tiles_m, st)
+                        : launch_gemm_t<128, 4, 1, 2>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);
+    default: return launch_gemm_t<256, 3, 1, 1>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);   // 64 KB staging: single
   }
 }
 
