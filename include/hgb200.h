@@ -187,6 +187,18 @@ int hgb_model_profile_all(hgb_model* m, int enable);
 int hgb_model_profile_count(const hgb_model* m);
 int hgb_model_profile_op(hgb_model* m, int i, int info[8], double* ms);
 
+/* Execution lanes.  Forward and backward run as a static schedule over several CUDA streams owned by the
+ * handle (the skip bottleneck of every hourglass level beside the deeper sub-hourglass, weight gradients
+ * beside the dgrad chain); `stream` only forks and joins.  Cross-lane dependencies are derived from every
+ * op's read/write byte ranges when the plan is created.  hgb_debug_set(8, 1) replays everything in order
+ * on `stream` instead.  These three calls expose the schedule so a test can prove that every pair of
+ * conflicting ops is ordered:
+ *   sched_op: info = {segment, op index, lane, signals another lane}; deps = (lane, sequence index) pairs
+ *   sched_access: rows of (space 0 = arena bytes | 1 = gradient floats, lo, hi, is_write); returns #rows */
+int hgb_model_sched_count(const hgb_model* m, int backward);
+int hgb_model_sched_op(const hgb_model* m, int backward, int k, int info[4], int* ndeps, int deps[16]);
+int hgb_model_sched_access(const hgb_model* m, int backward, int k, int cap, int64_t* ranges);
+
 /* number of kernels this handle has launched since creation (bench "gpu_launches") */
 int64_t hgb_model_launch_count(const hgb_model* m);
 

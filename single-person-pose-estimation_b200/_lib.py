@@ -70,6 +70,9 @@ PROTOTYPES = {
     "hgb_model_profile_all": (i32, [vp, i32]),
     "hgb_model_profile_count": (i32, [vp]),
     "hgb_model_profile_op": (i32, [vp, i32, C.POINTER(i32 * 8), C.POINTER(f64)]),
+    "hgb_model_sched_count": (i32, [vp, i32]),
+    "hgb_model_sched_op": (i32, [vp, i32, i32, C.POINTER(i32 * 4), C.POINTER(i32), C.POINTER(i32 * 16)]),
+    "hgb_model_sched_access": (i32, [vp, i32, i32, i32, C.POINTER(i64)]),
     "hgb_model_launch_count": (i64, [vp]),
 }
 

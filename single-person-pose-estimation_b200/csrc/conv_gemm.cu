@@ -122,10 +122,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     tmem_relinquish();
   }
   pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
-  for (int i = threadIdx.x; i < BLOCK_N; i += kGemmThreads) s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // the bias is needed by the epilogue only: its (cold) load overlaps the first TMA loads instead of delaying them
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < BLOCK_N; i += kEpiThreads) s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+  }
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t full0 = bar0, empty0 = bar0 + 8 * STAGES, tfull0 = bar0 + 16 * STAGES, tempty0 = tfull0 + 16;
   const uint32_t resbar = tempty0 + 16;
@@ -589,7 +593,7 @@ static int g_num_sms = 0;
 
 template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
-                         const GemmKernelParams& kp, int tiles_m, cudaStream_t st) {
+                         const GemmKernelParams& kp, int tiles_m, int max_ctas, cudaStream_t st) {
   constexpr int smem = STAGES * (TILES * kABytes + BLOCK_N * 128) + OUT_BUFS * (BLOCK_N / 64) * kABytes + (2 * STAGES + 5) * 8 + 16 +
                        BLOCK_N * 4 + 1024;
   static_assert(STAGES * (TILES * kABytes + BLOCK_N * 128) >= 2 * BLOCK_N * 4, "stats scratch aliases stage 0");
@@ -605,7 +609,8 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     HGB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int groups = (tiles_m + TILES - 1) / TILES;
-  const int grid = groups < g_num_sms ? groups : g_num_sms;
+  int grid = groups < g_num_sms ? groups : g_num_sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   HGB_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS>, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, tmC, tmR, kp));
   HGB_LAUNCH_CHECK();
   return HGB_OK;
@@ -644,11 +649,11 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   // weight-stationary 4-tile groups for the 3x3 convolutions when there are enough groups to fill the chip
   const bool ws = kp.tap3 && !g_debug[5] && tiles_m >= 8 * g_num_sms;
   switch (conv_gemm_block_n(a.Cout)) {
-    case 64: return ws ? launch_gemm_t<64, 2, 4, 2>(tmA, tmB, tmC, tmRr, kp, tiles_m, st)
-                       : launch_gemm_t<64, 6, 1, 2>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);
-    case 128: return ws ? launch_gemm_t<128, 2, 4, 2>(tmA, tmB, tmC, tmRr, kp, tiles_m, st)
-                        : launch_gemm_t<128, 4, 1, 2>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);
-    default: return launch_gemm_t<256, 3, 1, 1>(tmA, tmB, tmC, tmRr, kp, tiles_m, st);   // 64 KB staging: single
+    case 64: return ws ? launch_gemm_t<64, 2, 4, 2>(tmA, tmB, tmC, tmRr, kp, tiles_m, a.max_ctas, st)
+                       : launch_gemm_t<64, 6, 1, 2>(tmA, tmB, tmC, tmRr, kp, tiles_m, a.max_ctas, st);
+    case 128: return ws ? launch_gemm_t<128, 2, 4, 2>(tmA, tmB, tmC, tmRr, kp, tiles_m, a.max_ctas, st)
+                        : launch_gemm_t<128, 4, 1, 2>(tmA, tmB, tmC, tmRr, kp, tiles_m, a.max_ctas, st);
+    default: return launch_gemm_t<256, 3, 1, 1>(tmA, tmB, tmC, tmRr, kp, tiles_m, a.max_ctas, st);   // 64 KB staging: single
   }
 }
 

@@ -28,6 +28,7 @@ struct ConvGemmArgs {
   __nv_bfloat16* out;
   float* stats;             // [2*Cout] (sum, sumsq), added to; or null
   const __nv_bfloat16* bn_y; // non-null: stats = (sum out, sum out*bn_y) -- fused BatchNorm-backward reduction
+  int max_ctas = 0;         // > 0: cap of the persistent grid (side lanes leave SMs to the main chain)
 };
 // tmA: activation map of the input; tmB: weight matrix [>=Cout rows][ksize^2*Cin], box rows = block_n
 int conv_gemm_block_n(int Cout);

@@ -32,6 +32,9 @@ __device__ __forceinline__ void st16(bf16* p, const uint4& v) { *reinterpret_cas
 
 static inline int row_blocks(int M, int C, int rows_per_thread = 4) {
   const int R = 256 / (C / 8);
+  // small tensors are latency-bound: fewer rows per thread (no serial chain of dependent loads) until the grid
+  // covers the chip twice
+  while (rows_per_thread > 1 && cdiv(M, R * rows_per_thread) < 2 * 148) rows_per_thread >>= 1;
   int b = cdiv(M, R * rows_per_thread);
   if (b > 148 * 8) b = 148 * 8;   // 8 resident 256-thread blocks per SM
   return b < 1 ? 1 : b;

@@ -72,6 +72,27 @@ struct Op {
   int conv = -1, bn = -1;
   int a0 = -1, a1 = -1, a2 = -1, a3 = -1;
   int flag = 0;
+  int lane = -1;   // execution lane (CUDA stream); -1 = the lane current at emission
+};
+
+// Execution lanes.  The hourglass is not a chain: the skip ("short") bottleneck of every level is independent
+// of the whole deeper sub-hourglass, and weight gradients are leaves of the backward graph.  Every op carries a
+// lane; lanes map to CUDA streams and cross-lane dependencies (derived from the ops' read/write sets when the
+// plan is built) become events.  At small per-GPU batches the low-resolution levels are latency-bound chains
+// of tiny kernels; running them beside the 64x64 skip branch and beside the weight gradients hides them.
+constexpr int kLaneMain = 0;    // the critical chain: down path, bottom, merges, heads
+constexpr int kLaneWgrad = 1;   // weight / bias gradients of the main chain
+constexpr int kLaneShort0 = 2;  // + level (f1, f2, f4, f8): the skip bottleneck of that level
+constexpr int kNumLanes = 6;
+constexpr int kScratchKinds = 4;                  // dp3 | dz(mid) | dp(mid, conv2) | dp(mid, conv1)
+constexpr int kScratchSets = 2 + 4;               // main chain ping-pong + one per skip lane
+
+struct Range { int space; size_t lo, hi; };       // space 0: arena bytes, 1: gradient buffer (floats)
+struct Dep { int lane, idx; };
+struct SchedOp {
+  int seg, idx;                 // position in fwd_ops / bwd_ops
+  std::vector<Dep> deps;        // cross-lane: wait for the event of op `idx` (sequence index) of lane `lane`
+  bool signal = false;          // some later op of another lane waits for this one
 };
 
 struct BneckRec {
@@ -129,11 +150,21 @@ struct hgb_model {
   int prof_all = 0;
   std::vector<Op> prof_ops;
 
+  // ---- lanes: forward / backward sequences with cross-lane dependencies (build_schedule), streams + events
+  std::vector<SchedOp> fwd_seq, bwd_seq;           // fwd: segments 0..S; bwd: segments S..0
+  std::vector<int> bwd_seq_begin;                  // first sequence index of each segment's backward ops
+  cudaStream_t lane_stream[kNumLanes] = {nullptr};
+  std::vector<cudaEvent_t> fwd_ev, bwd_ev;         // one per sequence op that signals another lane
+  cudaEvent_t fork_ev = nullptr, join_ev[kNumLanes] = {nullptr};
+  bool lanes_ready = false;
+  int num_sms = 0;
+
   // ---- build-time state
   size_t arena_cur = 0;
   int bn_counter = 0;
   int cur_seg = 0;
-  size_t scratch_off[3] = {0, 0, 0}, scratch_bytes[3] = {0, 0, 0};
+  int cur_lane = kLaneMain, cur_set = 0, main_set = 0;
+  size_t scratch_off[kScratchSets * kScratchKinds] = {0}, scratch_bytes[kScratchSets * kScratchKinds] = {0};
   size_t grad_base = 0, grad_cur = 0, grad_max = 0;
   bool sizing_pass = true;
 
@@ -211,8 +242,10 @@ struct hgb_model {
     bns.push_back(b);
     return (int)bns.size() - 1;
   }
-  void emit_f(const Op& o) { fwd_ops[cur_seg].push_back(o); }
-  void emit_b(const Op& o) { bwd_ops[cur_seg].push_back(o); }
+  void emit_f(Op o) { if (o.lane < 0) o.lane = cur_lane; fwd_ops[cur_seg].push_back(o); }
+  void emit_b(Op o) { if (o.lane < 0) o.lane = cur_lane; bwd_ops[cur_seg].push_back(o); }
+  // weight / bias gradients are leaves: the main chain hands them to its side lane
+  int leaf_lane() const { return cur_lane == kLaneMain ? kLaneWgrad : cur_lane; }
 
   // conv (+ReLU) [+ BN] -> returns the tensor the next layer consumes; y/z report both stages
   int conv_unit(const std::string& name, int in_act, int real_k, int real_cin, int cout, int relu, bool bn, bool need_dgrad,
@@ -266,10 +299,10 @@ struct hgb_model {
   }
 
   // ---------------- backward emission
-  void need_scratch(int which, size_t bytes) { scratch_bytes[which] = std::max(scratch_bytes[which], bytes); }
   int scratch_act(int which, int n, int h, int w, int c) {
-    need_scratch(which, (size_t)n * h * w * c * 2);
-    return alias_act(n, h, w, c, scratch_off[which]);
+    const int id = cur_set * kScratchKinds + which;
+    scratch_bytes[id] = std::max(scratch_bytes[id], (size_t)n * h * w * c * 2);
+    return alias_act(n, h, w, c, scratch_off[id]);
   }
   int grad_act(int n, int h, int w, int c) {
     const size_t bytes = align_up((size_t)n * h * w * c * 2, kAlign);
@@ -282,41 +315,46 @@ struct hgb_model {
     Op o;
     o = Op(); o.type = B_BN_REDUCE; o.bn = bn; o.a0 = dz; o.a1 = y; emit_b(o);
     o = Op(); o.type = B_BN_APPLY; o.bn = bn; o.conv = conv; o.a0 = dz; o.a1 = y; o.a2 = dp; emit_b(o);
-    o = Op(); o.type = B_WGRAD; o.conv = conv; o.a0 = dp; o.a1 = x_in; emit_b(o);
+    // the dgrad continues the chain and is emitted first; the weight gradient is a leaf
     if (dgrad_out >= 0) {
       o = Op(); o.type = B_DGRAD; o.conv = conv; o.a0 = dp; o.a1 = dgrad_out; o.a2 = res1; o.a3 = res2; emit_b(o);
     }
+    o = Op(); o.type = B_WGRAD; o.conv = conv; o.a0 = dp; o.a1 = x_in; o.lane = leaf_lane(); emit_b(o);
   }
   // g_out: gradient wrt the block output (read; masked in place when the skip is a conv);
   // g_x: gradient wrt the block input (written); extra: one more tensor summed into g_x.
   void bottleneck_bwd(const BneckRec& r, int g_out, int g_x, int extra) {
     const Act o = acts[r.out];
     const int cmid = convs[r.c1].cout;
+    // the main chain alternates between two scratch sets block by block, so the weight gradients of one block
+    // (side lane, reading its dp tensors) never hold up the next block; each dp tensor has its own buffer
+    if (cur_lane == kLaneMain) { cur_set = main_set; main_set ^= 1; }
     const int dp3 = scratch_act(0, o.n, o.h, o.w, o.c);
     const int dzm = scratch_act(1, o.n, o.h, o.w, cmid);
     const int dpm = scratch_act(2, o.n, o.h, o.w, cmid);
+    const int dpm1 = scratch_act(3, o.n, o.h, o.w, cmid);
     bn_conv_bwd(r.bn3, r.c3, g_out, r.y3, dp3, r.z2, dzm, -1, -1);
     bn_conv_bwd(r.bn2, r.c2, dzm, r.y2, dpm, r.z1, dzm, -1, -1);
     if (r.skip_conv >= 0) {
-      bn_conv_bwd(r.bn1, r.c1, dzm, r.y1, dpm, r.x, -1, -1, -1);
+      bn_conv_bwd(r.bn1, r.c1, dzm, r.y1, dpm1, r.x, -1, -1, -1);
       Op m;
       m.type = B_RELU_MASK; m.conv = r.skip_conv; m.a0 = g_out; m.a1 = r.s_act; m.flag = 1; emit_b(m);
-      m = Op(); m.type = B_WGRAD; m.conv = r.skip_conv; m.a0 = g_out; m.a1 = r.x; emit_b(m);
       if (g_x >= 0) {
         m = Op(); m.type = B_DGRAD; m.conv = r.skip_conv; m.a0 = g_out; m.a1 = g_x; m.a2 = extra; emit_b(m);
-        m = Op(); m.type = B_DGRAD; m.conv = r.c1; m.a0 = dpm; m.a1 = g_x; m.a2 = g_x; emit_b(m);
+        m = Op(); m.type = B_DGRAD; m.conv = r.c1; m.a0 = dpm1; m.a1 = g_x; m.a2 = g_x; emit_b(m);
       }
+      m = Op(); m.type = B_WGRAD; m.conv = r.skip_conv; m.a0 = g_out; m.a1 = r.x; m.lane = leaf_lane(); emit_b(m);
     } else {
-      bn_conv_bwd(r.bn1, r.c1, dzm, r.y1, dpm, r.x, g_x, g_out, extra);
+      bn_conv_bwd(r.bn1, r.c1, dzm, r.y1, dpm1, r.x, g_x, g_out, extra);
     }
   }
   void linear_conv_bwd(int conv, int dp, int x_in, int dgrad_out, int res1) {
     Op o;
-    o.type = B_COLSUM; o.conv = conv; o.a0 = dp; emit_b(o);
-    o = Op(); o.type = B_WGRAD; o.conv = conv; o.a0 = dp; o.a1 = x_in; emit_b(o);
     if (dgrad_out >= 0) {
-      o = Op(); o.type = B_DGRAD; o.conv = conv; o.a0 = dp; o.a1 = dgrad_out; o.a2 = res1; emit_b(o);
+      o.type = B_DGRAD; o.conv = conv; o.a0 = dp; o.a1 = dgrad_out; o.a2 = res1; emit_b(o);
     }
+    o = Op(); o.type = B_COLSUM; o.conv = conv; o.a0 = dp; o.lane = leaf_lane(); emit_b(o);
+    o = Op(); o.type = B_WGRAD; o.conv = conv; o.a0 = dp; o.a1 = x_in; o.lane = leaf_lane(); emit_b(o);
   }
 };
 
@@ -367,7 +405,9 @@ int build(hgb_model* m) {
     for (int u = 0; u < 4; ++u) {  // connect_downsample_upsample for f8, f4, f2, f1
       const int l = 3 - u;
       const std::string nm = hg + "_upsample_" + fnames[l];
+      m->cur_lane = kLaneShort0 + l;   // independent of everything below this level
       r.shortb[u] = m->bottleneck(r.down[l].out, C, nm + "_short");
+      m->cur_lane = kLaneMain;
       const Act sa = m->acts[r.shortb[u].out];
       r.up_low[u] = cur;
       r.up_a[u] = m->new_act(sa.n, sa.h, sa.w, sa.c);
@@ -425,9 +465,11 @@ int build(hgb_model* m) {
       if (pass == 1) {
         m->acts.resize(acts_mark);
         for (auto& v : m->bwd_ops) v.clear();
-        for (int i = 0; i < 3; ++i) m->scratch_off[i] = m->arena_alloc(m->scratch_bytes[i]);
+        for (int i = 0; i < kScratchSets * kScratchKinds; ++i)
+          if (m->scratch_bytes[i]) m->scratch_off[i] = m->arena_alloc(m->scratch_bytes[i]);
         m->grad_base = m->arena_alloc(m->grad_max);
       }
+      m->cur_lane = kLaneMain; m->cur_set = 0; m->main_set = 0;
       for (int s = S - 1; s >= 0; --s) {
         m->cur_seg = 1 + s;
         m->grad_cur = 0;
@@ -447,6 +489,7 @@ int build(hgb_model* m) {
         m->linear_conv_bwd(r.conv_p, g_logits, r.z_h, g_zh, last ? -1 : g_zh);
         int g_cur = m->grad_act(ha.n, ha.h, ha.w, ha.c);  // gradient wrt the last merged block's output
         {
+          m->cur_set = m->main_set; m->main_set ^= 1;
           const int dp_h = m->scratch_act(0, ha.n, ha.h, ha.w, ha.c);
           m->bn_conv_bwd(r.bn_h, r.conv_h, g_zh, r.y_h, dp_h, r.merged[3].out, g_cur, -1, -1);
         }
@@ -460,7 +503,9 @@ int build(hgb_model* m) {
           const int g_low = m->grad_act(lo.n, lo.h, lo.w, lo.c);
           { Op o; o.type = B_UPADD; o.a0 = g_a; o.a1 = g_low; m->emit_b(o); }
           g_f[l] = m->grad_act(aa.n, aa.h, aa.w, aa.c);
+          m->cur_lane = kLaneShort0 + l; m->cur_set = 2 + l;
           m->bottleneck_bwd(r.shortb[u], g_a, g_f[l], -1);
+          m->cur_lane = kLaneMain;
           g_cur = g_low;
         }
         for (int i = 2; i >= 0; --i) {
@@ -498,6 +543,7 @@ int build(hgb_model* m) {
         const Act az = m->acts[z0];
         const int g_z0 = m->grad_act(az.n, az.h, az.w, az.c);
         m->bottleneck_bwd(fb1, g_b1, g_z0, -1);
+        m->cur_set = m->main_set; m->main_set ^= 1;
         const int dp0 = m->scratch_act(0, az.n, az.h, az.w, az.c);
         m->bn_conv_bwd(bn0, conv0, g_z0, y0, dp0, m->col_act, -1, -1, -1);
       }
@@ -534,6 +580,133 @@ int build(hgb_model* m) {
   for (auto& b : m->bns) { b.mm_off += m->train_floats; b.mv_off += m->train_floats; }
   m->arena_bytes = m->arena_cur + kAlign;
   return HGB_OK;
+}
+
+
+
+// ---------------------------------------------------------------------------------------- lanes
+inline void add_act(const hgb_model* m, std::vector<Range>& v, int a) {
+  if (a < 0) return;
+  const Act& t = m->acts[a];
+  v.push_back({0, t.off, t.off + (size_t)t.n * t.h * t.w * t.c * 2});
+}
+inline void add_arena(std::vector<Range>& v, size_t off, size_t bytes) { v.push_back({0, off, off + bytes}); }
+inline void add_grad(std::vector<Range>& v, int64_t off, int64_t n) { v.push_back({1, (size_t)off, (size_t)(off + n)}); }
+
+// Everything an op reads (r) and writes (w) that another op of the same pass may touch: activations, scratch and
+// gradient tensors, BN statistics, heat maps, parameter gradients.  (Parameters and bf16 weight operands are
+// read-only during a pass; the BN moving statistics have a single writer.)  KEEP IN STEP WITH run_op_impl.
+void op_access(const hgb_model* m, const Op& o, std::vector<Range>& r, std::vector<Range>& w) {
+  r.clear(); w.clear();
+  const size_t hm_bytes = (size_t)m->B * m->hm_h * m->hm_w * m->K * 4;
+  switch (o.type) {
+    case F_IM2COL: add_act(m, w, o.a0); break;
+    case F_CONV:
+      add_act(m, r, o.a0); add_act(m, r, o.a2); add_act(m, r, o.a3); add_act(m, w, o.a1);
+      if (o.bn >= 0) add_arena(w, m->bns[o.bn].sums_off, 2 * (size_t)m->bns[o.bn].c * 4);
+      break;
+    case F_BN:
+      add_act(m, r, o.a0); add_act(m, r, o.a1); add_act(m, w, o.a2);
+      add_arena(r, m->bns[o.bn].sums_off, 2 * (size_t)m->bns[o.bn].c * 4);
+      add_arena(w, m->bns[o.bn].saved_off, 2 * (size_t)m->bns[o.bn].c * 4);
+      break;
+    case F_POOL: add_act(m, r, o.a0); add_act(m, w, o.a1); break;
+    case F_UPADD: add_act(m, r, o.a0); add_act(m, r, o.a1); add_act(m, w, o.a2); break;
+    case F_HEAD: add_act(m, r, o.a0); add_act(m, w, o.a1); add_arena(w, m->heat_off[o.flag], hm_bytes); break;
+    case B_BN_REDUCE:
+      add_act(m, r, o.a0); add_act(m, r, o.a1);
+      add_arena(w, m->bns[o.bn].bsums_off, 2 * (size_t)m->bns[o.bn].c * 4);
+      break;
+    case B_BN_APPLY: {
+      const BNL& b = m->bns[o.bn];
+      add_act(m, r, o.a0); add_act(m, r, o.a1); add_act(m, w, o.a2);
+      add_arena(r, b.bsums_off, 2 * (size_t)b.c * 4);
+      add_arena(r, b.saved_off, 2 * (size_t)b.c * 4);
+      add_grad(w, b.gamma_off, b.c); add_grad(w, b.beta_off, b.c);
+      add_grad(w, m->convs[o.conv].b_off, m->convs[o.conv].cout);
+      break;
+    }
+    case B_WGRAD: {
+      const ConvL& c = m->convs[o.conv];
+      add_act(m, r, o.a0); add_act(m, r, o.a1);
+      add_grad(w, c.w_off, (int64_t)c.cout * c.taps * c.cin);
+      break;
+    }
+    case B_DGRAD:
+      add_act(m, r, o.a0); add_act(m, r, o.a2); add_act(m, r, o.a3); add_act(m, w, o.a1);
+      if (o.bn >= 0) {
+        add_act(m, r, o.flag - 1);
+        add_arena(w, m->bns[o.bn].bsums_off, 2 * (size_t)m->bns[o.bn].c * 4);
+      }
+      break;
+    case B_RELU_MASK:
+      add_act(m, r, o.a0); add_act(m, r, o.a1); add_act(m, w, o.a0);
+      add_grad(w, m->convs[o.conv].b_off, m->convs[o.conv].cout);
+      break;
+    case B_COLSUM: add_act(m, r, o.a0); add_grad(w, m->convs[o.conv].b_off, m->convs[o.conv].cout); break;
+    case B_POOL: add_act(m, r, o.a0); add_act(m, r, o.a1); if (o.flag) add_act(m, r, o.a2); add_act(m, w, o.a2); break;
+    case B_UPADD: add_act(m, r, o.a0); add_act(m, w, o.a1); break;
+    case B_HEAD:
+      add_act(m, r, o.a0); add_act(m, w, o.a1);
+      add_arena(r, m->heat_off[o.flag], hm_bytes);
+      if (m->cfg.training) add_arena(r, m->dldp_off[o.flag], hm_bytes);
+      break;
+  }
+}
+
+inline bool overlaps(const std::vector<Range>& a, const std::vector<Range>& b) {
+  for (const Range& x : a)
+    for (const Range& y : b)
+      if (x.space == y.space && x.lo < y.hi && y.lo < x.hi) return true;
+  return false;
+}
+
+// For every op of the sequence: the latest earlier op of each OTHER lane it conflicts with (read-after-write,
+// write-after-read, write-after-write on overlapping byte ranges), unless its own lane already waited for that op
+// or a later one of the same lane.  Same-lane order is stream order.
+void build_sequence(const hgb_model* m, const std::vector<std::vector<Op>>& lists, const std::vector<int>& seg_order,
+                    std::vector<SchedOp>& seq, std::vector<int>* seg_begin) {
+  seq.clear();
+  if (seg_begin) seg_begin->assign(lists.size() + 1, 0);
+  for (int seg : seg_order) {
+    if (seg_begin) (*seg_begin)[seg] = (int)seq.size();
+    for (int i = 0; i < (int)lists[seg].size(); ++i) { SchedOp so; so.seg = seg; so.idx = i; seq.push_back(so); }
+  }
+  const int n = (int)seq.size();
+  std::vector<std::vector<Range>> R(n), W(n);
+  std::vector<int> lane(n);
+  for (int j = 0; j < n; ++j) {
+    const Op& o = lists[seq[j].seg][seq[j].idx];
+    op_access(m, o, R[j], W[j]);
+    lane[j] = o.lane;
+  }
+  // synced[a][b]: lane a has (transitively through its own order) waited for every op of lane b up to this index
+  std::vector<std::vector<int>> synced(kNumLanes, std::vector<int>(kNumLanes, -1));
+  for (int j = 0; j < n; ++j) {
+    const int lj = lane[j];
+    bool found[kNumLanes] = {false};
+    int nfound = 0;
+    for (int i = j - 1; i >= 0 && nfound < kNumLanes - 1; --i) {
+      const int li = lane[i];
+      if (li == lj || found[li]) continue;
+      if (i <= synced[lj][li]) { found[li] = true; ++nfound; continue; }   // everything older is already ordered
+      if (overlaps(W[i], R[j]) || overlaps(W[i], W[j]) || overlaps(R[i], W[j])) {
+        seq[j].deps.push_back({li, i});
+        seq[i].signal = true;
+        synced[lj][li] = i;
+        // what lane li had waited for when op i was issued is ordered before j as well
+        found[li] = true; ++nfound;
+      }
+    }
+  }
+}
+
+void build_schedule(hgb_model* m) {
+  std::vector<int> fo, bo;
+  for (int s = 0; s <= m->S; ++s) fo.push_back(s);
+  for (int s = m->S; s >= 0; --s) bo.push_back(s);
+  build_sequence(m, m->fwd_ops, fo, m->fwd_seq, nullptr);
+  build_sequence(m, m->bwd_ops, bo, m->bwd_seq, &m->bwd_seq_begin);
 }
 
 inline bf16* act_ptr(const hgb_model* m, int a) { return a < 0 ? nullptr : reinterpret_cast<bf16*>(m->p_arena + m->acts[a].off); }
@@ -590,6 +763,13 @@ int run_op(hgb_model* m, const Op& o, const float* images, int training, cudaStr
   return rc;
 }
 
+// persistent GEMMs of the skip lanes leave a few SMs free so the main chain's small kernels never queue behind them
+inline int side_lane_ctas(const hgb_model* m, const Op& o) {
+  if (o.lane < kLaneShort0 || !m->lanes_ready || hgb::g_debug[8] || m->prof_all) return 0;
+  const int reserve = hgb::g_debug[9] > 0 ? hgb::g_debug[9] : 20;
+  return m->num_sms > 2 * reserve ? m->num_sms - reserve : 0;
+}
+
 int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cudaStream_t st) {
   int rc = HGB_OK;
   switch (o.type) {
@@ -608,6 +788,7 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
       a.res1 = act_ptr(m, o.a2); a.res2 = act_ptr(m, o.a3); a.out = act_ptr(m, o.a1);
       a.stats = (o.bn >= 0 && training) ? arena_f(m, m->bns[o.bn].sums_off) : nullptr;
       a.bn_y = nullptr;
+      a.max_ctas = side_lane_ctas(m, o);
       rc = launch_conv_gemm(in.tmap, c.tm_wf, out.tmap, o.a2 >= 0 ? &m->acts[o.a2].tmap : nullptr, a, st);
       break;
     }
@@ -672,6 +853,7 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
       // fused BatchNorm-backward reduction of the BN that consumes this gradient (o.bn, y = act o.flag - 1)
       a.stats = o.bn >= 0 ? arena_f(m, m->bns[o.bn].bsums_off) : nullptr;
       a.bn_y = o.bn >= 0 ? act_ptr(m, o.flag - 1) : nullptr;
+      a.max_ctas = side_lane_ctas(m, o);
       rc = launch_conv_gemm(dp.tmap, c.tm_wd, out.tmap, o.a2 >= 0 ? &m->acts[o.a2].tmap : nullptr, a, st);
       break;
     }
@@ -709,6 +891,67 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
   return rc;
 }
 
+
+// ---- lane runtime.  The caller's stream only forks and joins; every op runs on a library-owned stream (the
+// main chain at the highest priority so that its small kernels are dispatched ahead of queued side-lane blocks).
+int ensure_lanes(hgb_model* m) {
+  if (m->lanes_ready) return HGB_OK;
+  int lo = 0, hi = 0;
+  HGB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = numerically smallest = highest priority
+  for (int l = 0; l < kNumLanes; ++l) {
+    HGB_CUDA(cudaStreamCreateWithPriority(&m->lane_stream[l], cudaStreamNonBlocking, l == kLaneMain ? hi : (hi + 1 <= lo ? hi + 1 : lo)));
+    HGB_CUDA(cudaEventCreateWithFlags(&m->join_ev[l], cudaEventDisableTiming));
+  }
+  HGB_CUDA(cudaEventCreateWithFlags(&m->fork_ev, cudaEventDisableTiming));
+  m->fwd_ev.assign(m->fwd_seq.size(), nullptr);
+  m->bwd_ev.assign(m->bwd_seq.size(), nullptr);
+  for (size_t i = 0; i < m->fwd_seq.size(); ++i)
+    if (m->fwd_seq[i].signal) HGB_CUDA(cudaEventCreateWithFlags(&m->fwd_ev[i], cudaEventDisableTiming));
+  for (size_t i = 0; i < m->bwd_seq.size(); ++i)
+    if (m->bwd_seq[i].signal) HGB_CUDA(cudaEventCreateWithFlags(&m->bwd_ev[i], cudaEventDisableTiming));
+  int dev = 0;
+  HGB_CUDA(cudaGetDevice(&dev));
+  HGB_CUDA(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  m->lanes_ready = true;
+  return HGB_OK;
+}
+
+// Ops [begin, end) of a sequence.  Single-lane mode (hgb_debug_set(8, 1), or per-op profiling) replays them in
+// order on the caller's stream -- the reference behaviour the lanes must reproduce.
+int run_sequence(hgb_model* m, bool backward, int begin, int end, const float* images, int training, cudaStream_t st) {
+  const std::vector<SchedOp>& seq = backward ? m->bwd_seq : m->fwd_seq;
+  const std::vector<std::vector<Op>>& lists = backward ? m->bwd_ops : m->fwd_ops;
+  if (begin >= end) return HGB_OK;
+  if (hgb::g_debug[8] || m->prof_all) {
+    for (int k = begin; k < end; ++k) {
+      int rc = run_op(m, lists[seq[k].seg][seq[k].idx], images, training, st);
+      if (rc) return rc;
+    }
+    return HGB_OK;
+  }
+  int rc = ensure_lanes(m);
+  if (rc) return rc;
+  std::vector<cudaEvent_t>& ev = backward ? m->bwd_ev : m->fwd_ev;
+  bool used[kNumLanes] = {false};
+  HGB_CUDA(cudaEventRecord(m->fork_ev, st));
+  for (int k = begin; k < end; ++k) {
+    const Op& o = lists[seq[k].seg][seq[k].idx];
+    cudaStream_t ls = m->lane_stream[o.lane];
+    if (!used[o.lane]) { HGB_CUDA(cudaStreamWaitEvent(ls, m->fork_ev, 0)); used[o.lane] = true; }
+    for (const Dep& d : seq[k].deps)
+      if (d.idx >= begin) HGB_CUDA(cudaStreamWaitEvent(ls, ev[d.idx], 0));   // older ops were joined by an earlier call
+    rc = run_op(m, o, images, training, ls);
+    if (rc) return rc;
+    if (seq[k].signal) HGB_CUDA(cudaEventRecord(ev[k], ls));
+  }
+  for (int l = 0; l < kNumLanes; ++l)
+    if (used[l]) {
+      HGB_CUDA(cudaEventRecord(m->join_ev[l], m->lane_stream[l]));
+      HGB_CUDA(cudaStreamWaitEvent(st, m->join_ev[l], 0));
+    }
+  return HGB_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------- C ABI
@@ -729,12 +972,22 @@ extern "C" int hgb_model_create(const hgb_model_config* cfg, int device, hgb_mod
   m->S = cfg->num_stacks; m->C = cfg->num_channels; m->K = cfg->num_classes; m->B = cfg->batch;
   int rc = build(m);
   if (rc) { delete m; return rc; }
+  build_schedule(m);
   *out = m;
   return HGB_OK;
 }
 
 extern "C" int hgb_model_destroy(hgb_model* m) {
-  if (m) for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
+  if (m) {
+    for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : m->fwd_ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : m->bwd_ev) if (e) cudaEventDestroy(e);
+    if (m->fork_ev) cudaEventDestroy(m->fork_ev);
+    for (int l = 0; l < kNumLanes; ++l) {
+      if (m->join_ev[l]) cudaEventDestroy(m->join_ev[l]);
+      if (m->lane_stream[l]) cudaStreamDestroy(m->lane_stream[l]);
+    }
+  }
   delete m;
   return HGB_OK;
 }
@@ -828,11 +1081,10 @@ extern "C" int hgb_model_forward(hgb_model* m, const float* images, int training
     HGB_CUDA(cudaMemsetAsync(m->p_arena + m->zero_off, 0, m->zero_bytes, st));
     HGB_CUDA(cudaMemsetAsync(m->p_grads, 0, (size_t)m->train_floats * 4, st));
   }
-  for (int seg = 0; seg <= m->S; ++seg)
-    for (const Op& o : m->fwd_ops[seg]) {
-      int rc = run_op(m, o, images, training, st);
-      if (rc) return rc;
-    }
+  {
+    int rc = run_sequence(m, false, 0, (int)m->fwd_seq.size(), images, training, st);
+    if (rc) return rc;
+  }
   if (heatmaps_out) {
     const size_t bytes = (size_t)m->B * m->hm_h * m->hm_w * m->K * 4;
     for (int s = 0; s < m->S; ++s)
@@ -871,12 +1123,10 @@ extern "C" int hgb_model_backward(hgb_model* m, int seg_lo, int seg_hi, void* st
   HGB_REQUIRE_READY(m);
   HGB_CHECK_ARG(seg_lo >= 0 && seg_hi <= m->S + 1 && seg_lo < seg_hi, "hgb_model_backward: bad segment range");
   if (!m->cfg.training || !m->fwd_training_done) { set_error("hgb_model_backward: needs a training forward pass first"); return HGB_ERR_STATE; }
-  for (int seg = seg_hi - 1; seg >= seg_lo; --seg)
-    for (const Op& o : m->bwd_ops[seg]) {
-      int rc = run_op(m, o, nullptr, 1, (cudaStream_t)stream);
-      if (rc) return rc;
-    }
-  return HGB_OK;
+  // the backward sequence runs segments S..0: [seg_lo, seg_hi) is the contiguous range that starts with seg_hi - 1
+  const int begin = m->bwd_seq_begin[seg_hi - 1];
+  const int end = seg_lo == 0 ? (int)m->bwd_seq.size() : m->bwd_seq_begin[seg_lo - 1];
+  return run_sequence(m, true, begin, end, nullptr, 1, (cudaStream_t)stream);
 }
 
 extern "C" int hgb_model_segment_grads(const hgb_model* m, int seg, int64_t* offset, int64_t* count) {
@@ -963,6 +1213,36 @@ extern "C" int hgb_model_head_buffers(const hgb_model* m, int stack, int64_t off
   offs[0] = (int64_t)m->heat_off[stack];
   offs[1] = m->cfg.training ? (int64_t)m->dldp_off[stack] : -1;
   return HGB_OK;
+}
+
+// ---- lane schedule introspection (tests/test_cpu_host.py proves every conflicting pair is ordered)
+extern "C" int hgb_model_sched_count(const hgb_model* m, int backward) {
+  return (int)(backward ? m->bwd_seq.size() : m->fwd_seq.size());
+}
+// info: segment, index in the segment's op list, lane, signals; deps: (lane, sequence index) pairs
+extern "C" int hgb_model_sched_op(const hgb_model* m, int backward, int k, int info[4], int* ndeps, int deps[16]) {
+  const std::vector<SchedOp>& seq = backward ? m->bwd_seq : m->fwd_seq;
+  HGB_CHECK_ARG(k >= 0 && k < (int)seq.size(), "hgb_model_sched_op: index out of range");
+  const std::vector<std::vector<Op>>& lists = backward ? m->bwd_ops : m->fwd_ops;
+  info[0] = seq[k].seg; info[1] = seq[k].idx; info[2] = lists[seq[k].seg][seq[k].idx].lane; info[3] = seq[k].signal;
+  const int n = (int)seq[k].deps.size();
+  HGB_CHECK_ARG(n <= 8, "hgb_model_sched_op: too many dependencies");
+  *ndeps = n;
+  for (int i = 0; i < n; ++i) { deps[2 * i] = seq[k].deps[i].lane; deps[2 * i + 1] = seq[k].deps[i].idx; }
+  return HGB_OK;
+}
+// ranges: up to `cap` rows of (space, lo, hi, is_write); returns the number of rows (or < 0)
+extern "C" int hgb_model_sched_access(const hgb_model* m, int backward, int k, int cap, int64_t* ranges) {
+  const std::vector<SchedOp>& seq = backward ? m->bwd_seq : m->fwd_seq;
+  HGB_CHECK_ARG(k >= 0 && k < (int)seq.size(), "hgb_model_sched_access: index out of range");
+  const std::vector<std::vector<Op>>& lists = backward ? m->bwd_ops : m->fwd_ops;
+  std::vector<Range> r, w;
+  op_access(m, lists[seq[k].seg][seq[k].idx], r, w);
+  HGB_CHECK_ARG((int)(r.size() + w.size()) <= cap, "hgb_model_sched_access: capacity");
+  int n = 0;
+  for (const Range& x : r) { ranges[4 * n] = x.space; ranges[4 * n + 1] = (int64_t)x.lo; ranges[4 * n + 2] = (int64_t)x.hi; ranges[4 * n + 3] = 0; ++n; }
+  for (const Range& x : w) { ranges[4 * n] = x.space; ranges[4 * n + 1] = (int64_t)x.lo; ranges[4 * n + 2] = (int64_t)x.hi; ranges[4 * n + 3] = 1; ++n; }
+  return n;
 }
 
 // time every launch of one conv class with CUDA event pairs on the launching stream.
