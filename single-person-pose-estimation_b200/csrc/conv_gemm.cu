@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ CUtensorMap tmC,
                                                                 const __grid_constant__ CUtensorMap tmR,
+                                                                const __grid_constant__ CUtensorMap tmY,
                                                                 const GemmKernelParams p) {
   constexpr int kBBytes = BLOCK_N * 128;
   constexpr int kStageBytes = TILES * kABytes + kBBytes;
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmC);
     if (p.res1_tma) prefetch_tmap(&tmR);
+    if (p.bn_y) prefetch_tmap(&tmY);
     for (int s = 0; s < 2 * STAGES + 2; ++s) mbar_init(bar0 + 8 * s, 1);
     mbar_init(bar0 + 8 * (2 * STAGES + 2), 8);  // tmem_empty: one arrival per epilogue warp
     mbar_init(bar0 + 8 * (2 * STAGES + 3), 8);
@@ -243,6 +245,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       // it while this tile's MMAs may still be running
       if (et == 0) { if (OUT_BUFS == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (p.bn_y && et == 32) {
+        // BatchNorm-backward statistics stream y from global memory: pull the NEXT tile's boxes into L2 now
+        // (and this tile's, the first time) so those loads are L2 hits when the statistics pass issues them
+        for (int ahead = (nt == 1 ? 0 : 1); ahead <= 1; ++ahead) {
+          const int tl = (ahead == 0) ? tile : ((t + 1 < TILES && tile + 1 < num_tiles) ? tile + 1 : (grp + (int)gridDim.x) * TILES);
+          if (tl < num_tiles) {
+            const int pp = tl * kBlockM, nn = pp / p.HW, yy0 = (pp - nn * p.HW) / p.W;
+            for (int g = 0; g < BLOCK_N / 64; ++g)
+              if (g * 64 < p.Cout) tma_prefetch_4d(&tmY, g * 64, 0, yy0, nn);
+          }
+        }
+      }
       if (p.res1_tma) {
         if (et == 0) {
           const int n0 = p0 / p.HW;
@@ -487,12 +501,18 @@ struct WgradKernelParams {
   float* dw;
 };
 
-template <int BLOCK_N, int STAGES>
+// MT = 128-row output-channel tiles per CTA (1 or 2, one TMEM accumulator each).  The 1x1 convolutions of the
+// bottleneck are HBM-bound, so the CTA tile is made as wide as the layer -- <BLOCK_N 256, MT 1> for 256->128,
+// <128, 2> for 128->256 -- and every activation byte is fetched once instead of once per tile column/row.
+template <int BLOCK_N, int MT, int STAGES>
 __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY,
                                                               const __grid_constant__ CUtensorMap tmX,
                                                               const WgradKernelParams p) {
   constexpr int kBBytes = (BLOCK_N / 64) * kABytes;
-  constexpr int kStageBytes = 2 * kABytes + kBBytes;
+  constexpr int kDyBytes = MT * 2 * kABytes;
+  constexpr int kStageBytes = kDyBytes + kBBytes;
+  constexpr int kCols = MT * BLOCK_N < 32 ? 32 : MT * BLOCK_N;
+  static_assert(kCols <= 512, "TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -503,7 +523,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = blockIdx.x;
   const int tap = blockIdx.y / p.cin_tiles, cin_tile = blockIdx.y - tap * p.cin_tiles;
-  const int cout_tile = blockIdx.z;
+  const int cout_tile = blockIdx.z;   // in units of MT * 128 output channels
   const int t_begin = split * p.tiles_per_split;
   int t_end = t_begin + p.tiles_per_split;
   if (t_end > p.M_tiles) t_end = p.M_tiles;
@@ -517,7 +537,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), BLOCK_N < 32 ? 32 : BLOCK_N);
+    tmem_alloc(smem_u32(tmem_slot), kCols);
     tmem_relinquish();
   }
   pdl_wait();
@@ -541,11 +561,12 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
           const int y0 = (p0 - n0 * p.HW) / p.W;
           const uint32_t sa = base + s * kStageBytes;
           mbar_expect_tx(full0 + 8 * s, kStageBytes);
-          tma_load_4d(sa, &tmDY, full0 + 8 * s, cout_tile * 128, 0, y0, n0);
-          tma_load_4d(sa + kABytes, &tmDY, full0 + 8 * s, cout_tile * 128 + 64, 0, y0, n0);
+#pragma unroll
+          for (int i = 0; i < 2 * MT; ++i)   // boxes past the (padded) channel count are zero-filled by TMA
+            tma_load_4d(sa + i * kABytes, &tmDY, full0 + 8 * s, cout_tile * (128 * MT) + i * 64, 0, y0, n0);
 #pragma unroll
           for (int i = 0; i < BLOCK_N / 64; ++i)
-            tma_load_4d(sa + (2 + i) * kABytes, &tmX, full0 + 8 * s, cin_tile * BLOCK_N + i * 64, dx, y0 + dy, n0);
+            tma_load_4d(sa + kDyBytes + i * kABytes, &tmX, full0 + 8 * s, cin_tile * BLOCK_N + i * 64, dx, y0 + dy, n0);
         }
       }
     } else if (warp == 1) {
@@ -562,10 +583,13 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
           tc_fence_after();
           const uint32_t sa = base + s * kStageBytes;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {  // 16 pixels per MMA
-            const uint64_t adesc = make_smem_desc_sw128(sa + k * 2048, lbo, sbo);
-            const uint64_t bdesc = make_smem_desc_sw128(sa + 2 * kABytes + k * 2048, lbo, sbo);
-            umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0);
+          for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {  // 16 pixels per MMA
+              const uint64_t adesc = make_smem_desc_sw128(sa + mt * 2 * kABytes + k * 2048, lbo, sbo);
+              const uint64_t bdesc = make_smem_desc_sw128(sa + kDyBytes + k * 2048, lbo, sbo);
+              umma_bf16(tmem_base + (uint32_t)(mt * BLOCK_N), adesc, bdesc, idesc, (kb | k) != 0);
+            }
           }
           umma_commit(empty0 + 8 * s);
         }
@@ -573,30 +597,33 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
       }
     } else {
       const int q = warp & 3;
-      const int row = cout_tile * 128 + q * 32 + lane;  // output channel
       mbar_wait(tfull, 0);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
-        const int col0 = cin_tile * BLOCK_N + c * 32;
-        if (row < p.Cout && col0 < p.Cin_valid) {
-          float* d = p.dw + (size_t)row * p.ldw + (size_t)tap * p.Cin_valid + col0;
-          if (col0 + 32 <= p.Cin_valid && p.vec4) {
+      for (int mt = 0; mt < MT; ++mt) {
+        const int row = cout_tile * (128 * MT) + mt * 128 + q * 32 + lane;  // output channel
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * BLOCK_N + c * 32), v);
+          tmem_ld_wait();
+          const int col0 = cin_tile * BLOCK_N + c * 32;
+          if (row < p.Cout && col0 < p.Cin_valid) {
+            float* d = p.dw + (size_t)row * p.ldw + (size_t)tap * p.Cin_valid + col0;
+            if (col0 + 32 <= p.Cin_valid && p.vec4) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)   // 16-byte vector reductions: a quarter of the atomic instructions
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4 * j), "f"(__uint_as_float(v[4 * j])),
-                           "f"(__uint_as_float(v[4 * j + 1])), "f"(__uint_as_float(v[4 * j + 2])),
-                           "f"(__uint_as_float(v[4 * j + 3])) : "memory");
-          } else if (col0 + 32 <= p.Cin_valid) {
+              for (int j = 0; j < 8; ++j)   // 16-byte vector reductions: a quarter of the atomic instructions
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4 * j), "f"(__uint_as_float(v[4 * j])),
+                             "f"(__uint_as_float(v[4 * j + 1])), "f"(__uint_as_float(v[4 * j + 2])),
+                             "f"(__uint_as_float(v[4 * j + 3])) : "memory");
+            } else if (col0 + 32 <= p.Cin_valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(d + j, __uint_as_float(v[j]));
-          } else {
+              for (int j = 0; j < 32; ++j) atomicAdd(d + j, __uint_as_float(v[j]));
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.Cin_valid) atomicAdd(d + j, __uint_as_float(v[j]));
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.Cin_valid) atomicAdd(d + j, __uint_as_float(v[j]));
+            }
           }
         }
       }
@@ -606,7 +633,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BLOCK_N < 32 ? 32 : BLOCK_N);
+    tmem_dealloc(tmem_base, kCols);
   }
 }
 
@@ -677,7 +704,7 @@ static int g_num_sms = 0;
 
 template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
-                         const GemmKernelParams& kp, int tiles_m, int max_ctas, cudaStream_t st) {
+                         const CUtensorMap& tmY, const GemmKernelParams& kp, int tiles_m, int max_ctas, cudaStream_t st) {
   constexpr int smem = STAGES * (TILES * kABytes + BLOCK_N * 128) + OUT_BUFS * (BLOCK_N / 64) * kABytes + (2 * STAGES + 5) * 8 + 16 +
                        BLOCK_N * 4 + 1024;
   static_assert(STAGES * (TILES * kABytes + BLOCK_N * 128) >= 16 * 1024, "stats scratch (16 KB) aliases the pipeline stages");
@@ -695,13 +722,13 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   const int groups = (tiles_m + TILES - 1) / TILES;
   int grid = groups < g_num_sms ? groups : g_num_sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  HGB_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS>, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, tmC, tmR, kp));
+  HGB_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS>, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, tmC, tmR, tmY, kp));
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
 
 int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap* tmR,
-                     const ConvGemmArgs& a, cudaStream_t st) {
+                     const CUtensorMap* tmY, const ConvGemmArgs& a, cudaStream_t st) {
   HGB_CHECK_ARG(a.ksize == 1 || a.ksize == 3, "conv_gemm: kernel size must be 1 or 3");
   HGB_CHECK_ARG(a.Cin % 64 == 0 && a.Cin > 0, "conv_gemm: Cin must be a multiple of 64 (got %d)", a.Cin);
   HGB_CHECK_ARG(a.Cout % 64 == 0 && a.Cout > 0, "conv_gemm: Cout must be a multiple of 64 (got %d)", a.Cout);
@@ -722,6 +749,8 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   kp.bn_y = a.bn_y;
   kp.res1_tma = (a.res1 != nullptr && tmR != nullptr && !g_debug[3]) ? 1 : 0;
   const CUtensorMap& tmRr = kp.res1_tma ? *tmR : tmC;
+  HGB_CHECK_ARG(a.bn_y == nullptr || tmY != nullptr, "conv_gemm: bn_y needs its tensor map");
+  const CUtensorMap& tmYr = a.bn_y ? *tmY : tmC;
   if (kp.M_total == 0) return HGB_OK;
   HGB_CHECK_ARG(a.Cout <= 256, "conv_gemm: Cout must be <= 256 (one N tile per CTA), got %d", a.Cout);
   const int tiles_m = cdiv(kp.M_total, kBlockM);
@@ -733,23 +762,24 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   // weight-stationary 4-tile groups for the 3x3 convolutions when there are enough groups to fill the chip
   const bool ws = kp.tap3 && !g_debug[5] && tiles_m >= 8 * g_num_sms;
   switch (conv_gemm_block_n(a.Cout)) {
-    case 64: return ws ? launch_gemm_t<64, 2, 4, 2>(tmA, tmB, tmC, tmRr, kp, tiles_m, a.max_ctas, st)
-                       : launch_gemm_t<64, 6, 1, 2>(tmA, tmB, tmC, tmRr, kp, tiles_m, a.max_ctas, st);
-    case 128: return ws ? launch_gemm_t<128, 2, 4, 2>(tmA, tmB, tmC, tmRr, kp, tiles_m, a.max_ctas, st)
-                        : launch_gemm_t<128, 4, 1, 2>(tmA, tmB, tmC, tmRr, kp, tiles_m, a.max_ctas, st);
-    default: return launch_gemm_t<256, 3, 1, 1>(tmA, tmB, tmC, tmRr, kp, tiles_m, a.max_ctas, st);   // 64 KB staging: single
+    case 64: return ws ? launch_gemm_t<64, 2, 4, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
+                       : launch_gemm_t<64, 6, 1, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
+    case 128: return ws ? launch_gemm_t<128, 2, 4, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
+                        : launch_gemm_t<128, 4, 1, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
+    default: return launch_gemm_t<256, 3, 1, 1>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);   // 64 KB staging: single
   }
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int MT, int STAGES>
 static int launch_wgrad_t(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradKernelParams& kp, dim3 grid, cudaStream_t st) {
-  constexpr int smem = STAGES * (2 + BLOCK_N / 64) * kABytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr int smem = STAGES * (2 * MT + BLOCK_N / 64) * kABytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    HGB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HGB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BLOCK_N, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
-  HGB_CUDA(launch_pdl(conv_wgrad_kernel<BLOCK_N, STAGES>, grid, dim3(kThreads), smem, st, tmDY, tmX, kp));
+  HGB_CUDA(launch_pdl(conv_wgrad_kernel<BLOCK_N, MT, STAGES>, grid, dim3(kThreads), smem, st, tmDY, tmX, kp));
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -771,9 +801,16 @@ int launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const Wgr
   kp.Cout = a.Cout_valid > 0 ? a.Cout_valid : a.Cout;
   kp.ldw = taps * kp.Cin_valid;
   kp.tap3 = a.ksize == 3;
-  const int bn = (a.Cin % 128 == 0) ? 128 : 64;
+  // CTA tile: the HBM-bound 1x1 layers take the widest tile that fits (every activation byte fetched once when the
+  // whole layer is one tile); 3x3 layers keep 128 x 128 per tap.  Wide tiles need enough pixel tiles per CTA to
+  // amortise their larger fp32 reduction epilogue.
+  int bn = (a.Cin % 128 == 0) ? 128 : 64, mt = 1;
+  if (a.ksize == 1 && !g_debug[11] && kp.M_tiles >= 8 * 148) {
+    if (a.Cin % 256 == 0 && a.Cout <= 128) bn = 256;
+    else if (a.Cout % 256 == 0 && a.Cin == 128) mt = 2;   // (256 -> 256 measured slower with wide tiles: two stages only)
+  }
   kp.cin_tiles = a.Cin / bn;
-  const int cout_tiles = cdiv(a.Cout, 128);
+  const int cout_tiles = cdiv(a.Cout, 128 * mt);
   const int groups = taps * kp.cin_tiles * cout_tiles;
   // split-K over pixel tiles: enough CTAs to fill the chip, but at least 8 tiles per CTA so the fp32
   // atomic epilogue (a full 128 x N tile per CTA) is amortised -- it dominated the low-resolution levels
@@ -786,8 +823,10 @@ int launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const Wgr
   kp.vec4 = (kp.ldw % 4 == 0) && (kp.Cin_valid % 4 == 0) && (((uintptr_t)a.dw & 15) == 0);
   kp.dw = a.dw;
   dim3 grid(splits, taps * kp.cin_tiles, cout_tiles);
-  if (bn == 128) return launch_wgrad_t<128, 3>(tmDY, tmX, kp, grid, st);
-  return launch_wgrad_t<64, 4>(tmDY, tmX, kp, grid, st);
+  if (bn == 256) return launch_wgrad_t<256, 1, 2>(tmDY, tmX, kp, grid, st);
+  if (mt == 2) return launch_wgrad_t<128, 2, 2>(tmDY, tmX, kp, grid, st);
+  if (bn == 128) return launch_wgrad_t<128, 1, 3>(tmDY, tmX, kp, grid, st);
+  return launch_wgrad_t<64, 1, 4>(tmDY, tmX, kp, grid, st);
 }
 
 }  // namespace hgb
@@ -820,7 +859,7 @@ extern "C" int hgb_conv_gemm(const void* in, const void* w, const float* bias, c
     rc = make_tmap_act(&tmR, res1, N, H, W, ldc);
     if (rc) return rc;
   }
-  return launch_conv_gemm(tmA, tmB, tmC, res1 ? &tmR : nullptr, a, (cudaStream_t)stream);
+  return launch_conv_gemm(tmA, tmB, tmC, res1 ? &tmR : nullptr, nullptr, a, (cudaStream_t)stream);
 }
 
 #ifdef HGB_KTIME

@@ -34,8 +34,9 @@ struct ConvGemmArgs {
 int conv_gemm_block_n(int Cout);
 // tmC: activation map of the output tensor (the epilogue writes the tile with TMA bulk stores)
 // tmR: activation map of res1 (or null): the residual tile is then fetched by TMA into the staging buffer
+// tmY: activation map of bn_y (or null): used to prefetch its tiles into L2 ahead of the statistics pass
 int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap* tmR,
-                     const ConvGemmArgs& a, cudaStream_t st);
+                     const CUtensorMap* tmY, const ConvGemmArgs& a, cudaStream_t st);
 
 struct WgradArgs {
   int N, H, W, Cin, Cout;

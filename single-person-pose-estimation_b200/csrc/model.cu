@@ -315,11 +315,13 @@ struct hgb_model {
     Op o;
     o = Op(); o.type = B_BN_REDUCE; o.bn = bn; o.a0 = dz; o.a1 = y; emit_b(o);
     o = Op(); o.type = B_BN_APPLY; o.bn = bn; o.conv = conv; o.a0 = dz; o.a1 = y; o.a2 = dp; emit_b(o);
-    // the dgrad continues the chain and is emitted first; the weight gradient is a leaf
+    // the dgrad continues the chain; the weight gradient is a leaf of the backward graph (side lane)
+    const bool wfirst = hgb::g_debug[10] != 0;
+    if (wfirst) { o = Op(); o.type = B_WGRAD; o.conv = conv; o.a0 = dp; o.a1 = x_in; o.lane = leaf_lane(); emit_b(o); }
     if (dgrad_out >= 0) {
       o = Op(); o.type = B_DGRAD; o.conv = conv; o.a0 = dp; o.a1 = dgrad_out; o.a2 = res1; o.a3 = res2; emit_b(o);
     }
-    o = Op(); o.type = B_WGRAD; o.conv = conv; o.a0 = dp; o.a1 = x_in; o.lane = leaf_lane(); emit_b(o);
+    if (!wfirst) { o = Op(); o.type = B_WGRAD; o.conv = conv; o.a0 = dp; o.a1 = x_in; o.lane = leaf_lane(); emit_b(o); }
   }
   // g_out: gradient wrt the block output (read; masked in place when the skip is a conv);
   // g_x: gradient wrt the block input (written); extra: one more tensor summed into g_x.
@@ -789,7 +791,7 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
       a.stats = (o.bn >= 0 && training) ? arena_f(m, m->bns[o.bn].sums_off) : nullptr;
       a.bn_y = nullptr;
       a.max_ctas = side_lane_ctas(m, o);
-      rc = launch_conv_gemm(in.tmap, c.tm_wf, out.tmap, o.a2 >= 0 ? &m->acts[o.a2].tmap : nullptr, a, st);
+      rc = launch_conv_gemm(in.tmap, c.tm_wf, out.tmap, o.a2 >= 0 ? &m->acts[o.a2].tmap : nullptr, nullptr, a, st);
       break;
     }
     case F_BN: {
@@ -854,7 +856,8 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
       a.stats = o.bn >= 0 ? arena_f(m, m->bns[o.bn].bsums_off) : nullptr;
       a.bn_y = o.bn >= 0 ? act_ptr(m, o.flag - 1) : nullptr;
       a.max_ctas = side_lane_ctas(m, o);
-      rc = launch_conv_gemm(dp.tmap, c.tm_wd, out.tmap, o.a2 >= 0 ? &m->acts[o.a2].tmap : nullptr, a, st);
+      rc = launch_conv_gemm(dp.tmap, c.tm_wd, out.tmap, o.a2 >= 0 ? &m->acts[o.a2].tmap : nullptr,
+                            o.bn >= 0 ? &m->acts[o.flag - 1].tmap : nullptr, a, st);
       break;
     }
     case B_RELU_MASK: {

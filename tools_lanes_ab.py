@@ -10,8 +10,10 @@ from hgb200 import ops, _lib
 ap = argparse.ArgumentParser()
 ap.add_argument("--batches", default="32,64,128,256")
 ap.add_argument("--reserves", default="20")
+ap.add_argument("--wfirst", type=int, default=0)
 a = ap.parse_args()
 lib = _lib.lib
+lib.hgb_debug_set(10, a.wfirst)
 for B in [int(b) for b in a.batches.split(",")]:
     model = hgb200.HourglassModel(17, 8, 256, (256, 256, 3), "sigmoid", seed=1)
     model.compile(optimizer=hgb200.Adam(1e-3), loss=hgb200.loss.weighted_mse)
