@@ -86,7 +86,14 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
 //   TILES == 4: weight-stationary: every weight box feeds four pixel tiles (four TMEM accumulators), which
 //               cuts the shared-memory fill per MAC by 37 % -- the 3x3 convolutions, whose MMA rate is
 //               bounded by the bytes that fit in flight (ncu: tensor pipe 40 % with TILES == 1).
-template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS>
+//   HALO       : 3x3 only, TILES consecutive tiles of ONE image.  The weight-stationary ring still fetches every
+//               input pixel nine times from L2 (once per tap), and L2 -> shared memory bandwidth, not the tensor
+//               pipe, bounds it.  Here a (64-channel block, horizontal shift) "strip" of the TILES tiles plus one
+//               halo row above and below is fetched once (TILES + 1 boxes) and serves the three vertical taps
+//               through descriptor offsets of whole image rows (multiples of 1024 bytes: same swizzle phase):
+//               2.4x fewer activation bytes per MAC.  Strip boxes and weight boxes are recycled slot by slot
+//               (tile-major MMA order), accumulators are handed over and released tile by tile.
+template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ CUtensorMap tmC,
@@ -98,14 +105,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   constexpr int kAccStages = TILES == 1 ? 2 : 1;
   static_assert(kAccStages * TILES * BLOCK_N <= 512, "TMEM columns");
   constexpr int kOutBytes = (BLOCK_N / 64) * kABytes;
-  constexpr int kNumBars = 2 * STAGES + 5;  // full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | residual
+  constexpr int kASlots = TILES + 1, kBSlots = 6;             // HALO: strip boxes | two sets of three weight boxes
+  constexpr int kRingBytes = HALO ? kASlots * kABytes + kBSlots * kBBytes : STAGES * kStageBytes;
+  // full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | residual
+  // HALO: fullA[T+1] | emptyA[T+1] | fullB[6] | emptyB[6] | tmem_full[T] | tmem_empty[T] | residual
+  constexpr int kNumBars = HALO ? 2 * kASlots + 2 * kBSlots + 2 * TILES + 1 : 2 * STAGES + 5;
+  static_assert(!HALO || (TILES > 1 && TILES * BLOCK_N <= 512), "HALO needs one accumulator per tile");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // 128-byte swizzle atoms need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t outbase = base + STAGES * kStageBytes;       // OUT_BUFS epilogue staging buffers (1024-aligned)
+  const uint32_t outbase = base + kRingBytes;                 // OUT_BUFS epilogue staging buffers (1024-aligned)
   const uint32_t bar0 = outbase + OUT_BUFS * kOutBytes;
-  uint8_t* tail = smem + STAGES * kStageBytes + OUT_BUFS * kOutBytes + kNumBars * 8;
+  uint8_t* tail = smem + kRingBytes + OUT_BUFS * kOutBytes + kNumBars * 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail);
   float* s_bias = reinterpret_cast<float*>(tail + 16);        // [BLOCK_N]
   float* s_stats = reinterpret_cast<float*>(smem);            // [row groups][2*BLOCK_N] = 16 KB, aliases pipeline stage 0: used only after the last tile
@@ -122,10 +134,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     prefetch_tmap(&tmC);
     if (p.res1_tma) prefetch_tmap(&tmR);
     if (p.bn_y) prefetch_tmap(&tmY);
-    for (int s = 0; s < 2 * STAGES + 2; ++s) mbar_init(bar0 + 8 * s, 1);
-    mbar_init(bar0 + 8 * (2 * STAGES + 2), 8);  // tmem_empty: one arrival per epilogue warp
-    mbar_init(bar0 + 8 * (2 * STAGES + 3), 8);
-    mbar_init(bar0 + 8 * (2 * STAGES + 4), 1);  // residual tile landed in the staging buffer
+    if (HALO) {
+      for (int s = 0; s < kNumBars; ++s) {
+        const bool tmem_empty = s >= 2 * kASlots + 2 * kBSlots + TILES && s < kNumBars - 1;
+        mbar_init(bar0 + 8 * s, tmem_empty ? 8 : 1);
+      }
+    } else {
+      for (int s = 0; s < 2 * STAGES + 2; ++s) mbar_init(bar0 + 8 * s, 1);
+      mbar_init(bar0 + 8 * (2 * STAGES + 2), 8);  // tmem_empty: one arrival per epilogue warp
+      mbar_init(bar0 + 8 * (2 * STAGES + 3), 8);
+      mbar_init(bar0 + 8 * (2 * STAGES + 4), 1);  // residual tile landed in the staging buffer
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -145,10 +164,82 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     asm volatile("bar.sync 1, 256;" ::: "memory");
   }
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t full0 = bar0, empty0 = bar0 + 8 * STAGES, tfull0 = bar0 + 16 * STAGES, tempty0 = tfull0 + 16;
-  const uint32_t resbar = tempty0 + 16;
+  const uint32_t full0 = bar0, empty0 = bar0 + 8 * STAGES;
+  const uint32_t tfull0 = HALO ? bar0 + 8 * (2 * kASlots + 2 * kBSlots) : bar0 + 16 * STAGES;
+  const uint32_t tempty0 = tfull0 + (HALO ? 8 * TILES : 16);
+  const uint32_t resbar = bar0 + 8 * (kNumBars - 1);
+  // HALO barriers and buffers
+  const uint32_t fullA = bar0, emptyA = bar0 + 8 * kASlots, fullB = bar0 + 16 * kASlots, emptyB = fullB + 8 * kBSlots;
+  const uint32_t ringB = base + kASlots * kABytes;
+  const int rpt = kBlockM / p.W;   // image rows per tile
 
-  if (warp == 0) {
+  if (HALO && warp == 0) {
+    if (lane == 0) {
+      int sc = 0;   // running strip counter
+      for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
+        const int p0 = grp * TILES * kBlockM;
+        const int n0 = p0 / p.HW;
+        const int y0 = (p0 - n0 * p.HW) / p.W;
+        for (int st = 0; st < 3 * p.cblk; ++st, ++sc) {
+          const int cb = st / 3, dxi = st - cb * 3;
+          const int dx = (dxi - 1) * p.tap_sign;
+          const int set = sc & 1;
+          const uint32_t bph = (sc >> 1) & 1, aph = sc & 1;
+#pragma unroll
+          for (int dyi = 0; dyi < 3; ++dyi) {   // the three weight boxes of this column of taps
+            const int slot = set * 3 + dyi;
+            mbar_wait(emptyB + 8 * slot, bph ^ 1);
+            mbar_expect_tx(fullB + 8 * slot, kBBytes);
+            tma_load_2d(ringB + slot * kBBytes, &tmB, fullB + 8 * slot, ((dyi * 3 + dxi) * p.cblk + cb) * 64, 0);
+          }
+#pragma unroll
+          for (int j = 0; j < kASlots; ++j) {   // strip rows y0 - 1 ... y0 + TILES * rpt (+ slack), shifted by dx
+            mbar_wait(emptyA + 8 * j, aph ^ 1);
+            mbar_expect_tx(fullA + 8 * j, kABytes);
+            tma_load_4d(base + j * kABytes, &tmA, fullA + 8 * j, cb * 64, dx, y0 - 1 + j * rpt, n0);
+          }
+        }
+      }
+    }
+  } else if (HALO && warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+      const uint32_t row_bytes = (uint32_t)p.W * 128u;
+      int sc = 0, lt = 0;
+      for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x, ++lt) {
+        const int nst = 3 * p.cblk;
+        for (int st = 0; st < nst; ++st, ++sc) {
+          const int set = sc & 1;
+          const uint32_t bph = (sc >> 1) & 1, aph = sc & 1;
+#pragma unroll
+          for (int dyi = 0; dyi < 3; ++dyi) mbar_wait(fullB + 8 * (set * 3 + dyi), bph);
+          mbar_wait(fullA, aph);
+#pragma unroll
+          for (int t = 0; t < TILES; ++t) {
+            mbar_wait(fullA + 8 * (t + 1), aph);      // tile t reads strip boxes t and t + 1
+            if (st == 0) mbar_wait(tempty0 + 8 * t, (lt & 1) ^ 1);   // the epilogue has drained this accumulator
+            tc_fence_after();
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              const int dy = (dyi - 1) * p.tap_sign;
+              const uint64_t adesc = make_smem_desc_sw128(base + (uint32_t)(t * rpt + dy + 1) * row_bytes, 16, 1024);
+              const uint64_t bdesc = make_smem_desc_sw128(ringB + (set * 3 + dyi) * kBBytes, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base + (uint32_t)(t * BLOCK_N), adesc + 2 * k, bdesc + 2 * k, idesc, (st | dyi | k) != 0);
+            }
+            umma_commit(emptyA + 8 * t);              // later tiles start at box t + 1
+            if (t == TILES - 1) {
+              umma_commit(emptyA + 8 * TILES);
+#pragma unroll
+              for (int dyi = 0; dyi < 3; ++dyi) umma_commit(emptyB + 8 * (set * 3 + dyi));
+            }
+            if (st == nst - 1) umma_commit(tfull0 + 8 * t);   // accumulator of tile t complete
+          }
+        }
+      }
+    }
+  } else if (warp == 0) {
     if (lane == 0) {
       int kbt = 0;  // running k-block counter: the smem ring continues across tiles
       for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
@@ -227,8 +318,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     for (int j = 0; j < 4; ++j) { sa2[j] = 0ull; sq2[j] = 0ull; }
     int lt = 0, rt = 0, nt = 0;   // groups / residual tiles / tiles processed by this CTA
     for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x, ++lt) {
-      const int acc = lt % kAccStages;
-      const uint32_t aph = (lt / kAccStages) & 1;
+      const int acc = HALO ? 0 : lt % kAccStages;
+      const uint32_t aph = HALO ? (lt & 1) : (lt / kAccStages) & 1;
 #pragma unroll 1
       for (int t = 0; t < TILES; ++t) {
       const int tile = grp * TILES + t;
@@ -268,7 +359,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             if (g * 64 < p.Cout) tma_load_4d(out0 + (uint32_t)g * kABytes, &tmR, resbar, g * 64, 0, y0, n0);
         }
       }
-      mbar_wait(tfull0 + 8 * acc, aph);
+      mbar_wait(tfull0 + 8 * (HALO ? t : acc), aph);
       tc_fence_after();
       if (et == 0 && nt == 1) KT(6);
       if (p.res1_tma) { mbar_wait(resbar, rt & 1); ++rt; }
@@ -358,10 +449,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         if (two) stage_chunk(vb, g + 1);
       }
       // last tile of the group: the accumulator stage is fully read, hand it back to the MMA warp
-      if (t == TILES - 1 || tile + 1 >= num_tiles) {
+      if (HALO || t == TILES - 1 || tile + 1 >= num_tiles) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        if (lane == 0) mbar_arrive(tempty0 + 8 * (HALO ? t : acc));
       }
       fence_proxy_async();                            // generic-proxy smem writes -> visible to the TMA engine
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps: tile fully staged
@@ -702,16 +793,17 @@ int conv_gemm_block_n(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 
 
 static int g_num_sms = 0;
 
-template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS>
+template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                          const CUtensorMap& tmY, const GemmKernelParams& kp, int tiles_m, int max_ctas, cudaStream_t st) {
-  constexpr int smem = STAGES * (TILES * kABytes + BLOCK_N * 128) + OUT_BUFS * (BLOCK_N / 64) * kABytes + (2 * STAGES + 5) * 8 + 16 +
-                       BLOCK_N * 4 + 1024;
-  static_assert(STAGES * (TILES * kABytes + BLOCK_N * 128) >= 16 * 1024, "stats scratch (16 KB) aliases the pipeline stages");
+  constexpr int ring = HALO ? (TILES + 1) * kABytes + 6 * BLOCK_N * 128 : STAGES * (TILES * kABytes + BLOCK_N * 128);
+  constexpr int nbars = HALO ? 2 * (TILES + 1) + 12 + 2 * TILES + 1 : 2 * STAGES + 5;
+  constexpr int smem = ring + OUT_BUFS * (BLOCK_N / 64) * kABytes + nbars * 8 + 16 + BLOCK_N * 4 + 1024;
+  static_assert(ring >= 16 * 1024, "stats scratch (16 KB) aliases the pipeline stages");
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    HGB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HGB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
   if (!g_num_sms) {
@@ -722,7 +814,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   const int groups = (tiles_m + TILES - 1) / TILES;
   int grid = groups < g_num_sms ? groups : g_num_sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  HGB_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS>, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, tmC, tmR, tmY, kp));
+  HGB_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS, HALO>, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, tmC, tmR, tmY, kp));
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -761,6 +853,10 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   }
   // weight-stationary 4-tile groups for the 3x3 convolutions when there are enough groups to fill the chip
   const bool ws = kp.tap3 && !g_debug[5] && tiles_m >= 8 * g_num_sms;
+  // strip reuse across the vertical taps: groups of 4 tiles inside one image, at least two image rows per tile
+  const int rpt = kBlockM / a.W;
+  const bool halo = ws && !g_debug[12] && a.W <= 64 && rpt >= 2 && a.H % (4 * rpt) == 0 && a.Cout == 128;
+  if (halo) return launch_gemm_t<128, 1, 4, 1, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
   switch (conv_gemm_block_n(a.Cout)) {
     case 64: return ws ? launch_gemm_t<64, 2, 4, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
                        : launch_gemm_t<64, 6, 1, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);

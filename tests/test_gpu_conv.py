@@ -58,6 +58,7 @@ CASES = [
     # >= 8*148 pixel tiles: the weight-stationary 4-tile path of the 3x3 kernel (incl. a group tail: 1186 tiles)
     (40, 64, 128, 128, 3),
     (593, 16, 128, 128, 3),
+    (152, 32, 128, 128, 3),      # strip-reuse (HALO) path at 32x32: four image rows per tile
     (10, 128, 64, 64, 3),
 ]
 
@@ -94,7 +95,7 @@ def test_conv_linear_residuals_and_pitch(ops, torch):
     assert (y2.float() - ref2).abs().max().item() <= 3e-2 * max(1.0, ref2.abs().max().item())
 
 
-@pytest.mark.parametrize("N,H,C", [(2, 64, 128), (3, 8, 128), (2, 4, 128), (38, 64, 128)])
+@pytest.mark.parametrize("N,H,C", [(2, 64, 128), (3, 8, 128), (2, 4, 128), (38, 64, 128), (150, 32, 128)])
 def test_conv_dgrad_mirrored_taps(ops, torch, N, H, C):
     """tap_sign=-1 with the same tap-major weights == correlation with the flipped kernel."""
     dy = _rand(torch, (N, H, H, C), 7)

