@@ -729,6 +729,150 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------
+// 3x3 weight gradient, 128 -> 128 channels, one CTA per (horizontal tap offset dx, range of pixel tiles).
+// The per-tap kernel above re-reads dy and x from L2 for each of the nine taps (128 bytes per SM per clock:
+// L2-bandwidth bound at half the tensor rate).  Here the three vertical taps of one dx share everything: the
+// dy tile is fetched once and multiplied with three row-shifted windows of a ROLLING strip of x (one new
+// 128-pixel box per tile, rows y0-1 ... of the image, shifted by dx through the tensor map; out-of-image rows
+// and columns arrive as zeros = 'same' padding).  Windows never need to be contiguous across ring slots because
+// every MMA covers 16 pixels of one image row and gets its own descriptor.  42 bytes per SM per clock.
+// ------------------------------------------------------------------------------------------
+constexpr int kW3XSlots = 4, kW3DSlots = 3;
+
+__global__ void __launch_bounds__(kThreads) conv_wgrad3_kernel(const __grid_constant__ CUtensorMap tmDY,
+                                                               const __grid_constant__ CUtensorMap tmX,
+                                                               const WgradKernelParams p) {
+  constexpr int kXRing = kW3XSlots * kABytes;           // one ring per 64-channel half of x
+  constexpr int kSmemX = 2 * kXRing, kSmemD = kW3DSlots * 2 * kABytes;
+  constexpr int kNumBars = 2 * kW3XSlots + 2 * kW3DSlots + 1;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t ringX = base, ringD = base + kSmemX;
+  const uint32_t bar0 = base + kSmemX + kSmemD;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemX + kSmemD + kNumBars * 8);
+  const uint32_t fullX = bar0, emptyX = bar0 + 8 * kW3XSlots, fullD = bar0 + 16 * kW3XSlots, emptyD = fullD + 8 * kW3DSlots;
+  const uint32_t tfull = emptyD + 8 * kW3DSlots;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dxi = blockIdx.y, dx = dxi - 1;
+  const int t_begin = blockIdx.x * p.tiles_per_split;
+  int t_end = t_begin + p.tiles_per_split;
+  if (t_end > p.M_tiles) t_end = p.M_tiles;
+  const int rpt = kBlockM / p.W;            // image rows per 128-pixel tile
+  const int tpi = p.H / rpt;                // tiles per image
+  pdl_trigger();
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmDY);
+    prefetch_tmap(&tmX);
+    for (int s = 0; s < kNumBars; ++s) mbar_init(bar0 + 8 * s, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);   // three 128-column accumulators
+    tmem_relinquish();
+  }
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (t_end > t_begin) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int xc = 0;   // x boxes issued so far (ring slot = xc % slots)
+        auto load_x = [&](int n, int b) {
+          const int s = xc % kW3XSlots;
+          mbar_wait(emptyX + 8 * s, ((xc / kW3XSlots) & 1) ^ 1);
+          mbar_expect_tx(fullX + 8 * s, 2 * kABytes);
+          tma_load_4d(ringX + s * kABytes, &tmX, fullX + 8 * s, 0, dx, b * rpt - 1, n);
+          tma_load_4d(ringX + kXRing + s * kABytes, &tmX, fullX + 8 * s, 64, dx, b * rpt - 1, n);
+          ++xc;
+        };
+        for (int T = t_begin, dc = 0; T < t_end; ++T, ++dc) {
+          const int n = T / tpi, lt = T - n * tpi;
+          if (lt == 0 || T == t_begin) load_x(n, lt);   // leading box of a new image / of this CTA's range
+          load_x(n, lt + 1);
+          const int s = dc % kW3DSlots;
+          mbar_wait(emptyD + 8 * s, ((dc / kW3DSlots) & 1) ^ 1);
+          mbar_expect_tx(fullD + 8 * s, 2 * kABytes);
+          tma_load_4d(ringD + s * 2 * kABytes, &tmDY, fullD + 8 * s, 0, 0, lt * rpt, n);
+          tma_load_4d(ringD + s * 2 * kABytes + kABytes, &tmDY, fullD + 8 * s, 64, 0, lt * rpt, n);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, 128, 1, 1);
+        int xc = 0;   // index of the window's LOW box in issue order
+        bool first = true;
+        for (int T = t_begin, dc = 0; T < t_end; ++T, ++dc) {
+          const int n = T / tpi, lt = T - n * tpi;
+          if (T != t_begin && lt != 0) ++xc;            // same image: the window slides by one box
+          else if (T != t_begin) xc += 2;               // new image: both boxes are new
+          const int slo = xc % kW3XSlots, shi = (xc + 1) % kW3XSlots;
+          // a box is complete when its fill number matches: box i is the (i / slots)-th fill of slot i % slots
+          if (T == t_begin || lt == 0) mbar_wait(fullX + 8 * slo, (xc / kW3XSlots) & 1);
+          mbar_wait(fullX + 8 * shi, ((xc + 1) / kW3XSlots) & 1);
+          const int sd = dc % kW3DSlots;
+          mbar_wait(fullD + 8 * sd, (dc / kW3DSlots) & 1);
+          tc_fence_after();
+          const uint32_t da = ringD + sd * 2 * kABytes;
+#pragma unroll
+          for (int dyi = 0; dyi < 3; ++dyi) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {   // 16 pixels per MMA, always inside one image row of one box
+              const int q = dyi * p.W + 16 * k;          // pixel offset of this chunk inside the two-box window
+              const uint32_t xs = ringX + (uint32_t)((q >> 7) ? shi : slo) * kABytes + (uint32_t)(q & 127) * 128u;
+              const uint64_t adesc = make_smem_desc_sw128(da + k * 2048, (uint32_t)kABytes, 1024);
+              const uint64_t bdesc = make_smem_desc_sw128(xs, (uint32_t)kXRing, 1024);
+              umma_bf16(tmem_base + (uint32_t)(dyi * 128), adesc, bdesc, idesc, !(first && k == 0));
+            }
+          }
+          first = false;
+          // the low box is done unless the next tile of the same image reuses... it never does: the window
+          // slides by one box, so the low box is free; the high box stays (it is the next tile's low box)
+          umma_commit(emptyX + 8 * slo);
+          const bool last_of_image = (lt == tpi - 1) || (T + 1 == t_end);
+          if (last_of_image) umma_commit(emptyX + 8 * shi);
+          umma_commit(emptyD + 8 * sd);
+        }
+        umma_commit(tfull);
+      }
+    } else {
+      const int q = warp & 3;
+      const int row = q * 32 + lane;  // output channel
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int dyi = 0; dyi < 3; ++dyi) {
+        const int tap = dyi * 3 + dxi;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dyi * 128 + c * 32), v);
+          tmem_ld_wait();
+          float* d = p.dw + (size_t)row * p.ldw + (size_t)tap * 128 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4 * j), "f"(__uint_as_float(v[4 * j])),
+                         "f"(__uint_as_float(v[4 * j + 1])), "f"(__uint_as_float(v[4 * j + 2])),
+                         "f"(__uint_as_float(v[4 * j + 3])) : "memory");
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -900,6 +1044,28 @@ int launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const Wgr
   // CTA tile: the HBM-bound 1x1 layers take the widest tile that fits (every activation byte fetched once when the
   // whole layer is one tile); 3x3 layers keep 128 x 128 per tap.  Wide tiles need enough pixel tiles per CTA to
   // amortise their larger fp32 reduction epilogue.
+  // 3x3, 128 -> 128, tiles inside one image: the three vertical taps share dy and a rolling strip of x
+  const int rpt3 = kBlockM / a.W;
+  if (a.ksize == 3 && !g_debug[13] && a.Cin == 128 && a.Cout == 128 && kp.Cin_valid == 128 && kp.Cout == 128 && a.W >= 16 &&
+      a.W <= 64 && rpt3 >= 2 && a.H % rpt3 == 0 && kp.M_tiles >= 4 * 148 && (((uintptr_t)a.dw & 15) == 0)) {
+    // whole waves of one CTA per SM (3 * splits <= 148 * waves); two waves only when every CTA still gets >= 64 tiles,
+    // so the 192 KB fp32 reduction epilogue of a CTA stays a small fraction of its work
+    int splits = (2 * 148) / 3;
+    if (kp.M_tiles / splits < 64) splits = 148 / 3;
+    kp.tiles_per_split = cdiv(kp.M_tiles, splits);
+    splits = cdiv(kp.M_tiles, kp.tiles_per_split);
+    kp.cin_tiles = 1; kp.swap_lbo_sbo = 0; kp.vec4 = 1; kp.dw = a.dw;
+    constexpr int smem = (2 * kW3XSlots + 2 * kW3DSlots) * kABytes + (2 * kW3XSlots + 2 * kW3DSlots + 1) * 8 + 16 + 1024;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    static bool attr_done = false;
+    if (!attr_done) {
+      HGB_CUDA(cudaFuncSetAttribute(conv_wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_done = true;
+    }
+    HGB_CUDA(launch_pdl(conv_wgrad3_kernel, dim3(splits, 3, 1), dim3(kThreads), smem, st, tmDY, tmX, kp));
+    HGB_LAUNCH_CHECK();
+    return HGB_OK;
+  }
   int bn = (a.Cin % 128 == 0) ? 128 : 64, mt = 1;
   if (a.ksize == 1 && !g_debug[11] && kp.M_tiles >= 8 * 148) {
     if (a.Cin % 256 == 0 && a.Cout <= 128) bn = 256;

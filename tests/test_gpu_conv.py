@@ -50,11 +50,6 @@ CASES = [
     (1, 128, 64, 128, 1),
     (2, 64, 64, 256, 1),
     (1, 64, 192, 64, 1),
-    # >= 8 * 148 pixel tiles: the wide CTA tiles of the HBM-bound 1x1 layers (<256,1>, <128,2>, <128,2> x 2 cin tiles)
-    (40, 64, 256, 128, 1),
-    (40, 64, 128, 256, 1),
-    (38, 64, 256, 256, 1),
-    (40, 64, 256, 64, 1),
     # >= 8*148 pixel tiles: the weight-stationary 4-tile path of the 3x3 kernel (incl. a group tail: 1186 tiles)
     (40, 64, 128, 128, 3),
     (593, 16, 128, 128, 3),
@@ -116,6 +111,15 @@ WG_CASES = [
     (1, 128, 64, 64, 3),
     (1, 64, 192, 64, 1),
     (2, 64, 64, 256, 1),
+    # >= 8 * 148 pixel tiles: the wide CTA tiles of the HBM-bound 1x1 layers (<256,1>, <128,2>) and their neighbours
+    (40, 64, 256, 128, 1),
+    (40, 64, 128, 256, 1),
+    (38, 64, 256, 256, 1),
+    (40, 64, 256, 64, 1),
+    # >= 4 * 148 pixel tiles: the rolling-strip 3x3 kernel (three vertical taps per CTA; ranges start mid-image)
+    (20, 64, 128, 128, 3),
+    (19, 64, 128, 128, 3),
+    (75, 32, 128, 128, 3),
 ]
 
 
