@@ -348,6 +348,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
           }
         }
       }
+      if (p.res1_tma && et == 64) {
+        // same for the residual tile: the NEXT tile's boxes travel HBM -> L2 while this tile is processed, so the
+        // TMA fetch into the (single) staging buffer at the top of the next tile is an L2 hit
+        const int tl = (t + 1 < TILES && tile + 1 < num_tiles) ? tile + 1 : (grp + (int)gridDim.x) * TILES;
+        if (tl < num_tiles) {
+          const int pp = tl * kBlockM, nn = pp / p.HW, yy0 = (pp - nn * p.HW) / p.W;
+          for (int g = 0; g < BLOCK_N / 64; ++g)
+            if (g * 64 < p.Cout) tma_prefetch_4d(&tmR, g * 64, 0, yy0, nn);
+        }
+      }
       if (p.res1_tma) {
         if (et == 0) {
           const int n0 = p0 / p.HW;
@@ -381,6 +391,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
               w[j] = cvt_bf16x2(add_f32x2(pack_f32x2(v[8 * j4 + 2 * j], v[8 * j4 + 2 * j + 1]), b2[4 * j4 + j]), p.relu != 0);
             const uint32_t dst = box + ((((uint32_t)hsel * 4u + j4) ^ ((uint32_t)row & 7u)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                         : "memory");
+          }
+          return;
+        }
+        if (p.res1_tma && !p.res2 && !p.relu) {
+          // the dgrad shape (skip-gradient accumulate): residual tile already in the staging box, packed adds
+          const uint64_t* b2 = reinterpret_cast<const uint64_t*>(s_bias + n0c);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const uint32_t adr = box + ((((uint32_t)hsel * 4u + j4) ^ ((uint32_t)row & 7u)) << 4);
+            uint32_t u[4], w[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]) : "r"(adr));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint64_t x2 = pack_f32x2(v[8 * j4 + 2 * j], v[8 * j4 + 2 * j + 1]);
+              if (p.bias) x2 = add_f32x2(x2, b2[4 * j4 + j]);
+              x2 = add_f32x2(x2, pack_f32x2(u[j] << 16, u[j] & 0xffff0000u));
+              w[j] = cvt_bf16x2(x2, false);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(adr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
                          : "memory");
           }
           return;

@@ -531,40 +531,47 @@ int head_act_bwd(const float* dLdp, const bf16* g_p, const float* heat, bf16* dl
 }
 
 // ---------------------------------------------------------------------------------- stem patches
-__global__ void __launch_bounds__(256) im2col_7x7s2_kernel(const float* __restrict__ img, bf16* __restrict__ col, int64_t total,
-                                                           int H, int W) {
+// One block = 32 consecutive output pixels of one output row.  The 7 input rows x 69 input columns x 3 channels
+// they touch are staged in shared memory with coalesced loads (zeros outside the image = TF 'same' padding,
+// 2 before / 3 after); for a fixed kernel row the 21 K-elements of a pixel are then CONTIGUOUS in the staged row,
+// so every thread assembles its 8 K-elements from shared memory and writes one 16-byte chunk.
+constexpr int kStemPix = 32;                       // output pixels per block
+constexpr int kStemCols = (2 * kStemPix + 5) * 3;  // staged floats per input row (207)
+
+__global__ void __launch_bounds__(256) im2col_7x7s2_kernel(const float* __restrict__ img, bf16* __restrict__ col, int H, int W) {
   pdl_trigger();
   pdl_wait();
-  // thread = (output pixel, group of 8 K-elements); 24 groups per pixel (192 = 147 + padding)
-  const int oh = H / 2, ow = W / 2;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % 24);
-    int64_t pix = i / 24;
-    const int ox = (int)(pix % ow);
-    pix /= ow;
-    const int oy = (int)(pix % oh);
-    const int n = (int)(pix / oh);
+  __shared__ float tile[7][kStemCols + 1];
+  const int ow = W / 2, oh = H / 2;
+  const int xb = blockIdx.x * kStemPix, oy = blockIdx.y, n = blockIdx.z;
+  const int ix0 = xb * 2 - 2;
+  for (int i = threadIdx.x; i < 7 * kStemCols; i += 256) {
+    const int r = i / kStemCols, cc = i - r * kStemCols;
+    const int iy = oy * 2 + r - 2, ix = ix0 + cc / 3;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + (((size_t)n * H + iy) * W + ix0) * 3 + cc);
+    tile[r][cc] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kStemPix * 24; i += 256) {   // (pixel, group of 8 K-elements); 192 = 147 + padding
+    const int px = i / 24, g = i - px * 24;
+    if (xb + px >= ow) continue;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int kk = g * 8 + j;
-      float v = 0.f;
-      if (kk < 147) {
-        const int ky = kk / 21, rem = kk - ky * 21, kx = rem / 3, c = rem - kx * 3;
-        const int iy = oy * 2 + ky - 2, ix = ox * 2 + kx - 2;  // TF 'same', stride 2, k 7: pad 2 before / 3 after
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + (((size_t)n * H + iy) * W + ix) * 3 + c);
-      }
-      f[j] = v;
+      const int ky = kk / 21;
+      f[j] = kk < 147 ? tile[ky][6 * px + (kk - ky * 21)] : 0.f;
     }
-    st16(col + (size_t)i * 8, pack8(f));
+    st16(col + ((((size_t)n * oh + oy) * ow + xb + px) * 24 + g) * 8, pack8(f));
   }
 }
 
 int im2col_7x7s2(const float* img, bf16* col, int N, int H, int W, cudaStream_t st) {
   HGB_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "im2col: even image size required");
-  const int64_t total = (int64_t)N * (H / 2) * (W / 2) * 24;
-  if (total == 0) return HGB_OK;
-  launch_pdl(im2col_7x7s2_kernel, dim3(flat_blocks(total)), dim3(256), 0, st, img, col, total, H, W);
+  if (N == 0) return HGB_OK;
+  HGB_CHECK_ARG(N <= 65535 && H / 2 <= 65535, "im2col: batch / height exceed the grid limits");
+  launch_pdl(im2col_7x7s2_kernel, dim3(cdiv(W / 2, kStemPix), H / 2, N), dim3(256), 0, st, img, col, H, W);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
