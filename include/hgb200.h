@@ -164,6 +164,13 @@ int hgb_model_adam_step(hgb_model* m, double lr, double beta1, double beta2, dou
  * dims = {N,H,W,C_padded}, as a byte offset into the bound arena */
 int hgb_model_conv_output(const hgb_model* m, int index, int64_t* arena_offset, int dims[4]);
 
+/* Deferred BatchNorm: a BN whose output feeds only 1x1 convolutions is never written to memory; those convolutions
+ * (forward GEMM and weight gradient) normalise their operand tile in shared memory, bit-identically to the stand-alone
+ * pass.  Returns the index of the BN applied to the INPUT of conv `conv` inside the kernel (the conv's input tensor is
+ * then the pre-BN tensor), or -1.  Forward op info: flag & 0xffff = 1 + that BN index, flag & 0x10000 = this launch
+ * stores the saved statistics / moving averages; weight-gradient op info: bn = that BN index. */
+int hgb_model_conv_input_bn(const hgb_model* m, int conv);
+
 /* plan introspection and single-op stepping: lets a test replay EVERY op of the real execution plan
  * (forward and backward) against an fp32 reference computed from the device's own input tensors.
  * op info = {type, conv, bn, a0, a1, a2, a3, flag}; see csrc/model.cu (OpType) for the roles. */

@@ -57,6 +57,7 @@ PROTOTYPES = {
     "hgb_model_segment_grads": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i64)]),
     "hgb_model_adam_step": (i32, [vp, f64, f64, f64, f64, i64, f64, vp]),
     "hgb_model_conv_output": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i32 * 4)]),
+    "hgb_model_conv_input_bn": (i32, [vp, i32]),
     "hgb_model_num_ops": (i32, [vp, i32, i32]),
     "hgb_model_op_info": (i32, [vp, i32, i32, i32, C.POINTER(i32 * 8)]),
     "hgb_model_act_info": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i32 * 4)]),

@@ -30,8 +30,12 @@ __device__ long long g_ktime[32];
 
 constexpr int kBlockM = 128;
 constexpr int kABytes = kBlockM * 128;  // 128 pixels x 64 bf16
-constexpr int kThreads = 192;       // wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
-constexpr int kGemmThreads = 320;   // forward/dgrad kernel: TMA warp, MMA warp, 8 epilogue warps
+constexpr int kThreads = 192;       // 3x3 wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
+constexpr int kWgradThreads = 256;  // wgrad kernel: + 2 operand-transform warps (deferred BatchNorm)
+constexpr int kGemmThreads = 384;   // forward/dgrad kernel: TMA warp, MMA warp, 8 epilogue warps, 2 operand-transform warps
+constexpr int kXformThreads = 64;
+constexpr float kBnEpsIn = 1e-3f;       // Keras BatchNormalization defaults (as in layer_kernels.cu)
+constexpr float kBnMomentumIn = 0.99f;
 constexpr int kEpiThreads = 256;
 
 struct GemmKernelParams {
@@ -48,6 +52,7 @@ struct GemmKernelParams {
   float* stats;
   const __nv_bfloat16* bn_y;  // non-null: second statistic is sum(out * bn_y) (BatchNorm backward) instead of sum(out^2)
   int res1_tma;               // res1 is fetched by TMA (tmR) into the staging buffer
+  BnInput bn_in;              // gamma != null: normalise the A tile in shared memory before the MMAs read it
 };
 
 template <int OFF>
@@ -76,6 +81,65 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
   for (int i = 0; i < 4; ++i) {
     f[2 * i] = __uint_as_float(w[i] << 16);
     f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// scale / shift of a deferred BatchNorm into shared memory (same fp32 arithmetic as bn_apply_fwd_kernel, so the
+// normalised operand is bit-identical to what the stand-alone pass would have stored); `writer` stores the saved
+// statistics and moving averages.  Backward (sums == null): rebuilt from the saved (mean, rstd).
+__device__ __forceinline__ void bn_input_setup(const BnInput& b, float* s_sc, float* s_sh, int tid, int nthreads, bool writer) {
+  const float invM = 1.f / (float)b.M;
+  for (int c = tid; c < b.C; c += nthreads) {
+    float mean, rstd;
+    if (b.mode == 2) {   // weight gradient: saved statistics
+      mean = b.saved[c];
+      rstd = b.saved[b.C + c];
+    } else {
+      float var;
+      if (b.mode == 0) {
+        mean = b.sums[c] * invM;
+        var = fmaxf(b.sums[b.C + c] * invM - mean * mean, 0.f);
+      } else {
+        mean = b.moving_mean[c];
+        var = b.moving_var[c];
+      }
+      rstd = rsqrtf(var + kBnEpsIn);
+      if (b.mode == 0 && writer) {
+        b.saved[c] = mean;
+        b.saved[b.C + c] = rstd;
+        const float unbiased = b.M > 1 ? var * ((float)b.M / (float)(b.M - 1)) : var;
+        b.moving_mean[c] = b.moving_mean[c] * kBnMomentumIn + mean * (1.f - kBnMomentumIn);
+        b.moving_var[c] = b.moving_var[c] * kBnMomentumIn + unbiased * (1.f - kBnMomentumIn);
+      }
+    }
+    const float sc = b.gamma[c] * rstd;
+    s_sc[c] = sc;
+    s_sh[c] = b.beta[c] - mean * sc;
+  }
+}
+
+// z = bf16(y * sc + sh) on one 128-pixel x 64-channel swizzled box, in place, by the 64 transform threads.
+// Thread tw always meets the same logical 16-byte channel chunk (its position XOR its row phase are constant).
+__device__ __forceinline__ void bn_input_transform_box(uint32_t box, const float* s_sc, const float* s_sh, int ch0, int tw) {
+  const uint32_t c = (uint32_t)tw & 7u, r0 = (uint32_t)tw >> 3;          // chunk position, first row (0..7)
+  const int ch = ch0 + (int)((c ^ (r0 & 7u)) << 3);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = s_sc[ch + j]; sh[j] = s_sh[ch + j]; }
+#pragma unroll 4
+  for (int j = 0; j < 16; ++j) {
+    const uint32_t adr = box + (r0 + 8u * (uint32_t)j) * 128u + (c << 4);
+    uint4 u;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(adr));
+    float f[8];
+    unpack_bf16x8(u, f);
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k] * sc[2 * k] + sh[2 * k], f[2 * k + 1] * sc[2 * k + 1] + sh[2 * k + 1]);
+      w[k] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(adr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
   }
 }
 
@@ -109,7 +173,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   constexpr int kRingBytes = HALO ? kASlots * kABytes + kBSlots * kBBytes : STAGES * kStageBytes;
   // full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | residual
   // HALO: fullA[T+1] | emptyA[T+1] | fullB[6] | emptyB[6] | tmem_full[T] | tmem_empty[T] | residual
-  constexpr int kNumBars = HALO ? 2 * kASlots + 2 * kBSlots + 2 * TILES + 1 : 2 * STAGES + 5;
+  // (non-HALO) ... | ready[S]: operand tile normalised by the transform warps (deferred BatchNorm) | residual
+  constexpr int kNumBars = HALO ? 2 * kASlots + 2 * kBSlots + 2 * TILES + 1 : 3 * STAGES + 5;
   static_assert(!HALO || (TILES > 1 && TILES * BLOCK_N <= 512), "HALO needs one accumulator per tile");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -120,6 +185,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   uint8_t* tail = smem + kRingBytes + OUT_BUFS * kOutBytes + kNumBars * 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail);
   float* s_bias = reinterpret_cast<float*>(tail + 16);        // [BLOCK_N]
+  float* s_sc = s_bias + BLOCK_N;                             // [256] scale / [256] shift of a deferred input BatchNorm
+  float* s_sh = s_sc + 256;
   float* s_stats = reinterpret_cast<float*>(smem);            // [row groups][2*BLOCK_N] = 16 KB, aliases pipeline stage 0: used only after the last tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -143,7 +210,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       for (int s = 0; s < 2 * STAGES + 2; ++s) mbar_init(bar0 + 8 * s, 1);
       mbar_init(bar0 + 8 * (2 * STAGES + 2), 8);  // tmem_empty: one arrival per epilogue warp
       mbar_init(bar0 + 8 * (2 * STAGES + 3), 8);
-      mbar_init(bar0 + 8 * (2 * STAGES + 4), 1);  // residual tile landed in the staging buffer
+      for (int s = 0; s < STAGES; ++s) mbar_init(bar0 + 8 * (2 * STAGES + 4 + s), 2);  // ready: two transform warps
+      mbar_init(bar0 + 8 * (3 * STAGES + 4), 1);  // residual tile landed in the staging buffer
     }
     fence_barrier_init();
   }
@@ -154,12 +222,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   if (threadIdx.x == 0) KT(1);
   pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
   if (threadIdx.x == 0) KT(2);
+  const bool xform = !HALO && TILES == 1 && p.bn_in.gamma != nullptr;
+  if (xform) bn_input_setup(p.bn_in, s_sc, s_sh, threadIdx.x, kGemmThreads, blockIdx.x == 0 && p.bn_in.write != 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (threadIdx.x == 0) KT(3);
   // the bias is needed by the epilogue only: its (cold) load overlaps the first TMA loads instead of delaying them
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 10) {
     for (int i = threadIdx.x - 64; i < BLOCK_N; i += kEpiThreads) s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
     asm volatile("bar.sync 1, 256;" ::: "memory");
   }
@@ -168,6 +238,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   const uint32_t tfull0 = HALO ? bar0 + 8 * (2 * kASlots + 2 * kBSlots) : bar0 + 16 * STAGES;
   const uint32_t tempty0 = tfull0 + (HALO ? 8 * TILES : 16);
   const uint32_t resbar = bar0 + 8 * (kNumBars - 1);
+  const uint32_t ready0 = bar0 + 8 * (2 * STAGES + 4);   // non-HALO only
   // HALO barriers and buffers
   const uint32_t fullA = bar0, emptyA = bar0 + 8 * kASlots, fullB = bar0 + 16 * kASlots, emptyB = fullB + 8 * kBSlots;
   const uint32_t ringB = base + kASlots * kABytes;
@@ -282,7 +353,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         for (int kb = 0; kb < p.nkb; ++kb, ++kbt) {
           const int s = kbt % STAGES;
           const uint32_t ph = (kbt / STAGES) & 1;
-          mbar_wait(full0 + 8 * s, ph);
+          mbar_wait((xform ? ready0 : full0) + 8 * s, ph);
           tc_fence_after();
           if (kbt == 0) KT(4);
           const uint32_t sa = base + s * kStageBytes;
@@ -298,6 +369,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         }
         umma_commit(tfull0 + 8 * acc);
         if (lt == 0) KT(5);
+      }
+    }
+  } else if (warp >= 10) {
+    // ---------------- operand transform (deferred BatchNorm of the input): as soon as TMA has delivered the
+    // 128-pixel x 64-channel box of a stage, z = bf16(y * scale + shift) is applied in place; the MMA warp waits
+    // for `ready` instead of `full`.  Zero-filled rows past the end of the tensor become `shift`: they only reach
+    // accumulator rows that the store clips and the statistics skip.
+    if (xform) {
+      const int tw = threadIdx.x - 320;
+      int kbt = 0;
+      for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
+        for (int kb = 0; kb < p.nkb; ++kb, ++kbt) {
+          const int s = kbt % STAGES;
+          mbar_wait(full0 + 8 * s, (kbt / STAGES) & 1);
+          bn_input_transform_box(base + s * kStageBytes, s_sc, s_sh, (kb % p.cblk) * 64, tw);
+          fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's shared-memory reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ready0 + 8 * s);
+        }
       }
     }
   } else {
@@ -620,13 +710,14 @@ struct WgradKernelParams {
   int swap_lbo_sbo;  // debug knob
   int vec4;          // dw rows are 16-byte aligned: vector reductions allowed
   float* dw;
+  BnInput bn_in;     // gamma != null: x is normalised in shared memory (1x1 only)
 };
 
 // MT = 128-row output-channel tiles per CTA (1 or 2, one TMEM accumulator each).  The 1x1 convolutions of the
 // bottleneck are HBM-bound, so the CTA tile is made as wide as the layer -- <BLOCK_N 256, MT 1> for 256->128,
 // <128, 2> for 128->256 -- and every activation byte is fetched once instead of once per tile column/row.
 template <int BLOCK_N, int MT, int STAGES>
-__global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY,
+__global__ void __launch_bounds__(kWgradThreads) conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY,
                                                               const __grid_constant__ CUtensorMap tmX,
                                                               const WgradKernelParams p) {
   constexpr int kBBytes = (BLOCK_N / 64) * kABytes;
@@ -638,13 +729,16 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t bar0 = base + STAGES * kStageBytes;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * kStageBytes + (2 * STAGES + 1) * 8);
+  const uint32_t bar0 = base + STAGES * kStageBytes;   // full[S] | empty[S] | tmem_full | ready[S]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * kStageBytes + (3 * STAGES + 1) * 8);
+  float* s_sc = reinterpret_cast<float*>(tmem_slot + 4);   // [256] scale | [256] shift of a deferred input BatchNorm
+  float* s_sh = s_sc + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = blockIdx.x;
   const int tap = blockIdx.y / p.cin_tiles, cin_tile = blockIdx.y - tap * p.cin_tiles;
   const int cout_tile = blockIdx.z;   // in units of MT * 128 output channels
+  const bool xform = p.bn_in.gamma != nullptr;
   const int t_begin = split * p.tiles_per_split;
   int t_end = t_begin + p.tiles_per_split;
   if (t_end > p.M_tiles) t_end = p.M_tiles;
@@ -655,6 +749,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
     prefetch_tmap(&tmDY);
     prefetch_tmap(&tmX);
     for (int s = 0; s < 2 * STAGES + 1; ++s) mbar_init(bar0 + 8 * s, 1);
+    for (int s = 0; s < STAGES; ++s) mbar_init(bar0 + 8 * (2 * STAGES + 1 + s), 2);   // ready: two transform warps
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -662,11 +757,12 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
     tmem_relinquish();
   }
   pdl_wait();
+  if (xform) bn_input_setup(p.bn_in, s_sc, s_sh, threadIdx.x, kWgradThreads, false);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t full0 = bar0, empty0 = bar0 + 8 * STAGES, tfull = bar0 + 16 * STAGES;
+  const uint32_t full0 = bar0, empty0 = bar0 + 8 * STAGES, tfull = bar0 + 16 * STAGES, ready0 = tfull + 8;
 
   if (nkb > 0) {
     if (warp == 0) {
@@ -700,7 +796,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
         for (int kb = 0; kb < nkb; ++kb) {
           const int s = kb % STAGES;
           const uint32_t ph = (kb / STAGES) & 1;
-          mbar_wait(full0 + 8 * s, ph);
+          mbar_wait((xform ? ready0 : full0) + 8 * s, ph);
           tc_fence_after();
           const uint32_t sa = base + s * kStageBytes;
 #pragma unroll
@@ -715,6 +811,22 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
           umma_commit(empty0 + 8 * s);
         }
         umma_commit(tfull);
+      }
+    } else if (warp >= 6) {
+      // operand transform: x boxes of every stage are normalised in place (deferred BatchNorm of the conv input)
+      if (xform) {
+        const int tw = threadIdx.x - 192;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int s = kb % STAGES;
+          mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+          const uint32_t sx = base + s * kStageBytes + kDyBytes;
+#pragma unroll
+          for (int i = 0; i < BLOCK_N / 64; ++i)
+            bn_input_transform_box(sx + i * kABytes, s_sc, s_sh, cin_tile * BLOCK_N + i * 64, tw);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ready0 + 8 * s);
+        }
       }
     } else {
       const int q = warp & 3;
@@ -971,8 +1083,8 @@ template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                          const CUtensorMap& tmY, const GemmKernelParams& kp, int tiles_m, int max_ctas, cudaStream_t st) {
   constexpr int ring = HALO ? (TILES + 1) * kABytes + 6 * BLOCK_N * 128 : STAGES * (TILES * kABytes + BLOCK_N * 128);
-  constexpr int nbars = HALO ? 2 * (TILES + 1) + 12 + 2 * TILES + 1 : 2 * STAGES + 5;
-  constexpr int smem = ring + OUT_BUFS * (BLOCK_N / 64) * kABytes + nbars * 8 + 16 + BLOCK_N * 4 + 1024;
+  constexpr int nbars = HALO ? 2 * (TILES + 1) + 12 + 2 * TILES + 1 : 3 * STAGES + 5;
+  constexpr int smem = ring + OUT_BUFS * (BLOCK_N / 64) * kABytes + nbars * 8 + 16 + BLOCK_N * 4 + (TILES == 1 ? 2 * 256 * 4 : 0) + 1024;   // scale/shift only for the 1x1 variants
   static_assert(ring >= 16 * 1024, "stats scratch (16 KB) aliases the pipeline stages");
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
@@ -1013,6 +1125,9 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   kp.Cout = a.Cout; kp.ldc = a.ldc; kp.relu = a.relu;
   kp.bias = a.bias; kp.res1 = a.res1; kp.res2 = a.res2; kp.out = a.out; kp.stats = a.stats;
   kp.bn_y = a.bn_y;
+  kp.bn_in = a.bn_in;
+  HGB_CHECK_ARG(a.bn_in.gamma == nullptr || (a.ksize == 1 && a.bn_in.C == a.Cin && a.Cin <= 256),
+                "conv_gemm: an input BatchNorm needs a 1x1 convolution with Cin <= 256");
   kp.res1_tma = (a.res1 != nullptr && tmR != nullptr && !g_debug[3]) ? 1 : 0;
   const CUtensorMap& tmRr = kp.res1_tma ? *tmR : tmC;
   HGB_CHECK_ARG(a.bn_y == nullptr || tmY != nullptr, "conv_gemm: bn_y needs its tensor map");
@@ -1042,14 +1157,14 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
 
 template <int BLOCK_N, int MT, int STAGES>
 static int launch_wgrad_t(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradKernelParams& kp, dim3 grid, cudaStream_t st) {
-  constexpr int smem = STAGES * (2 * MT + BLOCK_N / 64) * kABytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr int smem = STAGES * (2 * MT + BLOCK_N / 64) * kABytes + (3 * STAGES + 1) * 8 + 16 + 2 * 256 * 4 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
     HGB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BLOCK_N, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
-  HGB_CUDA(launch_pdl(conv_wgrad_kernel<BLOCK_N, MT, STAGES>, grid, dim3(kThreads), smem, st, tmDY, tmX, kp));
+  HGB_CUDA(launch_pdl(conv_wgrad_kernel<BLOCK_N, MT, STAGES>, grid, dim3(kWgradThreads), smem, st, tmDY, tmX, kp));
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -1071,6 +1186,9 @@ int launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const Wgr
   kp.Cout = a.Cout_valid > 0 ? a.Cout_valid : a.Cout;
   kp.ldw = taps * kp.Cin_valid;
   kp.tap3 = a.ksize == 3;
+  kp.bn_in = a.bn_in;
+  HGB_CHECK_ARG(a.bn_in.gamma == nullptr || (a.ksize == 1 && a.bn_in.C == a.Cin && a.Cin <= 256),
+                "conv_wgrad: an input BatchNorm needs a 1x1 convolution with Cin <= 256");
   // CTA tile: the HBM-bound 1x1 layers take the widest tile that fits (every activation byte fetched once when the
   // whole layer is one tile); 3x3 layers keep 128 x 128 per tap.  Wide tiles need enough pixel tiles per CTA to
   // amortise their larger fp32 reduction epilogue.

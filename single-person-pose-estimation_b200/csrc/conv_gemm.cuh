@@ -16,6 +16,22 @@ int make_tmap_act(CUtensorMap* out, const void* ptr, int N, int H, int W, int C)
 // 2-D map over a row-major bf16 matrix [rows][cols]; box (64 cols, box_rows rows), 128-byte swizzle.
 int make_tmap_mat(CUtensorMap* out, const void* ptr, int rows, int cols, int box_rows);
 
+// BatchNorm applied to the INPUT operand inside the kernel (deferred BN: the normalised tensor is never stored).
+// Forward: statistics from `sums` (training) or the moving averages; `write` = this launch also stores the saved
+// (mean, rstd) pair and updates the moving averages, exactly like the stand-alone BN pass would.
+// Weight gradient: scale/shift are rebuilt from `saved`.
+struct BnInput {
+  const float* sums = nullptr;    // [2C] sum, sum of squares (forward, training)
+  const float* gamma = nullptr;   // non-null enables the transform
+  const float* beta = nullptr;
+  float* moving_mean = nullptr;
+  float* moving_var = nullptr;
+  float* saved = nullptr;         // [2C] mean, rstd
+  int mode = 0;                   // 0: batch statistics from sums (training forward), 1: moving averages (inference),
+                                  // 2: saved (mean, rstd) of the forward pass (weight gradient)
+  int write = 0, M = 0, C = 0;
+};
+
 struct ConvGemmArgs {
   int N, H, W, Cin, Cout;   // Cout = channels actually stored (multiple of 32)
   int ksize;                // 1 or 3
@@ -29,6 +45,7 @@ struct ConvGemmArgs {
   float* stats;             // [2*Cout] (sum, sumsq), added to; or null
   const __nv_bfloat16* bn_y; // non-null: stats = (sum out, sum out*bn_y) -- fused BatchNorm-backward reduction
   int max_ctas = 0;         // > 0: cap of the persistent grid (side lanes leave SMs to the main chain)
+  BnInput bn_in;            // 1x1 only
 };
 // tmA: activation map of the input; tmB: weight matrix [>=Cout rows][ksize^2*Cin], box rows = block_n
 int conv_gemm_block_n(int Cout);
@@ -43,6 +60,7 @@ struct WgradArgs {
   int ksize;
   int Cin_valid, Cout_valid; // 0 = all; otherwise only dw[:Cout_valid][tap][:Cin_valid] is written (padded tensors)
   float* dw;                // [Cout_valid][ksize^2*Cin_valid] fp32, added to
+  BnInput bn_in;            // 1x1 only: x is normalised in shared memory (saved statistics)
 };
 // tmDY: activation map of dy (C = Cout); tmX: activation map of x (C = Cin)
 int launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradArgs& a, cudaStream_t st);

@@ -27,6 +27,10 @@ struct Act {
   size_t off;  // bytes into the arena
   CUtensorMap tmap;
   bool has_tmap = false;
+  // Deferred BatchNorm: the BN output is never materialised.  `bn_of` >= 0 marks a virtual tensor = BN(bn_of)(acts[src]);
+  // its only consumers are 1x1 convolutions (forward GEMM and weight gradient), which normalise the operand tile in
+  // shared memory right after TMA delivers it (bit-identical to the stand-alone BN pass: same fp32 fma, same rounding).
+  int bn_of = -1, src = -1;
 };
 
 struct ConvL {
@@ -44,12 +48,13 @@ struct ConvL {
   CUtensorMap tm_wf, tm_wd;
   double flops;
   int seg;
-  int y_act = -1, in_act = -1, z_act = -1;
+  int y_act = -1, in_act = -1, z_act = -1, in_bn = -1;
 };
 
 struct BNL {
   std::string name;
   int c;
+  bool has_writer = false;   // deferred BN: one consumer (the first) stores saved statistics / moving averages
   int64_t gamma_off, beta_off, mm_off, mv_off;  // float offsets into the parameter buffer
   size_t sums_off, bsums_off, saved_off;        // byte offsets into the arena
 };
@@ -249,18 +254,28 @@ struct hgb_model {
 
   // conv (+ReLU) [+ BN] -> returns the tensor the next layer consumes; y/z report both stages
   int conv_unit(const std::string& name, int in_act, int real_k, int real_cin, int cout, int relu, bool bn, bool need_dgrad,
-                int bn_res, int* conv_idx, int* bn_idx, int* y_act, int res1 = -1, int res2 = -1) {
+                int bn_res, int* conv_idx, int* bn_idx, int* y_act, int res1 = -1, int res2 = -1, bool defer_bn = false) {
     const int ci = add_conv(name, in_act, real_k, real_cin, cout, relu, need_dgrad);
     const Act in = acts[in_act];
     const int y = new_act(in.n, in.h, in.w, convs[ci].cout_pad);
     Op o;
-    o.type = F_CONV; o.conv = ci; o.a0 = in_act; o.a1 = y; o.a2 = res1; o.a3 = res2; o.flag = bn ? 1 : 0;
+    // flag = 1 + index of the BatchNorm applied to the INPUT tile inside the kernel (0 = none); a0 = its source tensor
+    o.type = F_CONV; o.conv = ci; o.a0 = in.bn_of >= 0 ? in.src : in_act; o.a1 = y; o.a2 = res1; o.a3 = res2;
+    o.flag = in.bn_of >= 0 ? 1 + in.bn_of : 0;
+    if (in.bn_of >= 0 && !bns[in.bn_of].has_writer) { o.flag |= 0x10000; bns[in.bn_of].has_writer = true; }
     int bi = -1, out = y;
     if (bn) { bi = add_bn(cout); o.bn = bi; }
     emit_f(o);
     convs[ci].y_act = y;
-    convs[ci].in_act = in_act;
-    if (bn) {
+    convs[ci].in_act = in.bn_of >= 0 ? in.src : in_act;
+    convs[ci].in_bn = in.bn_of;
+    if (bn && defer_bn && !hgb::g_debug[14]) {
+      Act v;   // virtual: dims only
+      v.n = in.n; v.h = in.h; v.w = in.w; v.c = cout; v.off = 0; v.bn_of = bi; v.src = y;
+      acts.push_back(v);
+      out = (int)acts.size() - 1;
+      convs[ci].z_act = -1;
+    } else if (bn) {
       out = new_act(in.n, in.h, in.w, cout);
       Op b;
       b.type = F_BN; b.bn = bi; b.a0 = y; b.a1 = bn_res; b.a2 = out;
@@ -285,7 +300,8 @@ struct hgb_model {
       r.s_act = skip;
     }
     r.z1 = conv_unit(name + "_conv_1x1_1", x, 1, cin, cout / 2, 1, true, true, -1, &r.c1, &r.bn1, &r.y1);
-    r.z2 = conv_unit(name + "_conv_3x3_2", r.z1, 3, cout / 2, cout / 2, 1, true, true, -1, &r.c2, &r.bn2, &r.y2);
+    r.z2 = conv_unit(name + "_conv_3x3_2", r.z1, 3, cout / 2, cout / 2, 1, true, true, -1, &r.c2, &r.bn2, &r.y2, -1, -1,
+                     /*defer_bn=*/true);   // only consumer: the 1x1 conv_1x1_3
     r.out = conv_unit(name + "_conv_1x1_3", r.z2, 1, cout / 2, cout, 1, true, true, skip, &r.c3, &r.bn3, &r.y3);
     return r;
   }
@@ -317,11 +333,18 @@ struct hgb_model {
     o = Op(); o.type = B_BN_APPLY; o.bn = bn; o.conv = conv; o.a0 = dz; o.a1 = y; o.a2 = dp; emit_b(o);
     // the dgrad continues the chain; the weight gradient is a leaf of the backward graph (side lane)
     const bool wfirst = hgb::g_debug[10] != 0;
-    if (wfirst) { o = Op(); o.type = B_WGRAD; o.conv = conv; o.a0 = dp; o.a1 = x_in; o.lane = leaf_lane(); emit_b(o); }
+    if (wfirst) emit_wgrad(conv, dp, x_in);
     if (dgrad_out >= 0) {
       o = Op(); o.type = B_DGRAD; o.conv = conv; o.a0 = dp; o.a1 = dgrad_out; o.a2 = res1; o.a3 = res2; emit_b(o);
     }
-    if (!wfirst) { o = Op(); o.type = B_WGRAD; o.conv = conv; o.a0 = dp; o.a1 = x_in; o.lane = leaf_lane(); emit_b(o); }
+    if (!wfirst) emit_wgrad(conv, dp, x_in);
+  }
+  // weight gradient: a virtual (deferred-BN) input is read from its source tensor and normalised inside the kernel
+  void emit_wgrad(int conv, int dp, int x_in) {
+    Op o;
+    const Act& x = acts[x_in];
+    o.type = B_WGRAD; o.conv = conv; o.a0 = dp; o.a1 = x.bn_of >= 0 ? x.src : x_in; o.bn = x.bn_of; o.lane = leaf_lane();
+    emit_b(o);
   }
   // g_out: gradient wrt the block output (read; masked in place when the skip is a conv);
   // g_x: gradient wrt the block input (written); extra: one more tensor summed into g_x.
@@ -345,7 +368,7 @@ struct hgb_model {
         m = Op(); m.type = B_DGRAD; m.conv = r.skip_conv; m.a0 = g_out; m.a1 = g_x; m.a2 = extra; emit_b(m);
         m = Op(); m.type = B_DGRAD; m.conv = r.c1; m.a0 = dpm1; m.a1 = g_x; m.a2 = g_x; emit_b(m);
       }
-      m = Op(); m.type = B_WGRAD; m.conv = r.skip_conv; m.a0 = g_out; m.a1 = r.x; m.lane = leaf_lane(); emit_b(m);
+      emit_wgrad(r.skip_conv, g_out, r.x);
     } else {
       bn_conv_bwd(r.bn1, r.c1, dzm, r.y1, dpm1, r.x, g_x, g_out, extra);
     }
@@ -356,7 +379,7 @@ struct hgb_model {
       o.type = B_DGRAD; o.conv = conv; o.a0 = dp; o.a1 = dgrad_out; o.a2 = res1; emit_b(o);
     }
     o = Op(); o.type = B_COLSUM; o.conv = conv; o.a0 = dp; o.lane = leaf_lane(); emit_b(o);
-    o = Op(); o.type = B_WGRAD; o.conv = conv; o.a0 = dp; o.a1 = x_in; o.lane = leaf_lane(); emit_b(o);
+    emit_wgrad(conv, dp, x_in);
   }
 };
 
@@ -418,7 +441,8 @@ int build(hgb_model* m) {
       cur = r.merged[u].out;
     }
     // create_heads
-    r.z_h = m->conv_unit(hg + "_conv_1x1_1", cur, 1, C, C, 1, true, true, -1, &r.conv_h, &r.bn_h, &r.y_h);
+    r.z_h = m->conv_unit(hg + "_conv_1x1_1", cur, 1, C, C, 1, true, true, -1, &r.conv_h, &r.bn_h, &r.y_h, -1, -1,
+                         /*defer_bn=*/true);   // consumers: conv_1x1_predict and conv_1x1_2, both 1x1
     r.logits = m->conv_unit(hg + "_conv_1x1_predict", r.z_h, 1, C, cfg.num_classes, 0, false, true, -1, &r.conv_p, nullptr, nullptr);
     const Act la = m->acts[r.logits];
     r.pbf = m->new_act(la.n, la.h, la.w, 64);
@@ -606,6 +630,11 @@ void op_access(const hgb_model* m, const Op& o, std::vector<Range>& r, std::vect
     case F_CONV:
       add_act(m, r, o.a0); add_act(m, r, o.a2); add_act(m, r, o.a3); add_act(m, w, o.a1);
       if (o.bn >= 0) add_arena(w, m->bns[o.bn].sums_off, 2 * (size_t)m->bns[o.bn].c * 4);
+      if (o.flag & 0xffff) {
+        const BNL& b = m->bns[(o.flag & 0xffff) - 1];
+        add_arena(r, b.sums_off, 2 * (size_t)b.c * 4);
+        if (o.flag & 0x10000) add_arena(w, b.saved_off, 2 * (size_t)b.c * 4);
+      }
       break;
     case F_BN:
       add_act(m, r, o.a0); add_act(m, r, o.a1); add_act(m, w, o.a2);
@@ -631,6 +660,7 @@ void op_access(const hgb_model* m, const Op& o, std::vector<Range>& r, std::vect
     case B_WGRAD: {
       const ConvL& c = m->convs[o.conv];
       add_act(m, r, o.a0); add_act(m, r, o.a1);
+      if (o.bn >= 0) add_arena(r, m->bns[o.bn].saved_off, 2 * (size_t)m->bns[o.bn].c * 4);
       add_grad(w, c.w_off, (int64_t)c.cout * c.taps * c.cin);
       break;
     }
@@ -717,7 +747,7 @@ inline float* arena_f(const hgb_model* m, size_t off) { return reinterpret_cast<
 int build_maps(hgb_model* m) {
   for (auto& a : m->acts) {
     a.has_tmap = false;
-    if (a.c % 64 != 0 || a.w > 128) continue;
+    if (a.bn_of >= 0 || a.c % 64 != 0 || a.w > 128) continue;   // virtual (deferred-BN) tensors own no memory
     int rc = make_tmap_act(&a.tmap, m->p_arena + a.off, a.n, a.h, a.w, a.c);
     if (rc) return rc;
     a.has_tmap = true;
@@ -791,6 +821,14 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
       a.stats = (o.bn >= 0 && training) ? arena_f(m, m->bns[o.bn].sums_off) : nullptr;
       a.bn_y = nullptr;
       a.max_ctas = side_lane_ctas(m, o);
+      if (o.flag & 0xffff) {   // deferred BatchNorm of the input, applied to the operand tile inside the kernel
+        const BNL& b = m->bns[(o.flag & 0xffff) - 1];
+        a.bn_in.sums = arena_f(m, b.sums_off); a.bn_in.saved = arena_f(m, b.saved_off);
+        a.bn_in.gamma = m->p_params + b.gamma_off; a.bn_in.beta = m->p_params + b.beta_off;
+        a.bn_in.moving_mean = m->p_params + b.mm_off; a.bn_in.moving_var = m->p_params + b.mv_off;
+        a.bn_in.mode = training ? 0 : 1; a.bn_in.write = (o.flag & 0x10000) ? 1 : 0;
+        a.bn_in.M = in.n * in.h * in.w; a.bn_in.C = b.c;
+      }
       rc = launch_conv_gemm(in.tmap, c.tm_wf, out.tmap, o.a2 >= 0 ? &m->acts[o.a2].tmap : nullptr, nullptr, a, st);
       break;
     }
@@ -841,6 +879,12 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
       a.N = x.n; a.H = x.h; a.W = x.w; a.Cin = c.cin_pad; a.Cout = c.cout_pad; a.ksize = c.ksize;
       a.Cin_valid = c.cin; a.Cout_valid = c.cout;
       a.dw = m->p_grads + c.w_off;
+      if (o.bn >= 0) {   // x = BatchNorm(o.bn)(source tensor), rebuilt from the saved statistics
+        const BNL& b = m->bns[o.bn];
+        a.bn_in.saved = arena_f(m, b.saved_off);
+        a.bn_in.gamma = m->p_params + b.gamma_off; a.bn_in.beta = m->p_params + b.beta_off;
+        a.bn_in.mode = 2; a.bn_in.M = x.n * x.h * x.w; a.bn_in.C = b.c;
+      }
       rc = launch_conv_wgrad(dp.tmap, x.tmap, a, st);
       break;
     }
@@ -1163,6 +1207,13 @@ extern "C" int hgb_model_conv_output(const hgb_model* m, int index, int64_t* are
   if (arena_offset) *arena_offset = (int64_t)a.off;
   if (dims) { dims[0] = a.n; dims[1] = a.h; dims[2] = a.w; dims[3] = a.c; }
   return HGB_OK;
+}
+
+// deferred BatchNorm: index of the BN the conv applies to its INPUT tile inside the kernel (its input tensor, as
+// reported by hgb_model_conv_output / op info, is then the PRE-BN tensor), or -1
+extern "C" int hgb_model_conv_input_bn(const hgb_model* m, int conv) {
+  if (conv < 0 || conv >= (int)m->convs.size()) return -1;
+  return m->convs[conv].in_bn;
 }
 
 // ---- plan introspection / single-op stepping (tests replay every op against fp32 torch)

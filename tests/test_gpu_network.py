@@ -275,6 +275,7 @@ def test_every_layer_in_isolation(hgb, torch):
         return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
 
     worst_conv, worst_bn = ("", 0.0), ("", 0.0)
+    n_deferred = 0
     for i, c in enumerate(model.conv_table()):
         name = c["name"]
         y = fetch(i, 0)[..., :c["cout"]]
@@ -288,6 +289,15 @@ def test_every_layer_in_isolation(hgb, torch):
             if linear and not name.endswith("_predict"):
                 continue    # re-injection convs carry fused residuals; covered by the end-to-end gate
             x = fetch(i, 1)[..., :c["cin"]]
+            ib = lib.hgb_model_conv_input_bn(plan.handle, i)
+            if ib >= 0:   # deferred BatchNorm: the kernel normalises this (pre-BN) tensor tile by tile before the MMAs
+                bname = "batch_normalization" + (f"_{ib}" if ib else "")
+                g_ = torch.as_tensor(weights[bname + "/gamma"], device="cuda")
+                b_ = torch.as_tensor(weights[bname + "/beta"], device="cuda")
+                mean_ = x.mean(dim=(0, 1, 2))
+                var_ = x.var(dim=(0, 1, 2), unbiased=False)
+                x = ((x - mean_) / torch.sqrt(var_ + 1e-3) * g_ + b_).to(torch.bfloat16).float()
+                n_deferred += 1
             w = torch.as_tensor(weights[name + "/kernel"], device="cuda").to(torch.bfloat16).float().permute(3, 2, 0, 1)
             r = F.conv2d(x.permute(0, 3, 1, 2), w, torch.as_tensor(weights[name + "/bias"], device="cuda"), padding=c["k"] // 2)
             r = r.permute(0, 2, 3, 1)
@@ -313,3 +323,4 @@ def test_every_layer_in_isolation(hgb, torch):
     print("worst isolated conv error:", worst_conv, " worst isolated BN error:", worst_bn)
     assert worst_conv[1] <= 1e-2
     assert worst_bn[1] <= 1e-2
+    assert n_deferred >= 20      # conv_1x1_3 of every bottleneck and the prediction conv read a deferred BatchNorm

@@ -117,6 +117,7 @@ def test_replay_every_op(request):
     torch.cuda.synchronize()
     bf = torch.bfloat16
 
+    deferred, writers = [0], [0]
     # ------------------------------------------------------------------ forward
     for seg in range(S + 1):
         for i, (ty, ci, bi, a0, a1, a2, a3, flag) in R.ops(seg, 0):
@@ -132,8 +133,30 @@ def test_replay_every_op(request):
                 bnd = R.bn(bi) if bi >= 0 else None
                 s0 = R.arena_f32(bnd["sums"], 2 * bnd["c"]).clone() if bnd else None
                 x = R.act(a0).float()[..., :c["cin"]]
+                in_bn = (flag & 0xffff) - 1          # deferred BatchNorm applied to the input tile inside the kernel
+                if in_bn >= 0:
+                    ib = R.bn(in_bn)
+                    Ci = ib["c"]
+                    mean_i = x.mean(dim=(0, 1, 2))
+                    var_i = x.var(dim=(0, 1, 2), unbiased=False)
+                    gi, bei = R.params[ib["gamma"]:ib["gamma"] + Ci], R.params[ib["beta"]:ib["beta"] + Ci]
+                    mm0 = R.params[ib["mm"]:ib["mm"] + Ci].clone()
+                    mv0 = R.params[ib["mv"]:ib["mv"] + Ci].clone()
+                    M_i = x.numel() // Ci
+                    x = ((x - mean_i) / torch.sqrt(var_i + 1e-3) * gi + bei).to(bf).float()   # what the MMAs must read
+                    deferred[0] += 1
                 res = sum(R.act(a).float().clone() for a in (a2, a3) if a >= 0) if (a2 >= 0 or a3 >= 0) else None
                 R.run(seg, 0, i)
+                if in_bn >= 0 and (flag & 0x10000):   # this launch also stores what the stand-alone BN pass would
+                    saved = R.arena_f32(ib["saved"], 2 * Ci)
+                    torch.testing.assert_close(saved[:Ci], mean_i, rtol=1e-3, atol=1e-4)
+                    torch.testing.assert_close(saved[Ci:], torch.rsqrt(var_i + 1e-3), rtol=2e-3, atol=1e-4)
+                    torch.testing.assert_close(R.params[ib["mm"]:ib["mm"] + Ci], 0.99 * mm0 + 0.01 * mean_i, rtol=1e-4, atol=1e-5)
+                    torch.testing.assert_close(R.params[ib["mv"]:ib["mv"] + Ci], 0.99 * mv0 + 0.01 * var_i * M_i / (M_i - 1),
+                                               rtol=1e-3, atol=1e-5)
+                    writers[0] += 1
+                elif in_bn >= 0:
+                    torch.testing.assert_close(R.params[ib["mm"]:ib["mm"] + Ci], mm0, rtol=0, atol=0)   # written once only
                 y = R.act(a1).float()
                 bias = R.params[c["b_off"]:c["b_off"] + c["cout"]]
                 ref = F.conv2d(x.permute(0, 3, 1, 2), R.weight_oihw(c), bias, padding=c["ksize"] // 2).permute(0, 2, 3, 1)
@@ -240,6 +263,13 @@ def test_replay_every_op(request):
                 R.run(seg, 1, i)
                 dp = R.act(a0).float()[..., :c["cout"]]
                 x = R.act(a1).float()[..., :c["cin"]]
+                if bi >= 0:      # deferred BatchNorm: the kernel normalises x in shared memory from the saved statistics
+                    ib = R.bn(bi)
+                    Ci = ib["c"]
+                    saved = R.arena_f32(ib["saved"], 2 * Ci)
+                    gi, bei = R.params[ib["gamma"]:ib["gamma"] + Ci], R.params[ib["beta"]:ib["beta"] + Ci]
+                    x = ((x - saved[:Ci]) * saved[Ci:] * gi + bei).to(bf).float()
+                    deferred[0] += 1
                 w = torch.zeros((c["cout"], c["cin"], c["ksize"], c["ksize"]), device="cuda", requires_grad=True)
                 F.conv2d(x.permute(0, 3, 1, 2), w, padding=c["ksize"] // 2).backward(dp.permute(0, 3, 1, 2))
                 ref = w.grad.permute(0, 2, 3, 1).reshape(-1)
@@ -319,6 +349,8 @@ def test_replay_every_op(request):
     print("worst relative error per op type:", {k: round(v, 5) for k, v in R.worst.items()},
           "fused BN-backward reductions checked:", fused_reduces[0])
     assert fused_reduces[0] > 20
+    print("convolutions / weight gradients with a deferred input BatchNorm:", deferred[0], "statistic writers:", writers[0])
+    assert deferred[0] > 50 and writers[0] > 20
 
     # the stepped run and one whole training step see the same loss (gradients are not compared end to
     # end: fp32 atomics ordering differs between two runs and a random-init hourglass in training mode
