@@ -10,8 +10,10 @@ One JSON line on stdout (rank 0).  `value` = images/s with inputs resident in HB
 events, max over ranks; `e2e` = images/s through the public Python API with pinned host buffers
 (H2D of images + keypoints, device-side target rendering, D2H of the losses) inside the timed region;
 `roofline` = the dominant kernel (3x3 128->128 convolution at 64x64, 43.8 % of the FLOPs) timed live
-with CUDA event pairs inside the step; `cpu_baseline` = the fp32 CPU restatement of the reference
-(oracle/network_oracle.py; TensorFlow cannot be installed here) on a bounded sample.
+with CUDA event pairs inside the step; `heatmap_kernels` = achieved HBM GB/s of target rendering, weighted-MSE
+loss+gradient and v2 decode (BASELINE config 5 point: 64x64x17, batch 1024; full sweep: tools_heatmap_bench.py);
+`cpu_baseline` = the fp32 CPU restatement of the reference (oracle/network_oracle.py; TensorFlow cannot be
+installed here) on a bounded sample.
 """
 import argparse
 import json
@@ -246,12 +248,23 @@ def run_ours(args):
                 "d2h_bytes_per_step": d2h, "api": "HourglassModel.train_on_keypoints(pinned images, kps_x, kps_y, kps_v)"},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel<128,3> forward 3x3 128->128 @64x64",
+        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel<128,1,4,1,HALO> forward 3x3 128->128 @64x64",
                      "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": (ach / peak_tf) if ach else None,
                      "traffic": traffic, "launches_timed": pn.value, "avg_launch_ms": pm.value / max(pn.value, 1),
                      "peak_source": peak_src},
         "model_flops_utilization": 3 * FWD_GFLOP_PER_IMG * args.stacks / STACKS * value / 1e3 / world / peak_tf,
     }
+    if world == 1:
+        try:     # BASELINE.json metric: "decode GB/s" (+ the other heat-map kernels), algorithmic bytes / CUDA-event time
+            import tools_heatmap_bench
+            peak_bw = float(peaks.get("hbm_gbs", 6500.0))
+            line["heatmap_kernels"] = {
+                "shape": "64x64x17, batch 1024, inputs evicted from L2 between launches",
+                "peak_gbps": peak_bw,
+                "kernels": {k: {"us": round(t * 1e6, 1), "gbps": round(by / t / 1e9, 1), "frac": round(by / t / 1e9 / peak_bw, 3)}
+                            for k, _h, _b, t, by in tools_heatmap_bench.sweep(batches=(1024,), sizes=(64,), iters=5)}}
+        except Exception as ex:   # the sweep is auxiliary: never lose the headline line over it
+            line["heatmap_kernels"] = {"error": f"{type(ex).__name__}: {ex}"}
     if world == 1 and not args.no_cpu_baseline:
         ips, threads, sec = cpu_train_steps(args.stacks, args.cpu_batch, 2, 1)
         line["cpu_baseline"] = {"value": ips, "unit": "img/s", "cores": threads, "kind": "port",

@@ -324,30 +324,60 @@ __global__ void decode_kernel(const T* __restrict__ hm, int H, int W, int K, dou
 
   float bv[VEC];
   int bi[VEC];
-#pragma unroll
-  for (int j = 0; j < VEC; ++j) { bv[j] = -CUDART_INF_F; bi[j] = 0x7fffffff; }
-
   constexpr int UNROLL = 4;
+  // Fast path: a thread meets the elements of a slot in increasing index order, so "first maximum" is a strict
+  // greater-than update (3-4 instructions per element).  It is exact unless a NaN shows up after a slot's first
+  // element (numpy: a NaN beats everything); any NaN re-runs the sample through the exact comparison below.
+  int nan_seen = 0;
   int v = t < S ? t : nvec;  // the padding threads of the last warp only help in the reduction
+  if (v < nvec) {            // slot initialisation from the thread's first vector (argmax of all -inf is index 0)
+    float r[VEC];
+    DecLoad<T, VEC>::load(base + (size_t)v * VEC, r);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { bv[j] = r[j]; bi[j] = v * VEC + j; nan_seen |= (r[j] != r[j]); }
+    v += S;
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { bv[j] = -CUDART_INF_F; bi[j] = 0x7fffffff; }
+  }
   for (; v + (UNROLL - 1) * S < nvec; v += UNROLL * S) {
     float r[UNROLL][VEC];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) DecLoad<T, VEC>::load(base + (size_t)(v + u * S) * VEC, r[u]);
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u)
+    for (int u = 0; u < UNROLL; ++u) {
+      const int e0 = (v + u * S) * VEC;
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        const int e = (v + u * S) * VEC + j;
-        if (better(r[u][j], e, bv[j], bi[j])) { bv[j] = r[u][j]; bi[j] = e; }
+        const bool gt = r[u][j] > bv[j];
+        bv[j] = gt ? r[u][j] : bv[j];
+        bi[j] = gt ? e0 + j : bi[j];
+        nan_seen |= (r[u][j] != r[u][j]);
       }
+    }
   }
   for (; v < nvec; v += S) {
     float r[VEC];
     DecLoad<T, VEC>::load(base + (size_t)v * VEC, r);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      const int e = v * VEC + j;
-      if (better(r[j], e, bv[j], bi[j])) { bv[j] = r[j]; bi[j] = e; }
+      const bool gt = r[j] > bv[j];
+      bv[j] = gt ? r[j] : bv[j];
+      bi[j] = gt ? v * VEC + j : bi[j];
+      nan_seen |= (r[j] != r[j]);
+    }
+  }
+  if (__syncthreads_or(nan_seen)) {   // block-uniform: exact numpy order (NaN first, then value, then lower index)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { bv[j] = -CUDART_INF_F; bi[j] = 0x7fffffff; }
+    for (v = t < S ? t : nvec; v < nvec; v += S) {
+      float r[VEC];
+      DecLoad<T, VEC>::load(base + (size_t)v * VEC, r);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int e = v * VEC + j;
+        if (better(r[j], e, bv[j], bi[j])) { bv[j] = r[j]; bi[j] = e; }
+      }
     }
   }
   if (t < S) {
