@@ -1144,7 +1144,10 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   const bool ws = kp.tap3 && !g_debug[5] && tiles_m >= 8 * g_num_sms;
   // strip reuse across the vertical taps: groups of 4 tiles inside one image, at least two image rows per tile
   const int rpt = kBlockM / a.W;
-  const bool halo = ws && !g_debug[12] && a.W <= 64 && rpt >= 2 && a.H % (4 * rpt) == 0 && a.Cout == 128;
+  // (HALO pays off as soon as there is one 4-tile group per SM; g_debug[15] overrides the tile threshold)
+  const int halo_min = g_debug[15] > 0 ? g_debug[15] : 4 * g_num_sms;
+  const bool halo = kp.tap3 && !g_debug[5] && tiles_m >= halo_min && !g_debug[12] && a.W <= 64 && rpt >= 2 &&
+                    a.H % (4 * rpt) == 0 && a.Cout == 128;
   if (halo) return launch_gemm_t<128, 1, 4, 1, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
   switch (conv_gemm_block_n(a.Cout)) {
     case 64: return ws ? launch_gemm_t<64, 2, 4, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
