@@ -347,8 +347,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x, ++lt) {
         const int acc = lt % kAccStages;
         const uint32_t aph = (lt / kAccStages) & 1;
+        if (lt == 3 || lt == 4) KT(23 + (lt - 3) * 3);
         mbar_wait(tempty0 + 8 * acc, aph ^ 1);  // the epilogue has drained this accumulator stage
         tc_fence_after();
+        if (lt == 3 || lt == 4) KT(24 + (lt - 3) * 3);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TILES * BLOCK_N);
         for (int kb = 0; kb < p.nkb; ++kb, ++kbt) {
           const int s = kbt % STAGES;
@@ -369,6 +371,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         }
         umma_commit(tfull0 + 8 * acc);
         if (lt == 0) KT(5);
+        if (lt == 3 || lt == 4) KT(25 + (lt - 3) * 3);
       }
     }
   } else if (warp >= 10) {
@@ -459,9 +462,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             if (g * 64 < p.Cout) tma_load_4d(out0 + (uint32_t)g * kABytes, &tmR, resbar, g * 64, 0, y0, n0);
         }
       }
+      if (et == 0 && (nt == 4 || nt == 5)) KT(13 + (nt - 4) * 5);
       mbar_wait(tfull0 + 8 * (HALO ? t : acc), aph);
       tc_fence_after();
       if (et == 0 && nt == 1) KT(6);
+      if (et == 0 && (nt == 4 || nt == 5)) KT(14 + (nt - 4) * 5);
       if (p.res1_tma) { mbar_wait(resbar, rt & 1); ++rt; }
       // one 32-column chunk of this thread's row: bias / ReLU / residuals -> bf16 -> swizzled staging box
       auto stage_chunk = [&](const uint32_t (&v)[32], int g) {
@@ -577,6 +582,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       fence_proxy_async();                            // generic-proxy smem writes -> visible to the TMA engine
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps: tile fully staged
       if (et == 0 && nt == 1) KT(7);
+      if (et == 0 && (nt == 4 || nt == 5)) KT(15 + (nt - 4) * 5);
       if (et == 0) {
         const int n0 = p0 / p.HW;
         const int y0 = (p0 - n0 * p.HW) / p.W;
@@ -584,6 +590,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
           if (g * 64 < p.Cout) tma_store_4d(&tmC, out0 + (uint32_t)g * kABytes, g * 64, 0, y0, n0);
         tma_store_commit();
         if (nt == 1) KT(8);
+        if (nt == 4 || nt == 5) KT(16 + (nt - 4) * 5);
       }
       if (p.stats && sch * 8 < p.Cout) {
         // per-channel sums of the values as stored (bf16), read back from the staged tile with one 16-byte
@@ -654,6 +661,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
           }
         }
       }
+      if (et == 0 && (nt == 4 || nt == 5)) KT(17 + (nt - 4) * 5);
       }  // tiles of the group
     }
     if (et == 0) KT(9);
@@ -1218,8 +1226,8 @@ int launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const Wgr
     return HGB_OK;
   }
   int bn = (a.Cin % 128 == 0) ? 128 : 64, mt = 1;
-  if (a.ksize == 1 && !g_debug[11] && kp.M_tiles >= 8 * 148) {
-    if (a.Cin % 256 == 0 && a.Cout <= 128) bn = 256;
+  if (a.ksize == 1 && g_debug[11] != 1 && kp.M_tiles >= 8 * 148) {
+    if (a.Cin % 256 == 0 && (a.Cout <= 128 || g_debug[11] == 2)) bn = 256;
     else if (a.Cout % 256 == 0 && a.Cin == 128) mt = 2;   // (256 -> 256 measured slower with wide tiles: two stages only)
   }
   kp.cin_tiles = a.Cin / bn;
