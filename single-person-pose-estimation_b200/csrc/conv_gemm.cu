@@ -53,6 +53,7 @@ struct GemmKernelParams {
   const __nv_bfloat16* bn_y;  // non-null: second statistic is sum(out * bn_y) (BatchNorm backward) instead of sum(out^2)
   int res1_tma;               // res1 is fetched by TMA (tmR) into the staging buffer
   BnInput bn_in;              // gamma != null: normalise the A tile in shared memory before the MMAs read it
+  int single_store;           // debug: one thread issues all output boxes (hgb_debug_set(16, 1))
 };
 
 template <int OFF>
@@ -400,6 +401,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     const int hsel = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;                 // 0..255
+    // lane 0 of epilogue warps 0, 2, 4, 6 issues (and tracks) the bulk store of output box 0, 1, 2, 3
+    const int store_box = p.single_store ? (et == 0 ? 0 : -1)
+                        : (lane == 0 && ((warp - 2) & 1) == 0 && ((warp - 2) >> 1) < BLOCK_N / 64) ? ((warp - 2) >> 1) : -1;
     // BN statistics: thread -> (16-byte chunk = 8 channels, group of kRowsPer pixel rows) of the staged tile
     constexpr int kChunks = BLOCK_N / 8;
     constexpr int kRowsPer = kBlockM / (kEpiThreads / kChunks);   // 16 / 8 / 4 rows for N = 256 / 128 / 64
@@ -427,7 +431,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       // the bulk store issued two tiles ago must be done reading this staging buffer (the previous tile's
       // store may still be draining from the other one); then the residual tile (if any) is fetched into
       // it while this tile's MMAs may still be running
-      if (et == 0) { if (OUT_BUFS == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
+      // (box g of every tile is stored by lane 0 of epilogue warp 2g, which also owns that bulk group: one thread
+      // issuing all boxes delayed its whole warp -- and with it the tile -- by 0.35 us at N = 256)
+      if (store_box >= 0) { if (OUT_BUFS == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (p.bn_y && et == 32) {
         // BatchNorm-backward statistics stream y from global memory: pull the NEXT tile's boxes into L2 now
@@ -583,14 +589,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps: tile fully staged
       if (et == 0 && nt == 1) KT(7);
       if (et == 0 && (nt == 4 || nt == 5)) KT(15 + (nt - 4) * 5);
-      if (et == 0) {
+      if (store_box >= 0) {
         const int n0 = p0 / p.HW;
         const int y0 = (p0 - n0 * p.HW) / p.W;
-        for (int g = 0; g < BLOCK_N / 64; ++g)
-          if (g * 64 < p.Cout) tma_store_4d(&tmC, out0 + (uint32_t)g * kABytes, g * 64, 0, y0, n0);
+        if (p.single_store) {
+          for (int g = 0; g < BLOCK_N / 64; ++g)
+            if (g * 64 < p.Cout) tma_store_4d(&tmC, out0 + (uint32_t)g * kABytes, g * 64, 0, y0, n0);
+        } else if (store_box * 64 < p.Cout) {
+          tma_store_4d(&tmC, out0 + (uint32_t)store_box * kABytes, store_box * 64, 0, y0, n0);
+        }
         tma_store_commit();
-        if (nt == 1) KT(8);
-        if (nt == 4 || nt == 5) KT(16 + (nt - 4) * 5);
+        if (et == 0 && nt == 1) KT(8);
+        if (et == 0 && (nt == 4 || nt == 5)) KT(16 + (nt - 4) * 5);
       }
       if (p.stats && sch * 8 < p.Cout) {
         // per-channel sums of the values as stored (bf16), read back from the staged tile with one 16-byte
@@ -665,7 +675,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       }  // tiles of the group
     }
     if (et == 0) KT(9);
-    if (et == 0) tma_store_wait_read();               // smem must stay valid until the last bulk store has read it
+    if (store_box >= 0) tma_store_wait_read();        // smem must stay valid until the last bulk store has read it
     if (et == 0) KT(10);
     if (p.stats) {
       // the pipeline stages are idle now: stage 0 doubles as the cross-thread reduction scratch.  Every thread
@@ -1134,6 +1144,7 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   kp.bias = a.bias; kp.res1 = a.res1; kp.res2 = a.res2; kp.out = a.out; kp.stats = a.stats;
   kp.bn_y = a.bn_y;
   kp.bn_in = a.bn_in;
+  kp.single_store = g_debug[16];
   HGB_CHECK_ARG(a.bn_in.gamma == nullptr || (a.ksize == 1 && a.bn_in.C == a.Cin && a.Cin <= 256),
                 "conv_gemm: an input BatchNorm needs a 1x1 convolution with Cin <= 256");
   kp.res1_tma = (a.res1 != nullptr && tmR != nullptr && !g_debug[3]) ? 1 : 0;

@@ -12,10 +12,12 @@ ap.add_argument("--batches", default="32,64,128,256")
 ap.add_argument("--reserves", default="20")
 ap.add_argument("--wfirst", type=int, default=0)
 ap.add_argument("--halo-min", type=int, default=0)
+ap.add_argument("--single-store", type=int, default=0)
 a = ap.parse_args()
 lib = _lib.lib
 lib.hgb_debug_set(10, a.wfirst)
 lib.hgb_debug_set(15, a.halo_min)
+lib.hgb_debug_set(16, a.single_store)
 for B in [int(b) for b in a.batches.split(",")]:
     model = hgb200.HourglassModel(17, 8, 256, (256, 256, 3), "sigmoid", seed=1)
     model.compile(optimizer=hgb200.Adam(1e-3), loss=hgb200.loss.weighted_mse)
