@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t outbase = base + kRingBytes;                 // OUT_BUFS epilogue staging buffers (1024-aligned)
   const uint32_t bar0 = outbase + OUT_BUFS * kOutBytes;
-  uint8_t* tail = smem + kRingBytes + OUT_BUFS * kOutBytes + kNumBars * 8;
+  uint8_t* tail = smem + kRingBytes + OUT_BUFS * kOutBytes + (kNumBars * 8 + 15) / 16 * 16;   // 16-byte aligned
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail);
   float* s_bias = reinterpret_cast<float*>(tail + 16);        // [BLOCK_N]
   float* s_sc = s_bias + BLOCK_N;                             // [256] scale / [256] shift of a deferred input BatchNorm
@@ -483,7 +483,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         const uint32_t box = out0 + (uint32_t)g * kABytes + (uint32_t)row * 128u;
         if (!p.res1 && !p.res2) {
           // no residual: bias on packed fp32 pairs, ReLU on the packed bf16 pairs -- 3 instructions per 2 channels
-          const uint64_t* b2 = reinterpret_cast<const uint64_t*>(s_bias + n0c);
+          // the 32 bias values of the chunk are fetched up front (8 x 16 bytes, broadcast): issued back to back, their
+          // latency is paid once instead of in front of every packed add
+          uint64_t b2[16];
+          const uint32_t badr = smem_u32(s_bias + n0c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b2[2 * j]), "=l"(b2[2 * j + 1]) : "r"(badr + 16u * j));
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             uint32_t w[4];
@@ -1102,7 +1108,8 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
                          const CUtensorMap& tmY, const GemmKernelParams& kp, int tiles_m, int max_ctas, cudaStream_t st) {
   constexpr int ring = HALO ? (TILES + 1) * kABytes + 6 * BLOCK_N * 128 : STAGES * (TILES * kABytes + BLOCK_N * 128);
   constexpr int nbars = HALO ? 2 * (TILES + 1) + 12 + 2 * TILES + 1 : 3 * STAGES + 5;
-  constexpr int smem = ring + OUT_BUFS * (BLOCK_N / 64) * kABytes + nbars * 8 + 16 + BLOCK_N * 4 + (TILES == 1 ? 2 * 256 * 4 : 0) + 1024;   // scale/shift only for the 1x1 variants
+  constexpr int smem = ring + OUT_BUFS * (BLOCK_N / 64) * kABytes + (nbars * 8 + 15) / 16 * 16 + 16 + BLOCK_N * 4 +
+                       (TILES == 1 ? 2 * 256 * 4 : 0) + 1024;   // scale/shift only for the 1x1 variants
   static_assert(ring >= 16 * 1024, "stats scratch (16 KB) aliases the pipeline stages");
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;

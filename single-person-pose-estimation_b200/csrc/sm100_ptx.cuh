@@ -157,12 +157,12 @@ __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
   return r;
 }
-// two fp32 -> packed bf16x2 (lo in the low half), optionally clamped at zero (ReLU commutes with the rounding)
+// two fp32 -> packed bf16x2 (lo in the low half), optionally clamped at zero inside the convert instruction
 __device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v, bool relu) {
   uint32_t a, b, r;
   asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(b)), "f"(__uint_as_float(a)));
-  if (relu) asm("max.bf16x2 %0, %0, %1;" : "+r"(r) : "r"(0u));
+  if (relu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(b)), "f"(__uint_as_float(a)));   // F2FP.RELU
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(b)), "f"(__uint_as_float(a)));
   return r;
 }
 
