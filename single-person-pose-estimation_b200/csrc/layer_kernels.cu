@@ -280,20 +280,28 @@ int upsample_add_bwd(const bf16* dout, bf16* dlow, int N, int h, int w, int C, c
 }
 
 // ---------------------------------------------------------------------------------- BN backward
-// Block-level combine of per-thread 8-channel partials: threads with the same channel group add into smem.
+// Block-level combine of per-thread 8-channel partials: every thread parks its partial sums in shared memory
+// ([row group][stat][channel], 2048 floats per statistic for any C), one thread per channel adds the row groups up and
+// issues one global reduction.  (Shared-memory float atomicAdd compiles to a compare-and-swap spin loop: with R
+// threads contending per address it cost several microseconds per block.)
 template <int NSTAT>
-__device__ __forceinline__ void block_channel_flush(float (&acc)[NSTAT][8], float* s_acc /*[NSTAT*C]*/, float* const* dst,
+__device__ __forceinline__ void block_channel_flush(float (&acc)[NSTAT][8], float* s_acc /*[R*NSTAT*C]*/, float* const* dst,
                                                     int C, int g, int c_valid) {
-  for (int i = threadIdx.x; i < NSTAT * C; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
+  const int G = C >> 3, R = 256 / G, r0 = threadIdx.x / G;
 #pragma unroll
-  for (int s = 0; s < NSTAT; ++s)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[s * C + g * 8 + j], acc[s][j]);
+  for (int s = 0; s < NSTAT; ++s) {
+    float4* d = reinterpret_cast<float4*>(s_acc + ((size_t)r0 * NSTAT + s) * C + g * 8);
+    d[0] = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
+    d[1] = make_float4(acc[s][4], acc[s][5], acc[s][6], acc[s][7]);
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < NSTAT * C; i += blockDim.x) {
     const int s = i / C, c = i - s * C;
-    if (dst[s] && c < c_valid) atomicAdd(dst[s] + c, s_acc[i]);
+    if (dst[s] && c < c_valid) {
+      float t = 0.f;
+      for (int r = 0; r < R; ++r) t += s_acc[(size_t)r * NSTAT * C + i];
+      atomicAdd(dst[s] + c, t);
+    }
   }
 }
 
@@ -337,7 +345,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
 int bn_bwd_reduce(const bf16* dz, const bf16* y, float* bsums, int M, int C, cudaStream_t st) {
   HGB_CHECK_ARG(C % 8 == 0 && 256 % (C / 8) == 0, "bn_bwd_reduce: unsupported channel count %d", C);
   if (M == 0) return HGB_OK;
-  launch_pdl(bn_bwd_reduce_kernel, dim3(row_blocks(M, C, 16)), dim3(256), 2 * C * sizeof(float), st, dz, y, bsums, M, C);
+  launch_pdl(bn_bwd_reduce_kernel, dim3(row_blocks(M, C, 8)), dim3(256), 2 * 2048 * sizeof(float), st, dz, y, bsums, M, C);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -414,7 +422,7 @@ int bn_bwd_apply(const bf16* dz, const bf16* y, bf16* dp, const float* bsums, co
                  float* dgamma, float* dbeta, float* dbias, int M, int C, cudaStream_t st) {
   HGB_CHECK_ARG(C % 8 == 0 && 256 % (C / 8) == 0, "bn_bwd_apply: unsupported channel count %d", C);
   if (M == 0) return HGB_OK;
-  launch_pdl(bn_bwd_apply_kernel, dim3(row_blocks(M, C, 16)), dim3(256), C * sizeof(float), st, dz, y, dp, bsums, saved, gamma, dgamma, dbeta,
+  launch_pdl(bn_bwd_apply_kernel, dim3(row_blocks(M, C, 8)), dim3(256), 2048 * sizeof(float), st, dz, y, dp, bsums, saved, gamma, dgamma, dbeta,
                                                                            dbias, M, C);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
@@ -453,7 +461,7 @@ int relu_mask_colsum(const bf16* g, const bf16* y, bf16* dp, float* dbias, int M
                      cudaStream_t st) {
   HGB_CHECK_ARG(C % 8 == 0 && 256 % (C / 8) == 0, "relu_mask_colsum: unsupported channel count %d", C);
   if (M == 0) return HGB_OK;
-  launch_pdl(relu_mask_colsum_kernel, dim3(row_blocks(M, C, 16)), dim3(256), C * sizeof(float), st, g, y, dp, dbias, M, C, c_valid, relu);
+  launch_pdl(relu_mask_colsum_kernel, dim3(row_blocks(M, C, 8)), dim3(256), 2048 * sizeof(float), st, g, y, dp, dbias, M, C, c_valid, relu);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
