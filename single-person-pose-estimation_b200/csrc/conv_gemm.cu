@@ -53,6 +53,7 @@ struct GemmKernelParams {
   const __nv_bfloat16* bn_y;  // non-null: second statistic is sum(out * bn_y) (BatchNorm backward) instead of sum(out^2)
   int res1_tma;               // res1 is fetched by TMA (tmR) into the staging buffer
   BnInput bn_in;              // gamma != null: normalise the A tile in shared memory before the MMAs read it
+  BnInput bn_out;             // gamma != null (inference): scale/shift of the BatchNorm that follows, applied in the epilogue
   int single_store;           // debug: one thread issues all output boxes (hgb_debug_set(16, 1))
 };
 
@@ -188,6 +189,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   float* s_bias = reinterpret_cast<float*>(tail + 16);        // [BLOCK_N]
   float* s_sc = s_bias + BLOCK_N;                             // [256] scale / [256] shift of a deferred input BatchNorm
   float* s_sh = s_sc + 256;
+  float* s_osc = s_sh + 256;                                  // [256] / [256]: inference BatchNorm of the OUTPUT (epilogue)
+  float* s_osh = s_osc + 256;
   float* s_stats = reinterpret_cast<float*>(smem);            // [row groups][2*BLOCK_N] = 16 KB, aliases pipeline stage 0: used only after the last tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -225,6 +228,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   if (threadIdx.x == 0) KT(2);
   const bool xform = !HALO && TILES == 1 && p.bn_in.gamma != nullptr;
   if (xform) bn_input_setup(p.bn_in, s_sc, s_sh, threadIdx.x, kGemmThreads, blockIdx.x == 0 && p.bn_in.write != 0);
+  const bool post_bn = !HALO && TILES == 1 && p.bn_out.gamma != nullptr;
+  if (post_bn) bn_input_setup(p.bn_out, s_osc, s_osh, threadIdx.x, kGemmThreads, false);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -481,7 +486,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         // staging: 128-pixel x 64-channel boxes in the 128-byte-swizzled layout TMA expects
         // (16-byte chunk index XOR (row mod 8)); a TMA-fetched residual sits at the very same addresses
         const uint32_t box = out0 + (uint32_t)g * kABytes + (uint32_t)row * 128u;
-        if (!p.res1 && !p.res2) {
+        if (!p.res1 && !p.res2 && !post_bn) {
           // no residual: bias on packed fp32 pairs, ReLU on the packed bf16 pairs -- 3 instructions per 2 channels
           // the 32 bias values of the chunk are fetched up front (8 x 16 bytes, broadcast): issued back to back, their
           // latency is paid once instead of in front of every packed add
@@ -528,6 +533,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         if (p.relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (post_bn) {   // inference: the BatchNorm that follows is a per-channel affine map of this accumulator
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = f[j] * s_osc[n0c + j] + s_osh[n0c + j];
         }
         if (p.res1_tma) {
 #pragma unroll
@@ -1109,7 +1118,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   constexpr int ring = HALO ? (TILES + 1) * kABytes + 6 * BLOCK_N * 128 : STAGES * (TILES * kABytes + BLOCK_N * 128);
   constexpr int nbars = HALO ? 2 * (TILES + 1) + 12 + 2 * TILES + 1 : 3 * STAGES + 5;
   constexpr int smem = ring + OUT_BUFS * (BLOCK_N / 64) * kABytes + (nbars * 8 + 15) / 16 * 16 + 16 + BLOCK_N * 4 +
-                       (TILES == 1 ? 2 * 256 * 4 : 0) + 1024;   // scale/shift only for the 1x1 variants
+                       (TILES == 1 ? 4 * 256 * 4 : 0) + 1024;   // input / output BatchNorm scale+shift only for the 1x1 variants
   static_assert(ring >= 16 * 1024, "stats scratch (16 KB) aliases the pipeline stages");
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
@@ -1152,6 +1161,9 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   kp.bn_y = a.bn_y;
   kp.bn_in = a.bn_in;
   kp.single_store = g_debug[16];
+  kp.bn_out = a.bn_out;
+  HGB_CHECK_ARG(a.bn_out.gamma == nullptr || (a.ksize == 1 && a.bn_out.C == a.Cout && a.Cout <= 256 && a.bn_out.mode == 1),
+                "conv_gemm: an output BatchNorm needs a 1x1 convolution with Cout <= 256 in inference mode");
   HGB_CHECK_ARG(a.bn_in.gamma == nullptr || (a.ksize == 1 && a.bn_in.C == a.Cin && a.Cin <= 256),
                 "conv_gemm: an input BatchNorm needs a 1x1 convolution with Cin <= 256");
   kp.res1_tma = (a.res1 != nullptr && tmR != nullptr && !g_debug[3]) ? 1 : 0;

@@ -46,6 +46,7 @@ struct ConvGemmArgs {
   const __nv_bfloat16* bn_y; // non-null: stats = (sum out, sum out*bn_y) -- fused BatchNorm-backward reduction
   int max_ctas = 0;         // > 0: cap of the persistent grid (side lanes leave SMs to the main chain)
   BnInput bn_in;            // 1x1 only
+  BnInput bn_out;           // 1x1 only, inference: out = BN(relu(conv + bias)) (+ residuals) straight from the accumulator
 };
 // tmA: activation map of the input; tmB: weight matrix [>=Cout rows][ksize^2*Cin], box rows = block_n
 int conv_gemm_block_n(int Cout);

@@ -829,6 +829,12 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
         a.bn_in.mode = training ? 0 : 1; a.bn_in.write = (o.flag & 0x10000) ? 1 : 0;
         a.bn_in.M = in.n * in.h * in.w; a.bn_in.C = b.c;
       }
+      if (o.flag & 0x20000) {   // inference: the BatchNorm that follows this conv is applied in the epilogue (fuse_inference_bn)
+        const BNL& b = m->bns[o.bn];
+        a.bn_out.gamma = m->p_params + b.gamma_off; a.bn_out.beta = m->p_params + b.beta_off;
+        a.bn_out.moving_mean = m->p_params + b.mm_off; a.bn_out.moving_var = m->p_params + b.mv_off;
+        a.bn_out.mode = 1; a.bn_out.M = in.n * in.h * in.w; a.bn_out.C = b.c;
+      }
       rc = launch_conv_gemm(in.tmap, c.tm_wf, out.tmap, o.a2 >= 0 ? &m->acts[o.a2].tmap : nullptr, nullptr, a, st);
       break;
     }
@@ -963,16 +969,33 @@ int ensure_lanes(hgb_model* m) {
   return HGB_OK;
 }
 
+// Inference: BatchNorm is a per-channel affine map with constant statistics, so a 1x1 convolution followed by its
+// (stored) BatchNorm runs as ONE launch: the epilogue computes BN(relu(conv + bias)) (+ the BN's residual) from the fp32
+// accumulator and writes the BN's output tensor; the pre-BN tensor is never stored and the BN pass disappears.
+bool fuse_inference_bn(const hgb_model* m, const Op& conv, const Op* next, int training, Op* fused) {
+  if (training || hgb::g_debug[17] || !next || conv.type != F_CONV || next->type != F_BN || conv.bn < 0 || next->bn != conv.bn) return false;
+  if (m->convs[conv.conv].ksize != 1 || conv.a2 >= 0 || conv.a3 >= 0 || next->a0 != conv.a1 || conv.lane != next->lane) return false;
+  *fused = conv;
+  fused->a1 = next->a2;      // write the BN's output tensor
+  fused->a2 = next->a1;      // + the BN's residual (identity / projected skip)
+  fused->flag |= 0x20000;
+  return true;
+}
+
 // Ops [begin, end) of a sequence.  Single-lane mode (hgb_debug_set(8, 1), or per-op profiling) replays them in
 // order on the caller's stream -- the reference behaviour the lanes must reproduce.
 int run_sequence(hgb_model* m, bool backward, int begin, int end, const float* images, int training, cudaStream_t st) {
   const std::vector<SchedOp>& seq = backward ? m->bwd_seq : m->fwd_seq;
   const std::vector<std::vector<Op>>& lists = backward ? m->bwd_ops : m->fwd_ops;
   if (begin >= end) return HGB_OK;
+  auto op_at = [&](int k) -> const Op& { return lists[seq[k].seg][seq[k].idx]; };
   if (hgb::g_debug[8] || m->prof_all) {
     for (int k = begin; k < end; ++k) {
-      int rc = run_op(m, lists[seq[k].seg][seq[k].idx], images, training, st);
+      Op fused;
+      const bool fz = !backward && fuse_inference_bn(m, op_at(k), k + 1 < end ? &op_at(k + 1) : nullptr, training, &fused);
+      int rc = run_op(m, fz ? fused : op_at(k), images, training, st);
       if (rc) return rc;
+      if (fz) ++k;
     }
     return HGB_OK;
   }
@@ -982,14 +1005,21 @@ int run_sequence(hgb_model* m, bool backward, int begin, int end, const float* i
   bool used[kNumLanes] = {false};
   HGB_CUDA(cudaEventRecord(m->fork_ev, st));
   for (int k = begin; k < end; ++k) {
-    const Op& o = lists[seq[k].seg][seq[k].idx];
+    Op fused;
+    const bool fz = !backward && fuse_inference_bn(m, op_at(k), k + 1 < end ? &op_at(k + 1) : nullptr, training, &fused);
+    const Op& o = fz ? fused : op_at(k);
     cudaStream_t ls = m->lane_stream[o.lane];
     if (!used[o.lane]) { HGB_CUDA(cudaStreamWaitEvent(ls, m->fork_ev, 0)); used[o.lane] = true; }
-    for (const Dep& d : seq[k].deps)
-      if (d.idx >= begin) HGB_CUDA(cudaStreamWaitEvent(ls, ev[d.idx], 0));   // older ops were joined by an earlier call
+    for (int q = k; q <= k + (fz ? 1 : 0); ++q)    // a fused launch inherits the dependencies of both ops
+      for (const Dep& d : seq[q].deps)
+        if (d.idx >= begin) HGB_CUDA(cudaStreamWaitEvent(ls, ev[d.idx], 0));   // older ops were joined by an earlier call
     rc = run_op(m, o, images, training, ls);
     if (rc) return rc;
     if (seq[k].signal) HGB_CUDA(cudaEventRecord(ev[k], ls));
+    if (fz) {
+      ++k;
+      if (seq[k].signal) HGB_CUDA(cudaEventRecord(ev[k], ls));
+    }
   }
   for (int l = 0; l < kNumLanes; ++l)
     if (used[l]) {

@@ -97,3 +97,28 @@ def test_backward_matches_in_order_replay_on_the_same_activations(env, stacks, B
         # a race corrupts whole tensors; atomics order moves cosines by the in-order replay's own run-to-run amount
         assert tot >= min(0.99999, 1 - 10 * (1 - floor_tot)), (trial, tot, floor_tot)
         assert c >= min(0.9999, 1 - 10 * (1 - floor)), (trial, name, c, floor)
+
+
+def test_inference_bn_fused_into_conv_epilogue_matches_separate_pass(env):
+    """Inference folds each stored BatchNorm into the epilogue of the 1x1 convolution that feeds it (one launch, the
+    pre-BN tensor is never rounded to bf16 / stored).  Against the two-pass path (hgb_debug_set(17, 1)) the heat maps
+    may differ only by that one bf16 rounding per layer."""
+    hgb, torch = env
+    lib = hgb._lib.lib
+    from oracle import network_oracle as norc
+    weights = norc.init_params(norc.param_spec(17, 2, 256), seed=9, perturb_bn=True)
+    model = hgb.HourglassModel(17, 2, 256, (256, 256, 3), "sigmoid")
+    model.set_weights_dict(weights)
+    images = torch.rand((5, 256, 256, 3), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    try:
+        lib.hgb_debug_set(17, 1)
+        ref = [o.clone() for o in model.forward_device(images, training=False)]
+        lib.hgb_debug_set(17, 0)
+        out = model.forward_device(images, training=False)
+        torch.cuda.synchronize()
+    finally:
+        lib.hgb_debug_set(17, 0)
+    for a, b in zip(out, ref):
+        rel = float((a - b).norm() / b.norm())
+        print(f"fused vs two-pass inference: rel-L2 {rel:.3e}, max abs {float((a - b).abs().max()):.3e}")
+        assert rel < 1e-2 and not torch.equal(a, b)      # close, and really a different (fused) code path
