@@ -102,23 +102,30 @@ def test_backward_matches_in_order_replay_on_the_same_activations(env, stacks, B
 def test_inference_bn_fused_into_conv_epilogue_matches_separate_pass(env):
     """Inference folds each stored BatchNorm into the epilogue of the 1x1 convolution that feeds it (one launch, the
     pre-BN tensor is never rounded to bf16 / stored).  Against the two-pass path (hgb_debug_set(17, 1)) the heat maps
-    may differ only by that one bf16 rounding per layer."""
+    differ only through that one bf16 rounding per layer: the fused path must be at least as close to the fp32 oracle
+    as the two-pass path, and the two must agree to the bf16 band."""
     hgb, torch = env
     lib = hgb._lib.lib
     from oracle import network_oracle as norc
     weights = norc.init_params(norc.param_spec(17, 2, 256), seed=9, perturb_bn=True)
     model = hgb.HourglassModel(17, 2, 256, (256, 256, 3), "sigmoid")
     model.set_weights_dict(weights)
-    images = torch.rand((5, 256, 256, 3), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    images = torch.rand((4, 256, 256, 3), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
     try:
         lib.hgb_debug_set(17, 1)
-        ref = [o.clone() for o in model.forward_device(images, training=False)]
+        two_pass = [o.clone() for o in model.forward_device(images, training=False)]
         lib.hgb_debug_set(17, 0)
-        out = model.forward_device(images, training=False)
+        fused = [o.clone() for o in model.forward_device(images, training=False)]
         torch.cuda.synchronize()
     finally:
         lib.hgb_debug_set(17, 0)
-    for a, b in zip(out, ref):
+    ref, _ = norc.forward(weights, images.cpu().numpy(), 17, 2, 256, training=False)
+    for s_, (a, b) in enumerate(zip(fused, two_pass)):
+        r = torch.as_tensor(ref[s_].detach().numpy(), device="cuda")
+        d_f = float((a - r).norm() / r.norm())
+        d_t = float((b - r).norm() / r.norm())
         rel = float((a - b).norm() / b.norm())
-        print(f"fused vs two-pass inference: rel-L2 {rel:.3e}, max abs {float((a - b).abs().max()):.3e}")
-        assert rel < 1e-2 and not torch.equal(a, b)      # close, and really a different (fused) code path
+        print(f"stack {s_}: rel-L2 from the fp32 oracle: fused {d_f:.3e}, two-pass {d_t:.3e}; fused vs two-pass {rel:.3e}")
+        assert not torch.equal(a, b)                    # really a different (fused) code path
+        assert d_f <= 1.25 * d_t + 2e-3                 # one rounding fewer per layer: never further from fp32
+        assert rel <= 2.5 * d_t + 5e-3                  # and inside the band bf16 storage itself spans
