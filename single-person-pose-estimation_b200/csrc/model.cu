@@ -162,6 +162,7 @@ struct hgb_model {
   std::vector<cudaEvent_t> fwd_ev, bwd_ev;         // one per sequence op that signals another lane
   cudaEvent_t fork_ev = nullptr, join_ev[kNumLanes] = {nullptr};
   bool lanes_ready = false;
+  bool pdl_suppressed = false;   // set while a multi-lane backward pass is being issued
   int num_sms = 0;
 
   // ---- build-time state
@@ -779,7 +780,10 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
 int run_op(hgb_model* m, const Op& o, const float* images, int training, cudaStream_t st) {
   // programmatic dependent launch pays off when kernels are short (measured: -6.5 % step time at batch 32,
   // +2.5 % at batch 256), so it follows the plan's batch unless forced by hgb_debug_set(7, 1 = on / 2 = off)
-  hgb::g_debug[6] = hgb::g_debug[7] == 1 ? 0 : hgb::g_debug[7] == 2 ? 1 : (m->B > 64);
+  // With the lanes active, an early-launched dependent CTA parks on an SM (holding ~200 KB of shared memory) until its
+  // predecessor finishes and keeps the OTHER lanes' kernels off that SM: measured -1.7 % in the backward pass, where the
+  // side lanes carry a third of the work, so there it stays off.
+  hgb::g_debug[6] = hgb::g_debug[7] == 1 ? 0 : hgb::g_debug[7] == 2 ? 1 : (m->B > 64 || (m->pdl_suppressed && !hgb::g_debug[19]));
   bool timed = false;
   if (m->prof_all) {
     timed = m->prof_used + 2 <= m->prof_ev.size();
@@ -1003,6 +1007,7 @@ int run_sequence(hgb_model* m, bool backward, int begin, int end, const float* i
   if (rc) return rc;
   std::vector<cudaEvent_t>& ev = backward ? m->bwd_ev : m->fwd_ev;
   bool used[kNumLanes] = {false};
+  m->pdl_suppressed = backward;
   HGB_CUDA(cudaEventRecord(m->fork_ev, st));
   for (int k = begin; k < end; ++k) {
     Op fused;
@@ -1021,6 +1026,7 @@ int run_sequence(hgb_model* m, bool backward, int begin, int end, const float* i
       if (seq[k].signal) HGB_CUDA(cudaEventRecord(ev[k], ls));
     }
   }
+  m->pdl_suppressed = false;
   for (int l = 0; l < kNumLanes; ++l)
     if (used[l]) {
       HGB_CUDA(cudaEventRecord(m->join_ev[l], m->lane_stream[l]));
