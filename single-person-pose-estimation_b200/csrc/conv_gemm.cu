@@ -1248,6 +1248,7 @@ int launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const Wgr
     // so the 192 KB fp32 reduction epilogue of a CTA stays a small fraction of its work
     int splits = (2 * 148) / 3;
     if (kp.M_tiles / splits < 64) splits = 148 / 3;
+    if (a.max_ctas > 0 && 3 * splits > a.max_ctas) splits = a.max_ctas / 3 > 0 ? a.max_ctas / 3 : 1;
     kp.tiles_per_split = cdiv(kp.M_tiles, splits);
     splits = cdiv(kp.M_tiles, kp.tiles_per_split);
     kp.cin_tiles = 1; kp.swap_lbo_sbo = 0; kp.vec4 = 1; kp.dw = a.dw;
@@ -1273,6 +1274,7 @@ int launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const Wgr
   // split-K over pixel tiles: enough CTAs to fill the chip, but at least 8 tiles per CTA so the fp32
   // atomic epilogue (a full 128 x N tile per CTA) is amortised -- it dominated the low-resolution levels
   int splits = cdiv(2 * 148, groups);
+  if (a.max_ctas > 0 && splits * groups > a.max_ctas) splits = a.max_ctas / groups;
   if (splits > kp.M_tiles / 8) splits = kp.M_tiles / 8;
   if (splits < 1) splits = 1;
   kp.tiles_per_split = cdiv(kp.M_tiles, splits);

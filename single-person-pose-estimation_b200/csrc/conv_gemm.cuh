@@ -62,6 +62,7 @@ struct WgradArgs {
   int Cin_valid, Cout_valid; // 0 = all; otherwise only dw[:Cout_valid][tap][:Cin_valid] is written (padded tensors)
   float* dw;                // [Cout_valid][ksize^2*Cin_valid] fp32, added to
   BnInput bn_in;            // 1x1 only: x is normalised in shared memory (saved statistics)
+  int max_ctas = 0;         // > 0: cap of the grid (the weight-gradient lane leaves SMs to the main chain)
 };
 // tmDY: activation map of dy (C = Cout); tmX: activation map of x (C = Cin)
 int launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradArgs& a, cudaStream_t st);
