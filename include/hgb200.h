@@ -151,6 +151,12 @@ int hgb_model_loss(hgb_model* m, int kind, const float* y_true, double inv_count
  * Must be called from the highest segment down.  Gradients are written (not accumulated). */
 int hgb_model_num_segments(const hgb_model* m);
 int hgb_model_backward(hgb_model* m, int seg_lo, int seg_hi, void* stream);
+/* Same, but `stream` is NOT ordered after the lanes on return: the main chain of the next segment starts while this
+ * segment's weight gradients are still draining.  hgb_model_lanes_join(m, s, 0) orders a side stream `s` (the one the
+ * gradient all-reduce of the segment is issued on) after everything issued so far; hgb_model_lanes_join(m, stream, 1)
+ * must be called on the caller's stream before the optimizer step. */
+int hgb_model_backward_nojoin(hgb_model* m, int seg_lo, int seg_hi, void* stream);
+int hgb_model_lanes_join(hgb_model* m, void* stream, int is_caller);
 /* contiguous range of the gradient buffer that segment `seg` owns (for bucketed allreduce) */
 int hgb_model_segment_grads(const hgb_model* m, int seg, int64_t* offset, int64_t* count);
 

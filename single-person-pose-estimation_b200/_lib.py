@@ -54,6 +54,8 @@ PROTOTYPES = {
     "hgb_model_loss": (i32, [vp, i32, vp, f64, vp, vp]),
     "hgb_model_num_segments": (i32, [vp]),
     "hgb_model_backward": (i32, [vp, i32, i32, vp]),
+    "hgb_model_backward_nojoin": (i32, [vp, i32, i32, vp]),
+    "hgb_model_lanes_join": (i32, [vp, vp, i32]),
     "hgb_model_segment_grads": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i64)]),
     "hgb_model_adam_step": (i32, [vp, f64, f64, f64, f64, i64, f64, vp]),
     "hgb_model_conv_output": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i32 * 4)]),

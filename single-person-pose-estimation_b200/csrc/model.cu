@@ -163,6 +163,8 @@ struct hgb_model {
   cudaEvent_t fork_ev = nullptr, join_ev[kNumLanes] = {nullptr};
   bool lanes_ready = false;
   bool pdl_suppressed = false;   // set while a multi-lane backward pass is being issued
+  int bwd_unjoined_from = 1 << 30;   // first backward sequence index issued since the lanes were last joined into the caller
+  bool lane_dirty[kNumLanes] = {false};   // lane has work the caller's stream has not been ordered after yet
   int num_sms = 0;
 
   // ---- build-time state
@@ -993,7 +995,22 @@ bool fuse_inference_bn(const hgb_model* m, const Op& conv, const Op* next, int t
 
 // Ops [begin, end) of a sequence.  Single-lane mode (hgb_debug_set(8, 1), or per-op profiling) replays them in
 // order on the caller's stream -- the reference behaviour the lanes must reproduce.
-int run_sequence(hgb_model* m, bool backward, int begin, int end, const float* images, int training, cudaStream_t st) {
+int join_lanes(hgb_model* m, cudaStream_t st, bool caller) {
+  for (int l = 0; l < kNumLanes; ++l)
+    if (m->lane_dirty[l]) {
+      HGB_CUDA(cudaEventRecord(m->join_ev[l], m->lane_stream[l]));
+      HGB_CUDA(cudaStreamWaitEvent(st, m->join_ev[l], 0));
+      if (caller) m->lane_dirty[l] = false;
+    }
+  if (caller) m->bwd_unjoined_from = 1 << 30;
+  return HGB_OK;
+}
+
+// join = false (backward only): the caller's stream is NOT ordered after the lanes when the call returns; a later
+// hgb_model_lanes_join does that.  Data parallelism issues one segment per call and must not stall the main chain at
+// every segment boundary until that segment's (capped, low-priority) weight gradients have drained.
+int run_sequence(hgb_model* m, bool backward, int begin, int end, const float* images, int training, cudaStream_t st,
+                 bool join = true) {
   const std::vector<SchedOp>& seq = backward ? m->bwd_seq : m->fwd_seq;
   const std::vector<std::vector<Op>>& lists = backward ? m->bwd_ops : m->fwd_ops;
   if (begin >= end) return HGB_OK;
@@ -1021,8 +1038,8 @@ int run_sequence(hgb_model* m, bool backward, int begin, int end, const float* i
     cudaStream_t ls = m->lane_stream[o.lane];
     if (!used[o.lane]) { HGB_CUDA(cudaStreamWaitEvent(ls, m->fork_ev, 0)); used[o.lane] = true; }
     for (int q = k; q <= k + (fz ? 1 : 0); ++q)    // a fused launch inherits the dependencies of both ops
-      for (const Dep& d : seq[q].deps)
-        if (d.idx >= begin) HGB_CUDA(cudaStreamWaitEvent(ls, ev[d.idx], 0));   // older ops were joined by an earlier call
+      for (const Dep& d : seq[q].deps)   // ops of earlier calls need no wait once the caller's stream has joined them
+        if (d.idx >= begin || (backward && d.idx >= m->bwd_unjoined_from)) HGB_CUDA(cudaStreamWaitEvent(ls, ev[d.idx], 0));
     rc = run_op(m, o, images, training, ls);
     if (rc) return rc;
     if (seq[k].signal) HGB_CUDA(cudaEventRecord(ev[k], ls));
@@ -1032,11 +1049,9 @@ int run_sequence(hgb_model* m, bool backward, int begin, int end, const float* i
     }
   }
   m->pdl_suppressed = false;
-  for (int l = 0; l < kNumLanes; ++l)
-    if (used[l]) {
-      HGB_CUDA(cudaEventRecord(m->join_ev[l], m->lane_stream[l]));
-      HGB_CUDA(cudaStreamWaitEvent(st, m->join_ev[l], 0));
-    }
+  for (int l = 0; l < kNumLanes; ++l) m->lane_dirty[l] = m->lane_dirty[l] || used[l];
+  if (backward && begin < m->bwd_unjoined_from) m->bwd_unjoined_from = begin;
+  if (join) return join_lanes(m, st, true);
   return HGB_OK;
 }
 
@@ -1215,6 +1230,23 @@ extern "C" int hgb_model_backward(hgb_model* m, int seg_lo, int seg_hi, void* st
   const int begin = m->bwd_seq_begin[seg_hi - 1];
   const int end = seg_lo == 0 ? (int)m->bwd_seq.size() : m->bwd_seq_begin[seg_lo - 1];
   return run_sequence(m, true, begin, end, nullptr, 1, (cudaStream_t)stream);
+}
+
+extern "C" int hgb_model_backward_nojoin(hgb_model* m, int seg_lo, int seg_hi, void* stream) {
+  HGB_REQUIRE_READY(m);
+  HGB_CHECK_ARG(seg_lo >= 0 && seg_hi <= m->S + 1 && seg_lo < seg_hi, "hgb_model_backward_nojoin: bad segment range");
+  if (!m->cfg.training || !m->fwd_training_done) { set_error("hgb_model_backward_nojoin: needs a training forward pass first"); return HGB_ERR_STATE; }
+  const int begin = m->bwd_seq_begin[seg_hi - 1];
+  const int end = seg_lo == 0 ? (int)m->bwd_seq.size() : m->bwd_seq_begin[seg_lo - 1];
+  return run_sequence(m, true, begin, end, nullptr, 1, (cudaStream_t)stream, /*join=*/hgb::g_debug[8] || m->prof_all);
+}
+
+// order `stream` after everything issued on the lanes so far; is_caller != 0 marks the lanes as joined (the stream the
+// next forward / backward / optimizer call is issued on), 0 is for a side stream (e.g. the gradient all-reduce)
+extern "C" int hgb_model_lanes_join(hgb_model* m, void* stream, int is_caller) {
+  HGB_REQUIRE_READY(m);
+  if (!m->lanes_ready) return HGB_OK;
+  return join_lanes(m, (cudaStream_t)stream, is_caller != 0);
 }
 
 extern "C" int hgb_model_segment_grads(const hgb_model* m, int seg, int64_t* offset, int64_t* count) {

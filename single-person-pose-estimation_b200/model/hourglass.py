@@ -122,6 +122,7 @@ class HourglassModel:
         self._plans = {}
         self._weights_version = 0
         self._params = self._grads = self._adam_m = self._adam_v = None
+        self._comm_stream = None
         # a host-only handle: parameter table and counts (no GPU needed)
         cfg = _lib.ModelConfig(self.num_classes, self.num_stacks, self.num_channels, self.input_shape[0],
                                self.input_shape[1], self._act, 1, 0)
@@ -397,10 +398,18 @@ class HourglassModel:
         else:
             world = allreduce.world_size
             off, cnt = C.c_int64(), C.c_int64()
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream()
+            comm = self._comm_stream
             for seg in range(nseg - 1, -1, -1):
-                check(lib.hgb_model_backward(plan.handle, seg, seg + 1, st))
+                # the segment's backward does not join its lanes into the main stream (the next segment's chain starts
+                # at once); the all-reduce is issued from a side stream that is ordered after everything issued so far
+                check(lib.hgb_model_backward_nojoin(plan.handle, seg, seg + 1, st))
+                check(lib.hgb_model_lanes_join(plan.handle, C.c_void_p(comm.cuda_stream), 0))
                 check(lib.hgb_model_segment_grads(plan.handle, seg, C.byref(off), C.byref(cnt)))
-                allreduce(self._grads[off.value:off.value + cnt.value])
+                with torch.cuda.stream(comm):
+                    allreduce(self._grads[off.value:off.value + cnt.value])
+            check(lib.hgb_model_lanes_join(plan.handle, st, 1))
             allreduce.wait()
         opt = self.optimizer
         opt.iterations += 1

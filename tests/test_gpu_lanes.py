@@ -72,12 +72,28 @@ def test_backward_matches_in_order_replay_on_the_same_activations(env, stacks, B
     model.forward_device(images, training=True, plan=plan)
     chk(lib.hgb_model_loss(plan.handle, model._loss_kind, ptr(targets), 1.0 / (B * 64 * 64 * 17), ptr(losses), sp()))
 
-    def backward(single_lane, per_segment=False):
+    comm = torch.cuda.Stream()
+    import ctypes as C
+
+    def backward(single_lane, per_segment=0):
         lib.hgb_debug_set(8, 1 if single_lane else 0)
         chk(lib.hgb_model_begin_step(plan.handle, sp()))
-        if per_segment:                                  # the data-parallel call pattern: one call per segment
+        if per_segment == 1:                             # one joining call per segment
             for seg in range(stacks, -1, -1):
                 chk(lib.hgb_model_backward(plan.handle, seg, seg + 1, sp()))
+        elif per_segment == 2:                           # the data-parallel pattern: no join between segments, a side
+            seen = []                                    # stream (the all-reduce's) ordered after each finished segment
+            off, cnt = C.c_int64(), C.c_int64()
+            for seg in range(stacks, -1, -1):
+                chk(lib.hgb_model_backward_nojoin(plan.handle, seg, seg + 1, sp()))
+                chk(lib.hgb_model_lanes_join(plan.handle, C.c_void_p(comm.cuda_stream), 0))
+                chk(lib.hgb_model_segment_grads(plan.handle, seg, C.byref(off), C.byref(cnt)))
+                with torch.cuda.stream(comm):            # what the all-reduce would read: the finished bucket
+                    seen.append((off.value, model._grads[off.value:off.value + cnt.value].clone()))
+            chk(lib.hgb_model_lanes_join(plan.handle, sp(), 1))
+            torch.cuda.synchronize()
+            for o, snap in seen:                         # a bucket is complete when its segment's join has passed
+                assert torch.equal(snap, model._grads[o:o + snap.numel()])
         else:
             chk(lib.hgb_model_backward(plan.handle, 0, stacks + 1, sp()))
         torch.cuda.synchronize()
@@ -90,7 +106,7 @@ def test_backward_matches_in_order_replay_on_the_same_activations(env, stacks, B
     print(f"in-order twice: worst per-tensor gradient cosine {floor:.8f} ({floor_name}), whole-gradient cosine {floor_tot:.10f}")
     assert float(g_ref.norm()) > 0 and torch.isfinite(g_ref).all()
     for trial in range(6):
-        g = backward(False, per_segment=(trial % 2 == 1))
+        g = backward(False, per_segment=trial % 3)
         c, name = _worst_cos(g, g_ref, table)
         tot = _cos(g, g_ref)
         print(f"lanes trial {trial}: worst per-tensor cosine {c:.8f} ({name}), whole-gradient cosine {tot:.10f}")
