@@ -41,7 +41,18 @@ extern "C" {
 
 const char* hgb_last_error(void);
 int         hgb_version(void);
-/* debug/tuning knobs (key, value); unknown keys -> HGB_ERR_INVALID */
+/* debug/tuning knobs (key, value); key outside [0,32) -> HGB_ERR_INVALID.  Every knob exists so that an optimisation
+ * can be A/B-ed inside one process (tools_lanes_ab.py, tools_profile_step.py --debug k=v); 0 is always the default.
+ *    1  wgrad: swap LBO/SBO of the MN-major descriptors (bring-up)      2  conv_output selector (tests)
+ *    3  residual via per-thread loads instead of the TMA fetch          4  no fusion of BN-backward reductions (plan build)
+ *    5  no weight-stationary / strip-reuse 3x3 paths                    7  PDL: 1 force on, 2 force off (default adaptive)
+ *    8  replay every op in order on the caller's stream (no lanes)      9  SMs the skip lanes leave free (default 20)
+ *   10  emit weight gradients before dgrads (plan build)               11  1: no wide 1x1 wgrad tiles, 2: also 256->256
+ *   12  no strip reuse (HALO) in the 3x3 forward/dgrad kernel          13  no rolling-strip 3x3 weight-gradient kernel
+ *   14  no deferred BatchNorm (plan build)                             15  HALO tile threshold (default 4 x #SMs)
+ *   16  one thread issues all output boxes                             17  no BatchNorm folding in inference
+ *   18  PDL trigger at kernel start instead of after the last load     19  PDL also in the multi-lane backward pass
+ *   20  CTA cap of side-lane weight gradients (default 64, -1 none)                                                     */
 int         hgb_debug_set(int key, int value);
 
 /* ------------------------------------------------------------------------- */

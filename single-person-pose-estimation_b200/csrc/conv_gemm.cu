@@ -33,7 +33,6 @@ constexpr int kABytes = kBlockM * 128;  // 128 pixels x 64 bf16
 constexpr int kThreads = 192;       // 3x3 wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
 constexpr int kWgradThreads = 256;  // wgrad kernel: + 2 operand-transform warps (deferred BatchNorm)
 constexpr int kGemmThreads = 384;   // forward/dgrad kernel: TMA warp, MMA warp, 8 epilogue warps, 2 operand-transform warps
-constexpr int kXformThreads = 64;
 constexpr float kBnEpsIn = 1e-3f;       // Keras BatchNormalization defaults (as in layer_kernels.cu)
 constexpr float kBnMomentumIn = 0.99f;
 constexpr int kEpiThreads = 256;

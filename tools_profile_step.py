@@ -18,8 +18,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--stacks", type=int, default=8)
 ap.add_argument("--out", default=None)
+ap.add_argument("--debug", default="", help="comma-separated key=value pairs for hgb_debug_set")
 a = ap.parse_args()
 lib = _lib.lib
+for kv in [x for x in a.debug.split(",") if x]:
+    k, v = kv.split("=")
+    lib.hgb_debug_set(int(k), int(v))
 model = hgb200.HourglassModel(17, a.stacks, 256, (256, 256, 3), "sigmoid", seed=1)
 model.compile(optimizer=hgb200.Adam(1e-3), loss=hgb200.loss.weighted_mse)
 B = a.batch
