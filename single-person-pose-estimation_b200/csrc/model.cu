@@ -963,7 +963,10 @@ int ensure_lanes(hgb_model* m) {
   int lo = 0, hi = 0;
   HGB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = numerically smallest = highest priority
   for (int l = 0; l < kNumLanes; ++l) {
-    HGB_CUDA(cudaStreamCreateWithPriority(&m->lane_stream[l], cudaStreamNonBlocking, l == kLaneMain ? hi : (hi + 1 <= lo ? hi + 1 : lo)));
+    int pr = l == kLaneMain ? hi : hi + 1;
+    if (l == kLaneWgrad && hgb::g_debug[21]) pr = hi + 1 + hgb::g_debug[21];   // experiment: weight gradients below the skip lanes
+    if (pr > lo) pr = lo;
+    HGB_CUDA(cudaStreamCreateWithPriority(&m->lane_stream[l], cudaStreamNonBlocking, pr));
     HGB_CUDA(cudaEventCreateWithFlags(&m->join_ev[l], cudaEventDisableTiming));
   }
   HGB_CUDA(cudaEventCreateWithFlags(&m->fork_ev, cudaEventDisableTiming));
