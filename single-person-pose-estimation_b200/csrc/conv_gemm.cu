@@ -1263,7 +1263,7 @@ int launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const Wgr
     return HGB_OK;
   }
   int bn = (a.Cin % 128 == 0) ? 128 : 64, mt = 1;
-  if (a.ksize == 1 && g_debug[11] != 1 && kp.M_tiles >= 8 * 148) {
+  if (a.ksize == 1 && g_debug[11] != 1 && kp.M_tiles >= (g_debug[22] > 0 ? g_debug[22] : 8 * 148)) {
     if (a.Cin % 256 == 0 && (a.Cout <= 128 || g_debug[11] == 2)) bn = 256;
     else if (a.Cout % 256 == 0 && a.Cin == 128) mt = 2;   // (256 -> 256 measured slower with wide tiles: two stages only)
   }

@@ -18,6 +18,7 @@ ap.add_argument("--late", type=int, default=0, help="1 = early trigger (old beha
 ap.add_argument("--bwd-pdl", type=int, default=0)
 ap.add_argument("--wgrad-ctas", type=int, default=0)
 ap.add_argument("--wgrad-prio", type=int, default=0)
+ap.add_argument("--wide-min", type=int, default=0)
 a = ap.parse_args()
 lib = _lib.lib
 lib.hgb_debug_set(10, a.wfirst)
@@ -28,6 +29,7 @@ lib.hgb_debug_set(18, a.late)
 lib.hgb_debug_set(19, a.bwd_pdl)
 lib.hgb_debug_set(20, a.wgrad_ctas)
 lib.hgb_debug_set(21, a.wgrad_prio)
+lib.hgb_debug_set(22, a.wide_min)
 for B in [int(b) for b in a.batches.split(",")]:
     model = hgb200.HourglassModel(17, 8, 256, (256, 256, 3), "sigmoid", seed=1)
     model.compile(optimizer=hgb200.Adam(1e-3), loss=hgb200.loss.weighted_mse)
