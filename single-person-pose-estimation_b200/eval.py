@@ -2,8 +2,8 @@
 the same prediction-dict / JSON schema (eval.py:131-139), the arithmetic on the GPU:
   predict_ds  -> model forward, batched heat-map decode on device (only (B,K,3) floats come back)
   eval_PCK    -> hgb_pck_reduce (2*K integer counters)
-  eval_OKS    -> per-prediction OKS similarity on device (hgb_oks_similarity); the COCO AP matching /
-                 accumulation stays with pycocotools exactly as in the reference when it is installed.
+  eval_OKS    -> COCO keypoint AP/AR: every (detection, ground truth) OKS of the evaluation in one hgb_oks_similarity
+                 launch, matching / precision-recall accumulation restated in cocoeval.py (no pycocotools needed).
 """
 from __future__ import annotations
 
@@ -116,25 +116,31 @@ def _create_oks_obj(ann_id, image_id, pred_kpts, score):
     return {"image_id": image_id, "ann_id": ann_id, "category_id": 1, "keypoints": pred_kpts, "score": score}
 
 
-def eval_OKS(predictions, gt_path):
-    """eval.py:9-51.  AP matching / accumulation is pycocotools' (third party in the reference too)."""
-    try:
+def eval_OKS(predictions, gt_path, backend="hgb", oks_fn=None):
+    """eval.py:9-51.  Same call, same printed summary, same `stats[10]` (AP, AP50, AP75, APm, APl, AR, AR50, AR75, ARm, ARl).
+    The reference delegates to pycocotools; here the protocol is restated in `cocoeval.py` with every OKS value of the
+    evaluation computed by one CUDA launch.  `backend="pycocotools"` runs the third-party package instead (cross-check,
+    needs it installed); `oks_fn` replaces the device OKS (tests only)."""
+    if backend == "pycocotools":
         from pycocotools.coco import COCO
         from pycocotools.cocoeval import COCOeval
-    except ImportError as e:  # pragma: no cover - pycocotools is absent from the build image
-        raise ImportError("eval_OKS delegates AP accumulation to pycocotools exactly like the reference (eval.py:39-49); "
-                          "install it, or use oks_per_prediction() for the per-annotation similarity") from e
+        make_eval = COCOeval
+    elif backend == "hgb":
+        from .cocoeval import COCO, COCOeval
+        make_eval = lambda gt, dt, kind: COCOeval(gt, dt, kind, oks_fn=oks_fn)  # noqa: E731
+    else:
+        raise ValueError(f"unknown eval_OKS backend {backend!r}")
     if isinstance(predictions, str):
         predictions = _load_predictions(predictions)
     results, image_ids = [], []
     for p in predictions:
         kp = []
         for x, y in zip(p["xs/pred"], p["ys/pred"]):
-            kp += [int(x), int(y), 1]
+            kp += [int(x), int(y), 1]                    # coordinates truncated, visibility always 1 (eval.py:25-27)
         results.append(_create_oks_obj(p["ann_id"], p["image_id"], kp, float(np.mean(p["confs"]))))
         image_ids.append(p["image_id"])
     gt = COCO(gt_path)
-    ev = COCOeval(gt, gt.loadRes(results), "keypoints")
+    ev = make_eval(gt, gt.loadRes(results), "keypoints")
     ev.params.imgIds = image_ids
     ev.params.catIds = [1]
     ev.evaluate()

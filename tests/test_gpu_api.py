@@ -118,3 +118,26 @@ def test_trainer_train_and_resume(hgb, tmp_path, capsys):
     assert set(best) == set(w_saved)
     latest = hgb.Trainer(hgb.create_hourglass_model(17, 2, 256, (256, 256, 3), "sigmoid"), builder, 1, 1e-3, "mse", cfg).get_lattest_weights_model()
     np.testing.assert_array_equal(latest.get_weights_dict()["hg1_conv_1x1_predict/kernel"], w_saved["hg1_conv_1x1_predict/kernel"])
+
+
+def test_eval_oks_ap_protocol_on_device_matches_host_oracle(hgb, tmp_path):
+    """eval.py:9-51 without pycocotools: every (detection, ground truth) OKS of the evaluation comes from ONE launch of the
+    CUDA kernel; AP/AR are identical to the same protocol fed by the numpy OKS oracle."""
+    from tests.test_cpu_cocoeval import _dataset, _person, _prediction, _skeleton
+    rng = np.random.default_rng(11)
+    anns, preds = [], []
+    for i in range(64):
+        img = 1 + i // 2                                          # two people per image: the OKS matrix is 2x2 per image
+        sk = _skeleton(rng, offset=50.0 + 300.0 * (i % 2))
+        vis = rng.integers(0, 3, 17)
+        if i % 9 == 0:
+            vis[:] = 0                                            # unlabelled person: doubled-bbox rule + ignored
+        a = _person(1000 + i, img, sk, vis, area=rng.uniform(40 ** 2, 200 ** 2))
+        anns.append(a)
+        preds.append(_prediction(a, sk + rng.normal(0, rng.choice([1.0, 6.0, 25.0]), (17, 2)), float(rng.uniform(0.05, 0.95))))
+    gt_path = tmp_path / "gt.json"
+    gt_path.write_text(json.dumps(_dataset(anns)))
+    want = hgb.eval.eval_OKS(preds, str(gt_path), oks_fn=horc.oks_similarity)
+    got = hgb.eval.eval_OKS(preds, str(gt_path))
+    assert 0 < want[0] < 1
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
