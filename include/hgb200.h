@@ -32,6 +32,7 @@ extern "C" {
 
 #define HGB_F32   0
 #define HGB_BF16  1
+#define HGB_U8    2   /* input-path source images only */
 
 /* loss kinds: trainer.py:224-245 string table */
 #define HGB_LOSS_WEIGHTED_MSE           0   /* loss.py:2-21 */
@@ -104,6 +105,41 @@ int hgb_pck_reduce(const double* xs_pred, const double* ys_pred, const double* x
 int hgb_oks_similarity(const double* xs_pred, const double* ys_pred, const double* xs_gt, const double* ys_gt,
                        const int32_t* vs, const double* area, const double* bbox_xywh, int N, int K,
                        double* oks_out, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Input path: frame -> network input / keypoints      */
+/* ------------------------------------------------------------------------- */
+
+/* tf.image.convert_image_dtype(uint8 -> float32) + crop_and_pad (utilities/data_utils.py:48-98) +
+ * tf.image.resize(bilinear, half-pixel centres, no antialias) in one pass: demo.py:44-50 (N person crops of a frame),
+ * dataset_builder.py:99 / :133 (whole image, crop_xywh = NULL).
+ * src_ptrs: DEVICE array of N device pointers to (h,w,3) images of `src_dtype` (HGB_U8 or HGB_F32; U8 values are
+ * multiplied by float32(1/255)); src_hw: device (N,2) int32 [height,width]; crop_xywh: device (N,4) int32
+ * [x0, y0, crop_w, crop_h] -- crop pixel (cy,cx) reads source pixel (cy+y0, cx+x0), zero outside the source (the host
+ * shim derives these integers with the reference's own Python arithmetic); out: (N,out_h,out_w,3) float32. */
+int hgb_crop_resize(const void* const* src_ptrs, const int32_t* src_hw, int src_dtype, const int32_t* crop_xywh, int N,
+                    int out_h, int out_w, float* out, void* stream);
+
+/* Image half of DatasetBuilder.np_augment_1 (dataset_builder.py:143-172): optional Fliplr, then imgaug
+ * Affine(scale, rotate) = cv2.warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) with OpenCV's 10-bit fixed-point source
+ * coordinates and 5-bit interpolation fractions.  images/out: (N,H,W,3) float32 (out != images); inv_mats: device (N,6)
+ * double, the INVERSE 2x3 map OpenCV derives from the forward matrix (host shim); flip: device (N,) int32. */
+int hgb_augment_affine(const float* images, const double* inv_mats, const int32_t* flip, int N, int H, int W, float* out,
+                       void* stream);
+
+/* Keypoint half of np_augment_1 + flip_labels (dataset_builder.py:150-185, 270-300): joints with v <= 0 become (0,0);
+ * flip maps x -> label_w - x and slot k takes joint flip_partner[k] (x, y and v); forward affine (N,6) double about the
+ * label-map centre; coordinates of slots whose (swapped) v <= 0 are zeroed.  kps_* (N,K); out_x/out_y (N,K) float32. */
+int hgb_augment_keypoints(const float* kps_x, const float* kps_y, const int32_t* kps_v, const int32_t* flip,
+                          const double* fwd_mats, const int32_t* flip_partner, int N, int K, int label_w, float* out_x,
+                          float* out_y, void* stream);
+
+/* DatasetBuilder.augment_2 (dataset_builder.py:190-204) with its four random draws supplied: params (N,4) float32 =
+ * [brightness delta, contrast factor, saturation factor, hue delta] -> tf.image.adjust_brightness, adjust_contrast
+ * (per-channel mean), adjust_saturation (HSV), adjust_hue, then (x - min)/(max - min) over the whole image.
+ * images (N,H,W,3) float32, IN PLACE.  workspace: hgb_color_workspace_bytes(N) bytes. */
+int64_t hgb_color_workspace_bytes(int N);
+int hgb_color_augment(float* images, const float* params, int N, int H, int W, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Hourglass network  (model/hourglass.py:5-206)                             */

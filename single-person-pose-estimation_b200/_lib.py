@@ -12,7 +12,7 @@ if not os.path.exists(LIB_PATH):
 
 lib = C.CDLL(LIB_PATH)
 
-F32, BF16 = 0, 1
+F32, BF16, U8 = 0, 1, 2
 LOSS_KINDS = {"weighted_mse": 0, "mse": 1, "iou": 2, "weighted_keypoint_mse": 3}
 BUF_PARAMS, BUF_GRADS, BUF_ADAM_M, BUF_ADAM_V, BUF_ARENA = range(5)
 
@@ -36,6 +36,11 @@ PROTOTYPES = {
     "hgb_decode": (i32, [vp, i32, i32, i32, i32, i32, f64, i32, vp, vp, vp]),
     "hgb_pck_reduce": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, f64, vp, vp]),
     "hgb_oks_similarity": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]),
+    "hgb_crop_resize": (i32, [vp, vp, i32, vp, i32, i32, i32, vp, vp]),
+    "hgb_augment_affine": (i32, [vp, vp, vp, i32, i32, i32, vp, vp]),
+    "hgb_augment_keypoints": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]),
+    "hgb_color_workspace_bytes": (i64, [i32]),
+    "hgb_color_augment": (i32, [vp, vp, i32, i32, i32, vp, vp]),
     "hgb_conv_gemm": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "hgb_conv_wgrad": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "hgb_model_create": (i32, [C.POINTER(ModelConfig), i32, C.POINTER(vp)]),

@@ -136,6 +136,82 @@ def oks_similarity(xs_pred, ys_pred, xs_gt, ys_gt, vs, area, bbox_xywh):
     return out
 
 
+# ------------------------------------------------------------------ input path
+def crop_resize(sources, crops=None, out_h: int = 256, out_w: int = 256, source_index=None):
+    """Fused uint8->float32 conversion, crop_and_pad and bilinear resize (demo.py:44-50, dataset_builder.py:99,133).
+
+    sources: list of (h,w,3) uint8 or float32 arrays / CUDA tensors (one dtype per call); crops: None (whole images) or
+    (N,4) integers [x0, y0, crop_w, crop_h] from `data_utils.crop_and_pad_params`; source_index: which source each of the
+    N outputs reads (default: output n reads source n).  Returns (N,out_h,out_w,3) float32 on device and keeps nothing."""
+    torch = _torch()
+    srcs = []
+    for im in sources:
+        if not isinstance(im, torch.Tensor):
+            im = torch.as_tensor(np.ascontiguousarray(im))
+        if im.dtype not in (torch.uint8, torch.float32):
+            im = im.to(torch.float32)
+        if im.dim() != 3 or im.shape[2] != 3:
+            raise ValueError("source images must be (h, w, 3)")
+        srcs.append(im.to(device="cuda").contiguous())
+    if not srcs:
+        return torch.empty((0, out_h, out_w, 3), dtype=torch.float32, device="cuda")
+    if any(t.dtype != srcs[0].dtype for t in srcs):
+        raise ValueError("all sources of one call must share a dtype")
+    index = list(range(len(srcs))) if source_index is None else [int(i) for i in source_index]
+    N = len(index)
+    if N == 0:
+        return torch.empty((0, out_h, out_w, 3), dtype=torch.float32, device="cuda")
+    table = torch.tensor([srcs[i].data_ptr() for i in index], dtype=torch.int64).cuda()
+    hw = torch.tensor([[srcs[i].shape[0], srcs[i].shape[1]] for i in index], dtype=torch.int32).cuda()
+    crop_t = None
+    if crops is not None:
+        crop_t = torch.as_tensor(np.asarray(crops, dtype=np.int32).reshape(N, 4)).cuda()
+    out = torch.empty((N, out_h, out_w, 3), dtype=torch.float32, device="cuda")
+    check(lib.hgb_crop_resize(ptr(table), ptr(hw), _lib.U8 if srcs[0].dtype == torch.uint8 else _lib.F32, ptr(crop_t), N,
+                              out_h, out_w, ptr(out), stream_ptr()))
+    for t in srcs:                                        # the launch is asynchronous: keep sources alive on this stream
+        t.record_stream(torch.cuda.current_stream())
+    return out
+
+
+def augment_affine(images, inv_mats, flip, out=None):
+    """Fliplr + cv2.warpAffine(INTER_LINEAR, constant 0) of (N,H,W,3) float32 images; inv_mats (N,2,3) float64 inverse maps."""
+    torch = _torch()
+    x = _dev(images, torch.float32)
+    N, H, W, _ = x.shape
+    m = _dev(np.asarray(inv_mats, np.float64).reshape(N, 6), torch.float64)
+    f = _dev(np.asarray(flip).astype(np.int32).reshape(N), torch.int32)
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.hgb_augment_affine(ptr(x), ptr(m), ptr(f), N, H, W, ptr(out), stream_ptr()))
+    return out
+
+
+def augment_keypoints(kps_x, kps_y, kps_v, flip, fwd_mats, flip_partner, label_w: int = 64):
+    torch = _torch()
+    kx, ky, kv = _dev(kps_x, torch.float32), _dev(kps_y, torch.float32), _dev(kps_v, torch.int32)
+    N, K = kx.shape
+    m = _dev(np.asarray(fwd_mats, np.float64).reshape(N, 6), torch.float64)
+    f = _dev(np.asarray(flip).astype(np.int32).reshape(N), torch.int32)
+    pt = _dev(np.asarray(flip_partner, np.int32).reshape(K), torch.int32)
+    ox, oy = torch.empty_like(kx), torch.empty_like(ky)
+    check(lib.hgb_augment_keypoints(ptr(kx), ptr(ky), ptr(kv), ptr(f), ptr(m), ptr(pt), N, K, int(label_w), ptr(ox), ptr(oy),
+                                    stream_ptr()))
+    return ox, oy
+
+
+def color_augment(images, params):
+    """IN PLACE on a CUDA float32 (N,H,W,3) tensor; params (N,4) = brightness delta, contrast, saturation, hue delta."""
+    torch = _torch()
+    if not (isinstance(images, torch.Tensor) and images.is_cuda and images.dtype == torch.float32 and images.is_contiguous()):
+        raise ValueError("color_augment works in place on a contiguous CUDA float32 tensor")
+    N, H, W, _ = images.shape
+    p = _dev(np.asarray(params, np.float32).reshape(N, 4) if not isinstance(params, torch.Tensor) else params, torch.float32)
+    ws = torch.empty(int(lib.hgb_color_workspace_bytes(N)), dtype=torch.uint8, device="cuda")
+    check(lib.hgb_color_augment(ptr(images), ptr(p), N, H, W, ptr(ws), stream_ptr()))
+    return images
+
+
 # ------------------------------------------------------------------ convolution kernels (tests / microbench)
 def conv_gemm(x, w, bias=None, res1=None, res2=None, ksize=1, relu=False, tap_sign=1, stats=None, out=None):
     """x: (N,H,W,Cin) bf16; w: (Cout, k*k*Cin) bf16 -> (N,H,W,Cout) bf16."""
