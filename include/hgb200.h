@@ -141,6 +141,18 @@ int hgb_augment_keypoints(const float* kps_x, const float* kps_y, const int32_t*
 int64_t hgb_color_workspace_bytes(int N);
 int hgb_color_augment(float* images, const float* params, int N, int H, int W, void* workspace, void* stream);
 
+/* CRC-32C (Castagnoli) of a HOST buffer: the checksum of the TFRecord framing (length and payload, masked as
+ * ((crc >> 15 | crc << 17) + 0xa282ead8) by the caller) that tf.data.TFRecordDataset verifies (dataset_builder.py:39,48,63). */
+uint32_t hgb_crc32c(const void* host_data, int64_t len);
+
+/* tf.image.decode_image (dataset_builder.py:263) / tf.io.decode_jpeg (gen_tfrecords.py:112), JPEG only.
+ * hgb_jpeg_info parses the frame header of a HOST buffer; hgb_jpeg_decode decodes N HOST streams into N caller-owned
+ * DEVICE buffers of (h,w,3) interleaved RGB uint8 (grey streams are replicated to 3 channels) through nvJPEG, which is
+ * opened on first use (HGB_ERR_STATE if the toolkit library is missing).  datas / lens / outs / hw are HOST arrays;
+ * hw (N,2) = [height,width] the outputs were sized for (checked against the streams). */
+int hgb_jpeg_info(const uint8_t* host_data, int64_t len, int32_t* height, int32_t* width, int32_t* components);
+int hgb_jpeg_decode(const uint8_t* const* datas, const int64_t* lens, int N, uint8_t* const* outs, const int32_t* hw, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* Hourglass network  (model/hourglass.py:5-206)                             */
 /* ------------------------------------------------------------------------- */

@@ -41,6 +41,9 @@ PROTOTYPES = {
     "hgb_augment_keypoints": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]),
     "hgb_color_workspace_bytes": (i64, [i32]),
     "hgb_color_augment": (i32, [vp, vp, i32, i32, i32, vp, vp]),
+    "hgb_crc32c": (C.c_uint32, [vp, i64]),
+    "hgb_jpeg_info": (i32, [vp, i64, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+    "hgb_jpeg_decode": (i32, [vp, vp, i32, vp, vp, vp]),
     "hgb_conv_gemm": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "hgb_conv_wgrad": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "hgb_model_create": (i32, [C.POINTER(ModelConfig), i32, C.POINTER(vp)]),

@@ -1,0 +1,154 @@
+// Host-side IO helpers of the input path: TFRecord framing checksum and JPEG decode.
+//   hgb_crc32c        : CRC-32C (Castagnoli) of the TFRecord framing tf.data.TFRecordDataset verifies
+//                       (dataset_builder.py:39,48,63), slicing-by-8 on the host
+//   hgb_jpeg_info     : size / component count from the SOF marker (what tf.image.decode_image reads first, :263)
+//   hgb_jpeg_decode   : baseline / progressive JPEG -> interleaved RGB uint8 in DEVICE memory through nvJPEG
+//                       (library decode = plumbing, like cuBLAS for a plain GEMM); libnvjpeg is opened at first use so
+//                       libhgb200.so itself has no load-time dependency on it
+#include <dlfcn.h>
+#include <nvjpeg.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace hgb {
+
+// ------------------------------------------------------------------------------------------------ CRC-32C
+static uint32_t g_crc_table[8][256];
+static std::once_flag g_crc_once;
+
+static void crc_init() {
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+    g_crc_table[0][i] = c;
+  }
+  for (uint32_t i = 0; i < 256; ++i)
+    for (int t = 1; t < 8; ++t) g_crc_table[t][i] = (g_crc_table[t - 1][i] >> 8) ^ g_crc_table[0][g_crc_table[t - 1][i] & 0xff];
+}
+
+// ------------------------------------------------------------------------------------------------ nvJPEG binding
+struct NvJpeg {
+  void* dso = nullptr;
+  nvjpegHandle_t handle = nullptr;
+  nvjpegJpegState_t state = nullptr;
+  nvjpegStatus_t (*create)(nvjpegHandle_t*) = nullptr;
+  nvjpegStatus_t (*state_create)(nvjpegHandle_t, nvjpegJpegState_t*) = nullptr;
+  nvjpegStatus_t (*decode)(nvjpegHandle_t, nvjpegJpegState_t, const unsigned char*, size_t, nvjpegOutputFormat_t, nvjpegImage_t*,
+                           cudaStream_t) = nullptr;
+  std::string error;
+  bool ok = false;
+};
+static NvJpeg g_nvjpeg;
+static std::mutex g_nvjpeg_mutex;
+
+static bool nvjpeg_ready() {
+  NvJpeg& j = g_nvjpeg;
+  if (j.ok) return true;
+  if (!j.error.empty()) return false;
+  const char* names[] = {"libnvjpeg.so.12", "/usr/local/cuda/lib64/libnvjpeg.so.12", "/usr/local/cuda/lib64/libnvjpeg.so", "libnvjpeg.so"};
+  for (const char* n : names) {
+    j.dso = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+    if (j.dso) break;
+  }
+  if (!j.dso) {
+    j.error = "libnvjpeg.so.12 not found (CUDA toolkit library); JPEG decode is unavailable";
+    return false;
+  }
+  j.create = (decltype(j.create))dlsym(j.dso, "nvjpegCreateSimple");
+  j.state_create = (decltype(j.state_create))dlsym(j.dso, "nvjpegJpegStateCreate");
+  j.decode = (decltype(j.decode))dlsym(j.dso, "nvjpegDecode");
+  if (!j.create || !j.state_create || !j.decode) {
+    j.error = "libnvjpeg lacks nvjpegCreateSimple / nvjpegJpegStateCreate / nvjpegDecode";
+    return false;
+  }
+  nvjpegStatus_t s = j.create(&j.handle);
+  if (s == NVJPEG_STATUS_SUCCESS) s = j.state_create(j.handle, &j.state);
+  if (s != NVJPEG_STATUS_SUCCESS) {
+    j.error = "nvjpeg initialisation failed with status " + std::to_string((int)s);
+    return false;
+  }
+  j.ok = true;
+  return true;
+}
+
+}  // namespace hgb
+
+using namespace hgb;
+
+extern "C" uint32_t hgb_crc32c(const void* data, int64_t len) {
+  std::call_once(g_crc_once, crc_init);
+  const uint8_t* p = (const uint8_t*)data;
+  uint32_t c = 0xffffffffu;
+  while (len > 0 && ((uintptr_t)p & 7)) {
+    c = g_crc_table[0][(c ^ *p++) & 0xff] ^ (c >> 8);
+    --len;
+  }
+  while (len >= 8) {
+    uint64_t w;
+    memcpy(&w, p, 8);
+    w ^= c;
+    c = g_crc_table[7][w & 0xff] ^ g_crc_table[6][(w >> 8) & 0xff] ^ g_crc_table[5][(w >> 16) & 0xff] ^ g_crc_table[4][(w >> 24) & 0xff] ^
+        g_crc_table[3][(w >> 32) & 0xff] ^ g_crc_table[2][(w >> 40) & 0xff] ^ g_crc_table[1][(w >> 48) & 0xff] ^ g_crc_table[0][w >> 56];
+    p += 8;
+    len -= 8;
+  }
+  while (len-- > 0) c = g_crc_table[0][(c ^ *p++) & 0xff] ^ (c >> 8);
+  return c ^ 0xffffffffu;
+}
+
+extern "C" int hgb_jpeg_info(const uint8_t* data, int64_t len, int32_t* height, int32_t* width, int32_t* components) {
+  HGB_CHECK_ARG(data && height && width && components, "hgb_jpeg_info: null pointer");
+  HGB_CHECK_ARG(len >= 4 && data[0] == 0xFF && data[1] == 0xD8, "hgb_jpeg_info: not a JPEG stream (no SOI marker)");
+  int64_t i = 2;
+  while (i + 4 <= len) {
+    if (data[i] != 0xFF) { ++i; continue; }
+    const uint8_t m = data[i + 1];
+    if (m == 0xFF) { ++i; continue; }                                   // fill byte
+    if (m == 0xD8 || m == 0x01 || (m >= 0xD0 && m <= 0xD7)) { i += 2; continue; }   // markers without a length
+    const int64_t seg = ((int64_t)data[i + 2] << 8) | data[i + 3];
+    const bool sof = m >= 0xC0 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC;
+    if (sof) {
+      HGB_CHECK_ARG(i + 10 <= len, "hgb_jpeg_info: truncated frame header");
+      *height = (data[i + 5] << 8) | data[i + 6];
+      *width = (data[i + 7] << 8) | data[i + 8];
+      *components = data[i + 9];
+      HGB_CHECK_ARG(*height > 0 && *width > 0, "hgb_jpeg_info: empty frame");
+      return HGB_OK;
+    }
+    if (m == 0xDA || m == 0xD9) break;                                   // start of scan / end of image before any frame
+    i += 2 + seg;
+  }
+  set_error("hgb_jpeg_info: no frame header found");
+  return HGB_ERR_INVALID;
+}
+
+extern "C" int hgb_jpeg_decode(const uint8_t* const* datas, const int64_t* lens, int N, uint8_t* const* outs, const int32_t* hw,
+                               void* stream) {
+  HGB_CHECK_ARG(N >= 0, "hgb_jpeg_decode: negative count");
+  if (N == 0) return HGB_OK;
+  HGB_CHECK_ARG(datas && lens && outs && hw, "hgb_jpeg_decode: null pointer");
+  std::lock_guard<std::mutex> lock(g_nvjpeg_mutex);
+  if (!nvjpeg_ready()) {
+    set_error("%s", g_nvjpeg.error.c_str());
+    return HGB_ERR_STATE;
+  }
+  for (int n = 0; n < N; ++n) {
+    HGB_CHECK_ARG(datas[n] && outs[n] && lens[n] > 0, "hgb_jpeg_decode: image %d: null pointer / empty stream", n);
+    int32_t h, w, c;
+    if (int rc = hgb_jpeg_info(datas[n], lens[n], &h, &w, &c)) return rc;
+    HGB_CHECK_ARG(h == hw[2 * n] && w == hw[2 * n + 1], "hgb_jpeg_decode: image %d is %dx%d, the output buffer was sized for %dx%d", n, h, w,
+                  hw[2 * n], hw[2 * n + 1]);
+    HGB_CHECK_ARG(c == 1 || c == 3, "hgb_jpeg_decode: image %d has %d components (grey and YCbCr/RGB only)", n, c);
+    nvjpegImage_t img = {};
+    img.channel[0] = outs[n];
+    img.pitch[0] = (size_t)w * 3;
+    nvjpegStatus_t s = g_nvjpeg.decode(g_nvjpeg.handle, g_nvjpeg.state, datas[n], (size_t)lens[n], NVJPEG_OUTPUT_RGBI, &img, (cudaStream_t)stream);
+    if (s != NVJPEG_STATUS_SUCCESS) {
+      set_error("hgb_jpeg_decode: nvjpegDecode failed on image %d with status %d", n, (int)s);
+      return HGB_ERR_CUDA;
+    }
+  }
+  return HGB_OK;
+}

@@ -135,3 +135,135 @@ def make_train_label_batch(images, kps_x, kps_y, kps_v, draws, label_shape=(64, 
 def make_valid_label_batch(images, kps_x, kps_y, kps_v, label_shape=(64, 64, 17)):
     """DatasetBuilder.make_valid_label (:81-85)."""
     return images, ops.render_targets(kps_x, kps_y, kps_v, label_shape[0], label_shape[1])
+
+
+# ------------------------------------------------------------------ the TFRecord-backed builder (dataset_builder.py:10-66)
+class DatasetBuilder:
+    """Drop-in for the reference's DatasetBuilder(config, ratio): same constructor arguments, attributes, console lines and
+    `build_datasets()` / `get_ds_prediction()` contracts, without TensorFlow.  Records are read and parsed on the host
+    (tfrecord.py); JPEG decode (nvJPEG), resize, augmentation and target rendering run per BATCH on the GPU, so a batch
+    costs a handful of launches instead of one Python callback per example (the reference's tf.numpy_function path).
+    Yields CUDA float32 tensors: (images (B,256,256,3), heatmaps (B,64,64,17))."""
+
+    def __init__(self, config, ratio=1, seed=None):
+        import glob
+        assert 0 < ratio <= 1
+        self.image_shape = tuple(config.IMAGE_SHAPE)
+        self.label_shape = tuple(config.LABEL_SHAPE)
+        self.num_keypoints = int(config.NUM_KEYPOINTS)
+        self.gaussian_kernel = getattr(config, "GAUSSIAN_KERNEL", 7)
+        self.sigma = getattr(config, "HM_SIGMA", 1)
+        self.index_flip_pairs = [list(p) for p in config.COCO_INDEX_FLIP_PAIRS]
+        self.batch_size = int(config.BATCH_SIZE)
+        self.shuffle_buffer = int(getattr(config, "SHUFFLE_BUFFER", 1000))
+        self.train_filenames = sorted(glob.glob(f"{config.TRAIN_TFRECORDS_DIR}/*.tfrec"))
+        self.valid_filenames = sorted(glob.glob(f"{config.VALID_TFRECORDS_DIR}/*.tfrec"))
+        if ratio < 1:
+            self.train_filenames = self.train_filenames[:int(np.ceil(ratio * len(self.train_filenames)))]
+            self.valid_filenames = self.valid_filenames[:int(np.ceil(ratio * len(self.valid_filenames)))]
+        self.num_train_examples = self.get_ds_length(self.train_filenames)
+        self.num_valid_examples = self.get_ds_length(self.valid_filenames)
+        self._rng = np.random.default_rng(seed)
+        print(f"Train dataset with {len(self.train_filenames)} tfrecords and {self.num_train_examples} examples.")
+        print(f"Valid dataset with {len(self.valid_filenames)} tfrecords and {self.num_valid_examples} examples.")
+
+    @staticmethod
+    def get_ds_length(filenames):
+        """dataset_builder.py:303-310: the example count is the number between the last '-' and the extension."""
+        length = 0
+        for name in filenames:
+            length += int(name.split("-")[-1].split(".")[0])
+        return length
+
+    @staticmethod
+    def parse_tfrecord_fn(example):
+        from . import tfrecord
+        return tfrecord.parse_tfrecord_fn(example)
+
+    @staticmethod
+    def flip_labels(xs, ys, vs, flip_index_pairs):
+        """dataset_builder.py:270-300 on plain arrays: swapped copies of x, y and v."""
+        partner = flip_partner(len(xs), flip_index_pairs)
+        return np.asarray(xs)[partner], np.asarray(ys)[partner], np.asarray(vs)[partner]
+
+    # -- record streams
+    def _records(self, filenames):
+        from . import tfrecord
+        for name in filenames:
+            yield from tfrecord.read_records(name)
+
+    def _shuffled(self, records):
+        """tf.data shuffle(buffer): fill the buffer, then emit a uniformly chosen slot and refill it."""
+        buf = []
+        for r in records:
+            if len(buf) < self.shuffle_buffer:
+                buf.append(r)
+                continue
+            i = int(self._rng.integers(len(buf)))
+            out, buf[i] = buf[i], r
+            yield out
+        while buf:
+            yield buf.pop(int(self._rng.integers(len(buf))))
+
+    def _batches(self, records):
+        batch = []
+        for r in records:
+            batch.append(self.parse_tfrecord_fn(r))
+            if len(batch) == self.batch_size:
+                yield batch
+                batch = []
+        if batch:
+            yield batch                                   # batch() before repeat(): the last batch of a pass may be short
+
+    # -- per-batch device work
+    def prepare_examples(self, examples):
+        """prepare_example (:88-111) for a batch: decode + resize on device, keypoints to label-map units (two float32 ops)."""
+        from . import tfrecord
+        from .utilities import data_utils
+        images = data_utils.resize_images(tfrecord.decode_jpeg_batch([e["image"] for e in examples]), self.image_shape[0], self.image_shape[1])
+        kx = np.stack([scale_keypoints(e["keypoints/x"], e["width"], self.label_shape[1]) for e in examples])
+        ky = np.stack([scale_keypoints(e["keypoints/y"], e["height"], self.label_shape[0]) for e in examples])
+        kv = np.stack([e["keypoints/vis"] for e in examples]).astype(np.int32)
+        return images, kx, ky, kv
+
+    def make_train_label(self, images, kps_x, kps_y, kps_v):
+        draws = draw_augmentation(self._rng, int(images.shape[0]))
+        aug, ax, ay = augment_1_batch(images, kps_x, kps_y, kps_v, draws["flip"], draws["scale"], draws["rotate_deg"], self.label_shape,
+                                      self.index_flip_pairs)
+        augment_2_batch(aug, draws["brightness_delta"], draws["contrast_factor"], draws["saturation_factor"], draws["hue_delta"])
+        return aug, ops.render_targets(ax, ay, kps_v, self.label_shape[0], self.label_shape[1])
+
+    def make_valid_label(self, images, kps_x, kps_y, kps_v):
+        return images, ops.render_targets(kps_x, kps_y, kps_v, self.label_shape[0], self.label_shape[1])
+
+    def np_gen_heatmaps(self, kps_x, kps_y, kps_v):
+        return np_gen_heatmaps(kps_x, kps_y, kps_v, self.label_shape)
+
+    def _train_stream(self):
+        while True:                                       # .repeat()
+            for batch in self._batches(self._shuffled(self._records(self.train_filenames))):
+                yield self.make_train_label(*self.prepare_examples(batch))
+
+    def _valid_stream(self):
+        while True:
+            for batch in self._batches(self._records(self.valid_filenames)):
+                yield self.make_valid_label(*self.prepare_examples(batch))
+
+    def build_datasets(self):
+        return self._train_stream(), self._valid_stream()
+
+    def get_ds_prediction(self):
+        """:58-66 + prepare_prediction_example (:113-137): one pass over the validation records, (images, meta) per batch
+        with the meta keys predict_ds reads (eval.py:117-139)."""
+        from . import tfrecord
+        from .utilities import data_utils
+        for batch in self._batches(self._records(self.valid_filenames)):
+            images = data_utils.resize_images(tfrecord.decode_jpeg_batch([e["image"] for e in batch]), self.image_shape[0], self.image_shape[1])
+            meta = {"ann_id": np.array([e["ann_id"] for e in batch]), "image_id": np.array([e["image_id"] for e in batch]),
+                    "coco_url": [e["coco_url"] for e in batch],
+                    "keypoints/x": np.stack([e["keypoints/x"] for e in batch]), "keypoints/y": np.stack([e["keypoints/y"] for e in batch]),
+                    "keypoints/vis": np.stack([e["keypoints/vis"] for e in batch]),
+                    "bbox_x": np.array([e["bbox_x"] for e in batch], np.float32), "bbox_y": np.array([e["bbox_y"] for e in batch], np.float32),
+                    "bbox_h": np.array([e["height"] for e in batch]), "bbox_w": np.array([e["width"] for e in batch]),
+                    "original_bbox": np.stack([e["original_bbox"] for e in batch])}
+            yield images, meta

@@ -1,0 +1,229 @@
+"""TFRecord files and tf.train.Example messages without TensorFlow.
+
+The reference stores its dataset as TFRecords of tf.train.Example (gen_tfrecords.py:12-86 writes them,
+dataset_builder.py:241-268 parses them).  Both formats are public and tiny:
+
+  record  := uint64 length | uint32 masked_crc32c(length) | payload | uint32 masked_crc32c(payload)        (little endian)
+  Example := { 1: Features { 1: map<string, Feature> } },  Feature := { 1: BytesList | 2: FloatList | 3: Int64List },
+             each list := { 1: repeated value } (floats / int64s packed, unpacked accepted)
+
+The CRC runs in libhgb200 (`hgb_crc32c`, host code); everything else here is byte bookkeeping.  JPEG payloads are decoded on
+the GPU (`decode_jpeg_batch` -> `hgb_jpeg_decode`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import struct
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+
+_MASK_DELTA = 0xA282EAD8
+
+
+def masked_crc32c(data: bytes) -> int:
+    crc = lib.hgb_crc32c(data, len(data))
+    return (((crc >> 15) | (crc << 17)) + _MASK_DELTA) & 0xFFFFFFFF
+
+
+# ------------------------------------------------------------------ record framing
+def read_records(path, verify=True):
+    """Yield the payload of every record of one .tfrec file; corrupt framing raises ValueError like TF's DataLossError."""
+    with open(path, "rb") as f:
+        while True:
+            head = f.read(12)
+            if not head:
+                return
+            if len(head) < 12:
+                raise ValueError(f"{path}: truncated record header")
+            (length,), (len_crc,) = struct.unpack("<Q", head[:8]), struct.unpack("<I", head[8:])
+            if verify and masked_crc32c(head[:8]) != len_crc:
+                raise ValueError(f"{path}: corrupted record length")
+            body = f.read(length + 4)
+            if len(body) < length + 4:
+                raise ValueError(f"{path}: truncated record")
+            payload = body[:length]
+            if verify and masked_crc32c(payload) != struct.unpack("<I", body[length:])[0]:
+                raise ValueError(f"{path}: corrupted record payload")
+            yield payload
+
+
+def write_records(path, payloads):
+    """tf.io.TFRecordWriter (gen_tfrecords.py:106-114)."""
+    with open(path, "wb") as f:
+        for payload in payloads:
+            head = struct.pack("<Q", len(payload))
+            f.write(head + struct.pack("<I", masked_crc32c(head)) + payload + struct.pack("<I", masked_crc32c(payload)))
+
+
+# ------------------------------------------------------------------ protobuf wire format (the subset Example uses)
+def _varint(buf, at):
+    value = shift = 0
+    while True:
+        b = buf[at]
+        at += 1
+        value |= (b & 0x7F) << shift
+        if not b & 0x80:
+            return value, at
+        shift += 7
+
+
+def _put_varint(value):
+    value &= 0xFFFFFFFFFFFFFFFF
+    out = bytearray()
+    while True:
+        b = value & 0x7F
+        value >>= 7
+        out.append(b | (0x80 if value else 0))
+        if not value:
+            return bytes(out)
+
+
+def _fields(buf):
+    at, end = 0, len(buf)
+    while at < end:
+        key, at = _varint(buf, at)
+        number, wire = key >> 3, key & 7
+        if wire == 0:
+            value, at = _varint(buf, at)
+        elif wire == 1:
+            value, at = buf[at:at + 8], at + 8
+        elif wire == 2:
+            size, at = _varint(buf, at)
+            value, at = buf[at:at + size], at + size
+        elif wire == 5:
+            value, at = buf[at:at + 4], at + 4
+        else:
+            raise ValueError(f"unsupported protobuf wire type {wire}")
+        yield number, wire, value
+
+
+def _len_delimited(number, payload):
+    return _put_varint((number << 3) | 2) + _put_varint(len(payload)) + payload
+
+
+def _parse_feature(buf):
+    for number, wire, value in _fields(buf):
+        if number == 1:                                                    # BytesList
+            return [bytes(v) for n, w, v in _fields(value) if n == 1]
+        if number == 2:                                                    # FloatList
+            out = []
+            for n, w, v in _fields(value):
+                if n == 1:
+                    out.append(np.frombuffer(v, dtype="<f4"))
+            return np.concatenate(out).astype(np.float32) if out else np.zeros(0, np.float32)
+        if number == 3:                                                    # Int64List
+            out = []
+            for n, w, v in _fields(value):
+                if n != 1:
+                    continue
+                if w == 0:
+                    out.append(v)
+                else:
+                    at = 0
+                    while at < len(v):
+                        x, at = _varint(v, at)
+                        out.append(x)
+            arr = np.array(out, dtype=np.uint64).astype(np.int64) if out else np.zeros(0, np.int64)
+            return arr
+    return None                                                            # Feature with no list set
+
+
+def parse_example(payload: bytes) -> dict:
+    """Serialized tf.train.Example -> {name: list[bytes] | float32 array | int64 array}."""
+    out = {}
+    for number, _, features in _fields(memoryview(payload)):
+        if number != 1:
+            continue
+        for n, _, entry in _fields(features):
+            if n != 1:
+                continue
+            name, feature = None, None
+            for en, _, ev in _fields(entry):
+                if en == 1:
+                    name = bytes(ev).decode("utf-8")
+                elif en == 2:
+                    feature = _parse_feature(ev)
+            if name is not None:
+                out[name] = feature
+    return out
+
+
+def build_example(features: dict) -> bytes:
+    """{name: bytes | str | list[bytes] | float array | int array} -> serialized tf.train.Example (map entries sorted by
+    name, the deterministic order protobuf serialisation uses)."""
+    entries = b""
+    for name in sorted(features):
+        v = features[name]
+        if isinstance(v, str):
+            v = v.encode()
+        if isinstance(v, (bytes, bytearray)):
+            v = [bytes(v)]
+        if isinstance(v, list) and v and isinstance(v[0], (bytes, bytearray)):
+            feature = _len_delimited(1, b"".join(_len_delimited(1, bytes(b)) for b in v))
+        else:
+            arr = np.atleast_1d(np.asarray(v))
+            if arr.dtype.kind == "f":
+                body = _len_delimited(1, arr.astype("<f4").tobytes()) if arr.size else b""
+                feature = _len_delimited(2, body)
+            elif arr.dtype.kind in "iub":
+                body = _len_delimited(1, b"".join(_put_varint(int(x)) for x in arr)) if arr.size else b""
+                feature = _len_delimited(3, body)
+            else:
+                raise TypeError(f"feature {name!r}: unsupported value type {arr.dtype}")
+        entries += _len_delimited(1, _len_delimited(1, name.encode()) + _len_delimited(2, feature))
+    return _len_delimited(1, entries)
+
+
+# ------------------------------------------------------------------ the reference's schema
+FIXED_INT = ("ann_id", "image_id", "width", "height", "keypoints/num")
+FIXED_BYTES = ("image", "image_path", "coco_url")
+FIXED_FLOAT = ("bbox_x", "bbox_y")
+VAR_FLOAT = ("keypoints/x", "keypoints/y", "original_bbox")
+VAR_INT = ("keypoints/vis",)
+
+
+def parse_tfrecord_fn(payload: bytes) -> dict:
+    """DatasetBuilder.parse_tfrecord_fn (dataset_builder.py:241-268) minus the image decode (done on the GPU in batches):
+    FixedLenFeature scalars, VarLenFeature -> dense arrays; `image` stays the encoded JPEG bytes."""
+    raw = parse_example(payload)
+    ex = {}
+    for name in FIXED_INT + FIXED_BYTES + FIXED_FLOAT:
+        v = raw.get(name)
+        if v is None or len(v) != 1:
+            raise ValueError(f"Feature: {name} (data type: {'string' if name in FIXED_BYTES else 'number'}) is required but could not be found.")
+        ex[name] = v[0] if name in FIXED_BYTES else (int(v[0]) if name in FIXED_INT else np.float32(v[0]))
+    for name in VAR_FLOAT:
+        v = raw.get(name)
+        ex[name] = np.zeros(0, np.float32) if v is None else np.asarray(v, np.float32)
+    for name in VAR_INT:
+        v = raw.get(name)
+        ex[name] = np.zeros(0, np.int64) if v is None else np.asarray(v, np.int64)
+    return ex
+
+
+# ------------------------------------------------------------------ JPEG
+def jpeg_info(data: bytes):
+    h, w, c = C.c_int(), C.c_int(), C.c_int()
+    check(lib.hgb_jpeg_info(data, len(data), C.byref(h), C.byref(w), C.byref(c)))
+    return h.value, w.value, c.value
+
+
+def decode_jpeg_batch(streams):
+    """List of encoded JPEG byte strings -> list of (h,w,3) uint8 CUDA tensors (RGB), decoded by nvJPEG on the current stream."""
+    torch = _lib.require_cuda()
+    n = len(streams)
+    if n == 0:
+        return []
+    sizes = [jpeg_info(s)[:2] for s in streams]
+    outs = [torch.empty((h, w, 3), dtype=torch.uint8, device="cuda") for h, w in sizes]
+    keep = [C.create_string_buffer(s, len(s)) for s in streams]
+    datas = (C.c_void_p * n)(*[C.cast(b, C.c_void_p) for b in keep])
+    lens = (C.c_int64 * n)(*[len(s) for s in streams])
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in outs])
+    hw = (C.c_int32 * (2 * n))(*[v for s in sizes for v in s])
+    check(lib.hgb_jpeg_decode(datas, lens, n, ptrs, hw, _lib.stream_ptr()))
+    torch.cuda.current_stream().synchronize()            # nvJPEG reads the host streams asynchronously: keep them until done
+    return outs

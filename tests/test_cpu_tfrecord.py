@@ -1,0 +1,143 @@
+"""TFRecord framing / tf.train.Example wire format / JPEG header parsing (tfrecord.py, csrc/io_host.cu) and the
+TFRecord-backed DatasetBuilder's host logic.  CPU only: no decode, no kernels."""
+import os
+import struct
+import types
+
+import cv2
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def hgb():
+    import hgb200
+    return hgb200
+
+
+def test_crc32c_known_answers(hgb):
+    from hgb200 import tfrecord
+    crc = hgb._lib.lib.hgb_crc32c
+    assert crc(b"", 0) == 0
+    assert crc(b"123456789", 9) == 0xE3069283                      # CRC-32C check value
+    assert crc(bytes(32), 32) == 0x8A9136AA                        # RFC 3720 B.4: 32 bytes of zeros
+    assert crc(bytes([0xFF] * 32), 32) == 0x62A8AB43               # RFC 3720 B.4: 32 bytes of ones
+    assert crc(bytes(range(32)), 32) == 0x46DD794E                 # RFC 3720 B.4: incrementing
+    data = np.random.default_rng(0).integers(0, 256, 10007, dtype=np.uint8).tobytes()
+    ref = 0xFFFFFFFF
+    for b in data[:999]:                                           # bitwise definition on a prefix with an odd length
+        ref ^= b
+        for _ in range(8):
+            ref = (ref >> 1) ^ 0x82F63B78 if ref & 1 else ref >> 1
+    assert crc(data, 999) == ref ^ 0xFFFFFFFF
+    assert crc(data[1:], 998) != crc(data, 998)                    # unaligned start goes through the byte prologue
+    masked = tfrecord.masked_crc32c(b"123456789")
+    assert masked == (((0xE3069283 >> 15) | (0xE3069283 << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+def test_example_wire_format_known_answer(hgb):
+    from hgb200 import tfrecord
+    # tf.train.Example(features=Features(feature={'a': Feature(int64_list=Int64List(value=[1]))})).SerializeToString()
+    want = b"\n\x0c\n\n\n\x01a\x12\x05\x1a\x03\n\x01\x01"
+    assert tfrecord.build_example({"a": np.array([1])}) == want
+    assert tfrecord.parse_example(want)["a"].tolist() == [1]
+    # unpacked repeated scalars (what old writers emit) parse to the same arrays
+    int64_list = b"\x08\x01" + b"\x08\xff\xff\xff\xff\x0f"
+    feature = b"\x1a" + bytes([len(int64_list)]) + int64_list
+    entry = b"\n\x01a" + b"\x12" + bytes([len(feature)]) + feature
+    features = b"\n" + bytes([len(entry)]) + entry
+    unpacked = b"\n" + bytes([len(features)]) + features
+    assert tfrecord.parse_example(unpacked)["a"].tolist() == [1, 0xFFFFFFFF]
+
+
+def _example(rng, k=17):
+    img = (rng.random((40, 40, 3)) * 255).astype(np.uint8)
+    ok, enc = cv2.imencode(".jpg", img)
+    assert ok
+    return {"ann_id": 1234567890123, "image_id": 42, "image": enc.tobytes(), "image_path": "dataset/images/x.jpg",
+            "coco_url": "http://images.cocodataset.org/x.jpg", "width": 40, "height": 40,
+            "keypoints/x": (rng.random(k) * 40).astype(np.float32), "keypoints/y": (rng.random(k) * 40).astype(np.float32),
+            "keypoints/vis": rng.integers(0, 3, k), "keypoints/num": 9, "bbox_x": np.float32(-3.25), "bbox_y": np.float32(17.5),
+            "original_bbox": np.array([1.5, 2.5, 30.0, 35.0], np.float32)}
+
+
+def test_record_round_trip_and_corruption(hgb, tmp_path):
+    from hgb200 import tfrecord
+    rng = np.random.default_rng(1)
+    exs = [_example(rng) for _ in range(5)]
+    path = str(tmp_path / "file_train_00-5.tfrec")
+    tfrecord.write_records(path, [tfrecord.build_example(e) for e in exs])
+    back = [tfrecord.parse_tfrecord_fn(p) for p in tfrecord.read_records(path)]
+    assert len(back) == 5
+    for a, b in zip(exs, back):
+        assert b["ann_id"] == a["ann_id"] and b["image_id"] == 42 and b["image"] == a["image"]
+        assert b["coco_url"] == a["coco_url"].encode() and b["bbox_x"] == a["bbox_x"] and b["bbox_x"].dtype == np.float32
+        np.testing.assert_array_equal(b["keypoints/x"], a["keypoints/x"])
+        np.testing.assert_array_equal(b["keypoints/vis"], a["keypoints/vis"])
+        assert b["keypoints/vis"].dtype == np.int64
+        np.testing.assert_array_equal(b["original_bbox"], a["original_bbox"])
+    # framing: length | masked crc | payload | masked crc
+    raw = open(path, "rb").read()
+    (n,) = struct.unpack("<Q", raw[:8])
+    assert raw[12:12 + n] == tfrecord.build_example(exs[0])
+    bad = bytearray(raw)
+    bad[40] ^= 0x10
+    open(path, "wb").write(bytes(bad))
+    with pytest.raises(ValueError, match="corrupted"):
+        list(tfrecord.read_records(path))
+    assert len(list(tfrecord.read_records(path, verify=False))) == 5
+    open(path, "wb").write(raw[:-7])
+    with pytest.raises(ValueError, match="truncated"):
+        list(tfrecord.read_records(path))
+    # a missing required feature is an error like tf.io.parse_single_example's
+    e = dict(exs[0])
+    del e["bbox_x"]
+    with pytest.raises(ValueError, match="bbox_x"):
+        tfrecord.parse_tfrecord_fn(tfrecord.build_example(e))
+    # negative int64 and empty lists survive
+    odd = tfrecord.parse_example(tfrecord.build_example({"n": np.array([-1, -2 ** 63, 7]), "e": np.zeros(0, np.float32)}))
+    assert odd["n"].tolist() == [-1, -2 ** 63, 7] and odd["e"] is None or len(odd["e"]) == 0
+
+
+def test_jpeg_header_parsing(hgb):
+    from hgb200 import tfrecord
+    rng = np.random.default_rng(2)
+    img = (rng.random((37, 53, 3)) * 255).astype(np.uint8)
+    for flags in ([], [cv2.IMWRITE_JPEG_PROGRESSIVE, 1], [cv2.IMWRITE_JPEG_QUALITY, 30]):
+        ok, enc = cv2.imencode(".jpg", img, flags)
+        assert tfrecord.jpeg_info(enc.tobytes()) == (37, 53, 3)
+    ok, enc = cv2.imencode(".jpg", img[:, :, 0])
+    assert tfrecord.jpeg_info(enc.tobytes()) == (37, 53, 1)
+    with pytest.raises(ValueError):
+        tfrecord.jpeg_info(b"\x89PNG\r\n\x1a\n" + bytes(32))
+    with pytest.raises(ValueError):
+        tfrecord.jpeg_info(enc.tobytes()[:12])
+
+
+def test_dataset_builder_host_contract(hgb, tmp_path, capsys):
+    from hgb200 import tfrecord
+    rng = np.random.default_rng(3)
+    train, valid = tmp_path / "train", tmp_path / "valid"
+    train.mkdir()
+    valid.mkdir()
+    for i, n in enumerate((3, 2, 4)):
+        tfrecord.write_records(str(train / f"file_train_{i:02d}-{n}.tfrec"), [tfrecord.build_example(_example(rng)) for _ in range(n)])
+    tfrecord.write_records(str(valid / "file_valid_00-2.tfrec"), [tfrecord.build_example(_example(rng)) for _ in range(2)])
+    cfg = types.SimpleNamespace(**{k: getattr(hgb.default_config, k) for k in dir(hgb.default_config) if k.isupper()})
+    cfg.TRAIN_TFRECORDS_DIR, cfg.VALID_TFRECORDS_DIR, cfg.BATCH_SIZE, cfg.SHUFFLE_BUFFER = str(train), str(valid), 4, 5
+    b = hgb.dataset_builder.DatasetBuilder(cfg, seed=0)
+    out = capsys.readouterr().out
+    assert "Train dataset with 3 tfrecords and 9 examples." in out and "Valid dataset with 1 tfrecords and 2 examples." in out
+    assert (b.num_train_examples, b.num_valid_examples, b.batch_size) == (9, 2, 4)
+    half = hgb.dataset_builder.DatasetBuilder(cfg, ratio=0.5)
+    assert len(half.train_filenames) == 2 and half.num_train_examples == 5
+    with pytest.raises(AssertionError):
+        hgb.dataset_builder.DatasetBuilder(cfg, ratio=0)
+    # shuffle: a permutation of the pass; batching: 4 + 4 + 1 per pass
+    recs = list(b._records(b.train_filenames))
+    assert len(recs) == 9
+    shuffled = list(b._shuffled(iter(recs)))
+    assert sorted(shuffled) == sorted(recs) and shuffled != recs
+    assert [len(x) for x in b._batches(iter(recs))] == [4, 4, 1]
+    xs, ys, vs = b.flip_labels(np.arange(17.0), np.arange(17.0) + 100, np.arange(17), cfg.COCO_INDEX_FLIP_PAIRS)
+    assert xs[:5].tolist() == [0, 2, 1, 4, 3] and ys[15:].tolist() == [116, 115] and vs[5:7].tolist() == [6, 5]
