@@ -250,13 +250,30 @@ class HourglassModel:
     def conv_table(self):
         return list(self._convs)
 
-    def save_weights(self, path):
-        """Keeps the reference's file-name protocol (`<path>.index` + `<path>.data-00000-of-00001`,
-        trainer.py:150-170) so its glob / rename logic works; the content is our own format:
-        weights + BN moving statistics + Adam slots + step."""
+    def _adam_slots(self):
+        """(iterations, m, v) with m / v as {weight name: array} in Keras layout, or None before the first training step."""
+        if self.optimizer is None or self._adam_m is None:
+            return None
+        pad = np.zeros(self._param_floats - self._train_floats, np.float32)
+        m = self._unpack(np.concatenate([self._adam_m.cpu().numpy(), pad]))
+        v = self._unpack(np.concatenate([self._adam_v.cpu().numpy(), pad]))
+        train = [k for k, (_s, _o, tr) in self._table.items() if tr]
+        return int(self.optimizer.iterations), {k: m[k] for k in train}, {k: v[k] for k in train}
+
+    def save_weights(self, path, save_format="tf"):
+        """keras.Model.save_weights (trainer.py:63-64,141).  `save_format="tf"` (default) writes a real TensorFlow checkpoint
+        -- `<path>.index` + `<path>.data-00000-of-00001` with Keras' object-graph keys, BN moving statistics, and the Adam
+        step / m / v slots (tf_checkpoint.py) -- so files interchange with the reference; "hgb" writes the same file pair
+        with an npz/json payload."""
         d = os.path.dirname(path)
         if d:
             os.makedirs(d, exist_ok=True)
+        if save_format == "tf":
+            from .. import tf_checkpoint
+            tf_checkpoint.save_keras_weights(self, path, adam=self._adam_slots())
+            return
+        if save_format != "hgb":
+            raise ValueError(f"unknown save_format {save_format!r}")
         blobs = OrderedDict(self.get_weights_dict())
         meta = {"format": "hgb200-ckpt-1", "num_stacks": self.num_stacks, "num_channels": self.num_channels,
                 "num_classes": self.num_classes, "iterations": 0, "optimizer": None}
@@ -271,6 +288,22 @@ class HourglassModel:
             json.dump(meta, f)
 
     def load_weights(self, path):
+        """keras.Model.load_weights (trainer.py:85,188,198): TensorFlow checkpoints written by the reference or by
+        save_weights (also a SavedModel's `variables/variables`), and the "hgb" payload; the format is detected."""
+        with open(path + ".index", "rb") as f:
+            is_json = f.read(1) == b"{"
+        if not is_json:
+            from .. import tf_checkpoint
+            weights, adam = tf_checkpoint.load_keras_weights(self, path)
+            self.set_weights_dict(weights)
+            self._pending_opt = None
+            if adam is not None:
+                iterations, m, v = adam
+                zeros = {k: np.zeros(sh, np.float32) for k, (sh, _o, tr) in self._table.items() if not tr}
+                self._pending_opt = (self._pack({**m, **zeros})[:self._train_floats], self._pack({**v, **zeros})[:self._train_floats],
+                                     iterations)
+            self._restore_optimizer_state()
+            return self
         with open(path + ".index") as f:
             meta = json.load(f)
         if (meta["num_stacks"], meta["num_channels"], meta["num_classes"]) != (self.num_stacks, self.num_channels, self.num_classes):
