@@ -265,6 +265,21 @@ def run_ours(args):
                             for k, _h, _b, t, by in tools_heatmap_bench.sweep(batches=(1024,), sizes=(64,), iters=5)}}
         except Exception as ex:   # the sweep is auxiliary: never lose the headline line over it
             line["heatmap_kernels"] = {"error": f"{type(ex).__name__}: {ex}"}
+    if world == 1:
+        try:     # the input path (decode / resize / augment) at batch 256, next to the reference's CPU ops
+            import tools_input_bench
+            peak_bw = float(peaks.get("hbm_gbs", 6500.0))
+            line["input_kernels"] = {
+                "shape": "batch 256 of 256x256x3 f32 (crop_resize from 640x480 u8), L2 flushed between launches; cpu = the "
+                         "reference's per-example op (cv2 / numpy restatement) on one host thread",
+                "peak_gbps": peak_bw,
+                "kernels": {k: {kk: (round(v, 6) if isinstance(v, float) else v) for kk, v in
+                                {"us": r["s"] * 1e6, "gbps": r.get("gbps"), "frac": (r["gbps"] / peak_bw) if "gbps" in r and not r.get("host_timed") else None,
+                                 "images_per_s": r.get("gpu_images_per_s", r.get("images_per_s")),
+                                 "cpu_images_per_s": r.get("cpu_images_per_s")}.items() if v is not None}
+                            for k, r in tools_input_bench.sweep(batch=256, iters=3).items()}}
+        except Exception as ex:
+            line["input_kernels"] = {"error": f"{type(ex).__name__}: {ex}"}
     if world == 1 and not args.no_cpu_baseline:
         ips, threads, sec = cpu_train_steps(args.stacks, args.cpu_batch, 2, 1)
         line["cpu_baseline"] = {"value": ips, "unit": "img/s", "cores": threads, "kind": "port",

@@ -7,7 +7,11 @@
 //   augment_keypoints : the same flip (x -> W - x, left/right label swap) and affine on the keypoints, visibility filter
 //                       (dataset_builder.py:143-185, 270-300)
 //   color_augment     : brightness, contrast, saturation, hue, min-max normalisation (dataset_builder.py:190-204)
-// All of it is HBM-bound streaming over 786 KB per image; no arithmetic is contracted into FMAs where the reference's
+// Measured (B200, batch 256, tools_input_bench.py): the two gather kernels run at 2.6-2.8 TB/s with DRAM traffic equal to
+// the algorithmic bytes; they are bound by per-pixel coordinate arithmetic + scattered 1/4-byte gathers, not by HBM (a
+// variant with 16-byte stores but 3x the coordinate work was 1.7x slower).  Next step: per-row / per-column coordinate
+// tables (OpenCV's own adelta/bdelta structure) so the inner loop is adds and shifts.
+// All of it streams over 786 KB per image; no arithmetic is contracted into FMAs where the reference's
 // CPU kernels round each operation (explicit __fmul_rn / __fadd_rn / __dmul_rn), so results match the oracle bit for
 // bit wherever the reference arithmetic is deterministic.
 #include "common.cuh"
@@ -164,10 +168,30 @@ __global__ void __launch_bounds__(256) color_sum_kernel(const float* __restrict_
   const int n = blockIdx.y;
   const float delta = params[4 * n];
   const float* p = img + (size_t)n * HW * 3;
+  const int total = HW * 3;
   double s[3] = {0.0, 0.0, 0.0};
-  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) s[c] += (double)__fadd_rn(__ldg(p + (size_t)pix * 3 + c), delta);
+  const int stride = gridDim.x * blockDim.x;
+  if ((total & 3) == 0) {                                   // 16-byte loads over the flat image; element j belongs to channel j % 3
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll 4
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total / 4; q += stride) {
+      const float4 v = __ldg(p4 + q);
+      const int r = q % 3;                                   // (4q) % 3
+      const double a = (double)__fadd_rn(v.x, delta) + (double)__fadd_rn(v.w, delta), b = (double)__fadd_rn(v.y, delta),
+                   c = (double)__fadd_rn(v.z, delta);
+      // channels of (x, y, z, w): r, r+1, r+2, r  (mod 3)
+      s[0] += r == 0 ? a : (r == 1 ? c : b);
+      s[1] += r == 0 ? b : (r == 1 ? a : c);
+      s[2] += r == 0 ? c : (r == 1 ? b : a);
+    }
+  } else {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += stride) {
+      const double v = (double)__fadd_rn(__ldg(p + j), delta);
+      const int c = j % 3;
+      s[0] += c == 0 ? v : 0.0;
+      s[1] += c == 1 ? v : 0.0;
+      s[2] += c == 2 ? v : 0.0;
+    }
   }
   __shared__ double sh[3][8];
 #pragma unroll
@@ -258,39 +282,63 @@ __device__ __forceinline__ void adjust_hue(float& r, float& g, float& b, float d
   }
 }
 
+// Pixels are processed whole (HSV needs the three channels), but global memory is touched only with coalesced 16-byte
+// accesses: a block stages tiles of 1024 pixels (12 KB) through shared memory; a thread owns pixels t, t+256, ... of the
+// tile (stride-3 word accesses: conflict-free).
+constexpr int kColorTile = 1024;
+
 __global__ void __launch_bounds__(256) color_apply_kernel(float* __restrict__ img, const float* __restrict__ params, int HW,
                                                           ColorWs* __restrict__ ws) {
+  __shared__ __align__(16) float tile[kColorTile * 3];
   const int n = blockIdx.y;
   const float delta = params[4 * n], contrast = params[4 * n + 1], sat = params[4 * n + 2], hue = params[4 * n + 3];
   float mean[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) mean[c] = (float)(ws[n].sum[c] / (double)HW);
   float* p = img + (size_t)n * HW * 3;
+  const bool vec = ((HW * 3) & 3) == 0;
   float lo = INFINITY, hi = -INFINITY;
-  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
-    float q[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float x = __fadd_rn(p[(size_t)pix * 3 + c], delta);
-      q[c] = __fadd_rn(__fmul_rn(__fsub_rn(x, mean[c]), contrast), mean[c]);
+  for (int base = blockIdx.x * kColorTile; base < HW; base += gridDim.x * kColorTile) {
+    const int npx = min(kColorTile, HW - base), nfl = npx * 3;
+    float* g = p + (size_t)base * 3;                        // base * 3 floats: 16-byte aligned because kColorTile * 3 % 4 == 0
+    if (vec && (nfl & 3) == 0) {
+      for (int q = threadIdx.x; q < nfl / 4; q += blockDim.x) reinterpret_cast<float4*>(tile)[q] = reinterpret_cast<const float4*>(g)[q];
+    } else {
+      for (int q = threadIdx.x; q < nfl; q += blockDim.x) tile[q] = g[q];
     }
-    float h, s, v;
-    rgb_to_hsv(q[0], q[1], q[2], h, s, v);
-    s = fminf(1.f, fmaxf(0.f, __fmul_rn(s, sat)));
-    hsv_to_rgb(h, s, v, q[0], q[1], q[2]);
-    adjust_hue(q[0], q[1], q[2], hue);
+    __syncthreads();
+    for (int t = threadIdx.x; t < npx; t += blockDim.x) {
+      float q[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      p[(size_t)pix * 3 + c] = q[c];
-      lo = fminf(lo, q[c]);
-      hi = fmaxf(hi, q[c]);
+      for (int c = 0; c < 3; ++c) {
+        const float x = __fadd_rn(tile[t * 3 + c], delta);
+        q[c] = __fadd_rn(__fmul_rn(__fsub_rn(x, mean[c]), contrast), mean[c]);
+      }
+      float h, s, v;
+      rgb_to_hsv(q[0], q[1], q[2], h, s, v);
+      s = fminf(1.f, fmaxf(0.f, __fmul_rn(s, sat)));
+      hsv_to_rgb(h, s, v, q[0], q[1], q[2]);
+      adjust_hue(q[0], q[1], q[2], hue);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        tile[t * 3 + c] = q[c];
+        lo = fminf(lo, q[c]);
+        hi = fmaxf(hi, q[c]);
+      }
     }
+    __syncthreads();
+    if (vec && (nfl & 3) == 0) {
+      for (int q = threadIdx.x; q < nfl / 4; q += blockDim.x) reinterpret_cast<float4*>(g)[q] = reinterpret_cast<const float4*>(tile)[q];
+    } else {
+      for (int q = threadIdx.x; q < nfl; q += blockDim.x) g[q] = tile[q];
+    }
+    __syncthreads();
   }
   for (int o = 16; o > 0; o >>= 1) {
     lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
-  if ((threadIdx.x & 31) == 0) {
+  if ((threadIdx.x & 31) == 0 && lo <= hi) {
     atomicMin(&ws[n].min_key, float_key(lo));
     atomicMax(&ws[n].max_key, float_key(hi));
   }
@@ -301,8 +349,21 @@ __global__ void __launch_bounds__(256) color_normalize_kernel(float* __restrict_
   const float lo = key_float(ws[n].min_key), hi = key_float(ws[n].max_key);
   const float span = __fsub_rn(hi, lo);
   float* p = img + (size_t)n * HW * 3;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW * 3; i += gridDim.x * blockDim.x)
-    p[i] = __fdiv_rn(__fsub_rn(p[i], lo), span);
+  const int total = HW * 3, stride = gridDim.x * blockDim.x;
+  if ((total & 3) == 0) {
+    float4* p4 = reinterpret_cast<float4*>(p);
+#pragma unroll 4
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total / 4; q += stride) {
+      float4 v = p4[q];
+      v.x = __fdiv_rn(__fsub_rn(v.x, lo), span);
+      v.y = __fdiv_rn(__fsub_rn(v.y, lo), span);
+      v.z = __fdiv_rn(__fsub_rn(v.z, lo), span);
+      v.w = __fdiv_rn(__fsub_rn(v.w, lo), span);
+      p4[q] = v;
+    }
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) p[i] = __fdiv_rn(__fsub_rn(p[i], lo), span);
+  }
 }
 
 }  // namespace hgb
@@ -352,15 +413,18 @@ extern "C" int64_t hgb_color_workspace_bytes(int N) { return (int64_t)sizeof(Col
 extern "C" int hgb_color_augment(float* images, const float* params, int N, int H, int W, void* workspace, void* stream) {
   HGB_CHECK_ARG(images && params && workspace, "hgb_color_augment: null pointer");
   HGB_CHECK_ARG(N >= 0 && N <= 65535 && H > 0 && W > 0, "hgb_color_augment: bad sizes");
+  HGB_CHECK_ARG(((uintptr_t)images & 15) == 0 && ((uintptr_t)workspace & 7) == 0, "hgb_color_augment: images must be 16-byte aligned");
   if (N == 0) return HGB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   ColorWs* ws = (ColorWs*)workspace;
   const int HW = H * W;
   // enough blocks per image to fill 148 SMs at small N, grid-stride beyond that
-  const int per_img = max(1, min(cdiv(HW, 256), cdiv(148 * 8, N)));
+  // ~8 resident blocks per SM in total; every thread keeps several 16-byte accesses in flight (grid-stride, unrolled)
+  const int per_img = max(1, min(cdiv(HW * 3, 4 * 256), cdiv(148 * 8, N)));
+  const int tiles = max(1, min(cdiv(HW, kColorTile), cdiv(148 * 8, N)));
   color_init_kernel<<<cdiv(N, 128), 128, 0, st>>>(ws, N);
   color_sum_kernel<<<dim3(per_img, N), 256, 0, st>>>(images, params, HW, ws);
-  color_apply_kernel<<<dim3(per_img, N), 256, 0, st>>>(images, params, HW, ws);
+  color_apply_kernel<<<dim3(tiles, N), 256, 0, st>>>(images, params, HW, ws);
   color_normalize_kernel<<<dim3(per_img, N), 256, 0, st>>>(images, HW, ws);
   HGB_LAUNCH_CHECK();
   return HGB_OK;

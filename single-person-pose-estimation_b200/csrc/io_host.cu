@@ -4,11 +4,16 @@
 //   hgb_jpeg_info     : size / component count from the SOF marker (what tf.image.decode_image reads first, :263)
 //   hgb_jpeg_decode   : baseline / progressive JPEG -> interleaved RGB uint8 in DEVICE memory through nvJPEG
 //                       (library decode = plumbing, like cuBLAS for a plain GEMM); libnvjpeg is opened at first use so
-//                       libhgb200.so itself has no load-time dependency on it
+//                       libhgb200.so itself has no load-time dependency on it.  nvJPEG's default backend runs the
+//                       Huffman stage on the host, so a batch is spread over host threads, each with its own decoder
+//                       state and CUDA stream; the caller's stream is ordered before and after them with events.
 #include <dlfcn.h>
 #include <nvjpeg.h>
 
+#include <atomic>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 
@@ -39,6 +44,14 @@ struct NvJpeg {
                            cudaStream_t) = nullptr;
   std::string error;
   bool ok = false;
+  struct Worker {
+    nvjpegJpegState_t state = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+  };
+  std::vector<Worker> workers;
+  cudaEvent_t begin = nullptr;
+  int device = -1;
 };
 static NvJpeg g_nvjpeg;
 static std::mutex g_nvjpeg_mutex;
@@ -141,14 +154,59 @@ extern "C" int hgb_jpeg_decode(const uint8_t* const* datas, const int64_t* lens,
     HGB_CHECK_ARG(h == hw[2 * n] && w == hw[2 * n + 1], "hgb_jpeg_decode: image %d is %dx%d, the output buffer was sized for %dx%d", n, h, w,
                   hw[2 * n], hw[2 * n + 1]);
     HGB_CHECK_ARG(c == 1 || c == 3, "hgb_jpeg_decode: image %d has %d components (grey and YCbCr/RGB only)", n, c);
-    nvjpegImage_t img = {};
-    img.channel[0] = outs[n];
-    img.pitch[0] = (size_t)w * 3;
-    nvjpegStatus_t s = g_nvjpeg.decode(g_nvjpeg.handle, g_nvjpeg.state, datas[n], (size_t)lens[n], NVJPEG_OUTPUT_RGBI, &img, (cudaStream_t)stream);
+  }
+  NvJpeg& j = g_nvjpeg;
+  int device = 0;
+  HGB_CUDA(cudaGetDevice(&device));
+  if (j.device != device) {                      // worker streams / events belong to one device
+    HGB_CHECK_ARG(j.device < 0, "hgb_jpeg_decode: the decoder was initialised on device %d, called on device %d", j.device, device);
+    j.device = device;
+    HGB_CUDA(cudaEventCreateWithFlags(&j.begin, cudaEventDisableTiming));
+  }
+  int want = (int)std::thread::hardware_concurrency();
+  if (const char* e = getenv("HGB_JPEG_THREADS")) want = atoi(e);
+  const int T = std::max(1, std::min(std::min(want, 32), N));
+  while ((int)j.workers.size() < T) {
+    NvJpeg::Worker w;
+    nvjpegStatus_t s = j.state_create(j.handle, &w.state);
     if (s != NVJPEG_STATUS_SUCCESS) {
-      set_error("hgb_jpeg_decode: nvjpegDecode failed on image %d with status %d", n, (int)s);
+      set_error("hgb_jpeg_decode: nvjpegJpegStateCreate failed with status %d", (int)s);
       return HGB_ERR_CUDA;
     }
+    HGB_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    HGB_CUDA(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+    j.workers.push_back(w);
+  }
+  cudaStream_t caller = (cudaStream_t)stream;
+  HGB_CUDA(cudaEventRecord(j.begin, caller));      // the output buffers may still be in use by earlier work on the caller's stream
+  std::atomic<int> failed_image{-1}, failed_status{0};
+  auto work = [&](int t) {
+    cudaSetDevice(device);
+    NvJpeg::Worker& w = j.workers[t];
+    cudaStreamWaitEvent(w.stream, j.begin, 0);
+    for (int n = t; n < N && failed_image.load() < 0; n += T) {
+      nvjpegImage_t img = {};
+      img.channel[0] = outs[n];
+      img.pitch[0] = (size_t)hw[2 * n + 1] * 3;
+      nvjpegStatus_t s = j.decode(j.handle, w.state, datas[n], (size_t)lens[n], NVJPEG_OUTPUT_RGBI, &img, w.stream);
+      if (s != NVJPEG_STATUS_SUCCESS) {
+        failed_status.store((int)s);
+        failed_image.store(n);
+      }
+    }
+    cudaEventRecord(w.done, w.stream);
+  };
+  if (T == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < T; ++t) pool.emplace_back(work, t);
+    for (auto& th : pool) th.join();
+  }
+  for (int t = 0; t < T; ++t) HGB_CUDA(cudaStreamWaitEvent(caller, j.workers[t].done, 0));
+  if (failed_image.load() >= 0) {
+    set_error("hgb_jpeg_decode: nvjpegDecode failed on image %d with status %d", failed_image.load(), failed_status.load());
+    return HGB_ERR_CUDA;
   }
   return HGB_OK;
 }
