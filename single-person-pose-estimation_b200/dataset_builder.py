@@ -145,9 +145,20 @@ class DatasetBuilder:
     costs a handful of launches instead of one Python callback per example (the reference's tf.numpy_function path).
     Yields CUDA float32 tensors: (images (B,256,256,3), heatmaps (B,64,64,17))."""
 
-    def __init__(self, config, ratio=1, seed=None):
+    def __init__(self, config, ratio=1, seed=None, shard=None):
+        """`shard=(rank, world_size)` keeps every world_size-th record starting at `rank` (tf.data's `shard`), so each data-
+        parallel process reads a disjoint slice with no exchange; default: the active hgb200.parallel context, else no sharding.
+        `num_*_examples` stay GLOBAL counts (steps per epoch = n // BATCH_SIZE with BATCH_SIZE the per-process batch means a
+        global batch of BATCH_SIZE * world_size, as with a mirrored strategy)."""
         import glob
         assert 0 < ratio <= 1
+        if shard is None:
+            from .parallel import current_allreduce
+            ar = current_allreduce()
+            shard = (ar.rank, ar.world_size) if ar is not None else (0, 1)
+        self.shard = (int(shard[0]), int(shard[1]))
+        if not 0 <= self.shard[0] < self.shard[1]:
+            raise ValueError(f"shard must be (rank, world_size) with 0 <= rank < world_size, got {shard}")
         self.image_shape = tuple(config.IMAGE_SHAPE)
         self.label_shape = tuple(config.LABEL_SHAPE)
         self.num_keypoints = int(config.NUM_KEYPOINTS)
@@ -189,8 +200,13 @@ class DatasetBuilder:
     # -- record streams
     def _records(self, filenames):
         from . import tfrecord
+        rank, world = self.shard
+        k = 0
         for name in filenames:
-            yield from tfrecord.read_records(name)
+            for record in tfrecord.read_records(name):
+                if k % world == rank:
+                    yield record
+                k += 1
 
     def _shuffled(self, records):
         """tf.data shuffle(buffer): fill the buffer, then emit a uniformly chosen slot and refill it."""

@@ -141,3 +141,26 @@ def test_dataset_builder_host_contract(hgb, tmp_path, capsys):
     assert [len(x) for x in b._batches(iter(recs))] == [4, 4, 1]
     xs, ys, vs = b.flip_labels(np.arange(17.0), np.arange(17.0) + 100, np.arange(17), cfg.COCO_INDEX_FLIP_PAIRS)
     assert xs[:5].tolist() == [0, 2, 1, 4, 3] and ys[15:].tolist() == [116, 115] and vs[5:7].tolist() == [6, 5]
+
+
+def test_dataset_builder_shards_records_across_ranks(hgb, tmp_path):
+    """Data-parallel input: rank r of w reads records r, r+w, ... (no collective); the union over ranks is the pass."""
+    from hgb200 import tfrecord
+    rng = np.random.default_rng(4)
+    d = tmp_path / "train"
+    d.mkdir()
+    (tmp_path / "valid").mkdir()
+    tfrecord.write_records(str(d / "file_train_00-5.tfrec"), [tfrecord.build_example(_example(rng)) for _ in range(5)])
+    tfrecord.write_records(str(d / "file_train_01-4.tfrec"), [tfrecord.build_example(_example(rng)) for _ in range(4)])
+    cfg = types.SimpleNamespace(**{k: getattr(hgb.default_config, k) for k in dir(hgb.default_config) if k.isupper()})
+    cfg.TRAIN_TFRECORDS_DIR, cfg.VALID_TFRECORDS_DIR, cfg.BATCH_SIZE = str(d), str(tmp_path / "valid"), 2
+    whole = list(hgb.dataset_builder.DatasetBuilder(cfg)._records(sorted(str(p) for p in d.iterdir())))
+    parts = []
+    for rank in range(3):
+        b = hgb.dataset_builder.DatasetBuilder(cfg, shard=(rank, 3))
+        assert b.num_train_examples == 9                                  # global count
+        parts.append(list(b._records(b.train_filenames)))
+    assert [len(p) for p in parts] == [3, 3, 3]
+    assert [parts[k % 3][k // 3] for k in range(9)] == whole
+    with pytest.raises(ValueError):
+        hgb.dataset_builder.DatasetBuilder(cfg, shard=(3, 3))
