@@ -7,10 +7,10 @@
 //   augment_keypoints : the same flip (x -> W - x, left/right label swap) and affine on the keypoints, visibility filter
 //                       (dataset_builder.py:143-185, 270-300)
 //   color_augment     : brightness, contrast, saturation, hue, min-max normalisation (dataset_builder.py:190-204)
-// Measured (B200, batch 256, tools_input_bench.py): the two gather kernels run at 2.6-2.8 TB/s with DRAM traffic equal to
-// the algorithmic bytes; they are bound by per-pixel coordinate arithmetic + scattered 1/4-byte gathers, not by HBM (a
-// variant with 16-byte stores but 3x the coordinate work was 1.7x slower).  Next step: per-row / per-column coordinate
-// tables (OpenCV's own adelta/bdelta structure) so the inner loop is adds and shifts.
+// Measured (B200, batch 256, tools_input_bench.py): with one thread per pixel recomputing its coordinates the two gather
+// kernels ran at 2.6-2.8 TB/s with DRAM traffic equal to the algorithmic bytes -- bound by coordinate arithmetic and
+// strided stores, not by HBM (a variant with 16-byte stores but 3x the coordinate work was 1.7x slower).  Hence the
+// column-in-registers / rows-in-shared-memory tiling and the warp-level store exchange below.
 // All of it streams over 786 KB per image; no arithmetic is contracted into FMAs where the reference's
 // CPU kernels round each operation (explicit __fmul_rn / __fadd_rn / __dmul_rn), so results match the oracle bit for
 // bit wherever the reference arithmetic is deterministic.
@@ -43,14 +43,35 @@ __device__ __forceinline__ float load_px<float>(const float* p) { return __ldg(p
 template <>
 __device__ __forceinline__ float load_px<uint8_t>(const uint8_t* p) { return __fmul_rn((float)__ldg(p), 0.00392156862745098f); }
 
+// A block covers a tile of 256 output columns x kRows rows of one image.  A thread owns one column: its horizontal
+// interpolation entry (two IEEE divisions, floor, ceil) is computed ONCE and kept in registers, the kRows vertical entries
+// of the tile are computed once per block into shared memory, so the per-pixel work is four gathers and three lerps
+// (measured: computing the coordinates per pixel cost a third of the kernel's time).  The three floats of a pixel are
+// exchanged through shared memory so that a warp stores 384 contiguous bytes with three fully coalesced instructions.
+constexpr int kRows = 16;
+
+__device__ __forceinline__ void store_pixels_coalesced(float* __restrict__ row_out, int x_first, int n_valid, float r0, float r1, float r2,
+                                                       float* __restrict__ stage) {
+  const int lane = threadIdx.x & 31;
+  stage[3 * lane] = r0;
+  stage[3 * lane + 1] = r1;
+  stage[3 * lane + 2] = r2;
+  __syncwarp();
+  float* o = row_out + (size_t)x_first * 3;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (lane + 32 * k < 3 * n_valid) o[lane + 32 * k] = stage[lane + 32 * k];
+  __syncwarp();
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) crop_resize_kernel(const void* const* __restrict__ src_ptrs, const int32_t* __restrict__ src_hw,
                                                           const int32_t* __restrict__ crop_xywh, int out_h, int out_w,
                                                           float* __restrict__ out) {
-  const int n = blockIdx.y;
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= out_h * out_w) return;
-  const int oy = pix / out_w, ox = pix - oy * out_w;
+  __shared__ Interp rows[kRows];
+  __shared__ float stage[8][96];
+  const int n = blockIdx.z;
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy0 = blockIdx.y * kRows;
   const T* src = (const T*)src_ptrs[n];
   const int sh = src_hw[2 * n], sw = src_hw[2 * n + 1];
   int x0 = 0, y0 = 0, cw = sw, ch = sh;
@@ -60,65 +81,91 @@ __global__ void __launch_bounds__(256) crop_resize_kernel(const void* const* __r
     cw = crop_xywh[4 * n + 2];
     ch = crop_xywh[4 * n + 3];
   }
-  const Interp iy = interp_of(oy, out_h, ch), ix = interp_of(ox, out_w, cw);
-  const int ys[2] = {iy.lo + y0, iy.hi + y0}, xs[2] = {ix.lo + x0, ix.hi + x0};
-  float v[2][2][3];
+  if (threadIdx.x < kRows && oy0 + threadIdx.x < out_h) rows[threadIdx.x] = interp_of(oy0 + threadIdx.x, out_h, ch);
+  __syncthreads();
+  const bool live = ox < out_w;
+  const Interp ix = interp_of(live ? ox : 0, out_w, cw);
+  const int xs[2] = {ix.lo + x0, ix.hi + x0};
+  const bool xok[2] = {live && xs[0] >= 0 && xs[0] < sw, live && xs[1] >= 0 && xs[1] < sw};
+  const int warp_x = blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  const int n_valid = max(0, min(32, out_w - warp_x));
+  if (n_valid == 0) return;                                 // whole warp beyond the image (warp-uniform)
+  float* img_out = out + (size_t)n * out_h * out_w * 3;
+  const int nrows = min(kRows, out_h - oy0);
+  for (int r = 0; r < nrows; ++r) {
+    const Interp iy = rows[r];
+    const int ys[2] = {iy.lo + y0, iy.hi + y0};
+    float v[2][2][3];
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 2; ++a) {
+      const bool yok = ys[a] >= 0 && ys[a] < sh;            // zero padding of crop_and_pad
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const bool ok = ys[a] >= 0 && ys[a] < sh && xs[b] >= 0 && xs[b] < sw;   // zero padding of crop_and_pad
-      const T* p = src + ((size_t)ys[a] * sw + xs[b]) * 3;
+      for (int b = 0; b < 2; ++b) {
+        const T* p = src + ((size_t)ys[a] * sw + xs[b]) * 3;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) v[a][b][c] = ok ? load_px<T>(p + c) : 0.f;
+        for (int c = 0; c < 3; ++c) v[a][b][c] = (yok && xok[b]) ? load_px<T>(p + c) : 0.f;
+      }
     }
-  float* o = out + ((size_t)n * out_h * out_w + pix) * 3;
+    float res[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float top = __fadd_rn(v[0][0][c], __fmul_rn(__fsub_rn(v[0][1][c], v[0][0][c]), ix.lerp));
-    float bot = __fadd_rn(v[1][0][c], __fmul_rn(__fsub_rn(v[1][1][c], v[1][0][c]), ix.lerp));
-    o[c] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), iy.lerp));
+    for (int c = 0; c < 3; ++c) {
+      const float top = __fadd_rn(v[0][0][c], __fmul_rn(__fsub_rn(v[0][1][c], v[0][0][c]), ix.lerp));
+      const float bot = __fadd_rn(v[1][0][c], __fmul_rn(__fsub_rn(v[1][1][c], v[1][0][c]), ix.lerp));
+      res[c] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), iy.lerp));
+    }
+    store_pixels_coalesced(img_out + (size_t)(oy0 + r) * out_w * 3, warp_x, n_valid, res[0], res[1], res[2], stage[threadIdx.x >> 5]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ flip + affine warp
+// Same tiling as crop_resize.  OpenCV itself splits the fixed-point source coordinate into a per-column part
+// (adelta, bdelta) and a per-row part (X0, Y0): a thread keeps its column's pair in registers, the block computes the kRows
+// row pairs once into shared memory, and the per-pixel coordinate is two 64-bit adds and shifts.
 __global__ void __launch_bounds__(256) augment_affine_kernel(const float* __restrict__ in, const double* __restrict__ inv_mats,
                                                              const int32_t* __restrict__ flip, int H, int W, float* __restrict__ out) {
-  const int n = blockIdx.y;
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= H * W) return;
-  const int y = pix / W, x = pix - y * W;
+  __shared__ long long row_x0[kRows], row_y0[kRows];
+  __shared__ float stage[8][96];
+  const int n = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y0 = blockIdx.y * kRows;
   const double* M = inv_mats + 6 * n;
-  // cv2.warpAffine: 10-bit fixed point, +16 rounds to the 1/32-pixel grid
+  if (threadIdx.x < kRows) {
+    const double y = (double)(y0 + threadIdx.x);
+    // cv2.warpAffine: 10-bit fixed point, +16 rounds to the 1/32-pixel grid
+    row_x0[threadIdx.x] = __double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(M[1], y), M[2]), 1024.0)) + 16;
+    row_y0[threadIdx.x] = __double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(M[4], y), M[5]), 1024.0)) + 16;
+  }
+  __syncthreads();
   const long long adelta = __double2ll_rn(__dmul_rn(__dmul_rn(M[0], (double)x), 1024.0));
   const long long bdelta = __double2ll_rn(__dmul_rn(__dmul_rn(M[3], (double)x), 1024.0));
-  const long long X0 = __double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(M[1], (double)y), M[2]), 1024.0)) + 16;
-  const long long Y0 = __double2ll_rn(__dmul_rn(__dadd_rn(__dmul_rn(M[4], (double)y), M[5]), 1024.0)) + 16;
-  const long long X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
-  const int sx = (int)max(-32768LL, min(32767LL, X >> 5)), sy = (int)max(-32768LL, min(32767LL, Y >> 5));
-  const float fx = __fmul_rn((float)(int)(X & 31), 0.03125f), fy = __fmul_rn((float)(int)(Y & 31), 0.03125f);
-  const float wx[2] = {__fsub_rn(1.f, fx), fx}, wy[2] = {__fsub_rn(1.f, fy), fy};
   const bool fl = flip[n] != 0;
+  const int warp_x = blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  const int n_valid = max(0, min(32, W - warp_x));
+  if (n_valid == 0) return;
   const float* img = in + (size_t)n * H * W * 3;
-  float acc[3] = {0.f, 0.f, 0.f};
+  float* img_out = out + (size_t)n * H * W * 3;
+  const int nrows = min(kRows, H - y0);
+  for (int r = 0; r < nrows; ++r) {
+    const long long X = (row_x0[r] + adelta) >> 5, Y = (row_y0[r] + bdelta) >> 5;
+    const int sx = (int)max(-32768LL, min(32767LL, X >> 5)), sy = (int)max(-32768LL, min(32767LL, Y >> 5));
+    const float fx = __fmul_rn((float)(int)(X & 31), 0.03125f), fy = __fmul_rn((float)(int)(Y & 31), 0.03125f);
+    const float wx[2] = {__fsub_rn(1.f, fx), fx}, wy[2] = {__fsub_rn(1.f, fy), fy};
+    float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int yy = sy + a, xx = sx + b;
-      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
-      const float w = __fmul_rn(wy[a], wx[b]);
-      const float* p = img + ((size_t)yy * W + (fl ? W - 1 - xx : xx)) * 3;
+      for (int b = 0; b < 2; ++b) {
+        const int yy = sy + a, xx = sx + b;
+        const bool ok = x < W && yy >= 0 && yy < H && xx >= 0 && xx < W;
+        const float w = __fmul_rn(wy[a], wx[b]);
+        const float* p = img + ((size_t)yy * W + (fl ? W - 1 - xx : xx)) * 3;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float t = __fmul_rn(ok ? __ldg(p + c) : 0.f, w);
-        acc[c] = (a == 0 && b == 0) ? t : __fadd_rn(acc[c], t);
+        for (int c = 0; c < 3; ++c) {
+          const float t = __fmul_rn(ok ? __ldg(p + c) : 0.f, w);
+          acc[c] = (a == 0 && b == 0) ? t : __fadd_rn(acc[c], t);
+        }
       }
-    }
-  float* o = out + ((size_t)n * H * W + pix) * 3;
-  o[0] = acc[0];
-  o[1] = acc[1];
-  o[2] = acc[2];
+    store_pixels_coalesced(img_out + (size_t)(y0 + r) * W * 3, warp_x, n_valid, acc[0], acc[1], acc[2], stage[threadIdx.x >> 5]);
+  }
 }
 
 __global__ void augment_keypoints_kernel(const float* __restrict__ kx, const float* __restrict__ ky, const int32_t* __restrict__ kv,
@@ -376,7 +423,8 @@ extern "C" int hgb_crop_resize(const void* const* src_ptrs, const int32_t* src_h
   HGB_CHECK_ARG(src_dtype == HGB_F32 || src_dtype == HGB_U8, "hgb_crop_resize: source dtype must be HGB_F32 or HGB_U8");
   HGB_CHECK_ARG(N >= 0 && N <= 65535 && out_h > 0 && out_w > 0, "hgb_crop_resize: bad sizes (N <= 65535)");
   if (N == 0) return HGB_OK;
-  dim3 grid(cdiv((int64_t)out_h * out_w, 256), N);
+  HGB_CHECK_ARG(cdiv(out_h, kRows) <= 65535, "hgb_crop_resize: out_h too large");
+  dim3 grid(cdiv(out_w, 256), cdiv(out_h, kRows), N);
   if (src_dtype == HGB_U8)
     crop_resize_kernel<uint8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(src_ptrs, src_hw, crop_xywh, out_h, out_w, out);
   else
@@ -391,7 +439,7 @@ extern "C" int hgb_augment_affine(const float* images, const double* inv_mats, c
   HGB_CHECK_ARG(images != out, "hgb_augment_affine: the warp is a gather and cannot run in place");
   HGB_CHECK_ARG(N >= 0 && N <= 65535 && H > 0 && W > 0 && H <= 32767 && W <= 32767, "hgb_augment_affine: bad sizes");
   if (N == 0) return HGB_OK;
-  augment_affine_kernel<<<dim3(cdiv((int64_t)H * W, 256), N), 256, 0, (cudaStream_t)stream>>>(images, inv_mats, flip, H, W, out);
+  augment_affine_kernel<<<dim3(cdiv(W, 256), cdiv(H, kRows), N), 256, 0, (cudaStream_t)stream>>>(images, inv_mats, flip, H, W, out);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
