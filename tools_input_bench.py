@@ -132,8 +132,10 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", action="store_true")
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU reference timings (profiling runs)")
     a = ap.parse_args()
-    rows = sweep(a.batch)
+    rows = sweep(a.batch, iters=a.iters, cpu=not a.no_cpu)
     if a.json:
         print(json.dumps(rows))
     else:
