@@ -166,3 +166,18 @@ def test_model_weights_round_trip_through_tf_checkpoint(hgb, tmp_path):
     c = hgb.create_hourglass_model(17, 2, 256, (256, 256, 3), "sigmoid")
     c.load_weights(prefix)
     np.testing.assert_array_equal(c.get_weights_dict()["hg0_conv_1x1_2/kernel"], w["hg0_conv_1x1_2/kernel"])
+
+
+def test_model_utils_checkpoint_helpers(hgb, tmp_path):
+    from hgb200.utilities import model_utils
+    a = hgb.create_hourglass_model(17, 1, 256, (256, 256, 3), "sigmoid")
+    d = tmp_path / "checkpoints"
+    for name in ("E5_2022-03-01_cont.ckpt", "E12_2022-03-02_cont.ckpt", "best_val_loss_weights.ckpt"):
+        a.save_weights(str(d / name))
+    names, epochs = model_utils.get_epochs_from_ckpt_path(str(d))
+    assert epochs == [12, 5, -1]                                   # name order, as the reference sorts them
+    assert names[-1].endswith("best_val_loss_weights.ckpt") and names[0].endswith("E12_2022-03-02_cont.ckpt")
+    b = hgb.create_hourglass_model(17, 1, 256, (256, 256, 3), "sigmoid")
+    out = model_utils.compile_model_from_checkpoint(b, names[1], hgb.Adam(1e-3), hgb.loss.weighted_mse)
+    assert out is b and b.optimizer is not None
+    np.testing.assert_array_equal(b.get_weights_dict()["front_conv_1x1_1/kernel"], a.get_weights_dict()["front_conv_1x1_1/kernel"])
