@@ -246,7 +246,7 @@ def loss_and_grads(params_np, images, y_true, kind, num_classes, num_stacks, num
     total = sum(losses)
     total.backward()
     grads = OrderedDict((k, v.grad.numpy()) for k, v in params.items() if v.requires_grad)
-    return [o.detach().numpy() for o in outs], [float(l) for l in losses], grads
+    return [o.detach().numpy() for o in outs], [float(l.detach()) for l in losses], grads
 
 
 def adam_step(w, g, m, v, t, lr=1e-3, b1=0.9, b2=0.999, eps=1e-7):

@@ -137,6 +137,103 @@ def make_valid_label_batch(images, kps_x, kps_y, kps_v, label_shape=(64, 64, 17)
     return images, ops.render_targets(kps_x, kps_y, kps_v, label_shape[0], label_shape[1])
 
 
+# ------------------------------------------------------------------ prefetch (dataset_builder.py:46,54,65: .prefetch(AUTOTUNE))
+class Prefetcher:
+    """Runs a batch generator in a background thread, `depth` batches ahead, on its own CUDA stream: record parsing, the
+    host half of JPEG decode and the input kernels of batch i+1 overlap the training step of batch i.  Batches are handed
+    over with a CUDA event (the consumer's stream waits on it; tensors are marked as used by the consumer's stream), so
+    the hand-over never blocks the host.  Iteration order is the generator's; exceptions surface at the consumer."""
+
+    _END = object()
+
+    def __init__(self, generator, depth=2):
+        import queue
+        import threading
+        self._gen = generator
+        self._q = queue.Queue(maxsize=max(1, int(depth)))
+        self._stop = False
+        self._done = False
+        self._device = None
+        try:
+            import torch
+            if torch.cuda.is_available():
+                self._device = torch.cuda.current_device()      # the worker thread must use the consumer's device
+        except Exception:  # pragma: no cover
+            pass
+        self._thread = threading.Thread(target=self._run, name="hgb200-prefetch", daemon=True)
+        self._thread.start()
+
+    @staticmethod
+    def _tensors(item):
+        if hasattr(item, "record_stream"):
+            yield item
+        elif isinstance(item, dict):
+            for v in item.values():
+                yield from Prefetcher._tensors(v)
+        elif isinstance(item, (tuple, list)):
+            for v in item:
+                yield from Prefetcher._tensors(v)
+
+    def _put(self, payload):
+        import queue
+        while not self._stop:
+            try:
+                self._q.put(payload, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def _run(self):
+        import contextlib
+        cuda = self._device is not None
+        if cuda:
+            import torch
+            torch.cuda.set_device(self._device)
+        stream = torch.cuda.Stream() if cuda else None
+        try:
+            with (torch.cuda.stream(stream) if cuda else contextlib.nullcontext()):
+                for item in self._gen:
+                    event = None
+                    if cuda:
+                        event = torch.cuda.Event()
+                        event.record(stream)
+                    if not self._put((item, event, None)):
+                        return
+            self._put((Prefetcher._END, None, None))
+        except BaseException as ex:  # noqa: BLE001 - handed to the consumer
+            self._put((None, None, ex))
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._done:
+            raise StopIteration
+        item, event, error = self._q.get()
+        if error is not None:
+            self._done = True
+            raise error
+        if item is Prefetcher._END:
+            self._done = True
+            raise StopIteration
+        if event is not None:
+            import torch
+            current = torch.cuda.current_stream()
+            current.wait_event(event)
+            for t in Prefetcher._tensors(item):
+                if t.is_cuda:
+                    t.record_stream(current)
+        return item
+
+    def close(self):
+        self._stop = True
+        self._done = True
+
+    def __del__(self):
+        self._stop = True
+
+
 # ------------------------------------------------------------------ the TFRecord-backed builder (dataset_builder.py:10-66)
 class DatasetBuilder:
     """Drop-in for the reference's DatasetBuilder(config, ratio): same constructor arguments, attributes, console lines and
@@ -145,8 +242,9 @@ class DatasetBuilder:
     costs a handful of launches instead of one Python callback per example (the reference's tf.numpy_function path).
     Yields CUDA float32 tensors: (images (B,256,256,3), heatmaps (B,64,64,17))."""
 
-    def __init__(self, config, ratio=1, seed=None, shard=None):
-        """`shard=(rank, world_size)` keeps every world_size-th record starting at `rank` (tf.data's `shard`), so each data-
+    def __init__(self, config, ratio=1, seed=None, shard=None, prefetch=2):
+        """`prefetch` batches are prepared ahead on a side stream by a background thread (0 = synchronous iteration).
+        `shard=(rank, world_size)` keeps every world_size-th record starting at `rank` (tf.data's `shard`), so each data-
         parallel process reads a disjoint slice with no exchange; default: the active hgb200.parallel context, else no sharding.
         `num_*_examples` stay GLOBAL counts (steps per epoch = n // BATCH_SIZE with BATCH_SIZE the per-process batch means a
         global batch of BATCH_SIZE * world_size, as with a mirrored strategy)."""
@@ -175,6 +273,7 @@ class DatasetBuilder:
         self.num_train_examples = self.get_ds_length(self.train_filenames)
         self.num_valid_examples = self.get_ds_length(self.valid_filenames)
         self._rng = np.random.default_rng(seed)
+        self.prefetch = int(prefetch)
         print(f"Train dataset with {len(self.train_filenames)} tfrecords and {self.num_train_examples} examples.")
         print(f"Valid dataset with {len(self.valid_filenames)} tfrecords and {self.num_valid_examples} examples.")
 
@@ -265,10 +364,16 @@ class DatasetBuilder:
             for batch in self._batches(self._records(self.valid_filenames)):
                 yield self.make_valid_label(*self.prepare_examples(batch))
 
+    def _ahead(self, generator):
+        return Prefetcher(generator, self.prefetch) if self.prefetch > 0 else generator
+
     def build_datasets(self):
-        return self._train_stream(), self._valid_stream()
+        return self._ahead(self._train_stream()), self._ahead(self._valid_stream())
 
     def get_ds_prediction(self):
+        return self._ahead(self._prediction_stream())
+
+    def _prediction_stream(self):
         """:58-66 + prepare_prediction_example (:113-137): one pass over the validation records, (images, meta) per batch
         with the meta keys predict_ds reads (eval.py:117-139)."""
         from . import tfrecord

@@ -164,3 +164,38 @@ def test_dataset_builder_shards_records_across_ranks(hgb, tmp_path):
     assert [parts[k % 3][k // 3] for k in range(9)] == whole
     with pytest.raises(ValueError):
         hgb.dataset_builder.DatasetBuilder(cfg, shard=(3, 3))
+
+
+def test_prefetcher_order_errors_and_shutdown(hgb):
+    import threading
+    import time
+    from hgb200.dataset_builder import Prefetcher
+    assert list(Prefetcher(iter(range(50)), depth=3)) == list(range(50))          # order kept, finite generators end
+
+    def boom():
+        yield 1
+        yield 2
+        raise RuntimeError("corrupted record")
+    p = Prefetcher(boom(), depth=2)
+    assert next(p) == 1 and next(p) == 2
+    with pytest.raises(RuntimeError, match="corrupted record"):
+        next(p)
+    with pytest.raises(StopIteration):
+        next(p)
+
+    produced = []
+
+    def endless():
+        k = 0
+        while True:
+            produced.append(k)
+            yield {"images": k, "meta": [k, (k,)]}
+            k += 1
+    p = Prefetcher(endless(), depth=2)
+    assert next(p)["images"] == 0
+    time.sleep(0.3)
+    assert len(produced) <= 4                                                    # runs at most `depth` (+ one in hand) ahead
+    p.close()
+    p._thread.join(timeout=2)
+    assert not p._thread.is_alive()
+    assert threading.active_count() >= 1
