@@ -145,6 +145,14 @@ int hgb_color_augment(float* images, const float* params, int N, int H, int W, v
  * ((crc >> 15 | crc << 17) + 0xa282ead8) by the caller) that tf.data.TFRecordDataset verifies (dataset_builder.py:39,48,63). */
 uint32_t hgb_crc32c(const void* host_data, int64_t len);
 
+/* tf.io.parse_single_example (dataset_builder.py:262): one serialized tf.train.Example in a HOST buffer.  Returns the number of
+ * features (>= 0) or an error.  table: max_features rows of 6 int64 = [name offset, name length, kind (1 bytes, 2 float,
+ * 3 int64, 0 unset), start, count, extra]: for float / int64 lists `start` indexes fvals / ivals and `count` values follow
+ * (packed or unpacked encodings); for bytes lists `start` / `extra` are the offset / length of the first value in `data`
+ * and `count` the number of values.  HGB_ERR_STATE when a capacity (max_features, fcap, icap) is too small. */
+int hgb_example_parse(const uint8_t* data, int64_t len, int max_features, int64_t* table, float* fvals, int64_t fcap,
+                      int64_t* ivals, int64_t icap);
+
 /* tf.image.decode_image (dataset_builder.py:263) / tf.io.decode_jpeg (gen_tfrecords.py:112), JPEG only.
  * hgb_jpeg_info parses the frame header of a HOST buffer; hgb_jpeg_decode decodes N HOST streams into N caller-owned
  * DEVICE buffers of (h,w,3) interleaved RGB uint8 (grey streams are replicated to 3 channels) through nvJPEG, which is

@@ -1,6 +1,8 @@
 // Host-side IO helpers of the input path: TFRecord framing checksum and JPEG decode.
 //   hgb_crc32c        : CRC-32C (Castagnoli) of the TFRecord framing tf.data.TFRecordDataset verifies
 //                       (dataset_builder.py:39,48,63), slicing-by-8 on the host
+//   hgb_example_parse : one serialized tf.train.Example -> feature table + decoded float / int64 values
+//                       (tf.io.parse_single_example, dataset_builder.py:262), a protobuf wire-format walk on the host
 //   hgb_jpeg_info     : size / component count from the SOF marker (what tf.image.decode_image reads first, :263)
 //   hgb_jpeg_decode   : baseline / progressive JPEG -> interleaved RGB uint8 in DEVICE memory through nvJPEG
 //                       (library decode = plumbing, like cuBLAS for a plain GEMM); libnvjpeg is opened at first use so
@@ -209,4 +211,119 @@ extern "C" int hgb_jpeg_decode(const uint8_t* const* datas, const int64_t* lens,
     return HGB_ERR_CUDA;
   }
   return HGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ tf.train.Example
+namespace {
+struct Cursor {
+  const uint8_t* p;
+  const uint8_t* end;
+  bool ok = true;
+  uint64_t varint() {
+    uint64_t v = 0;
+    for (int shift = 0; shift < 64; shift += 7) {
+      if (p >= end) { ok = false; return 0; }
+      const uint8_t b = *p++;
+      v |= (uint64_t)(b & 0x7f) << shift;
+      if (!(b & 0x80)) return v;
+    }
+    ok = false;
+    return 0;
+  }
+  // next field: returns false at the end; for wire type 2 `sub` is the payload, for 0 `value`, for 1 / 5 `sub` spans the fixed bytes
+  bool next(uint32_t& number, uint32_t& wire, uint64_t& value, Cursor& sub) {
+    if (p >= end || !ok) return false;
+    const uint64_t key = varint();
+    number = (uint32_t)(key >> 3);
+    wire = (uint32_t)(key & 7);
+    if (!ok) return false;
+    if (wire == 0) {
+      value = varint();
+    } else if (wire == 2 || wire == 1 || wire == 5) {
+      const uint64_t n = wire == 2 ? varint() : (wire == 1 ? 8 : 4);
+      if (!ok || n > (uint64_t)(end - p)) { ok = false; return false; }
+      sub.p = p;
+      sub.end = p + n;
+      sub.ok = true;
+      p += n;
+    } else {
+      ok = false;
+    }
+    return ok;
+  }
+};
+}  // namespace
+
+extern "C" int hgb_example_parse(const uint8_t* data, int64_t len, int max_features, int64_t* table, float* fvals, int64_t fcap,
+                                 int64_t* ivals, int64_t icap) {
+  HGB_CHECK_ARG(data && table && fvals && ivals && len >= 0 && max_features > 0, "hgb_example_parse: bad arguments");
+  Cursor ex{data, data + len};
+  int nfeat = 0;
+  int64_t nf = 0, ni = 0;
+  uint32_t num, wire;
+  uint64_t val;
+  Cursor features{nullptr, nullptr}, entry{nullptr, nullptr}, field{nullptr, nullptr}, list{nullptr, nullptr}, item{nullptr, nullptr};
+  while (ex.next(num, wire, val, features)) {
+    if (num != 1 || wire != 2) continue;                                  // Example.features
+    while (features.next(num, wire, val, entry)) {
+      if (num != 1 || wire != 2) continue;                                // Features.feature map entry
+      int64_t name_off = -1, name_len = 0, kind = 0, start = 0, count = 0, extra = 0;
+      while (entry.next(num, wire, val, field)) {
+        if (num == 1 && wire == 2) {
+          name_off = field.p - data;
+          name_len = field.end - field.p;
+        } else if (num == 2 && wire == 2) {                               // Feature: oneof bytes_list / float_list / int64_list
+          while (field.next(num, wire, val, list)) {
+            if (wire != 2 || num < 1 || num > 3) continue;
+            kind = num;
+            start = num == 2 ? nf : ni;
+            count = 0;
+            while (list.next(num, wire, val, item)) {
+              if (num != 1) continue;
+              if (kind == 1) {                                            // bytes: offset / length of the first value, count of values
+                if (wire != 2) { list.ok = false; break; }
+                if (count == 0) { start = item.p - data; extra = item.end - item.p; }
+                ++count;
+              } else if (kind == 2) {                                     // floats: packed chunk(s) or single fixed32 values
+                if (wire != 2 && wire != 5) { list.ok = false; break; }
+                const int64_t n = (item.end - item.p) / 4;
+                if ((item.end - item.p) % 4 || nf + n > fcap) { set_error("hgb_example_parse: float capacity exceeded / bad packing"); return HGB_ERR_STATE; }
+                memcpy(fvals + nf, item.p, (size_t)n * 4);
+                nf += n;
+                count += n;
+              } else {                                                    // int64: packed varints or single varints
+                if (wire == 0) {
+                  if (ni + 1 > icap) { set_error("hgb_example_parse: int64 capacity exceeded"); return HGB_ERR_STATE; }
+                  ivals[ni++] = (int64_t)val;
+                  ++count;
+                } else if (wire == 2) {
+                  while (item.p < item.end && item.ok) {
+                    const uint64_t v = item.varint();
+                    if (!item.ok) break;
+                    if (ni + 1 > icap) { set_error("hgb_example_parse: int64 capacity exceeded"); return HGB_ERR_STATE; }
+                    ivals[ni++] = (int64_t)v;
+                    ++count;
+                  }
+                  if (!item.ok) list.ok = false;
+                } else {
+                  list.ok = false;
+                }
+              }
+            }
+            if (!list.ok) field.ok = false;
+          }
+          if (!field.ok) entry.ok = false;
+        }
+      }
+      if (!entry.ok) features.ok = false;
+      if (name_off >= 0 && features.ok) {
+        if (nfeat >= max_features) { set_error("hgb_example_parse: more than %d features", max_features); return HGB_ERR_STATE; }
+        int64_t* row = table + 6 * nfeat++;
+        row[0] = name_off; row[1] = name_len; row[2] = kind; row[3] = start; row[4] = count; row[5] = extra;
+      }
+    }
+    if (!features.ok) ex.ok = false;
+  }
+  HGB_CHECK_ARG(ex.ok, "hgb_example_parse: malformed tf.train.Example");
+  return nfeat;
 }

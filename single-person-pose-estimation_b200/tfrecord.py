@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import struct
+import threading
 
 import numpy as np
 
@@ -21,6 +22,7 @@ from . import _lib
 from ._lib import check, lib
 
 _MASK_DELTA = 0xA282EAD8
+_lib_ERR_STATE = -3
 
 
 def masked_crc32c(data: bytes) -> int:
@@ -131,8 +133,8 @@ def _parse_feature(buf):
     return None                                                            # Feature with no list set
 
 
-def parse_example(payload: bytes) -> dict:
-    """Serialized tf.train.Example -> {name: list[bytes] | float32 array | int64 array}."""
+def _parse_example_py(payload: bytes) -> dict:
+    """Pure-Python walk of the wire format (the definition the native parser is tested against)."""
     out = {}
     for number, _, features in _fields(memoryview(payload)):
         if number != 1:
@@ -148,6 +150,37 @@ def parse_example(payload: bytes) -> dict:
                     feature = _parse_feature(ev)
             if name is not None:
                 out[name] = feature
+    return out
+
+
+_scratch = threading.local()
+
+
+def parse_example(payload: bytes) -> dict:
+    """Serialized tf.train.Example -> {name: list[bytes] | float32 array | int64 array | None}.  The walk runs in libhgb200
+    (`hgb_example_parse`); examples beyond its fixed capacities or with multi-valued bytes features take the Python path."""
+    sc = getattr(_scratch, "bufs", None)
+    if sc is None:
+        sc = _scratch.bufs = (np.empty((64, 6), np.int64), np.empty(4096, np.float32), np.empty(4096, np.int64))
+    table, fvals, ivals = sc
+    n = lib.hgb_example_parse(payload, len(payload), table.shape[0], table.ctypes.data, fvals.ctypes.data, fvals.size,
+                              ivals.ctypes.data, ivals.size)
+    if n == _lib_ERR_STATE:
+        return _parse_example_py(payload)
+    check(n if n < 0 else 0)
+    out = {}
+    for name_off, name_len, kind, start, count, extra in table[:n].tolist():
+        name = payload[name_off:name_off + name_len].decode("utf-8")
+        if kind == 1:
+            if count != 1:
+                return _parse_example_py(payload)
+            out[name] = [payload[start:start + extra]]
+        elif kind == 2:
+            out[name] = fvals[start:start + count].copy()
+        elif kind == 3:
+            out[name] = ivals[start:start + count].copy()
+        else:
+            out[name] = None
     return out
 
 

@@ -199,3 +199,46 @@ def test_prefetcher_order_errors_and_shutdown(hgb):
     p._thread.join(timeout=2)
     assert not p._thread.is_alive()
     assert threading.active_count() >= 1
+
+
+def test_native_example_parser_matches_the_python_walk(hgb):
+    from hgb200 import tfrecord
+    rng = np.random.default_rng(9)
+
+    def same(payload):
+        a, b = tfrecord.parse_example(payload), tfrecord._parse_example_py(payload)
+        assert list(a) == list(b)
+        for k in a:
+            if isinstance(b[k], list) or b[k] is None:
+                assert a[k] == b[k]
+            else:
+                assert a[k].dtype == b[k].dtype
+                np.testing.assert_array_equal(a[k], b[k])
+        return a
+
+    for _ in range(20):
+        ex = _example(rng, k=int(rng.integers(0, 40)))
+        ex["neg"] = rng.integers(-2 ** 62, 2 ** 62, int(rng.integers(0, 9)))
+        ex["blob"] = bytes(rng.integers(0, 256, int(rng.integers(0, 300)), dtype=np.uint8))
+        got = same(tfrecord.build_example(ex))
+        np.testing.assert_array_equal(got["neg"] if len(ex["neg"]) else np.zeros(0, np.int64), ex["neg"])
+    # unpacked encodings, a feature with no list, and a multi-valued bytes feature (Python path)
+    int64_list = b"\x08\x01" + b"\x08\xff\xff\xff\xff\xff\xff\xff\xff\xff\x01"
+    float_list = b"\x0d" + np.float32(1.5).tobytes() + b"\x0d" + np.float32(-2.0).tobytes()
+    multi = b"\n\x02ab\n\x03cde"
+
+    def entry(name, feature):
+        e = b"\n" + bytes([len(name)]) + name + b"\x12" + bytes([len(feature)]) + feature
+        return b"\n" + bytes([len(e)]) + e
+    body = (entry(b"i", b"\x1a" + bytes([len(int64_list)]) + int64_list) + entry(b"f", b"\x12" + bytes([len(float_list)]) + float_list) +
+            entry(b"none", b"") + entry(b"m", b"\n" + bytes([len(multi)]) + multi))
+    payload = b"\n" + bytes([len(body)]) + body
+    got = same(payload)
+    assert got["i"].tolist() == [1, -1] and got["f"].tolist() == [1.5, -2.0] and got["none"] is None and got["m"] == [b"ab", b"cde"]
+    # capacities: more values than the native scratch holds -> Python path, same result
+    big = tfrecord.build_example({"x": np.arange(10000, dtype=np.float32), "y": np.arange(5000)})
+    assert same(big)["x"].shape == (10000,)
+    # malformed input is an error, not a crash
+    for bad in (b"\n\xff", payload[:-3], b"\n\x05\n\x03\n\x05a"):
+        with pytest.raises(ValueError):
+            tfrecord.parse_example(bad)
