@@ -68,30 +68,44 @@ def flip_partner(num_keypoints, index_flip_pairs):
     return np.asarray(partner, np.int32)
 
 
+_SHIFT_CACHE = {}
+
+
+def _shift_matrices(height, width, shift_add):
+    key = (height, width, shift_add)
+    m = _SHIFT_CACHE.get(key)
+    if m is None:
+        sy, sx = height / 2.0 - shift_add, width / 2.0 - shift_add
+        m = _SHIFT_CACHE[key] = (np.array([[1.0, 0.0, -sx], [0.0, 1.0, -sy], [0.0, 0.0, 1.0]]),
+                                 np.array([[1.0, 0.0, sx], [0.0, 1.0, sy], [0.0, 0.0, 1.0]]))
+    return m
+
+
 def affine_matrix(height, width, scale, rotate_deg, shift_add):
     """Forward 3x3 float64 matrix of imgaug's Affine(scale, rotate): about (size/2 - shift_add); shift_add is 0.5 for
-    pixel arrays and 0 for keypoint coordinates (imgaug `to_matrix` / `to_matrix_cba`)."""
-    sy, sx = height / 2.0 - shift_add, width / 2.0 - shift_add
+    pixel arrays and 0 for keypoint coordinates (imgaug `to_matrix` / `to_matrix_cba`).  The two matrix products are
+    numpy's, as in imgaug/skimage, so the last bits are theirs."""
+    to_topleft, to_center = _shift_matrices(height, width, shift_add)
     rot = np.deg2rad(rotate_deg)
-    lin = np.array([[scale * np.cos(rot), -scale * np.sin(rot), 0.0], [scale * np.sin(rot), scale * np.cos(rot), 0.0], [0.0, 0.0, 1.0]])
-    to_topleft = np.array([[1.0, 0.0, -sx], [0.0, 1.0, -sy], [0.0, 0.0, 1.0]])
-    to_center = np.array([[1.0, 0.0, sx], [0.0, 1.0, sy], [0.0, 0.0, 1.0]])
+    c, s_ = scale * np.cos(rot), scale * np.sin(rot)
+    lin = np.array([[c, -s_, 0.0], [s_, c, 0.0], [0.0, 0.0, 1.0]])
     return to_center @ (lin @ to_topleft)
 
 
 def _opencv_inverse(forward):
-    """The inverse map cv2.warpAffine derives from a forward 2x3 matrix (its order of double operations)."""
-    m = np.array(forward[:2], dtype=np.float64).reshape(-1).copy()
-    det = m[0] * m[4] - m[1] * m[3]
+    """The inverse map cv2.warpAffine derives from a forward 2x3 matrix (its order of double operations; plain Python
+    floats are IEEE doubles, so this is the same arithmetic as numpy float64 scalars without their overhead)."""
+    m0, m1, m2 = float(forward[0][0]), float(forward[0][1]), float(forward[0][2])
+    m3, m4, m5 = float(forward[1][0]), float(forward[1][1]), float(forward[1][2])
+    det = m0 * m4 - m1 * m3
     det = 1.0 / det if det != 0 else 0.0
-    a11, a22 = m[4] * det, m[0] * det
-    m[0], m[4] = a11, a22
-    m[1] *= -det
-    m[3] *= -det
-    b1 = -m[0] * m[2] - m[1] * m[5]
-    b2 = -m[3] * m[2] - m[4] * m[5]
-    m[2], m[5] = b1, b2
-    return m.reshape(2, 3)
+    a11, a22 = m4 * det, m0 * det
+    m0, m4 = a11, a22
+    m1 *= -det
+    m3 *= -det
+    b1 = -m0 * m2 - m1 * m5
+    b2 = -m3 * m2 - m4 * m5
+    return np.array([[m0, m1, b1], [m3, m4, b2]])
 
 
 def augment_1_batch(images, kps_x, kps_y, kps_v, flip, scale, rotate_deg, label_shape=(64, 64, 17),

@@ -1,6 +1,5 @@
 """TFRecord framing / tf.train.Example wire format / JPEG header parsing (tfrecord.py, csrc/io_host.cu) and the
 TFRecord-backed DatasetBuilder's host logic.  CPU only: no decode, no kernels."""
-import os
 import struct
 import types
 

@@ -110,3 +110,17 @@ def test_hue_and_saturation_agree_with_colorsys():
         np.testing.assert_allclose([r[i], g[i], b[i]], want, atol=2e-6)
         want2 = colorsys.hsv_to_rgb(hh, min(1.0, ss * 1.2), vv)
         np.testing.assert_allclose([r2[i], g2[i], b2[i]], want2, atol=2e-6)
+
+
+def test_product_matrices_equal_the_oracle_on_random_draws():
+    """The host bookkeeping of augment_1_batch (forward matrices for image / keypoints, OpenCV's inverse) is bit-identical
+    to the oracle's for the whole range of the reference's draws."""
+    import hgb200
+    rng = np.random.default_rng(7)
+    for _ in range(500):
+        scale, rot = rng.uniform(0.75, 1.25), rng.uniform(-30, 30)
+        for h, w, shift in ((256, 256, 0.5), (64, 64, 0.0), (75, 50, 0.5)):
+            want = iorc.affine_matrix(h, w, scale, rot, shift)
+            got = hgb200.dataset_builder.affine_matrix(h, w, scale, rot, shift)
+            np.testing.assert_array_equal(got, want)
+            np.testing.assert_array_equal(hgb200.dataset_builder._opencv_inverse(got[:2]), iorc.invert_affine_cv(want[:2]))

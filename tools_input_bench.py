@@ -36,7 +36,7 @@ def _cpu_time(fn, min_seconds=1.0, max_iters=200):
 def sweep(batch=256, iters=5, cpu=True):
     import cv2
     import torch
-    import hgb200
+    import hgb200  # noqa: F401  (registers the package alias)
     from hgb200 import _lib, dataset_builder as db, tfrecord
     from hgb200._lib import check, lib, ptr, stream_ptr
 
