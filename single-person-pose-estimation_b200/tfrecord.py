@@ -99,6 +99,8 @@ def _fields(buf):
             value, at = buf[at:at + 4], at + 4
         else:
             raise ValueError(f"unsupported protobuf wire type {wire}")
+        if at > end:
+            raise ValueError("truncated protobuf field")
         yield number, wire, value
 
 
@@ -108,12 +110,16 @@ def _len_delimited(number, payload):
 
 def _parse_feature(buf):
     for number, wire, value in _fields(buf):
+        if wire != 2:
+            continue
         if number == 1:                                                    # BytesList
-            return [bytes(v) for n, w, v in _fields(value) if n == 1]
+            return [bytes(v) for n, w, v in _fields(value) if n == 1 and w == 2]
         if number == 2:                                                    # FloatList
             out = []
             for n, w, v in _fields(value):
-                if n == 1:
+                if n == 1 and w in (2, 5):
+                    if len(v) % 4:
+                        raise ValueError("malformed FloatList")
                     out.append(np.frombuffer(v, dtype="<f4"))
             return np.concatenate(out).astype(np.float32) if out else np.zeros(0, np.float32)
         if number == 3:                                                    # Int64List
@@ -123,7 +129,7 @@ def _parse_feature(buf):
                     continue
                 if w == 0:
                     out.append(v)
-                else:
+                elif w == 2:
                     at = 0
                     while at < len(v):
                         x, at = _varint(v, at)
@@ -136,20 +142,23 @@ def _parse_feature(buf):
 def _parse_example_py(payload: bytes) -> dict:
     """Pure-Python walk of the wire format (the definition the native parser is tested against)."""
     out = {}
-    for number, _, features in _fields(memoryview(payload)):
-        if number != 1:
-            continue
-        for n, _, entry in _fields(features):
-            if n != 1:
+    try:
+        for number, wire, features in _fields(memoryview(payload)):
+            if number != 1 or wire != 2:
                 continue
-            name, feature = None, None
-            for en, _, ev in _fields(entry):
-                if en == 1:
-                    name = bytes(ev).decode("utf-8")
-                elif en == 2:
-                    feature = _parse_feature(ev)
-            if name is not None:
-                out[name] = feature
+            for n, w, entry in _fields(features):
+                if n != 1 or w != 2:
+                    continue
+                name, feature = None, None
+                for en, ew, ev in _fields(entry):
+                    if en == 1 and ew == 2:
+                        name = bytes(ev).decode("utf-8")
+                    elif en == 2 and ew == 2:
+                        feature = _parse_feature(ev)
+                if name is not None:
+                    out[name] = feature
+    except (IndexError, TypeError, struct.error) as ex:
+        raise ValueError("malformed tf.train.Example") from ex
     return out
 
 
