@@ -64,3 +64,33 @@ def shard_batch(n_global: int, world_size: int, rank: int):
         raise ValueError(f"global batch {n_global} is not divisible by world size {world_size}")
     per = n_global // world_size
     return slice(rank * per, (rank + 1) * per)
+
+
+# ------------------------------------------------------------------ evaluation across ranks
+def gather_predictions(predictions, group=None):
+    """Inference, decode and scoring shard by batch with no collective in the data path; what is exchanged is the result.
+    Every rank passes the prediction dicts of ITS records (eval.predict_ds on a DatasetBuilder(shard=(rank, world))) and
+    receives the full list, interleaved back into record order (record k of the pass lives at position k // world of rank
+    k % world).  Uses all_gather_object: host-side, a few hundred bytes per person."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    parts = [None] * world
+    dist.all_gather_object(parts, list(predictions), group=group)
+    merged, longest = [], max(len(p) for p in parts)
+    for i in range(longest):
+        for p in parts:
+            if i < len(p):
+                merged.append(p[i])
+    return merged
+
+
+def sum_pck_counts(correct, visible, group=None):
+    """The optional 2*K-integer all-reduce of eval_PCK's counters (each rank scores its own shard with pck_counts)."""
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.as_tensor(np.concatenate([np.asarray(correct, np.int64), np.asarray(visible, np.int64)]), device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    out = t.cpu().numpy()
+    k = len(out) // 2
+    return out[:k], out[k:]

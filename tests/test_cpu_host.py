@@ -187,6 +187,12 @@ def _dp_worker(rank, world, port, q):
     ar.wait()
     loss = ar.sum_host(np.array([0.25 * (rank + 1), 1.0]))
     sl = hgb200.parallel.shard_batch(256, world, rank)
+    # evaluation: each rank holds the predictions of records rank, rank + world, ...; results are exchanged, not data
+    mine = [{"ann_id": k, "xs/pred": [float(k)]} for k in range(7) if k % world == rank]
+    merged = hgb200.parallel.gather_predictions(mine)
+    assert [p["ann_id"] for p in merged] == list(range(7))
+    c, v = hgb200.parallel.sum_pck_counts(np.arange(17) * (rank + 1), np.full(17, 10 * (rank + 1)))
+    assert c.tolist() == (np.arange(17) * 3).tolist() and v.tolist() == [30] * 17
     q.put((rank, grads.numpy().copy(), loss, (sl.start, sl.stop)))
     hgb200.parallel.disable()
     dist.destroy_process_group()
