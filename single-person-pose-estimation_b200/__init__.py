@@ -23,11 +23,11 @@ from .model import hourglass  # noqa: E402,F401
 from .model.hourglass import Adam, HourglassModel, create_hourglass_model  # noqa: E402,F401
 
 __all__ += ["loss", "parallel", "hourglass", "Adam", "HourglassModel", "create_hourglass_model"]
-from . import callbacks, cocoeval, dataset_builder, demo, eval, tfrecord, trainer  # noqa: E402,F401
+from . import callbacks, cocoeval, dataset_builder, demo, eval, gen_tfrecords, tfrecord, trainer  # noqa: E402,F401
 from .configs import default_config  # noqa: E402,F401
 from .trainer import Trainer  # noqa: E402,F401
 from .utilities import data_utils  # noqa: E402,F401
 from .utilities.data_utils import heatmaps_to_keypoints_v1, heatmaps_to_keypoints_v2  # noqa: E402,F401
 
-__all__ += ["callbacks", "cocoeval", "demo", "tfrecord", "dataset_builder", "eval", "trainer", "default_config", "Trainer", "data_utils",
+__all__ += ["callbacks", "cocoeval", "demo", "gen_tfrecords", "tfrecord", "dataset_builder", "eval", "trainer", "default_config", "Trainer", "data_utils",
             "heatmaps_to_keypoints_v1", "heatmaps_to_keypoints_v2"]

@@ -241,3 +241,53 @@ def test_native_example_parser_matches_the_python_walk(hgb):
     for bad in (b"\n\xff", payload[:-3], b"\n\x05\n\x03\n\x05a"):
         with pytest.raises(ValueError):
             tfrecord.parse_example(bad)
+
+
+def test_create_example_matches_the_reference_writer(hgb, golden_dir, tmp_path):
+    """gen_tfrecords.py:12-86 executed by the reference itself (tests/golden/make_tfrecord_golden.py) vs hgb200.gen_tfrecords:
+    every feature -- names, types, values, the crop bytes -- with the crop taken from the numpy oracle here (the device crop is
+    checked against the same oracle in test_gpu_input.py) and an identity encoder."""
+    import json
+    import os
+    import pandas as pd
+    from hgb200 import gen_tfrecords, tfrecord
+    from oracle import input_oracle as iorc
+    g = np.load(os.path.join(golden_dir, "tfrecord_golden.npz"))
+    image, rows = g["image"], json.loads(str(g["rows"]))
+    crop_fn = lambda img, bbox: iorc.crop_and_pad(img, bbox)          # noqa: E731
+    encode_fn = lambda crop: b"RAW" + crop.astype(np.uint8).tobytes()  # noqa: E731
+    for i, row in enumerate(rows):
+        for scale in (1.25, 1):
+            payload = gen_tfrecords.create_example(image, f"dataset/images/val2017/{i}.jpg", row, 5000 + i, scale, crop_fn, encode_fn)
+            got = tfrecord.parse_example(payload)
+            names = [k[len(f"ex{i}_{scale}_"):] for k in g.files if k.startswith(f"ex{i}_{scale}_")]
+            assert sorted(got) == sorted(names) and len(names) == 14
+            for name in names:
+                want = g[f"ex{i}_{scale}_{name}"]
+                if want.dtype == np.uint8:
+                    assert got[name] == [want.tobytes()], name
+                elif want.dtype == np.int64:
+                    assert got[name].dtype == np.int64 and got[name].tolist() == want.tolist(), name
+                else:
+                    assert got[name].dtype == np.float32
+                    np.testing.assert_array_equal(got[name], want.astype(np.float32), err_msg=name)   # what FloatList stores
+            ex = tfrecord.parse_tfrecord_fn(payload)                  # and the reader's schema accepts it
+            assert ex["width"] == ex["height"] and len(ex["keypoints/x"]) == 17
+    # the uint8 round trip of the device crop is exact: rint(float32(u) * float32(1/255) * 255) == u
+    u = np.arange(256, dtype=np.float32)
+    assert np.array_equal(np.rint((u * np.float32(1.0 / 255)).astype(np.float32) * np.float32(255.0)), u)
+    # shard naming / counts (gen_tfrecords.py:88-115)
+    df = pd.DataFrame([{**r, "image_path": "a.jpg"} for r in rows], index=[11, 12, 13, 14])
+    cfg = types.SimpleNamespace(NUM_EXAMPLER_PER_TFRECORD=3, TRAIN_TFRECORDS_DIR=str(tmp_path / "tfrecords" / "train"),
+                                VALID_TFRECORDS_DIR=str(tmp_path / "tfrecords" / "valid"), TRAIN_IMAGES_DIR="imgs", VALID_IMAGES_DIR="imgs", BBOX_SCALE=1.25)
+    real_create = gen_tfrecords.create_example
+    gen_tfrecords.create_example = lambda im, p, r, idx, s: real_create(im, p, r, idx, s, crop_fn, encode_fn)
+    try:
+        gen_tfrecords.gen_TFRecords(df, cfg, True, read_image=lambda path: image)
+    finally:
+        gen_tfrecords.create_example = real_create
+    files = sorted(os.listdir(cfg.TRAIN_TFRECORDS_DIR))
+    assert files == ["file_train_00-3.tfrec", "file_train_01-1.tfrec"]
+    assert hgb.dataset_builder.DatasetBuilder.get_ds_length([os.path.join(cfg.TRAIN_TFRECORDS_DIR, f) for f in files]) == 4
+    first = [tfrecord.parse_tfrecord_fn(p) for p in tfrecord.read_records(os.path.join(cfg.TRAIN_TFRECORDS_DIR, files[0]))]
+    assert [e["image_id"] for e in first] == [11, 12, 13] and first[0]["ann_id"] == 900000
