@@ -291,3 +291,56 @@ def test_create_example_matches_the_reference_writer(hgb, golden_dir, tmp_path):
     assert hgb.dataset_builder.DatasetBuilder.get_ds_length([os.path.join(cfg.TRAIN_TFRECORDS_DIR, f) for f in files]) == 4
     first = [tfrecord.parse_tfrecord_fn(p) for p in tfrecord.read_records(os.path.join(cfg.TRAIN_TFRECORDS_DIR, files[0]))]
     assert [e["image_id"] for e in first] == [11, 12, 13] and first[0]["ann_id"] == 900000
+
+
+def test_coco_dataframe_matches_reference_semantics_and_feeds_the_writer(hgb, tmp_path, capsys):
+    """coco_df.py:6-82 without pycocotools: filtering rules, index, columns; then annotations -> dataframe -> TFRecords ->
+    DatasetBuilder bookkeeping as one chain."""
+    import json
+    from hgb200 import coco_df, gen_tfrecords, tfrecord
+    from oracle import input_oracle as iorc
+    rng = np.random.default_rng(12)
+
+    def dataset(n_images, first_ann):
+        images, anns = [], []
+        for i in range(n_images):
+            images.append({"id": 100 + i, "file_name": f"{100 + i:012d}.jpg", "width": 200, "height": 150, "coco_url": f"http://x/{i}.jpg"})
+            for p in range(int(rng.integers(0, 4))):
+                nk = int(rng.integers(0, 12))
+                kps = []
+                for k in range(17):
+                    kps += [float(rng.integers(20, 120)), float(rng.integers(20, 120)), 2 if k < nk else 0]
+                anns.append({"id": first_ann + len(anns), "image_id": 100 + i, "category_id": 1, "iscrowd": int(rng.random() < 0.2),
+                             "bbox": [10.0, 12.0, 110.0, 120.0], "num_keypoints": nk, "keypoints": kps, "area": 100.0})
+        return {"images": images, "annotations": anns, "categories": [{"id": 1, "name": "person"}]}
+
+    train, valid = dataset(12, 1), dataset(6, 1000)
+    (tmp_path / "train.json").write_text(json.dumps(train))
+    (tmp_path / "valid.json").write_text(json.dumps(valid))
+    cfg = types.SimpleNamespace(**{k: getattr(hgb.default_config, k) for k in dir(hgb.default_config) if k.isupper()})
+    cfg.TRAIN_ANNOT_FILE, cfg.VALID_ANNOT_FILE = str(tmp_path / "train.json"), str(tmp_path / "valid.json")
+    train_df, valid_df = coco_df.gen_trainval_df(cfg, drop_min_num_kps=True)
+    out = capsys.readouterr().out
+    assert "num_keypoints >= 5 are chosen" in out and f"Length of train df: {len(train_df)}" in out
+    want = [a for a in train["annotations"] if a["iscrowd"] == 0 and a["num_keypoints"] >= 5]
+    assert sorted(train_df["ann_id"]) == sorted(a["id"] for a in want) and len(want) > 0
+    assert train_df.index.name == "image_id" and set(train_df.index) == {a["image_id"] for a in want}
+    assert list(train_df.columns) == ["coco_url", "image_path", "width", "height", "ann_id", "is_crowd", "bbox", "num_keypoints", "keypoints"]
+    loose, _ = coco_df.gen_trainval_df(cfg)
+    assert len(loose) == sum(a["iscrowd"] == 0 and a["num_keypoints"] >= 1 for a in train["annotations"])
+    # dataframe -> TFRecords -> reader
+    cfg.TRAIN_TFRECORDS_DIR, cfg.VALID_TFRECORDS_DIR = str(tmp_path / "rec" / "train"), str(tmp_path / "rec" / "valid")
+    cfg.NUM_EXAMPLER_PER_TFRECORD = 4
+    frame = rng.integers(0, 256, (150, 200, 3), dtype=np.uint8)
+    real_create = gen_tfrecords.create_example
+    gen_tfrecords.create_example = lambda im, p, r, idx, s: real_create(im, p, r, idx, s, lambda a, b: iorc.crop_and_pad(a, b),
+                                                                        lambda c: b"RAW" + c.tobytes())
+    try:
+        gen_tfrecords.gen_TFRecords(train_df, cfg, True, read_image=lambda path: frame)
+        gen_tfrecords.gen_TFRecords(valid_df, cfg, False, read_image=lambda path: frame)
+    finally:
+        gen_tfrecords.create_example = real_create
+    b = hgb.dataset_builder.DatasetBuilder(cfg)
+    assert b.num_train_examples == len(train_df) and b.num_valid_examples == len(valid_df)
+    recs = [tfrecord.parse_tfrecord_fn(r) for r in b._records(b.train_filenames)]
+    assert [r["ann_id"] for r in recs] == list(train_df["ann_id"]) and [r["image_id"] for r in recs] == list(train_df.index)
