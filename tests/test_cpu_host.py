@@ -193,6 +193,11 @@ def _dp_worker(rank, world, port, q):
     assert [p["ann_id"] for p in merged] == list(range(7))
     c, v = hgb200.parallel.sum_pck_counts(np.arange(17) * (rank + 1), np.full(17, 10 * (rank + 1)))
     assert c.tolist() == (np.arange(17) * 3).tolist() and v.tolist() == [30] * 17
+    # the TFRecord builder picks its record shard up from the active data-parallel context
+    import types
+    cfg = types.SimpleNamespace(**{k: getattr(hgb200.default_config, k) for k in dir(hgb200.default_config) if k.isupper()})
+    cfg.TRAIN_TFRECORDS_DIR = cfg.VALID_TFRECORDS_DIR = "/nonexistent"
+    assert hgb200.dataset_builder.DatasetBuilder(cfg).shard == (rank, world)
     q.put((rank, grads.numpy().copy(), loss, (sl.start, sl.stop)))
     hgb200.parallel.disable()
     dist.destroy_process_group()
