@@ -16,9 +16,11 @@ keras_graph.py), Adam slots as `<weight>/.OPTIMIZER_SLOT/optimizer/{m,v}/.ATTRIB
 (`full_name`, e.g. "hg0_conv_1x1_1/kernel").  The reader resolves weights through that graph when it is present and through
 the layer order otherwise, and insists that both agree.
 
-TensorFlow is absent from the build image, so no file written by real TF is available: **parity unpinned** for the container
-format (restated from the published formats, round-trip tested); the key naming is pinned through the reference's own saved
-`model.summary()` (keras_graph.py).  CRCs run in libhgb200 (`hgb_crc32c`).
+TensorFlow is absent from the build image, so no file written by real Keras is available.  What IS pinned
+(tests/test_cpu_format_pins.py, against TensorFlow's own code shipped inside tensorboard): the bundle header / entry protos
+(compiled TensorShapeProto, DataType, VersionDef), the masked CRC-32C, the string-tensor encoding and the TrackableObjectGraph
+proto in both directions; the key naming is pinned through the reference's own saved `model.summary()` (keras_graph.py).
+The LevelDB table container is restated from the published format only.  CRCs run in libhgb200 (`hgb_crc32c`).
 """
 from __future__ import annotations
 

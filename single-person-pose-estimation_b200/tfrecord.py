@@ -7,7 +7,9 @@ dataset_builder.py:241-268 parses them).  Both formats are public and tiny:
   Example := { 1: Features { 1: map<string, Feature> } },  Feature := { 1: BytesList | 2: FloatList | 3: Int64List },
              each list := { 1: repeated value } (floats / int64s packed, unpacked accepted)
 
-The CRC runs in libhgb200 (`hgb_crc32c`, host code); everything else here is byte bookkeeping.  JPEG payloads are decoded on
+Pinned against TensorFlow's own Python record writer / reader (shipped in tensorboard) and against the protobuf runtime's
+serialization of the published schema: files and messages are byte-identical (tests/test_cpu_format_pins.py).
+The CRC and the Example walk run in libhgb200 (`hgb_crc32c`, `hgb_example_parse`, host code); the rest is byte bookkeeping.  JPEG payloads are decoded on
 the GPU (`decode_jpeg_batch` -> `hgb_jpeg_decode`).
 """
 from __future__ import annotations
