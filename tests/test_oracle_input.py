@@ -44,6 +44,13 @@ def test_square_bbox_matches_reference(g):
             k += 1
 
 
+def test_square_bbox_known_answers_from_the_reference_notebook():
+    """dev/test_tfrecords.ipynb cells 15 and 39: the printed results of the reference's transform_bbox_square."""
+    import hgb200
+    assert hgb200.data_utils.transform_bbox_square([603.15, 125.6, 36.85, 66.16]) == (588.4949999999999, 125.60000000000001, 66.16, 66.16)
+    assert hgb200.data_utils.transform_bbox_square([163.73, 126.42, 265.69, 480.4], 1.25) == (-3.6750000000000114, 66.37, 600.5, 600.5)
+
+
 def test_crop_window_rejected_like_tensorflow():
     with pytest.raises(ValueError):
         iorc.crop_and_pad_params(90, 120, (10.0, 10.0, 0.5, 0.5))
