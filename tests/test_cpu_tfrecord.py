@@ -344,3 +344,27 @@ def test_coco_dataframe_matches_reference_semantics_and_feeds_the_writer(hgb, tm
     assert b.num_train_examples == len(train_df) and b.num_valid_examples == len(valid_df)
     recs = [tfrecord.parse_tfrecord_fn(r) for r in b._records(b.train_filenames)]
     assert [r["ann_id"] for r in recs] == list(train_df["ann_id"]) and [r["image_id"] for r in recs] == list(train_df.index)
+
+
+def test_shard_naming_reproduces_the_reference_dataset_counts(hgb, tmp_path, capsys):
+    """Train.ipynb cell 7: 'Train dataset with 66 tfrecords and 134214 examples. / Valid dataset with 3 tfrecords and 5647
+    examples.' -- 134214 and 5647 people (gen_tfrecords.ipynb cell 4) in shards of 2048, counted from the file names."""
+    train, valid = tmp_path / "train", tmp_path / "valid"
+    train.mkdir()
+    valid.mkdir()
+
+    def shards(folder, total, per=2048):
+        n = total // per + (1 if total % per else 0)
+        for k in range(n):
+            count = per if k < n - 1 or total % per == 0 else total % per
+            (folder / ("file_" + folder.name + "_%.2i-%i.tfrec" % (k, count))).touch()       # gen_tfrecords.py:107
+
+    shards(train, 134214)
+    shards(valid, 5647)
+    cfg = types.SimpleNamespace(**{k: getattr(hgb.default_config, k) for k in dir(hgb.default_config) if k.isupper()})
+    cfg.TRAIN_TFRECORDS_DIR, cfg.VALID_TFRECORDS_DIR = str(train), str(valid)
+    b = hgb.dataset_builder.DatasetBuilder(cfg)
+    assert capsys.readouterr().out == ("Train dataset with 66 tfrecords and 134214 examples.\n"
+                                       "Valid dataset with 3 tfrecords and 5647 examples.\n")
+    # and the steps per epoch the reference trained with (Train.ipynb cell 20): 8388 and 352 at batch 16
+    assert (b.num_train_examples // 16, b.num_valid_examples // 16) == (8388, 352)
