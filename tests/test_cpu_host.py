@@ -295,3 +295,17 @@ def test_lane_schedule_orders_every_conflicting_pair(backward):
     side = [k for k, o in enumerate(ops) if o["lane"] >= 2]
     main_before = {k: max((i for i in range(k) if ops[i]["lane"] == 0), default=-1) for k in side}
     assert sum(clock[k][0] < main_before[k] for k in side) > len(side) // 2
+
+
+def test_demo_reads_yolov5_style_detector_results():
+    """demo.py:28-41: only 'person' rows above the confidence threshold become (xmin, ymin, w, h) boxes, in detector order."""
+    import pandas as pd
+    import types
+    from hgb200.demo import _boxes_from_detector_result
+    df = pd.DataFrame({"xmin": [10.0, 50.0, 5.0, 200.0], "ymin": [20.0, 60.0, 6.0, 100.0], "xmax": [110.0, 90.0, 55.0, 260.0],
+                       "ymax": [220.0, 160.0, 66.0, 300.0], "confidence": [0.9, 0.8, 1e-7, 0.5], "class": [0, 16, 0, 0],
+                       "name": ["person", "dog", "person", "person"]})
+    result = types.SimpleNamespace(pandas=lambda: types.SimpleNamespace(xyxy=[df]))
+    assert _boxes_from_detector_result(result, 1e-6) == [(10.0, 20.0, 100.0, 200.0), (200.0, 100.0, 60.0, 200.0)]
+    assert _boxes_from_detector_result(np.array([[1.0, 2.0, 4.0, 8.0]]), 0.5) == [(1.0, 2.0, 3.0, 6.0)]
+    assert _boxes_from_detector_result(np.zeros((0, 4)), 0.5) == []
