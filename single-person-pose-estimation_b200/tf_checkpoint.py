@@ -368,6 +368,15 @@ def load_keras_weights(model, prefix):
     keys, _ = _layer_weights(model)
     bundle = read_checkpoint(prefix)
     named = parse_object_graph(bundle[OBJECT_GRAPH_KEY]) if isinstance(bundle.get(OBJECT_GRAPH_KEY), bytes) else {}
+    first = next(iter(keys.values()))
+    if first not in bundle:
+        # the model saved as an attribute of another object (tf.train.Checkpoint(model=m).save(...), wrappers): every key
+        # carries that attribute path in front, e.g. "model/layer_with_weights-0/kernel/..."
+        roots = sorted({k[:-len(first)] for k in bundle if k.endswith("/" + first)})
+        if len(roots) == 1:
+            root = roots[0]
+            bundle = OrderedDict((k[len(root):] if k.startswith(root) else k, v) for k, v in bundle.items())
+            named = {(k[len(root):] if k.startswith(root) else k): v for k, v in named.items()}
     weights, m, v = OrderedDict(), {}, {}
     for ours, key in keys.items():
         if key not in bundle:

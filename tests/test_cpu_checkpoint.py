@@ -161,6 +161,13 @@ def test_model_weights_round_trip_through_tf_checkpoint(hgb, tmp_path):
     keys = tc.read_checkpoint(prefix)
     assert "layer_with_weights-0/kernel/.OPTIMIZER_SLOT/optimizer/m/.ATTRIBUTES/VARIABLE_VALUE" in keys
     assert not any("moving_mean/.OPTIMIZER_SLOT" in k for k in keys)
+    # a checkpoint whose root object holds the model as an attribute (tf.train.Checkpoint(model=...)): keys carry the path
+    nested = {("model/" + k if k != "_CHECKPOINTABLE_OBJECT_GRAPH" else k): v for k, v in tc.read_checkpoint(prefix).items()}
+    nested["save_counter/.ATTRIBUTES/VARIABLE_VALUE"] = np.asarray(1, np.int64)
+    tc.write_checkpoint(str(tmp_path / "ckpt-1"), nested)
+    w2, adam2 = tc.load_keras_weights(b, str(tmp_path / "ckpt-1"))
+    np.testing.assert_array_equal(w2["hg1_conv_1x1_predict/kernel"], w["hg1_conv_1x1_predict/kernel"])
+    assert adam2 is None or adam2[0] == 777
     # the npz/json payload of earlier checkpoints still loads
     a.save_weights(prefix, save_format="hgb")
     c = hgb.create_hourglass_model(17, 2, 256, (256, 256, 3), "sigmoid")
