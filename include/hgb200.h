@@ -143,7 +143,8 @@ int hgb_color_augment(float* images, const float* params, int N, int H, int W, v
 
 /* CRC-32C (Castagnoli) of a HOST buffer: the checksum of the TFRecord framing (length and payload, masked as
  * ((crc >> 15 | crc << 17) + 0xa282ead8) by the caller) that tf.data.TFRecordDataset verifies (dataset_builder.py:39,48,63). */
-uint32_t hgb_crc32c(const void* host_data, int64_t len);
+uint32_t hgb_crc32c(const void* host_data, int64_t len);            /* SSE4.2 CRC32 instruction when the CPU has it */
+uint32_t hgb_crc32c_portable(const void* host_data, int64_t len);   /* slicing-by-8 tables; the definition the fast path is tested against */
 
 /* tf.io.parse_single_example (dataset_builder.py:262): one serialized tf.train.Example in a HOST buffer.  Returns the number of
  * features (>= 0) or an error.  table: max_features rows of 6 int64 = [name offset, name length, kind (1 bytes, 2 float,

@@ -92,7 +92,42 @@ static bool nvjpeg_ready() {
 
 using namespace hgb;
 
+#if defined(__x86_64__) && defined(__GNUC__)
+// The CRC32 instruction of SSE4.2 computes exactly this polynomial (what TensorFlow's own crc32c uses when available);
+// taken when the CPU reports it, the table walk below is the portable path and the definition both are tested against.
+__attribute__((target("sse4.2"))) static uint32_t crc32c_hw(const uint8_t* p, int64_t len) {
+  uint64_t c = 0xffffffffu;
+  while (len > 0 && ((uintptr_t)p & 7)) {
+    c = __builtin_ia32_crc32qi((uint32_t)c, *p++);
+    --len;
+  }
+  while (len >= 8) {
+    uint64_t w;
+    memcpy(&w, p, 8);
+    c = __builtin_ia32_crc32di(c, w);
+    p += 8;
+    len -= 8;
+  }
+  while (len-- > 0) c = __builtin_ia32_crc32qi((uint32_t)c, *p++);
+  return (uint32_t)c ^ 0xffffffffu;
+}
+static bool crc32c_has_hw() {
+  static const bool yes = __builtin_cpu_supports("sse4.2");
+  return yes;
+}
+#else
+static uint32_t crc32c_hw(const uint8_t*, int64_t) { return 0; }
+static bool crc32c_has_hw() { return false; }
+#endif
+
+extern "C" uint32_t hgb_crc32c_portable(const void* data, int64_t len);
+
 extern "C" uint32_t hgb_crc32c(const void* data, int64_t len) {
+  if (crc32c_has_hw()) return crc32c_hw((const uint8_t*)data, len);
+  return hgb_crc32c_portable(data, len);
+}
+
+extern "C" uint32_t hgb_crc32c_portable(const void* data, int64_t len) {
   std::call_once(g_crc_once, crc_init);
   const uint8_t* p = (const uint8_t*)data;
   uint32_t c = 0xffffffffu;

@@ -30,6 +30,15 @@ def test_crc32c_known_answers(hgb):
             ref = (ref >> 1) ^ 0x82F63B78 if ref & 1 else ref >> 1
     assert crc(data, 999) == ref ^ 0xFFFFFFFF
     assert crc(data[1:], 998) != crc(data, 998)                    # unaligned start goes through the byte prologue
+    # the dispatched routine (CRC32 instruction when the CPU has it) against the portable table walk, at every alignment
+    import ctypes
+    buf = ctypes.create_string_buffer(data, len(data))
+    portable = hgb._lib.lib.hgb_crc32c_portable
+    for off in range(9):
+        for n in (0, 1, 7, 8, 9, 31, 64, 1001, len(data) - 8):
+            ptr = ctypes.cast(ctypes.byref(buf, off), ctypes.c_void_p)
+            assert crc(ptr, n) == portable(ptr, n), (off, n)
+    assert portable(b"123456789", 9) == 0xE3069283
     masked = tfrecord.masked_crc32c(b"123456789")
     assert masked == (((0xE3069283 >> 15) | (0xE3069283 << 17)) + 0xA282EAD8) & 0xFFFFFFFF
 
