@@ -146,6 +146,13 @@ int hgb_color_augment(float* images, const float* params, int N, int H, int W, v
 uint32_t hgb_crc32c(const void* host_data, int64_t len);            /* SSE4.2 CRC32 instruction when the CPU has it */
 uint32_t hgb_crc32c_portable(const void* host_data, int64_t len);   /* slicing-by-8 tables; the definition the fast path is tested against */
 
+/* tf.data.TFRecordDataset (dataset_builder.py:39,48,63): walk the framing of a TFRecord file held in HOST memory (e.g. mmap)
+ * from byte `start`: for up to `cap` records writes the payload offset and length, verifies the masked CRC-32C of the length
+ * and of the payload when `verify`, and stores the offset of the first unread byte in *next.  Returns the number of records
+ * (0 at the end of the file) or HGB_ERR_INVALID with "truncated ..." / "corrupted ..." in hgb_last_error(). */
+int64_t hgb_tfrecord_scan(const uint8_t* data, int64_t len, int64_t start, int verify, int64_t* offsets, int64_t* lengths,
+                          int64_t cap, int64_t* next);
+
 /* tf.io.parse_single_example (dataset_builder.py:262): one serialized tf.train.Example in a HOST buffer.  Returns the number of
  * features (>= 0) or an error.  table: max_features rows of 6 int64 = [name offset, name length, kind (1 bytes, 2 float,
  * 3 int64, 0 unset), start, count, extra]: for float / int64 lists `start` indexes fvals / ivals and `count` values follow

@@ -43,6 +43,7 @@ PROTOTYPES = {
     "hgb_color_augment": (i32, [vp, vp, i32, i32, i32, vp, vp]),
     "hgb_crc32c": (C.c_uint32, [vp, i64]),
     "hgb_crc32c_portable": (C.c_uint32, [vp, i64]),
+    "hgb_tfrecord_scan": (i64, [vp, i64, i64, i32, vp, vp, i64, vp]),
     "hgb_example_parse": (i32, [vp, i64, i32, vp, vp, i64, vp, i64]),
     "hgb_jpeg_info": (i32, [vp, i64, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     "hgb_jpeg_decode": (i32, [vp, vp, i32, vp, vp, vp]),

@@ -1,6 +1,7 @@
 // Host-side IO helpers of the input path: TFRecord framing checksum and JPEG decode.
 //   hgb_crc32c        : CRC-32C (Castagnoli) of the TFRecord framing tf.data.TFRecordDataset verifies
 //                       (dataset_builder.py:39,48,63), slicing-by-8 on the host
+//   hgb_tfrecord_scan : walks the record framing of a whole (memory-mapped) TFRecord file, verifying both CRCs per record
 //   hgb_example_parse : one serialized tf.train.Example -> feature table + decoded float / int64 values
 //                       (tf.io.parse_single_example, dataset_builder.py:262), a protobuf wire-format walk on the host
 //   hgb_jpeg_info     : size / component count from the SOF marker (what tf.image.decode_image reads first, :263)
@@ -361,4 +362,40 @@ extern "C" int hgb_example_parse(const uint8_t* data, int64_t len, int max_featu
   }
   HGB_CHECK_ARG(ex.ok, "hgb_example_parse: malformed tf.train.Example");
   return nfeat;
+}
+
+// ------------------------------------------------------------------------------------------------ TFRecord framing
+static inline uint32_t masked_crc(const uint8_t* p, int64_t n) {
+  const uint32_t c = hgb_crc32c(p, n);
+  return ((c >> 15) | (c << 17)) + 0xa282ead8u;
+}
+
+extern "C" int64_t hgb_tfrecord_scan(const uint8_t* data, int64_t len, int64_t start, int verify, int64_t* offsets, int64_t* lengths,
+                                     int64_t cap, int64_t* next) {
+  if (!data || !offsets || !lengths || !next || len < 0 || start < 0 || start > len || cap <= 0) {
+    set_error("hgb_tfrecord_scan: bad arguments");
+    return HGB_ERR_INVALID;
+  }
+  int64_t at = start, n = 0;
+  while (at < len && n < cap) {
+    if (len - at < 12) { set_error("truncated record header at byte %lld", (long long)at); return HGB_ERR_INVALID; }
+    uint64_t size;
+    uint32_t crc;
+    memcpy(&size, data + at, 8);
+    memcpy(&crc, data + at + 8, 4);
+    if (verify && masked_crc(data + at, 8) != crc) { set_error("corrupted record length at byte %lld", (long long)at); return HGB_ERR_INVALID; }
+    if (size > (uint64_t)(len - at - 12) || (uint64_t)(len - at - 12) - size < 4) {
+      set_error("truncated record at byte %lld", (long long)at);
+      return HGB_ERR_INVALID;
+    }
+    const uint8_t* payload = data + at + 12;
+    memcpy(&crc, payload + size, 4);
+    if (verify && masked_crc(payload, (int64_t)size) != crc) { set_error("corrupted record payload at byte %lld", (long long)at); return HGB_ERR_INVALID; }
+    offsets[n] = at + 12;
+    lengths[n] = (int64_t)size;
+    ++n;
+    at += 12 + (int64_t)size + 4;
+  }
+  *next = at;
+  return n;
 }
