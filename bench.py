@@ -44,6 +44,12 @@ def parse():
     return ap.parse_args()
 
 
+def _oracle_color_augment():
+    """CPU leg only: the numpy restatement of the reference's colour augmentation, timed beside the kernel."""
+    from oracle import input_oracle
+    return input_oracle.color_augment
+
+
 # --------------------------------------------------------------------------------------- CPU arm
 def cpu_train_steps(stacks, batch, steps, warmup):
     """The reference's training step (model/hourglass.py + loss.py weighted_mse + Keras Adam) as restated in
@@ -277,7 +283,7 @@ def run_ours(args):
                                 {"us": r["s"] * 1e6, "gbps": r.get("gbps"), "frac": (r["gbps"] / peak_bw) if "gbps" in r and not r.get("host_timed") else None,
                                  "images_per_s": r.get("gpu_images_per_s", r.get("images_per_s")),
                                  "cpu_images_per_s": r.get("cpu_images_per_s")}.items() if v is not None}
-                            for k, r in tools_input_bench.sweep(batch=256, iters=3).items()}}
+                            for k, r in tools_input_bench.sweep(batch=256, iters=3, cpu_color_fn=_oracle_color_augment()).items()}}
         except Exception as ex:
             line["input_kernels"] = {"error": f"{type(ex).__name__}: {ex}"}
     if world == 1 and not args.no_cpu_baseline:

@@ -6,7 +6,7 @@ is how the reference runs them: one Python callback per example, dataset_builder
 
   crop_resize    uint8 640x480 frames -> (256,256,3) f32 : read 3 B/px of the source + write 12 B/px          cv2.resize
   augment_affine flip + affine warp                       : read + write 12 B/px                               cv2.warpAffine
-  color_augment  brightness/contrast/saturation/hue/norm  : 3 reads + 2 writes of 12 B/px (three passes)       numpy restatement
+  color_augment  brightness/contrast/saturation/hue/norm  : 3 reads + 2 writes of 12 B/px (three passes)       numpy restatement (bench.py only)
   jpeg_decode    nvJPEG, 256x256 4:2:0 q95                : decoded MB/s and images/s                          cv2.imdecode
   train_label    augment_1 + augment_2 + target rendering (make_train_label_batch), images/s
 
@@ -33,7 +33,7 @@ def _cpu_time(fn, min_seconds=1.0, max_iters=200):
     return (time.perf_counter() - t0) / n
 
 
-def sweep(batch=256, iters=5, cpu=True):
+def sweep(batch=256, iters=5, cpu=True, cpu_color_fn=None):
     import cv2
     import torch
     import hgb200  # noqa: F401  (registers the package alias)
@@ -114,8 +114,8 @@ def sweep(batch=256, iters=5, cpu=True):
         im = images[0].cpu().numpy()
         m = db.affine_matrix(H, W, 1.1, 17.0, 0.5)[:2]
         rows["augment_affine"]["cpu_s_per_image"] = _cpu_time(lambda: cv2.warpAffine(im, m, dsize=(W, H), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0))
-        from oracle import input_oracle as iorc
-        rows["color_augment"]["cpu_s_per_image"] = _cpu_time(lambda: iorc.color_augment(im, 0.1, 1.3, 1.1, 0.05), min_seconds=2.0, max_iters=20)
+        if cpu_color_fn is not None:      # the numpy restatement lives under oracle/: only bench.py's CPU leg hands it in
+            rows["color_augment"]["cpu_s_per_image"] = _cpu_time(lambda: cpu_color_fn(im, 0.1, 1.3, 1.1, 0.05), min_seconds=2.0, max_iters=20)
         arr = np.frombuffer(enc, np.uint8)
         rows["jpeg_decode nvJPEG 256x256"]["cpu_s_per_image"] = _cpu_time(lambda: cv2.imdecode(arr, cv2.IMREAD_COLOR))
     for k, r in rows.items():
