@@ -11,7 +11,13 @@ so the same arrays can be loaded into the CUDA model by name.
 Parity pin: TensorFlow is not installable here, so the numerics of this restatement are
 "parity unpinned" against live TF; the ARCHITECTURE is pinned by the reference's saved
 model.summary() parameter counts (3,659,665 / 7,034,530 / 13,784,260), checked in
-tests/test_network_oracle.py.
+tests/test_cpu_host.py (test_parameter_counts_match_reference_summaries); wherever TensorFlow IS importable,
+tests/test_tf_crosscheck.py loads shared weights into the real model/hourglass.py + loss.py + Keras Adam
+and pins this file against them.
+
+`device`: the restatement runs on the CPU by default; the GPU parity tests of the large BASELINE
+configurations (4-stack batch 64, 8-stack batch 32 / 128) pass device="cuda" so the fp32 reference
+finishes in seconds -- still plain fp32 torch (TF32 disabled), still test infrastructure only.
 """
 from __future__ import annotations
 
@@ -203,12 +209,20 @@ def init_params(spec, seed=2, perturb_bn=False):
     return out
 
 
+def _fp32_exact(device):
+    """fp32 means fp32: no TF32 in cuDNN / cuBLAS when the restatement runs on a GPU."""
+    if str(device) != "cpu":
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+
 def forward(params_np, images_nhwc, num_classes, num_stacks, num_channels, activation="sigmoid", training=True,
-            requires_grad=False, update_moving=False, return_taps=False, emulate_bf16=False):
+            requires_grad=False, update_moving=False, return_taps=False, emulate_bf16=False, device="cpu"):
     """images (B,H,W,3) f32 -> list of S tensors (B,h,w,K) f32 (NHWC).  Returns (outputs, torch params)."""
-    params = OrderedDict((k, torch.tensor(v, dtype=torch.float32, requires_grad=requires_grad and "moving_" not in k))
+    _fp32_exact(device)
+    params = OrderedDict((k, torch.tensor(v, dtype=torch.float32, device=device, requires_grad=requires_grad and "moving_" not in k))
                          for k, v in params_np.items())
-    x = torch.as_tensor(np.asarray(images_nhwc), dtype=torch.float32).permute(0, 3, 1, 2)
+    x = torch.as_tensor(np.asarray(images_nhwc), dtype=torch.float32).to(device).permute(0, 3, 1, 2)
     b = _Builder(params, training=training, update_moving=update_moving, emulate_bf16=emulate_bf16)
     outs = b.model(x, num_classes, num_stacks, num_channels, activation)
     outs = [o.permute(0, 2, 3, 1) for o in outs]
@@ -237,16 +251,16 @@ def torch_loss(kind, y_true, y_pred):
 
 
 def loss_and_grads(params_np, images, y_true, kind, num_classes, num_stacks, num_channels, activation="sigmoid",
-                   emulate_bf16=False):
+                   emulate_bf16=False, device="cpu"):
     """Training-mode forward, sum of per-stack losses (Keras compile with one loss fn), backward."""
     outs, params = forward(params_np, images, num_classes, num_stacks, num_channels, activation, training=True,
-                           requires_grad=True, emulate_bf16=emulate_bf16)
-    t = torch.as_tensor(np.asarray(y_true), dtype=torch.float32)
+                           requires_grad=True, emulate_bf16=emulate_bf16, device=device)
+    t = torch.as_tensor(np.asarray(y_true), dtype=torch.float32).to(device)
     losses = [torch_loss(kind, t, o) for o in outs]
     total = sum(losses)
     total.backward()
-    grads = OrderedDict((k, v.grad.numpy()) for k, v in params.items() if v.requires_grad)
-    return [o.detach().numpy() for o in outs], [float(l.detach()) for l in losses], grads
+    grads = OrderedDict((k, v.grad.cpu().numpy()) for k, v in params.items() if v.requires_grad)
+    return [o.detach().cpu().numpy() for o in outs], [float(l.detach()) for l in losses], grads
 
 
 def adam_step(w, g, m, v, t, lr=1e-3, b1=0.9, b2=0.999, eps=1e-7):

@@ -1,9 +1,17 @@
-"""Replay of EVERY op of the real execution plan (forward and backward, 2 stacks) against an fp32
+"""Replay of EVERY op of the real execution plan (forward and backward) against an fp32
 torch reference computed from the device's own input tensors, one op at a time
 (hgb_model_run_op).  This is the parity proof that does not depend on how the network amplifies
 noise: each convolution (forward, dgrad, wgrad -- incl. the padded 17-channel and 7x7-stem cases and
 fused residuals), BatchNorm forward/backward, pool, upsample-add and head op must match the fp32
 arithmetic of model/hourglass.py to bf16 output rounding; integer-like ops must match exactly.
+
+Two gates per floating-point op: max error <= 1e-2 of the tensor maximum, and -- the literal reading of the
+north-star "per-layer gradient cosine > 0.999" -- cosine > 0.999 between the op's output (activation, input
+gradient, weight gradient, BatchNorm-backward gradient) and the fp32 reference of the same op.
+
+Two plans are replayed: 2 stacks at batch 3 (inter-stack re-injection, small-tile kernel variants) and 1 stack at
+batch 80, where the dispatcher picks what the BASELINE configurations run: the strip-reuse (HALO) 3x3 kernel at 64x64 and
+32x32, the rolling-strip 3x3 weight-gradient kernel, the wide 1x1 weight-gradient tiles and the weight-stationary groups.
 """
 import ctypes as C
 
@@ -36,6 +44,7 @@ class Replay:
         self.targets = torch.as_tensor(targets, device="cuda")
         self.params, self.grads, self.arena = self.model._params, self.model._grads, self.plan.arena
         self.worst = {}
+        self.low_cos = {}
 
     # ---- views
     def act(self, a):
@@ -77,6 +86,15 @@ class Replay:
     def rel(a, b):
         return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
 
+    def cos(self, op_type, a, b):
+        """cosine between an op's output and its fp32 reference; the lowest per op type is kept."""
+        a, b = a.double().reshape(-1), b.double().reshape(-1)
+        na, nb = a.norm().item(), b.norm().item()
+        c = 1.0 if (na == 0 and nb == 0) else float((a @ b).item() / max(na * nb, 1e-300))
+        k = NAMES[op_type]
+        self.low_cos[k] = min(self.low_cos.get(k, 1.0), c)
+        return c
+
     def ops(self, seg, backward):
         n = self.lib.hgb_model_num_ops(self.h, seg, backward)
         for i in range(n):
@@ -106,11 +124,13 @@ def _unwindows(v, N, H, W, Cc):
     return v.view(N, H // 2, W // 2, 2, 2, Cc).permute(0, 1, 3, 2, 4, 5).reshape(N, H, W, Cc)
 
 
-def test_replay_every_op(request):
+@pytest.mark.parametrize("S,B", [(2, 3), (1, 80)])
+def test_replay_every_op(S, B):
     import hgb200 as hgb
     import torch
     import torch.nn.functional as F
-    S, B = 2, 3
+    torch.backends.cudnn.allow_tf32 = False          # the reference of every op is plain fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
     R = Replay(hgb, torch, S, B)
     lib, chk, ptr, sp = R.lib, R.chk, hgb._lib.ptr, hgb._lib.stream_ptr
     chk(lib.hgb_model_begin_step(R.h, sp()))
@@ -167,6 +187,7 @@ def test_replay_every_op(request):
                 e = R.rel(y[..., :c["cout"]], ref)
                 R.note(ty, e)
                 assert e <= 1e-2, f"conv {ci}: {e}"
+                assert R.cos(ty, y[..., :c["cout"]], ref) > 0.999, f"conv {ci}: cosine"
                 if bnd:
                     s1 = R.arena_f32(bnd["sums"], 2 * bnd["c"]) - s0
                     yy = y.reshape(-1, y.shape[-1])
@@ -188,6 +209,7 @@ def test_replay_every_op(request):
                 e = R.rel(out, ref)
                 R.note(ty, e)
                 assert e <= 1e-2, f"bn {bi}: {e}"
+                assert R.cos(ty, out, ref) > 0.999, f"bn {bi}: cosine"
                 saved = R.arena_f32(b["saved"], 2 * Cc)
                 torch.testing.assert_close(saved[:Cc], mean, rtol=1e-3, atol=1e-4)
                 torch.testing.assert_close(saved[Cc:], torch.rsqrt(var + 1e-3), rtol=2e-3, atol=1e-4)
@@ -251,6 +273,7 @@ def test_replay_every_op(request):
                 e = R.rel(dp, ref)
                 R.note(ty, e)
                 assert e <= 1.5e-2, f"bn_bwd {bi}: {e}"
+                assert R.cos(ty, dp, ref) > 0.999, f"bn_bwd {bi}: cosine"
                 scale = max(sdzx.abs().max().item(), sdz.abs().max().item(), 1e-20)
                 assert (R.grads[b["gamma"]:b["gamma"] + Cc] - sdzx).abs().max().item() <= 5e-3 * max(scale, (dz * xh).abs().sum(0).max().item())
                 assert (R.grads[b["beta"]:b["beta"] + Cc] - sdz).abs().max().item() <= 5e-3 * max(scale, dz.abs().sum(0).max().item())
@@ -277,6 +300,7 @@ def test_replay_every_op(request):
                 e = R.rel(got, ref)
                 R.note(ty, e)
                 assert e <= 3e-3, f"wgrad conv {ci}: {e}"
+                assert R.cos(ty, got, ref) > 0.999, f"wgrad conv {ci}: cosine"
             elif ty == B_DGRAD:
                 c = R.conv(ci)
                 dp = R.act(a0).float()[..., :c["cout"]].clone()
@@ -301,6 +325,7 @@ def test_replay_every_op(request):
                 e = R.rel(out[..., :c["cin"]], ref)
                 R.note(ty, e)
                 assert e <= 1e-2, f"dgrad conv {ci}: {e}"
+                assert R.cos(ty, out[..., :c["cin"]], ref) > 0.999, f"dgrad conv {ci}: cosine"
                 if out.shape[-1] > c["cin"] and not res:
                     assert out[..., c["cin"]:].abs().max().item() == 0
             elif ty in (B_RELU_MASK, B_COLSUM):
@@ -344,13 +369,18 @@ def test_replay_every_op(request):
                 e = R.rel(out[..., :17], ref)
                 R.note(ty, e)
                 assert e <= 1e-2 and out[..., 17:].abs().max().item() == 0
+                assert R.cos(ty, out[..., :17], ref) > 0.999
             else:
                 raise AssertionError(f"unexpected backward op {ty}")
     print("worst relative error per op type:", {k: round(v, 5) for k, v in R.worst.items()},
           "fused BN-backward reductions checked:", fused_reduces[0])
-    assert fused_reduces[0] > 20
+    print("lowest cosine vs the fp32 reference per op type:", {k: round(v, 7) for k, v in R.low_cos.items()})
+    assert all(v > 0.999 for v in R.low_cos.values())
+    assert {"F_CONV", "F_BN", "B_BN_APPLY", "B_WGRAD", "B_DGRAD"} <= set(R.low_cos)
+    n_bneck = 3 + 15 * S
+    assert fused_reduces[0] > n_bneck
     print("convolutions / weight gradients with a deferred input BatchNorm:", deferred[0], "statistic writers:", writers[0])
-    assert deferred[0] > 50 and writers[0] > 20
+    assert deferred[0] >= 2 * n_bneck and writers[0] >= n_bneck
 
     # the stepped run and one whole training step see the same loss (gradients are not compared end to
     # end: fp32 atomics ordering differs between two runs and a random-init hourglass in training mode
@@ -363,4 +393,6 @@ def test_replay_every_op(request):
     torch.cuda.synchronize()
     torch.testing.assert_close(losses[:1], stepped_loss[:1], rtol=2e-2, atol=0)
     torch.testing.assert_close(losses, stepped_loss, rtol=8e-2, atol=0)   # batch 3: later stacks move by a few % run to run
+    del R
+    torch.cuda.empty_cache()
     assert torch.isfinite(R.grads).all()
