@@ -151,6 +151,22 @@ def make_valid_label_batch(images, kps_x, kps_y, kps_v, label_shape=(64, 64, 17)
     return images, ops.render_targets(kps_x, kps_y, kps_v, label_shape[0], label_shape[1])
 
 
+class _Dataset:
+    """Restartable stand-in for a tf.data.Dataset: `iter(ds)` builds a new stream; `next(ds)` keeps working on a default one."""
+
+    def __init__(self, factory):
+        self._factory = factory
+        self._default = None
+
+    def __iter__(self):
+        return iter(self._factory())
+
+    def __next__(self):
+        if self._default is None:
+            self._default = iter(self)
+        return next(self._default)
+
+
 # ------------------------------------------------------------------ prefetch (dataset_builder.py:46,54,65: .prefetch(AUTOTUNE))
 class Prefetcher:
     """Runs a batch generator in a background thread, `depth` batches ahead, on its own CUDA stream: record parsing, the
@@ -314,12 +330,20 @@ class DatasetBuilder:
         return np.asarray(xs)[partner], np.asarray(ys)[partner], np.asarray(vs)[partner]
 
     # -- record streams
-    def _records(self, filenames):
+    def _records(self, filenames, equal_shards=False):
+        """Records of this rank's shard (record k belongs to rank k % world).  equal_shards: every rank gets the same
+        number of records (the remainder of a pass is dropped), so the training / validation batches of all ranks have the
+        same sizes -- the global batch, the BatchNorm statistics and the loss weighting of a data-parallel step assume it."""
         from . import tfrecord
         rank, world = self.shard
+        limit = None
+        if equal_shards and world > 1:
+            limit = self.get_ds_length(filenames) // world * world
         k = 0
         for name in filenames:
             for record in tfrecord.read_records(name):
+                if limit is not None and k >= limit:
+                    return
                 if k % world == rank:
                     yield record
                 k += 1
@@ -373,19 +397,21 @@ class DatasetBuilder:
 
     def _train_stream(self):
         while True:                                       # .repeat()
-            for batch in self._batches(self._shuffled(self._records(self.train_filenames))):
+            for batch in self._batches(self._shuffled(self._records(self.train_filenames, equal_shards=True))):
                 yield self.make_train_label(*self.prepare_examples(batch))
 
     def _valid_stream(self):
         while True:
-            for batch in self._batches(self._records(self.valid_filenames)):
+            for batch in self._batches(self._records(self.valid_filenames, equal_shards=True)):
                 yield self.make_valid_label(*self.prepare_examples(batch))
 
     def _ahead(self, generator):
         return Prefetcher(generator, self.prefetch) if self.prefetch > 0 else generator
 
     def build_datasets(self):
-        return self._ahead(self._train_stream()), self._ahead(self._valid_stream())
+        """(ds_train, ds_valid): infinite streams like the reference's (.repeat()); each `iter()` starts a fresh pass from
+        the first record -- what Keras does with the validation dataset at the start of every epoch."""
+        return (_Dataset(lambda: self._ahead(self._train_stream())), _Dataset(lambda: self._ahead(self._valid_stream())))
 
     def get_ds_prediction(self):
         return self._ahead(self._prediction_stream())

@@ -265,6 +265,18 @@ class HourglassModel:
         -- `<path>.index` + `<path>.data-00000-of-00001` with Keras' object-graph keys, BN moving statistics, and the Adam
         step / m / v slots (tf_checkpoint.py) -- so files interchange with the reference; "hgb" writes the same file pair
         with an npz/json payload."""
+        from ..parallel import current_allreduce
+        ar = current_allreduce()
+        if ar is not None:           # data parallel: replicas are identical; rank 0 writes, everyone waits for the file
+            try:
+                if ar.rank == 0:
+                    self._save_weights_local(path, save_format)
+            finally:
+                ar.barrier()
+            return
+        self._save_weights_local(path, save_format)
+
+    def _save_weights_local(self, path, save_format):
         d = os.path.dirname(path)
         if d:
             os.makedirs(d, exist_ok=True)
@@ -282,10 +294,13 @@ class HourglassModel:
             blobs["__adam_v__"] = self._adam_v.cpu().numpy()
             meta["iterations"] = int(self.optimizer.iterations)
             meta["optimizer"] = self.optimizer.get_config()
-        with open(path + ".data-00000-of-00001", "wb") as f:
+        # both files are written under temporary names and renamed (data first), so a reader never sees a torn pair
+        with open(path + ".data-00000-of-00001.tmp", "wb") as f:
             np.savez(f, **blobs)
-        with open(path + ".index", "w") as f:
+        with open(path + ".index.tmp", "w") as f:
             json.dump(meta, f)
+        os.replace(path + ".data-00000-of-00001.tmp", path + ".data-00000-of-00001")
+        os.replace(path + ".index.tmp", path + ".index")
 
     def load_weights(self, path):
         """keras.Model.load_weights (trainer.py:85,188,198): TensorFlow checkpoints written by the reference or by
@@ -334,10 +349,15 @@ class HourglassModel:
         key = (int(batch), bool(training))
         p = self._plans.get(key)
         if p is None:
-            for k in [k for k in self._plans if k[1] == key[1]]:   # one plan per mode keeps memory bounded
-                self._plans.pop(k).close()
+            # at most two plans per mode (the full batch + the short tail batch a pass over a dataset ends with): the
+            # least recently used one of the same mode goes first, so a tail batch no longer evicts the full-batch plan
+            same = [k for k in self._plans if k[1] == key[1]]
+            while len(same) >= 2:
+                self._plans.pop(same.pop(0)).close()
             p = _Plan(self, batch, training)
             self._plans[key] = p
+        else:
+            self._plans[key] = self._plans.pop(key)      # most recently used last
         if p.weights_version != self._weights_version:
             check(lib.hgb_model_sync_weights(p.handle, stream_ptr()))
             p.weights_version = self._weights_version
@@ -446,8 +466,13 @@ class HourglassModel:
             allreduce.wait()
         opt = self.optimizer
         opt.iterations += 1
+        # The loss kernel already divides by `gb`: with gb = the GLOBAL batch every rank's gradient carries 1/B_global and
+        # the SUM all-reduce is the global-mean gradient itself (grad_scale 1).  Only a caller that normalised by its
+        # LOCAL batch needs the remaining 1/world here.  Either way Adam sees exactly the single-device gradient of the
+        # concatenated batch, so m / v / epsilon behave as on one GPU (tests/test_gpu_multi.py).
+        grad_scale = gb / float(B * world)
         check(lib.hgb_model_adam_step(plan.handle, self._current_lr(), opt.beta_1, opt.beta_2, opt.epsilon,
-                                      int(opt.iterations), 1.0 / world, st))
+                                      int(opt.iterations), grad_scale, st))
         self._weights_version += 1
         plan.weights_version = self._weights_version   # adam_step refreshed this plan's bf16 operands
         return losses
@@ -491,10 +516,16 @@ class HourglassModel:
 
     def test_on_batch(self, x, y):
         from .. import ops
+        from ..parallel import current_allreduce
+        if self._loss_kind is None:
+            raise RuntimeError("compile(optimizer, loss) with one of the hgb200.loss functions before evaluate / validation")
         x = self._to_device_images(x.numpy() if hasattr(x, "numpy") and not isinstance(x, np.ndarray) and not hasattr(x, "is_cuda") else x)
         y = self._to_device_targets(y)
         outs = self.forward_device(x, training=False)
         per = [float(ops.loss_fwd_bwd(self._loss_kind, y, o, want_grad=False)[0].item()) for o in outs]
+        ar = current_allreduce()
+        if ar is not None:      # every rank must see the same val_loss (ModelCheckpoint decides on it): mean over equal shards
+            per = (ar.sum_host(np.asarray(per)) / ar.world_size).tolist()
         return [sum(per)] + per
 
     def _metric_names(self, prefix=""):
@@ -526,6 +557,8 @@ class HourglassModel:
         """keras.Model.fit over an (infinite) iterable of (images, heatmaps) batches (trainer.py:49-56)."""
         if steps_per_epoch is None:
             raise ValueError("steps_per_epoch is required (the reference datasets repeat forever)")
+        if int(steps_per_epoch) <= 0:
+            raise ValueError(f"steps_per_epoch must be positive, got {steps_per_epoch} (fewer examples than one batch?)")
         callbacks = list(callbacks or [])
         hist = History()
         for cb in callbacks:
@@ -534,7 +567,6 @@ class HourglassModel:
             if hasattr(cb, "on_train_begin"):
                 cb.on_train_begin()
         it = iter(ds)
-        val_it = iter(validation_data) if validation_data is not None else None
         names = self._metric_names()
         self.stop_training = False
         for epoch in range(initial_epoch, epochs):
@@ -548,7 +580,10 @@ class HourglassModel:
                 x, y = next(it)
                 tot += np.array(self.train_on_batch(x, y))
             logs = dict(zip(names, (tot / steps_per_epoch).tolist()))
-            if val_it is not None and validation_steps:
+            if validation_data is not None and validation_steps:
+                # Keras creates a fresh validation iterator every epoch: the same first `validation_steps` batches are
+                # scored each time.  A one-shot generator cannot restart and is consumed where it stands.
+                val_it = iter(validation_data)
                 vt = np.zeros(1 + self.num_stacks)
                 for _step in range(validation_steps):
                     x, y = next(val_it)

@@ -12,7 +12,8 @@ _CURRENT = None
 
 class GradAllReduce:
     """Callable handed to HourglassModel.train_step_device: sums gradient buckets across ranks.
-    The 1/world_size factor is folded into the Adam kernel (grad_scale)."""
+    The loss kernels already divide by the GLOBAL batch, so the summed buckets are the global-mean gradient; a caller
+    that normalised by its local batch gets the remaining 1/world_size through Adam's grad_scale."""
 
     def __init__(self, group=None):
         import torch.distributed as dist
@@ -32,6 +33,9 @@ class GradAllReduce:
         for w in self._pending:
             w.wait()
         self._pending.clear()
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
 
     def sum_host(self, values: np.ndarray) -> np.ndarray:
         """Per-shard losses already carry 1/global_batch, so the global loss is their sum."""
@@ -56,6 +60,11 @@ def disable():
 
 def current_allreduce():
     return _CURRENT
+
+
+def is_primary():
+    """True on the one rank that writes checkpoints / logs (rank 0), and always when data parallelism is off."""
+    return _CURRENT is None or _CURRENT.rank == 0
 
 
 def shard_batch(n_global: int, world_size: int, rank: int):

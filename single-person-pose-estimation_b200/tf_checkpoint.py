@@ -24,6 +24,7 @@ The LevelDB table container is restated from the published format only.  CRCs ru
 """
 from __future__ import annotations
 
+import os
 import struct
 from collections import OrderedDict
 
@@ -260,9 +261,13 @@ def write_checkpoint(prefix, tensors):
             entry = _build_entry(_DT[arr.dtype], arr.shape, len(data), len(blob), _mask(_crc(blob)))
         entries.append((name.encode("utf-8"), entry))
         data += blob
-    with open(prefix + ".data-00000-of-00001", "wb") as f:
+    # like BundleWriter: both files are written under temporary names and renamed, data first, so a crash or a concurrent
+    # reader (ModelCheckpoint runs every epoch) never sees an index that points into a different data file
+    with open(prefix + ".data-00000-of-00001.tmp", "wb") as f:
         f.write(bytes(data))
-    _write_table(prefix + ".index", entries)
+    _write_table(prefix + ".index.tmp", entries)
+    os.replace(prefix + ".data-00000-of-00001.tmp", prefix + ".data-00000-of-00001")
+    os.replace(prefix + ".index.tmp", prefix + ".index")
 
 
 # ------------------------------------------------------------------ TrackableObjectGraph
@@ -396,5 +401,10 @@ def load_keras_weights(model, prefix):
     adam = None
     it_key = f"optimizer/iter{_SUFFIX}"
     if it_key in bundle and m:
+        # a checkpoint may hold slots for only some variables (a frozen layer, an optimizer rebuilt mid-run): the missing
+        # moments start at zero, exactly what Keras does when it creates a slot
+        for ours, (shape, _off, trainable) in model._table.items():
+            if trainable and ours not in m:
+                m[ours], v[ours] = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
         adam = (int(bundle[it_key]), m, v)
     return weights, adam

@@ -14,6 +14,7 @@ from datetime import date, timedelta
 
 import pandas as pd
 
+from . import parallel
 from .callbacks import PrintLR, make_checkpoint_callback
 from .loss import IOU, mean_squared_error, weighed_keypoint_mse, weighted_mse
 from .model.hourglass import Adam
@@ -94,8 +95,9 @@ class Trainer:
 
     def _persist(self, history, today):
         """CSV log of the session and the `_cont` checkpoint the next session resumes from -> its path."""
-        os.makedirs(self.logs_path, exist_ok=True)
-        pd.DataFrame(history.history).to_csv(f"{self.logs_path}/log_E{self.epochs}_lr{self.learning_rate}.csv")
+        if parallel.is_primary():          # data parallel: one writer; save_weights gates and synchronises itself
+            os.makedirs(self.logs_path, exist_ok=True)
+            pd.DataFrame(history.history).to_csv(f"{self.logs_path}/log_E{self.epochs}_lr{self.learning_rate}.csv")
         path = self._ckpt(f"E{self.epochs}_{today}_cont.ckpt")
         self.model.save_weights(path)
         return path
@@ -151,6 +153,17 @@ class Trainer:
     resume_train = resume_training      # the README / BASELINE.json spelling
 
     def _promote_session_best(self, previous_best, session_best):
+        ar = parallel.current_allreduce()
+        if ar is not None:                 # every rank took the same decision (val_loss is all-reduced); rank 0 moves the files
+            try:
+                if ar.rank == 0:
+                    self._promote_local(previous_best, session_best)
+            finally:
+                ar.barrier()
+            return
+        self._promote_local(previous_best, session_best)
+
+    def _promote_local(self, previous_best, session_best):
         kept = [self._ckpt("best_val_loss_weights.ckpt") + part for part in _CKPT_PARTS]
         fresh = [self._ckpt("temp.ckpt") + part for part in _CKPT_PARTS]
         if not session_best < previous_best:

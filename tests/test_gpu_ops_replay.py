@@ -393,6 +393,6 @@ def test_replay_every_op(S, B):
     torch.cuda.synchronize()
     torch.testing.assert_close(losses[:1], stepped_loss[:1], rtol=2e-2, atol=0)
     torch.testing.assert_close(losses, stepped_loss, rtol=8e-2, atol=0)   # batch 3: later stacks move by a few % run to run
+    assert torch.isfinite(R.grads).all()
     del R
     torch.cuda.empty_cache()
-    assert torch.isfinite(R.grads).all()
