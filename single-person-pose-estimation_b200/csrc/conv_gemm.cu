@@ -32,10 +32,10 @@ constexpr int kBlockM = 128;
 constexpr int kABytes = kBlockM * 128;  // 128 pixels x 64 bf16
 constexpr int kThreads = 192;       // 3x3 wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
 constexpr int kWgradThreads = 256;  // wgrad kernel: + 2 operand-transform warps (deferred BatchNorm)
-constexpr int kGemmThreads = 384;   // forward/dgrad kernel: TMA warp, MMA warp, 8 epilogue warps, 2 operand-transform warps
+// forward/dgrad kernel: warp 0 TMA, warp 1 MMA, warps 2-3 operand transform, then EPI (8 or 16) epilogue warps
+__host__ __device__ constexpr int gemm_threads(int epi) { return 128 + 32 * epi; }
 constexpr float kBnEpsIn = 1e-3f;       // Keras BatchNormalization defaults (as in layer_kernels.cu)
 constexpr float kBnMomentumIn = 0.99f;
-constexpr int kEpiThreads = 256;
 
 struct GemmKernelParams {
   int M_total, H, W, HW;
@@ -159,8 +159,12 @@ __device__ __forceinline__ void bn_input_transform_box(uint32_t box, const float
 //               through descriptor offsets of whole image rows (multiples of 1024 bytes: same swizzle phase):
 //               2.4x fewer activation bytes per MAC.  Strip boxes and weight boxes are recycled slot by slot
 //               (tile-major MMA order), accumulators are handed over and released tile by tile.
-template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false>
-__global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+//   EPI        : epilogue warps.  8 = two per TMEM lane quarter.  16 = four per quarter, for the N = 256 tiles of the
+//               HBM-bound 1x1 layers: their epilogue (TMEM drain, bias / ReLU / residual, staging, BatchNorm statistics:
+//               ~700 instructions per thread per tile) ran at IPC 0.3 per scheduler with two warps each and took 2.85 us
+//               per tile against 2.2 us of HBM time; four warps per scheduler hide the TMEM / shared-memory round trips.
+template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false, int EPI = 8>
+__global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ CUtensorMap tmC,
                                                                 const __grid_constant__ CUtensorMap tmR,
@@ -169,6 +173,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   constexpr int kBBytes = BLOCK_N * 128;
   constexpr int kStageBytes = TILES * kABytes + kBBytes;
   constexpr int kAccStages = TILES == 1 ? 2 : 1;
+  constexpr int kGemmThreads = gemm_threads(EPI), kEpiThreads = 32 * EPI;
+  static_assert(EPI == 8 || EPI == 16, "two or four epilogue warps per TMEM lane quarter");
   static_assert(kAccStages * TILES * BLOCK_N <= 512, "TMEM columns");
   constexpr int kOutBytes = (BLOCK_N / 64) * kABytes;
   constexpr int kASlots = TILES + 1, kBSlots = 6;             // HALO: strip boxes | two sets of three weight boxes
@@ -211,12 +217,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     if (HALO) {
       for (int s = 0; s < kNumBars; ++s) {
         const bool tmem_empty = s >= 2 * kASlots + 2 * kBSlots + TILES && s < kNumBars - 1;
-        mbar_init(bar0 + 8 * s, tmem_empty ? 8 : 1);
+        mbar_init(bar0 + 8 * s, tmem_empty ? EPI : 1);
       }
     } else {
       for (int s = 0; s < 2 * STAGES + 2; ++s) mbar_init(bar0 + 8 * s, 1);
-      mbar_init(bar0 + 8 * (2 * STAGES + 2), 8);  // tmem_empty: one arrival per epilogue warp
-      mbar_init(bar0 + 8 * (2 * STAGES + 3), 8);
+      mbar_init(bar0 + 8 * (2 * STAGES + 2), EPI);  // tmem_empty: one arrival per epilogue warp
+      mbar_init(bar0 + 8 * (2 * STAGES + 3), EPI);
       for (int s = 0; s < STAGES; ++s) mbar_init(bar0 + 8 * (2 * STAGES + 4 + s), 2);  // ready: two transform warps
       mbar_init(bar0 + 8 * (3 * STAGES + 4), 1);  // residual tile landed in the staging buffer
     }
@@ -238,9 +244,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   tc_fence_after();
   if (threadIdx.x == 0) KT(3);
   // the bias is needed by the epilogue only: its (cold) load overlaps the first TMA loads instead of delaying them
-  if (warp >= 2 && warp < 10) {
-    for (int i = threadIdx.x - 64; i < BLOCK_N; i += kEpiThreads) s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (warp >= 4) {
+    for (int i = threadIdx.x - 128; i < BLOCK_N; i += kEpiThreads) s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
   }
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t full0 = bar0, empty0 = bar0 + 8 * STAGES;
@@ -385,13 +391,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         if (lt == 3 || lt == 4) KT(25 + (lt - 3) * 3);
       }
     }
-  } else if (warp >= 10) {
+  } else if (warp < 4) {
     // ---------------- operand transform (deferred BatchNorm of the input): as soon as TMA has delivered the
     // 128-pixel x 64-channel box of a stage, z = bf16(y * scale + shift) is applied in place; the MMA warp waits
     // for `ready` instead of `full`.  Zero-filled rows past the end of the tensor become `shift`: they only reach
     // accumulator rows that the store clips and the statistics skip.
     if (xform) {
-      const int tw = threadIdx.x - 320;
+      const int tw = threadIdx.x - 64;
       int kbt = 0;
       for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
         for (int kb = 0; kb < p.nkb; ++kb, ++kbt) {
@@ -405,15 +411,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       }
     }
   } else {
-    // ---------------- epilogue: 8 warps; TMEM lane quarter = warp % 4, the two warps of a quarter split
-    // every 64-channel box into its two 32-column halves
+    // ---------------- epilogue: EPI warps; TMEM lane quarter = warp % 4.  The EPI / 4 warps of a quarter split every
+    // 64-channel box into its two 32-column halves (hsel) and, with 16 warps, the boxes into even and odd ones (gsel)
     const int q = warp & 3;
-    const int hsel = (warp - 2) >> 2;
+    const int ew = warp - 4;                         // epilogue warp index
+    const int hsel = (ew >> 2) & 1;
+    const int gsel = ew >> 3;                        // 0 when EPI == 8
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;                 // 0..255
-    // lane 0 of epilogue warps 0, 2, 4, 6 issues (and tracks) the bulk store of output box 0, 1, 2, 3
+    const int et = threadIdx.x - 128;                // 0 .. kEpiThreads-1
+    // lane 0 of every (EPI / 4)-th epilogue warp issues (and tracks) the bulk store of output box 0, 1, 2, 3
+    constexpr int kWarpsPerBox = EPI / 4;
     const int store_box = p.single_store ? (et == 0 ? 0 : -1)
-                        : (lane == 0 && ((warp - 2) & 1) == 0 && ((warp - 2) >> 1) < BLOCK_N / 64) ? ((warp - 2) >> 1) : -1;
+                        : (lane == 0 && ew % kWarpsPerBox == 0 && ew / kWarpsPerBox < BLOCK_N / 64) ? ew / kWarpsPerBox : -1;
     // BN statistics: thread -> (16-byte chunk = 8 channels, group of kRowsPer pixel rows) of the staged tile
     constexpr int kChunks = BLOCK_N / 8;
     constexpr int kRowsPer = kBlockM / (kEpiThreads / kChunks);   // 16 / 8 / 4 rows for N = 256 / 128 / 64
@@ -444,7 +453,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       // (box g of every tile is stored by lane 0 of epilogue warp 2g, which also owns that bulk group: one thread
       // issuing all boxes delayed its whole warp -- and with it the tile -- by 0.35 us at N = 256)
       if (store_box >= 0) { if (OUT_BUFS == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       if (p.bn_y && et == 32) {
         // BatchNorm-backward statistics stream y from global memory: pull the NEXT tile's boxes into L2 now
         // (and this tile's, the first time) so those loads are L2 hits when the statistics pass issues them
@@ -495,20 +504,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
           // no residual: bias on packed fp32 pairs, ReLU on the packed bf16 pairs -- 3 instructions per 2 channels
           // the 32 bias values of the chunk are fetched up front (8 x 16 bytes, broadcast): issued back to back, their
           // latency is paid once instead of in front of every packed add
-          uint64_t b2[16];
+          // (with 16 epilogue warps the register budget is 96: the bias is fetched in two halves)
+          constexpr int kBiasParts = EPI == 16 ? 2 : 1;
           const uint32_t badr = smem_u32(s_bias + n0c);
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b2[2 * j]), "=l"(b2[2 * j + 1]) : "r"(badr + 16u * j));
+          for (int part = 0; part < kBiasParts; ++part) {
+            constexpr int kPer = 16 / kBiasParts;      // packed pairs per part
+            uint64_t b2[kPer];
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            uint32_t w[4];
+            for (int j = 0; j < kPer / 2; ++j)
+              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b2[2 * j]), "=l"(b2[2 * j + 1]) : "r"(badr + 16u * (j + part * (kPer / 2))));
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              w[j] = cvt_bf16x2(add_f32x2(pack_f32x2(v[8 * j4 + 2 * j], v[8 * j4 + 2 * j + 1]), b2[4 * j4 + j]), p.relu != 0);
-            const uint32_t dst = box + ((((uint32_t)hsel * 4u + j4) ^ ((uint32_t)row & 7u)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-                         : "memory");
+            for (int j4l = 0; j4l < kPer / 4; ++j4l) {
+              const int j4 = j4l + part * (kPer / 4);
+              uint32_t w[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                w[j] = cvt_bf16x2(add_f32x2(pack_f32x2(v[8 * j4 + 2 * j], v[8 * j4 + 2 * j + 1]), b2[4 * j4l + j]), p.relu != 0);
+              const uint32_t dst = box + ((((uint32_t)hsel * 4u + j4) ^ ((uint32_t)row & 7u)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                           : "memory");
+            }
           }
           return;
         }
@@ -585,19 +601,31 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
                        : "memory");
         }
       };
-      // two chunks per TMEM round trip: the second load is in flight while the first is converted
       constexpr int kBoxes = BLOCK_N / 64;
+      if constexpr (EPI == 8) {
+        // two chunks per TMEM round trip: the second load is in flight while the first is converted
 #pragma unroll 1
-      for (int g = 0; g < kBoxes; g += 2) {
-        if (g * 64 >= p.Cout) break;  // warp-uniform (Cout is a multiple of 64: whole boxes)
-        const bool two = kBoxes > 1 && (g + 1) * 64 < p.Cout;
-        uint32_t va[32], vb[32];
-        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(g * 64 + hsel * 32);
-        tmem_ld_32x32(t0, va);
-        if (two) tmem_ld_32x32(t0 + 64u, vb);
-        tmem_ld_wait();
-        stage_chunk(va, g);
-        if (two) stage_chunk(vb, g + 1);
+        for (int g = 0; g < kBoxes; g += 2) {
+          if (g * 64 >= p.Cout) break;  // warp-uniform (Cout is a multiple of 64: whole boxes)
+          const bool two = kBoxes > 1 && (g + 1) * 64 < p.Cout;
+          uint32_t va[32], vb[32];
+          const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(g * 64 + hsel * 32);
+          tmem_ld_32x32(t0, va);
+          if (two) tmem_ld_32x32(t0 + 64u, vb);
+          tmem_ld_wait();
+          stage_chunk(va, g);
+          if (two) stage_chunk(vb, g + 1);
+        }
+      } else {
+        // four warps per scheduler: one chunk at a time (96 registers), the other warps hide the TMEM round trip
+#pragma unroll 1
+        for (int g = gsel; g < kBoxes; g += 2) {
+          if (g * 64 >= p.Cout) break;
+          uint32_t va[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(g * 64 + hsel * 32), va);
+          tmem_ld_wait();
+          stage_chunk(va, g);
+        }
       }
       // last tile of the group: the accumulator stage is fully read, hand it back to the MMA warp
       if (HALO || t == TILES - 1 || tile + 1 >= num_tiles) {
@@ -606,7 +634,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         if (lane == 0) mbar_arrive(tempty0 + 8 * (HALO ? t : acc));
       }
       fence_proxy_async();                            // generic-proxy smem writes -> visible to the TMA engine
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps: tile fully staged
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // the eight epilogue warps: tile fully staged
       if (et == 0 && nt == 1) KT(7);
       if (et == 0 && (nt == 4 || nt == 5)) KT(15 + (nt - 4) * 5);
       if (store_box >= 0) {
@@ -630,7 +658,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         // (channel 2i in the low lane, 2i+1 in the high lane: exactly the two halves of a bf16x2 word).
         int rows = p.M_total - p0;
         if (rows > kBlockM) rows = kBlockM;
-        constexpr int kBatch = kRowsPer < 8 ? kRowsPer : 8;   // rows in flight per thread (bounds register use)
+        constexpr int kBatch = kRowsPer < 8 ? kRowsPer : (EPI == 16 ? 4 : 8);   // rows in flight per thread (bounds register use)
 #pragma unroll 1
         for (int rb = rg * kRowsPer; rb < (rg + 1) * kRowsPer; rb += kBatch) {
           uint4 vv[kBatch], yy[kBatch];
@@ -712,7 +740,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         d0[0] = make_float4(sa[0], sa[1], sa[2], sa[3]); d0[1] = make_float4(sa[4], sa[5], sa[6], sa[7]);
         d1[0] = make_float4(sq[0], sq[1], sq[2], sq[3]); d1[1] = make_float4(sq[4], sq[5], sq[6], sq[7]);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       for (int i = et; i < 2 * BLOCK_N; i += kEpiThreads) {
         const int stat = i / BLOCK_N, col = i - stat * BLOCK_N;
         if (col < p.Cout) {
@@ -1117,18 +1145,18 @@ int conv_gemm_block_n(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 
 
 static int g_num_sms = 0;
 
-template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false>
+template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false, int EPI = 8>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                          const CUtensorMap& tmY, const GemmKernelParams& kp, int tiles_m, int max_ctas, cudaStream_t st) {
   constexpr int ring = HALO ? (TILES + 1) * kABytes + 6 * BLOCK_N * 128 : STAGES * (TILES * kABytes + BLOCK_N * 128);
   constexpr int nbars = HALO ? 2 * (TILES + 1) + 12 + 2 * TILES + 1 : 3 * STAGES + 5;
   constexpr int smem = ring + OUT_BUFS * (BLOCK_N / 64) * kABytes + (nbars * 8 + 15) / 16 * 16 + 16 + BLOCK_N * 4 +
                        (TILES == 1 ? 4 * 256 * 4 : 0) + 1024;   // input / output BatchNorm scale+shift only for the 1x1 variants
-  static_assert(ring >= 16 * 1024, "stats scratch (16 KB) aliases the pipeline stages");
+  static_assert(ring >= (EPI == 16 ? 32 : 16) * 1024, "stats scratch (16 / 32 KB) aliases the pipeline stages");
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    HGB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HGB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS, HALO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
   if (!g_num_sms) {
@@ -1139,7 +1167,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   const int groups = (tiles_m + TILES - 1) / TILES;
   int grid = groups < g_num_sms ? groups : g_num_sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  HGB_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS, HALO>, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, tmC, tmR, tmY, kp));
+  HGB_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS, HALO, EPI>, dim3(grid), dim3(gemm_threads(EPI)), smem, st, tmA, tmB, tmC, tmR, tmY, kp));
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -1198,7 +1226,9 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
                        : launch_gemm_t<64, 6, 1, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
     case 128: return ws ? launch_gemm_t<128, 2, 4, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
                         : launch_gemm_t<128, 4, 1, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
-    default: return launch_gemm_t<256, 3, 1, 1>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);   // 64 KB staging: single
+    default:   // 64 KB staging: single.  16 epilogue warps (hgb_debug_set(25, 1): the 8-warp variant)
+      return g_debug[25] ? launch_gemm_t<256, 3, 1, 1>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
+                         : launch_gemm_t<256, 3, 1, 1, false, 16>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
   }
 }
 

@@ -24,11 +24,17 @@ __constant__ uint32_t c_gauss_lut[19] = {
     0x3c960aaeu /*8*/, 0x3c360282u /*9*/, 0x3bdcc9ffu /*10*/, 0u, 0u, 0x3ac50f0cu /*13*/, 0u, 0u, 0u, 0u,
     0x39016791u /*18*/};
 
+// grid: (chunks, B).  A block owns one CONTIGUOUS range of a sample's float4 vectors.  Nearly every byte of a target map is
+// zero, so the block first streams zeros over its range (three instructions per 16 bytes: the first version evaluated the
+// 7x7 window test per element and was instruction-issue bound at 0.47 of the HBM peak), then -- after a block barrier,
+// which orders the two writes to an address -- the K joints x 49 window values that fall inside the range are stored on
+// top (they land in L2 lines that are still dirty from the zero fill: no extra DRAM traffic).  Joint k owns channel k, so
+// windows of different joints never touch the same element; within a window every element is written once ('assigned',
+// data_utils.py:209-210).
 __global__ void __launch_bounds__(256) render_targets_kernel(const float* __restrict__ kx, const float* __restrict__ ky,
                                                              const int32_t* __restrict__ kv, int H, int W, int K,
-                                                             int vec_per_sample, float* __restrict__ out) {
-  // grid: (chunks, B).  One sample's K joints are staged in smem as integer centres.
-  extern __shared__ int s_joint[];  // [K][2]: cx, cy  (cx = INT_MIN/2 when the joint is not drawn)
+                                                             int vec_per_sample, int vec_per_block, float* __restrict__ out) {
+  extern __shared__ int s_joint[];  // [K][2]: cx, cy  (cx < 0 when the joint is not drawn)
   const int b = blockIdx.y;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     const float fx = kx[(size_t)b * K + k], fy = ky[(size_t)b * K + k];
@@ -37,27 +43,32 @@ __global__ void __launch_bounds__(256) render_targets_kernel(const float* __rest
     s_joint[2 * k] = ok ? x : -(1 << 28);
     s_joint[2 * k + 1] = y;
   }
+  float* ob = out + (size_t)b * H * W * K;
+  float4* o4 = reinterpret_cast<float4*>(ob);
+  const int v_begin = blockIdx.x * vec_per_block;
+  const int v_end = min(v_begin + vec_per_block, vec_per_sample);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  int v = v_begin + threadIdx.x;
+  for (; v + 3 * 256 < v_end; v += 4 * 256) {
+    __stcs(o4 + v, zero);
+    __stcs(o4 + v + 256, zero);
+    __stcs(o4 + v + 512, zero);
+    __stcs(o4 + v + 768, zero);
+  }
+  for (; v < v_end; v += 256) __stcs(o4 + v, zero);
   __syncthreads();
-  float4* o4 = reinterpret_cast<float4*>(out + (size_t)b * H * W * K);
-  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < vec_per_sample; v += gridDim.x * blockDim.x) {
-    const int e0 = v * 4;
-    int pix = e0 / K;
-    int k = e0 - pix * K;
-    int py = pix / W, px = pix - py * W;
-    float r[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int dx = px - s_joint[2 * k], dy = py - s_joint[2 * k + 1];
-      const int adx = dx < 0 ? -dx : dx, ady = dy < 0 ? -dy : dy;
-      float val = 0.f;
-      if (adx <= 3 && ady <= 3) val = __uint_as_float(c_gauss_lut[adx * adx + ady * ady]);
-      r[j] = val;
-      if (++k == K) {
-        k = 0;
-        if (++px == W) { px = 0; ++py; }
-      }
-    }
-    __stcs(o4 + v, make_float4(r[0], r[1], r[2], r[3]));
+  const int e_begin = v_begin * 4, e_end = v_end * 4;
+  for (int i = threadIdx.x; i < K * 49; i += blockDim.x) {
+    const int k = i / 49, pos = i - k * 49;
+    const int wy = pos / 7, wx = pos - wy * 7;
+    const int cx = s_joint[2 * k];
+    if (cx < 0) continue;
+    const int px = cx + wx - 3, py = s_joint[2 * k + 1] + wy - 3;
+    if (px < 0 || px >= W || py < 0 || py >= H) continue;          // the patch is clipped to the image (data_utils.py:204-208)
+    const int e = (py * W + px) * K + k;
+    if (e < e_begin || e >= e_end) continue;
+    const int dx = wx - 3, dy = wy - 3;
+    ob[e] = __uint_as_float(c_gauss_lut[dx * dx + dy * dy]);
   }
 }
 
@@ -308,45 +319,66 @@ __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-// One block (16*K threads) per sample.  The vector stride VEC*blockDim is a multiple of K, so
-// slot j of thread t always carries joint (VEC*t + j) % K: VEC running (value,index) pairs in
-// registers, no dynamic indexing.  UNROLL independent 16-byte loads are in flight per thread.
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory variable in CTA `rank` of this cluster (distributed shared memory)
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local, uint32_t rank) {
+  uint32_t l = (uint32_t)__cvta_generic_to_shared(local), r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(l), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int ld_dsmem_s32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+
+// A thread-block CLUSTER of `cs` CTAs (16*K threads each) per sample: CTA r scans the r-th contiguous share of the map, the
+// per-joint partial maxima are exchanged through distributed shared memory, and the joints are then spread over the
+// warps of all CTAs for the final step.  (One CTA per sample was a single ragged wave at batch 1024 -- every block
+// loading, then every block reducing -- and reached 0.54 / 0.35 of the HBM peak for f32 / bf16.)
+// The vector stride VEC*16*K and the share size are multiples of K, so slot j of thread t always carries joint
+// (VEC*t + j) % K: VEC running (value,index) pairs in registers, no dynamic indexing.  UNROLL independent 16-byte
+// loads are in flight per thread.
 template <typename T, int VEC>
 __global__ void decode_kernel(const T* __restrict__ hm, int H, int W, int K, double thr, int version,
                               int32_t* __restrict__ out_idx, float* __restrict__ out_kp) {
   extern __shared__ unsigned char s_raw[];
-  const int S = 16 * K, t = threadIdx.x, b = blockIdx.x;  // blockDim = S rounded up to a warp multiple
-  float* s_val = reinterpret_cast<float*>(s_raw);         // [S*VEC]
-  int* s_idx = reinterpret_cast<int*>(s_raw) + S * VEC;   // [S*VEC]
+  const int S = 16 * K, t = threadIdx.x, b = blockIdx.y;  // blockDim = S rounded up to a warp multiple
+  const int cs = gridDim.x, rank = blockIdx.x;            // cluster = the gridDim.x CTAs of one sample
+  float* s_pv = reinterpret_cast<float*>(s_raw);          // [64] this CTA's per-joint maximum ...
+  int* s_pi = reinterpret_cast<int*>(s_raw) + 64;         // [64] ... and its flat element index (read by the peers)
+  float* s_val = reinterpret_cast<float*>(s_raw) + 128;   // [S*VEC]
+  int* s_idx = reinterpret_cast<int*>(s_raw) + 128 + S * VEC;   // [S*VEC]
   const int HWK = H * W * K;
-  const int nvec = HWK / VEC;
+  const int nvec = HWK / VEC / cs;                        // vectors of this CTA's share
+  const int v0 = rank * nvec;
   const T* base = hm + (size_t)b * HWK;
 
   float bv[VEC];
   int bi[VEC];
-  constexpr int UNROLL = 4;
+  constexpr int UNROLL = 8;
   // Fast path: a thread meets the elements of a slot in increasing index order, so "first maximum" is a strict
-  // greater-than update (3-4 instructions per element).  It is exact unless a NaN shows up after a slot's first
-  // element (numpy: a NaN beats everything); any NaN re-runs the sample through the exact comparison below.
+  // greater-than update (3-4 instructions per element) starting from (-inf, the slot's first index) -- the argmax of an
+  // all -inf slot is its first element.  It is exact unless a NaN shows up (numpy: a NaN beats everything); any NaN
+  // re-runs the CTA's share through the exact comparison below.
   int nan_seen = 0;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { bv[j] = -CUDART_INF_F; bi[j] = t < S ? (v0 + t) * VEC + j : 0x7fffffff; }
   int v = t < S ? t : nvec;  // the padding threads of the last warp only help in the reduction
-  if (v < nvec) {            // slot initialisation from the thread's first vector (argmax of all -inf is index 0)
-    float r[VEC];
-    DecLoad<T, VEC>::load(base + (size_t)v * VEC, r);
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) { bv[j] = r[j]; bi[j] = v * VEC + j; nan_seen |= (r[j] != r[j]); }
-    v += S;
-  } else {
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) { bv[j] = -CUDART_INF_F; bi[j] = 0x7fffffff; }
-  }
   for (; v + (UNROLL - 1) * S < nvec; v += UNROLL * S) {
     float r[UNROLL][VEC];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) DecLoad<T, VEC>::load(base + (size_t)(v + u * S) * VEC, r[u]);
+    for (int u = 0; u < UNROLL; ++u) DecLoad<T, VEC>::load(base + (size_t)(v0 + v + u * S) * VEC, r[u]);
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const int e0 = (v + u * S) * VEC;
+      const int e0 = (v0 + v + u * S) * VEC;
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         const bool gt = r[u][j] > bv[j];
@@ -358,12 +390,12 @@ __global__ void decode_kernel(const T* __restrict__ hm, int H, int W, int K, dou
   }
   for (; v < nvec; v += S) {
     float r[VEC];
-    DecLoad<T, VEC>::load(base + (size_t)v * VEC, r);
+    DecLoad<T, VEC>::load(base + (size_t)(v0 + v) * VEC, r);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const bool gt = r[j] > bv[j];
       bv[j] = gt ? r[j] : bv[j];
-      bi[j] = gt ? v * VEC + j : bi[j];
+      bi[j] = gt ? (v0 + v) * VEC + j : bi[j];
       nan_seen |= (r[j] != r[j]);
     }
   }
@@ -372,10 +404,10 @@ __global__ void decode_kernel(const T* __restrict__ hm, int H, int W, int K, dou
     for (int j = 0; j < VEC; ++j) { bv[j] = -CUDART_INF_F; bi[j] = 0x7fffffff; }
     for (v = t < S ? t : nvec; v < nvec; v += S) {
       float r[VEC];
-      DecLoad<T, VEC>::load(base + (size_t)v * VEC, r);
+      DecLoad<T, VEC>::load(base + (size_t)(v0 + v) * VEC, r);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        const int e = v * VEC + j;
+        const int e = (v0 + v) * VEC + j;
         if (better(r[j], e, bv[j], bi[j])) { bv[j] = r[j]; bi[j] = e; }
       }
     }
@@ -391,7 +423,7 @@ __global__ void decode_kernel(const T* __restrict__ hm, int H, int W, int K, dou
 
   const int warp = t >> 5, lane = t & 31, nwarp = blockDim.x >> 5;
   const int ncand = 16 * VEC;  // candidates per joint: c = k + K*m
-  for (int k = warp; k < K; k += nwarp) {
+  for (int k = warp; k < K; k += nwarp) {   // this CTA's maximum of joint k
     float cv = -CUDART_INF_F;
     int ci = 0x7fffffff;
     for (int m = lane; m < ncand; m += 32) {
@@ -405,25 +437,52 @@ __global__ void decode_kernel(const T* __restrict__ hm, int H, int W, int K, dou
       const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
       if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
     }
-    if (lane == 0) {
-      const int index = ci / K;  // flat pixel index (row-major)
-      const int x = index % W;   // data_utils.py:121
-      const int y = index / H;   // data_utils.py:122 (height; square maps only)
-      const float conf = cv;
-      int pidx = 0;
-      if (version == 2) {        // data_utils.py:160-169
-        const int x1 = max(x - 1, 0), x2 = min(x + 2, W), y1 = max(y - 1, 0), y2 = min(y + 2, H);
-        const int pw = x2 - x1, ph = y2 - y1;
-        float pb = 0.f;
-        int pbi = 0x7fffffff;
-        for (int r = 0; r < ph; ++r)
-          for (int c = 0; c < pw; ++c) {
-            float a = (r == 1 && c == 1) ? 0.f : to_f32<T>(base[((size_t)(y1 + r) * W + (x1 + c)) * K + k]);
-            const int ia = r * pw + c;
-            if (pbi == 0x7fffffff || better(a, ia, pb, pbi)) { pb = a; pbi = ia; }
-          }
-        pidx = pbi;
+    if (lane == 0) { s_pv[k] = cv; s_pi[k] = ci; }
+  }
+  if (cs > 1) cluster_sync_all(); else __syncthreads();
+
+  // final step: joint k is handled by warp (k / cs) % nwarp of CTA k % cs
+  for (int k = rank + cs * warp; k < K; k += cs * nwarp) {
+    float cv = -CUDART_INF_F;
+    int ci = 0x7fffffff;
+    if (lane < cs) {
+      if (cs > 1) {
+        cv = ld_dsmem_f32(dsmem_addr(s_pv + k, (uint32_t)lane));
+        ci = ld_dsmem_s32(dsmem_addr(s_pi + k, (uint32_t)lane));
+      } else {
+        cv = s_pv[k]; ci = s_pi[k];
       }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+      if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
+    }
+    const int index = ci / K;  // flat pixel index (row-major)
+    const int x = index % W;   // data_utils.py:121
+    const int y = index / H;   // data_utils.py:122 (height; square maps only)
+    const float conf = cv;
+    int pidx = 0;
+    if (version == 2) {        // data_utils.py:160-169: one lane per element of the clipped 3x3 window (parallel loads)
+      const int x1 = max(x - 1, 0), x2 = min(x + 2, W), y1 = max(y - 1, 0), y2 = min(y + 2, H);
+      const int pw = x2 - x1, ph = y2 - y1;
+      float pb = -CUDART_INF_F;
+      int pbi = 0x7fffffff;
+      if (lane < pw * ph) {
+        const int r = lane / pw, c = lane - r * pw;
+        pb = (r == 1 && c == 1) ? 0.f : to_f32<T>(base[((size_t)(y1 + r) * W + (x1 + c)) * K + k]);   // :166 reads as 0
+        pbi = lane;
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, pb, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, pbi, o);
+        if (better(ov, oi, pb, pbi)) { pb = ov; pbi = oi; }
+      }
+      pidx = __shfl_sync(0xffffffffu, pbi, 0);
+    }
+    if (lane == 0) {
       const int px = pidx % 3, py = pidx / 3;  // always 3 (data_utils.py:168-169)
       int32_t* oi = out_idx + ((size_t)b * K + k) * 4;
       oi[0] = index; oi[1] = x; oi[2] = y; oi[3] = pidx;
@@ -439,6 +498,7 @@ __global__ void decode_kernel(const T* __restrict__ hm, int H, int W, int K, dou
       }
     }
   }
+  if (cs > 1) cluster_sync_all();   // a CTA's shared memory must outlive the peers' reads of it
 }
 
 // ------------------------------------------------------------------------------------
@@ -515,11 +575,16 @@ extern "C" int hgb_render_targets(const float* kps_x, const float* kps_y, const 
   HGB_CHECK_ARG(((int64_t)H * W * K) % 4 == 0, "hgb_render_targets: H*W*K must be a multiple of 4");
   if (B == 0) return HGB_OK;
   const int vec = H * W * K / 4;
-  int chunks = cdiv(vec, 256 * 4);
-  const int want = cdiv(148 * 8, B);
-  if (chunks > want) chunks = want < 1 ? 1 : want;
+  // blocks of >= 16 KB, and at least four waves of 8 resident blocks per SM where the batch allows it
+  int chunks = cdiv(148 * 8 * 4, B);
+  const int max_chunks = cdiv(vec, 1024);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  const int per = cdiv(vec, chunks);
+  chunks = cdiv(vec, per);
+  HGB_CHECK_ARG(B <= 65535, "hgb_render_targets: batch exceeds the grid limit");
   dim3 grid(chunks, B);
-  render_targets_kernel<<<grid, 256, 2 * K * sizeof(int), (cudaStream_t)stream>>>(kps_x, kps_y, kps_v, H, W, K, vec, out);
+  render_targets_kernel<<<grid, 256, 2 * K * sizeof(int), (cudaStream_t)stream>>>(kps_x, kps_y, kps_v, H, W, K, vec, per, out);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -630,13 +695,33 @@ extern "C" int hgb_decode(const void* heatmaps, int dtype, int B, int H, int W, 
   HGB_CHECK_ARG(((int64_t)H * W * K) % vec == 0, "hgb_decode: H*W*K must be a multiple of %d", vec);
   HGB_CHECK_ARG((int64_t)H * W * K < (1ll << 31), "hgb_decode: map too large");
   if (B == 0) return HGB_OK;
+  HGB_CHECK_ARG(B <= 65535, "hgb_decode: batch exceeds the grid limit");
   const int threads = (16 * K + 31) / 32 * 32;
-  const size_t smem = (size_t)(16 * K) * vec * 8;
+  const size_t smem = 512 + (size_t)(16 * K) * vec * 8;
   cudaStream_t st = (cudaStream_t)stream;
+  // cluster size: the largest of 8 / 4 / 2 / 1 whose share of a map is a whole number of 16-byte vectors and of pixels
+  // (K elements) -- 8 CTAs per sample while that is still less than ~4 waves of the chip, 4 otherwise
+  const int64_t nvec = (int64_t)H * W * K / vec;
+  int cs = (int64_t)B * 8 <= 148 * 7 * 4 ? 8 : 4;
+  if (g_debug[24] > 0) cs = g_debug[24];
+  while (cs > 1 && (nvec % cs != 0 || (nvec / cs * vec) % K != 0 || nvec / cs < 16 * K)) cs >>= 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cs, B);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cs > 1 ? 1 : 0;
   if (dtype == HGB_F32)
-    decode_kernel<float, 4><<<B, threads, smem, st>>>((const float*)heatmaps, H, W, K, conf_threshold, version, out_idx, out_kpts);
+    HGB_CUDA(cudaLaunchKernelEx(&cfg, decode_kernel<float, 4>, (const float*)heatmaps, H, W, K, conf_threshold, version, out_idx, out_kpts));
   else
-    decode_kernel<__nv_bfloat16, 8><<<B, threads, smem, st>>>((const __nv_bfloat16*)heatmaps, H, W, K, conf_threshold, version, out_idx, out_kpts);
+    HGB_CUDA(cudaLaunchKernelEx(&cfg, decode_kernel<__nv_bfloat16, 8>, (const __nv_bfloat16*)heatmaps, H, W, K, conf_threshold, version,
+                                out_idx, out_kpts));
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }

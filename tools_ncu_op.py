@@ -27,6 +27,9 @@ ap.add_argument("--stacks", type=int, default=1)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--fused-stats", type=int, default=-1, help="B_DGRAD only: 1 = must carry a fused BN reduction, 0 = must not")
 ap.add_argument("--debug", default="")
+ap.add_argument("--ab", default="", help="key=value: time every op a second time with this debug knob set (A/B in one process)")
+ap.add_argument("--specs", default="", help="several ops in one process: TYPE:k:cin:cout:h[:fused] separated by commas "
+                                            "(non-conv ops: TYPE:0:0:C:h); inputs are those left behind by one full step")
 a = ap.parse_args()
 lib, chk = _lib.lib, _lib.check
 for kv in [x for x in a.debug.split(",") if x]:
@@ -68,6 +71,49 @@ def matches(info):
     return dims[1] == a.h and (a.c == 0 or dims[3] == a.c)
 
 
+if a.specs:
+    chk(lib.hgb_model_backward(h, 0, S + 1, sp()))          # every tensor of the plan now holds valid data
+    torch.cuda.synchronize()
+    abk, abv = (int(x) for x in a.ab.split("=")) if a.ab else (None, None)
+    for spec in a.specs.split(","):
+        f = spec.split(":")
+        a.type, a.k, a.cin, a.cout, a.h = f[0], int(f[1]), int(f[2]), int(f[3]), int(f[4])
+        a.c = a.cout if a.k == 0 else 0
+        a.fused_stats = int(f[5]) if len(f) > 5 else -1
+        want = NAMES.index(a.type)
+        backward = 1 if want >= 6 else 0
+        hit = None
+        for seg in (range(S, -1, -1) if backward else range(S + 1)):
+            for i in range(lib.hgb_model_num_ops(h, seg, backward)):
+                chk(lib.hgb_model_op_info(h, seg, backward, i, C.byref(info)))
+                if matches(info):
+                    hit = (seg, i, tuple(info))
+                    break
+            if hit:
+                break
+        if not hit:
+            print(f"{spec}: no matching op")
+            continue
+        res = []
+        for setting in ([None] if abk is None else [None, abv]):
+            if abk is not None:
+                lib.hgb_debug_set(abk, 0 if setting is None else setting)
+            ts = []
+            for rep in range(a.reps + 1):
+                flush.zero_()               # evicts the operands from L2 and keeps the queue busy while the launch is enqueued
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                chk(lib.hgb_model_run_op(h, hit[0], backward, hit[1], _lib.ptr(img), 1, sp()))
+                e1.record()
+                torch.cuda.synchronize()
+                if rep:
+                    ts.append(e0.elapsed_time(e1) * 1e3)
+            res.append(min(ts))
+        if abk is not None:
+            lib.hgb_debug_set(abk, 0)
+        print(f"{spec:40s} info {hit[2]}  us: " + " | ".join(f"{r:.1f}" for r in res) + (f"   (second: debug {a.ab})" if a.ab else ""))
+    raise SystemExit(0)
+
 found = False
 segs = range(S, -1, -1) if backward else range(S + 1)
 for seg in segs:
@@ -84,9 +130,9 @@ for seg in segs:
         times = []
         for rep in range(a.reps):
             flush.zero_()
-            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             if rep == a.reps - 1:
+                torch.cuda.synchronize()
                 torch.cuda.profiler.start()
             e0.record()
             chk(lib.hgb_model_run_op(h, seg, backward, i, _lib.ptr(img), 1, sp()))
