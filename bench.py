@@ -1,19 +1,24 @@
 #!/usr/bin/env python
 """Benchmark of the stacked-hourglass hot path: 8-stack, 256-channel hourglass TRAINING step
 (forward, weighted-MSE loss, backward, Keras-Adam) at 256x256 with 64x64x17 heat maps -- the
-metric BASELINE.json quotes ("8-stack HG train img/s at 1/2/4/8 B200").
+metric BASELINE.json quotes ("8-stack HG train img/s at 1/2/4/8 B200; conv tensor-pipe util %; decode GB/s").
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, one process per GPU)
     python bench.py --impl reference --steps K --warmup W    # the reference path on the host CPU
 
-One JSON line on stdout (rank 0).  `value` = images/s with inputs resident in HBM, timed with CUDA
-events, max over ranks; `e2e` = images/s through the public Python API with pinned host buffers
-(H2D of images + keypoints, device-side target rendering, D2H of the losses) inside the timed region;
-`roofline` = the dominant kernel (3x3 128->128 convolution at 64x64, 43.8 % of the FLOPs) timed live
-with CUDA event pairs inside the step; `heatmap_kernels` = achieved HBM GB/s of target rendering, weighted-MSE
-loss+gradient and v2 decode (BASELINE config 5 point: 64x64x17, batch 1024; full sweep: tools_heatmap_bench.py);
-`cpu_baseline` = the fp32 CPU restatement of the reference (oracle/network_oracle.py; TensorFlow cannot be
-installed here) on a bounded sample.
+One JSON line on stdout (rank 0).
+  value      images/s with inputs resident in HBM, CUDA events, max over ranks (BASELINE config 3, strong scaling)
+  e2e        images/s through the public Python API with pinned host buffers (H2D of images + keypoints, device-side
+             target rendering, D2H of the losses) inside the timed region
+  roofline   the op class with the LARGEST TIME SHARE of the step (found by a per-op CUDA-event pass before the timed
+             region), then timed live with CUDA event pairs on its launching stream inside the timed steps; achieved =
+             algorithmic bytes (or FLOPs) per launch / average launch time, against MEASURED_PEAKS.json
+  classes    the per-class table behind that choice: time share, TFLOP/s, GB/s, bounding roofline, fraction
+  tensor_pipe_util_pct   ncu sm__inst_executed_pipe_tensor / tensor-pipe active % per convolution class (profiles/)
+  heatmap_kernels        config 5 sweep: rendering, weighted-MSE+grad, v2 decode at 64^2 / 128^2 x 17, batch 64..4096
+  config1 / config2 / config4   the other BASELINE configurations, each timed on this GPU (config 1 also on the host CPU)
+  cpu_baseline           the fp32 CPU restatement of the reference (oracle/network_oracle.py; TensorFlow cannot be
+             installed here) on BASELINE config 1: 1-stack, batch 8, 2 warm-up + 5 timed steps
 """
 import argparse
 import json
@@ -28,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 STACKS, CHANNELS, KPTS = 8, 256, 17
 GLOBAL_BATCH = 256
-FWD_GFLOP_PER_IMG = 68.870            # conv FLOPs (2*MAC), 8 stacks, forward
+FWD_GFLOP_PER_IMG = {1: 12.048, 4: 36.400, 8: 68.870}     # conv FLOPs (2*MAC), forward
 
 
 def parse():
@@ -39,8 +44,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
     ap.add_argument("--stacks", type=int, default=STACKS)
-    ap.add_argument("--cpu-batch", type=int, default=2, help="images per step of the CPU arm (bounded sample)")
+    ap.add_argument("--cpu-batch", type=int, default=4, help="images per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 1/2/4/5 and input-path measurements")
     return ap.parse_args()
 
 
@@ -50,10 +56,15 @@ def _oracle_color_augment():
     return input_oracle.color_augment
 
 
+def workload_name(stacks):
+    return (f"{stacks}-stack 256ch hourglass training step (fwd + weighted_MSE + bwd + Adam), 256x256x3 -> 64x64x17, "
+            f"random-init weights")
+
+
 # --------------------------------------------------------------------------------------- CPU arm
 def cpu_train_steps(stacks, batch, steps, warmup):
     """The reference's training step (model/hourglass.py + loss.py weighted_mse + Keras Adam) as restated in
-    oracle/network_oracle.py, fp32, all host threads.  Returns (images/s, threads)."""
+    oracle/network_oracle.py, fp32, all host threads.  Returns (images/s, threads, seconds per step)."""
     import numpy as np
     import torch
     from oracle import heatmap_oracle as horc
@@ -81,17 +92,19 @@ def cpu_train_steps(stacks, batch, steps, warmup):
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path (TensorFlow is absent: the fp32 restatement),
+    same workload, metric and unit as our arm; every step is a bounded sample (--cpu-batch images) of the global batch."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     ips, threads, sec = cpu_train_steps(args.stacks, args.cpu_batch, args.steps, max(args.warmup, 1))
-    sample = f"{args.stacks}-stack fwd+weighted_MSE+bwd+Adam, batch {args.cpu_batch} per step, fp32 torch-CPU restatement of the reference"
+    sample = (f"{args.stacks}-stack fwd+weighted_MSE+bwd+Adam on {args.cpu_batch} images per step (bounded sample of the "
+              f"{args.global_batch}-image global batch), fp32 torch-CPU restatement of the reference (TensorFlow not installable)")
     print(json.dumps({
         "impl": "reference", "metric": "hourglass_8stack_train_images_per_sec", "value": ips, "unit": "img/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.stacks}-stack 256ch hourglass training step, 256x256 -> 64x64x17, bounded CPU sample",
-                   "global_batch": args.cpu_batch},
+        "config": {"workload": workload_name(args.stacks), "global_batch": args.global_batch, "cpu_sample_batch": args.cpu_batch},
         "cpu_baseline": {"value": ips, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -136,14 +149,92 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# --------------------------------------------------------------------------------------- the other BASELINE configs
+def _event_time(torch, fn, warm, iters):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / iters
+
+
+def bench_train_config(stacks, batch, warm=3, iters=8):
+    """A training step with the Gaussian targets rendered on the device inside the step (BASELINE configs 1 and 2)."""
+    import torch
+    import hgb200
+    from hgb200 import ops
+    model = hgb200.HourglassModel(KPTS, stacks, CHANNELS, (256, 256, 3), "sigmoid", seed=7)
+    model.compile(optimizer=hgb200.Adam(1e-3), loss=hgb200.loss.weighted_mse)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    images = torch.rand((batch, 256, 256, 3), device="cuda", generator=g)
+    kx = torch.rand((batch, KPTS), device="cuda", generator=g) * 72 - 4
+    ky = torch.rand((batch, KPTS), device="cuda", generator=g) * 72 - 4
+    kv = torch.randint(0, 3, (batch, KPTS), device="cuda", generator=g, dtype=torch.int32)
+    targets = torch.empty((batch, 64, 64, KPTS), dtype=torch.float32, device="cuda")
+
+    def step():
+        ops.render_targets(kx, ky, kv, 64, 64, out=targets)
+        model.train_step_device(images, targets)
+    sec = _event_time(torch, step, warm, iters)
+    del model
+    torch.cuda.empty_cache()
+    return {"workload": f"{stacks}-stack training step, batch {batch}, targets rendered on the device inside the step",
+            "ms_per_step": sec * 1e3, "img_per_s": batch / sec,
+            "tflops": 3 * FWD_GFLOP_PER_IMG[stacks] * batch / sec / 1e3}
+
+
+def bench_infer_config(stacks=8, batch=128, iters=6):
+    """BASELINE config 4 at the per-GPU shard: predict -> v2 decode -> PCK + OKS scoring, everything on the device."""
+    import torch
+    import hgb200
+    from hgb200 import ops
+    model = hgb200.HourglassModel(KPTS, stacks, CHANNELS, (256, 256, 3), "sigmoid", seed=9)
+    g = torch.Generator(device="cuda").manual_seed(6)
+    images = torch.rand((batch, 256, 256, 3), device="cuda", generator=g)
+    bbox = torch.cat([torch.rand((batch, 2), device="cuda", generator=g, dtype=torch.float64) * 200,
+                      torch.rand((batch, 2), device="cuda", generator=g, dtype=torch.float64) * 240 + 60], 1)
+    xg = torch.rand((batch, KPTS), device="cuda", generator=g, dtype=torch.float64) * 300
+    yg = torch.rand((batch, KPTS), device="cuda", generator=g, dtype=torch.float64) * 300
+    vs = torch.randint(0, 3, (batch, KPTS), device="cuda", generator=g, dtype=torch.int32)
+    area = bbox[:, 2] * bbox[:, 3] * 0.5
+    state = {}
+
+    def fwd():
+        state["hm"] = model.forward_device(images, training=False)[-1]
+
+    def dec():
+        state["kp"] = ops.decode_batch(state["hm"], 1e-6, 2)[1]
+
+    def score():
+        kp = state["kp"].double()
+        xs = kp[..., 0] / 64 * bbox[:, 2:3] + bbox[:, 0:1]          # eval.py:114-126
+        ys = kp[..., 1] / 64 * bbox[:, 3:4] + bbox[:, 1:2]
+        ops.pck_counts(xs, ys, xg, yg, vs, bbox[:, 2:4], 0.05)
+        ops.oks_similarity(xs, ys, xg, yg, vs, area, bbox)
+    t_f = _event_time(torch, fwd, 2, iters)
+    t_d = _event_time(torch, dec, 2, iters)
+    t_s = _event_time(torch, score, 2, iters)
+    del model
+    torch.cuda.empty_cache()
+    tot = t_f + t_d + t_s
+    return {"workload": f"{stacks}-stack inference + v2 decode + PCK/OKS, batch {batch} (the per-GPU shard of 1024 over 8 GPUs)",
+            "forward_ms": t_f * 1e3, "decode_us": t_d * 1e6, "score_us": t_s * 1e6, "img_per_s": batch / tot,
+            "forward_tflops": FWD_GFLOP_PER_IMG[stacks] * batch / t_f / 1e3,
+            "decode_gbps": batch * 64 * 64 * KPTS * 4 / t_d / 1e9}
+
+
 # --------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import ctypes as C
-    import numpy as np
     import torch
     import torch.distributed as dist
     import hgb200
-    from hgb200 import _lib, ops, parallel
+    from hgb200 import _lib, ops, parallel, profiling
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -158,6 +249,16 @@ def run_ours(args):
         raise SystemExit(f"global batch {args.global_batch} is not divisible by {world} ranks")
     B = args.global_batch // world                                   # strong scaling: the global batch is fixed
     lib = _lib.lib
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_bw = float(peaks.get("hbm_gbs", 6500.0))
+    peak_src = ("MEASURED_PEAKS.json (hbm_gbs, bf16_tflops_sustained: kernels timed inside a long step)" if peaks
+                else "fallback 6.5 TB/s / 1.4 PFLOP/s (B200_PROFILING.md)")
 
     model = hgb200.HourglassModel(KPTS, args.stacks, CHANNELS, (256, 256, 3), "sigmoid", seed=1234)
     model.compile(optimizer=hgb200.Adam(1e-3), loss=hgb200.loss.weighted_mse)
@@ -181,11 +282,23 @@ def run_ours(args):
         step()
     barrier()
 
+    # ---- which op class takes the most time?  One step with an event pair around every op (in-order replay).
+    lib.hgb_model_profile_all(plan.handle, 1)
+    step()
+    barrier()
+    lib.hgb_model_profile_all(plan.handle, 0)
+    agg, op_ms = profiling.summarize(plan.handle, KPTS)
+    table = profiling.class_table(agg, op_ms, peak_tf, peak_bw)
+    top = table[0]
+    step()
+    barrier()
+
     # ---- timed region 1: inputs resident in HBM (activations of one step: tens of GB >> 126 MB L2)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    lib.hgb_model_profile_conv(plan.handle, 1, 1, 3, 128, 128, 64)      # forward 3x3 128->128 @ 64x64
+    sel = top["selector"]
+    lib.hgb_model_profile_conv(plan.handle, 1, *sel)                  # live event pairs around the top class
     launches0 = lib.hgb_model_launch_count(plan.handle)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -201,7 +314,7 @@ def run_ours(args):
     launches = int(lib.hgb_model_launch_count(plan.handle) - launches0)
     pm, pn, pf = C.c_double(), C.c_int(), C.c_double()
     lib.hgb_model_profile_read(plan.handle, C.byref(pm), C.byref(pn), C.byref(pf))
-    lib.hgb_model_profile_conv(plan.handle, 0, 1, 3, 128, 128, 64)
+    lib.hgb_model_profile_conv(plan.handle, 0, *sel)
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(losses.sum().item())
 
@@ -212,7 +325,7 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = model.train_on_keypoints(h_img, h_kx, h_ky, h_kv)
+        model.train_on_keypoints(h_img, h_kx, h_ky, h_kv)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -224,57 +337,69 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks = {}
+    ncu = {}
     try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
+        with open(os.path.join(ROOT, "profiles", "ncu_kernel_metrics.json")) as f:
+            ncu = json.load(f)
     except Exception:
         pass
-    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "top_kernel_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    except Exception:
-        pass
-    ach = (pf.value / max(pn.value, 1)) / (pm.value / max(pn.value, 1) * 1e-3) / 1e12 if pn.value else None
+    # live numbers of the top class: algorithmic work per launch (profiling.classify) / measured launch time
+    n_l = max(pn.value, 1)
+    avg_s = pm.value * 1e-3 / n_l
+    per_launch_flops = agg[top["op"]]["flops"] / agg[top["op"]]["launches"]
+    per_launch_bytes = agg[top["op"]]["bytes"] / agg[top["op"]]["launches"]
+    if top["bound"] == "tensor":
+        ach, peak, unit = per_launch_flops / avg_s / 1e12, peak_tf, "TFLOP/s"
+    else:
+        ach, peak, unit = per_launch_bytes / avg_s / 1e9, peak_bw, "GB/s"
+    fwd_gflop = FWD_GFLOP_PER_IMG.get(args.stacks, FWD_GFLOP_PER_IMG[8] * args.stacks / 8)
     value = args.global_batch * args.steps / (total_ms * 1e-3)
     line = {
         "metric": "hourglass_8stack_train_images_per_sec", "value": value, "unit": "img/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.stacks}-stack 256ch hourglass training step (fwd + weighted_MSE + bwd + Adam), "
-                               f"256x256x3 -> 64x64x17, random-init weights",
+        "config": {"workload": workload_name(args.stacks),
                    "global_batch": args.global_batch, "per_gpu_batch": B, "parallelism": f"dp{world}",
                    "l2_note": "per-step activation working set is tens of GB (>> 126 MB L2); no explicit flush needed",
                    "loss_last_step": loss_val,
-                   "model_tflops_per_step": 3 * FWD_GFLOP_PER_IMG * args.global_batch / 1e3 * args.stacks / STACKS},
+                   "model_tflops_per_step": 3 * fwd_gflop * args.global_batch / 1e3},
         "e2e": {"value": args.global_batch * args.steps / e2e_s.item(), "unit": "img/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "api": "HourglassModel.train_on_keypoints(pinned images, kps_x, kps_y, kps_v)"},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel<128,1,4,1,HALO> forward 3x3 128->128 @64x64",
-                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": (ach / peak_tf) if ach else None,
-                     "traffic": traffic, "launches_timed": pn.value, "avg_launch_ms": pm.value / max(pn.value, 1),
-                     "peak_source": peak_src},
-        "model_flops_utilization": 3 * FWD_GFLOP_PER_IMG * args.stacks / STACKS * value / 1e3 / world / peak_tf,
+        "roofline": {"bound": top["bound"], "kernel": top["op"], "chosen_by": "largest share of the summed per-op time of one step",
+                     "share_of_step": top["share"], "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                     "traffic": (ncu.get(top["op"]) or {}).get("dram_bytes_per_launch"),
+                     "algorithmic_bytes_per_launch": per_launch_bytes, "algorithmic_flops_per_launch": per_launch_flops,
+                     "launches_timed": pn.value, "avg_launch_ms": pm.value / n_l, "peak_source": peak_src},
+        "classes": [{k: v for k, v in r.items() if k != "selector"} for r in table[:14]],
+        "classes_note": "event pair around every op of ONE step replayed in order on one stream (no lane overlap); "
+                        f"sum of op times {op_ms:.1f} ms vs {total_ms / args.steps:.1f} ms for the real multi-lane step",
+        "tensor_pipe_util_pct": {k: v.get("tensor_pipe_pct") for k, v in ncu.items() if v.get("tensor_pipe_pct") is not None},
+        "model_flops_utilization": 3 * fwd_gflop * value / 1e3 / world / peak_tf,
     }
-    if world == 1:
+    del model, plan, images, targets
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_extras:
         try:     # BASELINE.json metric: "decode GB/s" (+ the other heat-map kernels), algorithmic bytes / CUDA-event time
             import tools_heatmap_bench
-            peak_bw = float(peaks.get("hbm_gbs", 6500.0))
+            rows = tools_heatmap_bench.sweep(iters=5)
             line["heatmap_kernels"] = {
-                "shape": "64x64x17, batch 1024, inputs evicted from L2 between launches",
+                "shape": "config 5 sweep: 64x64x17 and 128x128x17, batch 64..4096, inputs evicted from L2 between launches",
                 "peak_gbps": peak_bw,
-                "kernels": {k: {"us": round(t * 1e6, 1), "gbps": round(by / t / 1e9, 1), "frac": round(by / t / 1e9 / peak_bw, 3)}
-                            for k, _h, _b, t, by in tools_heatmap_bench.sweep(batches=(1024,), sizes=(64,), iters=5)}}
+                "rows": [{"kernel": k, "hw": h, "batch": b, "us": round(t * 1e6, 1), "gbps": round(by / t / 1e9, 1),
+                          "frac": round(by / t / 1e9 / peak_bw, 3)} for k, h, b, t, by in rows]}
         except Exception as ex:   # the sweep is auxiliary: never lose the headline line over it
             line["heatmap_kernels"] = {"error": f"{type(ex).__name__}: {ex}"}
-    if world == 1:
+        for key, fn in (("config1", lambda: bench_train_config(1, 8, warm=3, iters=10)),
+                        ("config2", lambda: bench_train_config(4, 64)),
+                        ("config4", lambda: bench_infer_config(8, 128))):
+            try:
+                line[key] = fn()
+            except Exception as ex:
+                line[key] = {"error": f"{type(ex).__name__}: {ex}"}
         try:     # the input path (decode / resize / augment) at batch 256, next to the reference's CPU ops
             import tools_input_bench
-            peak_bw = float(peaks.get("hbm_gbs", 6500.0))
             line["input_kernels"] = {
                 "shape": "batch 256 of 256x256x3 f32 (crop_resize from 640x480 u8), L2 flushed between launches; cpu = the "
                          "reference's per-example op (cv2 / numpy restatement) on one host thread",
@@ -287,10 +412,12 @@ def run_ours(args):
         except Exception as ex:
             line["input_kernels"] = {"error": f"{type(ex).__name__}: {ex}"}
     if world == 1 and not args.no_cpu_baseline:
-        ips, threads, sec = cpu_train_steps(args.stacks, args.cpu_batch, 2, 1)
+        # the CPU leg runs BASELINE config 1 (1-stack, batch 8), 2 warm-up + 5 timed steps
+        ips, threads, sec = cpu_train_steps(1, 8, 5, 2)
         line["cpu_baseline"] = {"value": ips, "unit": "img/s", "cores": threads, "kind": "port",
-                                "sample": f"{args.stacks}-stack training step, batch {args.cpu_batch}, 1 warm-up + 2 timed steps, "
-                                          f"fp32 torch-CPU restatement of the reference ({sec:.1f} s/step)"}
+                                "sample": f"BASELINE config 1: 1-stack training step, batch 8, 2 warm-up + 5 timed steps, fp32 torch-CPU "
+                                          f"restatement of the reference ({sec:.2f} s/step); the same configuration on this GPU is "
+                                          f"config1.img_per_s"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -265,9 +265,11 @@ int hgb_model_head_buffers(const hgb_model* m, int stack, int64_t offs[2]);
 int hgb_model_begin_step(hgb_model* m, void* stream);
 
 /* live timing of one convolution class inside a running step (bench.py roofline): CUDA event pairs
- * are recorded on the launching stream around every matching launch.  op_type: 1 forward, 8 wgrad,
- * 9 dgrad; (k, cin, cout, h) select the layer class by its Keras shape.  Read after a stream sync:
- * total milliseconds, number of launches, and their algorithmic FLOPs (2*MAC, forward count). */
+ * are recorded on the launching stream around every matching launch.  op_type: the plan's op type (1 forward conv,
+ * 8 wgrad, 9 dgrad, 2 BatchNorm forward, 7 BatchNorm backward, 12 pool backward ...); (k, cin, cout, h) select a
+ * convolution class by its Keras shape, k = 0 selects a non-convolution class by (channels = cout, height = h) of its
+ * first tensor.  Read after a stream sync: total milliseconds, number of launches, and (convolutions) their
+ * algorithmic FLOPs (2*MAC, forward count). */
 int hgb_model_profile_conv(hgb_model* m, int enable, int op_type, int k, int cin, int cout, int h);
 int hgb_model_profile_read(hgb_model* m, double* total_ms, int* launches, double* flops);
 /* time EVERY op (event pair per op) of the steps that follow; read back per op after a stream sync */

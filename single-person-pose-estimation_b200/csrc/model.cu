@@ -790,11 +790,16 @@ int run_op(hgb_model* m, const Op& o, const float* images, int training, cudaStr
   if (m->prof_all) {
     timed = m->prof_used + 2 <= m->prof_ev.size();
     if (timed) { cudaEventRecord(m->prof_ev[m->prof_used], st); m->prof_ops.push_back(o); }
-  } else if (m->prof_on && (int)o.type == m->prof_type && o.conv >= 0) {
+  } else if (m->prof_on && (int)o.type == m->prof_type && m->prof_k > 0 && o.conv >= 0) {
     const ConvL& c = m->convs[o.conv];
     timed = c.real_k == m->prof_k && c.real_cin == m->prof_cin && c.cout == m->prof_cout && c.h == m->prof_h &&
             m->prof_used + 2 <= m->prof_ev.size();
     if (timed) { cudaEventRecord(m->prof_ev[m->prof_used], st); m->prof_flops += c.flops; }
+  } else if (m->prof_on && (int)o.type == m->prof_type && m->prof_k == 0 && o.a0 >= 0) {
+    // non-convolution classes (BatchNorm, pool, merge ...): selected by the channel count and height of their first tensor
+    const Act& t = m->acts[o.a0];
+    timed = t.c == m->prof_cout && t.h == m->prof_h && m->prof_used + 2 <= m->prof_ev.size();
+    if (timed) cudaEventRecord(m->prof_ev[m->prof_used], st);
   }
   const int rc = run_op_impl(m, o, images, training, st);
   if (timed) { cudaEventRecord(m->prof_ev[m->prof_used + 1], st); m->prof_used += 2; }

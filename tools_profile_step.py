@@ -44,48 +44,25 @@ lib.hgb_model_profile_all(plan.handle, 1)
 model.train_step_device(img, tg)
 torch.cuda.synchronize()
 lib.hgb_model_profile_all(plan.handle, 0)
-n = lib.hgb_model_profile_count(plan.handle)
-agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])   # count, ms, flops, bytes
-info, ms = (C.c_int * 8)(), C.c_double()
-cinfo, coffs = (C.c_int * 8)(), (C.c_int64 * 2)()
-off, dims = C.c_int64(), (C.c_int * 4)()
-
-
-def act_dims(i):
-    lib.hgb_model_act_info(plan.handle, i, C.byref(off), C.byref(dims))
-    return tuple(dims)
-
-
-tot = 0.0
-for i in range(n):
-    _lib.check(lib.hgb_model_profile_op(plan.handle, i, C.byref(info), C.byref(ms)))
-    ty, conv, bn, a0, a1, a2, a3, flag = tuple(info)
-    key, flops, byt = NAMES[ty], 0.0, 0.0
-    if conv >= 0 and ty in (1, 8, 9):
-        lib.hgb_model_conv_detail(plan.handle, conv, C.byref(cinfo), C.byref(coffs))
-        ks, taps, cin, cout, cinp, coutp = cinfo[0], cinfo[1], cinfo[2], cinfo[3], cinfo[4], cinfo[5]
-        nn, hh, ww, _ = act_dims(a0)
-        key += f" k{ks} {cin}->{cout} @{hh}"
-        flops = 2.0 * nn * hh * ww * taps * cin * cout
-        byt = 2.0 * nn * hh * ww * (cinp + coutp)
-    elif a0 >= 0:
-        nn, hh, ww, cc = act_dims(a0 if ty != 5 else a0)
-        key += f" C{cc} @{hh}"
-        mult = {2: 2.3, 6: 2, 7: 3, 3: 1.25, 4: 2.25, 10: 3, 11: 1, 12: 2.25, 13: 1.25}.get(ty, 2)
-        byt = 2.0 * nn * hh * ww * cc * mult
-    agg[key][0] += 1
-    agg[key][1] += ms.value
-    agg[key][2] += flops
-    agg[key][3] += byt
-    tot += ms.value
+from hgb200 import profiling
+import json, os
+try:
+    peaks = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))
+except Exception:
+    peaks = {}
+peak_tf, peak_bw = float(peaks.get("bf16_tflops_sustained", 1400.0)), float(peaks.get("hbm_gbs", 6500.0))
+agg_d, tot = profiling.summarize(plan.handle, 17)
+n = sum(r["launches"] for r in agg_d.values())
+rows = profiling.class_table(agg_d, tot, peak_tf, peak_bw)
+agg = {r["op"]: [r["launches"], r["ms"], 0, 0] for r in rows}
 lines = [f"# Per-op CUDA-event breakdown of one training step: {a.stacks}-stack, batch {B}",
          "", f"Un-profiled step: {plain_ms:.2f} ms; sum of per-op event intervals: {tot:.2f} ms over {n} ops "
-         "(event pairs on the launching stream around every op; bytes are the op's algorithmic activation traffic).", "",
-         "| op class | launches | total ms | share | avg us | TFLOP/s | GB/s |", "|---|---:|---:|---:|---:|---:|---:|"]
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    tf = v[2] / (v[1] * 1e-3) / 1e12 if v[2] else 0
-    gb = v[3] / (v[1] * 1e-3) / 1e9 if v[3] else 0
-    lines.append(f"| {k} | {v[0]} | {v[1]:.3f} | {100 * v[1] / tot:.1f}% | {1e3 * v[1] / v[0]:.1f} | {tf:.0f} | {gb:.0f} |")
+         "(event pairs on the launching stream around every op of the in-order replay; bytes = every operand tensor of the op "
+         f"moved once, hgb200/profiling.py; roofline fractions against {peak_bw:.0f} GB/s / {peak_tf:.0f} TFLOP/s measured).", "",
+         "| op class | launches | total ms | share | avg us | TFLOP/s | GB/s | bound | frac |", "|---|---:|---:|---:|---:|---:|---:|---|---:|"]
+for r in rows:
+    lines.append(f"| {r['op']} | {r['launches']} | {r['ms']:.3f} | {100 * r['share']:.1f}% | {r['avg_us']:.1f} | {r['tflops']:.0f} | "
+                 f"{r['gbps']:.0f} | {r['bound']} | {r['frac']:.2f} |")
 by_type = collections.defaultdict(float)
 for k, v in agg.items():
     by_type[k.split()[0]] += v[1]
