@@ -236,10 +236,37 @@ int hgb_model_lanes_join(hgb_model* m, void* stream, int is_caller);
 int hgb_model_segment_grads(const hgb_model* m, int seg, int64_t* offset, int64_t* count);
 
 /* Keras legacy Adam (trainer.py:31): w -= lr_t*m/(sqrt(v)+eps) with
- * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); grads are multiplied by grad_scale first (1/world_size).
- * Also refreshes the bf16 GEMM weights. */
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); grads are multiplied by grad_scale first (1 when hgb_model_loss was given
+ * inv_count of the GLOBAL batch -- the summed buckets are then the global-mean gradient -- 1/world_size when the
+ * ranks normalised by their local batch).  Also refreshes the bf16 GEMM weights. */
 int hgb_model_adam_step(hgb_model* m, double lr, double beta1, double beta2, double eps, int64_t t,
                         double grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Data parallelism: the one collective of the path      */
+/* ------------------------------------------------------------------------- */
+/* The reference has no distributed code (trainer.py:49-56 is a single-device fit); training shards the batch over one
+ * process per GPU and exchanges gradients once per step.  The communicator is NCCL (NVLink / NVSwitch), bound at run time
+ * (dlopen of libnccl.so.2: inside a torch process that is the library torch already loaded).
+ *   hgb_comm_unique_id   rank 0 creates the 128-byte id; the caller ships it to the other ranks (any transport)
+ *   hgb_comm_init        collective over the nranks processes; one communicator per process / device
+ *   hgb_comm_allreduce_f32   in-place sum of a device buffer, asynchronous on `stream` */
+#define HGB_COMM_UNIQUE_ID_BYTES 128
+typedef struct hgb_comm hgb_comm;
+int hgb_comm_unique_id(void* id_out, int bytes);
+int hgb_comm_init(int nranks, int rank, const void* unique_id, hgb_comm** out);
+int hgb_comm_destroy(hgb_comm* c);
+int hgb_comm_info(const hgb_comm* c, int* nranks, int* rank, int* nccl_version);
+int hgb_comm_allreduce_f32(hgb_comm* c, float* buf, int64_t count, void* stream);
+/* Attach a communicator to a plan (NULL detaches).  sync_bn != 0: the BatchNorm batch statistics (forward sums, backward
+ * sums) of every layer are all-reduced as well -- one 2*C-float all-reduce per BatchNorm and pass, ops replayed in plan order
+ * on the caller's stream -- so N ranks compute exactly the single-device step of the concatenated batch (parity tests; the
+ * default, like Keras layers under mirrored replicas, is per-replica statistics). */
+int hgb_model_set_comm(hgb_model* m, hgb_comm* c, int sync_bn);
+/* Sum over all ranks of the gradient range owned by segments [seg_lo, seg_hi) -- consecutive segments are one contiguous
+ * bucket of the flat gradient buffer -- asynchronous on `stream` (order it after the segments' backward with
+ * hgb_model_lanes_join(m, stream, 0)). */
+int hgb_grad_allreduce_bucket(hgb_model* m, int seg_lo, int seg_hi, void* stream);
 
 /* debugging / layer-wise parity: where conv `index` wrote its (bias+activation) output, bf16 NHWC,
  * dims = {N,H,W,C_padded}, as a byte offset into the bound arena */

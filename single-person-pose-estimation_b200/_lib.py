@@ -69,6 +69,13 @@ PROTOTYPES = {
     "hgb_model_lanes_join": (i32, [vp, vp, i32]),
     "hgb_model_segment_grads": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i64)]),
     "hgb_model_adam_step": (i32, [vp, f64, f64, f64, f64, i64, f64, vp]),
+    "hgb_comm_unique_id": (i32, [vp, i32]),
+    "hgb_comm_init": (i32, [i32, i32, vp, C.POINTER(vp)]),
+    "hgb_comm_destroy": (i32, [vp]),
+    "hgb_comm_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+    "hgb_comm_allreduce_f32": (i32, [vp, vp, i64, vp]),
+    "hgb_model_set_comm": (i32, [vp, vp, i32]),
+    "hgb_grad_allreduce_bucket": (i32, [vp, i32, i32, vp]),
     "hgb_model_conv_output": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i32 * 4)]),
     "hgb_model_conv_input_bn": (i32, [vp, i32]),
     "hgb_model_num_ops": (i32, [vp, i32, i32]),

@@ -319,51 +319,48 @@ __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// address of the same shared-memory variable in CTA `rank` of this cluster (distributed shared memory)
-__device__ __forceinline__ uint32_t dsmem_addr(const void* local, uint32_t rank) {
-  uint32_t l = (uint32_t)__cvta_generic_to_shared(local), r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(l), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ float ld_dsmem_f32(uint32_t a) {
-  float v;
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ int ld_dsmem_s32(uint32_t a) {
-  int v;
-  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
+// Order-preserving 64-bit key of a (value, flat index) candidate: atomicMax over keys picks numpy's argmax -- a NaN beats
+// everything, then the larger value (-0.0 == +0.0), then the LOWER index.  Every real key is > 0 (the identity).
+__device__ __forceinline__ unsigned long long decode_key(float v, int idx) {
+  uint32_t ord;
+  if (v != v) {
+    ord = 0xffffffffu;
+  } else {
+    uint32_t b = __float_as_uint(v == 0.f ? 0.f : v);
+    ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  }
+  return ((unsigned long long)ord << 32) | (unsigned long long)(0xffffffffu - (uint32_t)idx);
 }
 
-// A thread-block CLUSTER of `cs` CTAs (16*K threads each) per sample: CTA r scans the r-th contiguous share of the map, the
-// per-joint partial maxima are exchanged through distributed shared memory, and the joints are then spread over the
-// warps of all CTAs for the final step.  (One CTA per sample was a single ragged wave at batch 1024 -- every block
-// loading, then every block reducing -- and reached 0.54 / 0.35 of the HBM peak for f32 / bf16.)
+// `split` independent CTAs (16*K threads each) per sample: CTA r scans the r-th contiguous share of the map and merges its
+// per-joint maxima into the sample's keys with one 64-bit atomicMax per joint; the CTA that arrives last (a counter, the
+// threadfence-reduction pattern) finishes the sample: confidence, clipped 3x3 window, outputs.  The keys and the counter
+// live in out_idx itself (words 0-1 of every (sample, joint) row; word 2 of joint 0), zeroed by the launcher, so no
+// workspace is needed.  (One CTA per sample was a single ragged wave at batch 1024 -- every block loading, then every
+// block reducing -- at 0.54 / 0.35 of the HBM peak for f32 / bf16; a thread-block cluster per sample with a DSMEM
+// exchange measured worse still: 4-8 co-scheduled CTAs and two cluster barriers per 35-70 KB of loads.)
 // The vector stride VEC*16*K and the share size are multiples of K, so slot j of thread t always carries joint
-// (VEC*t + j) % K: VEC running (value,index) pairs in registers, no dynamic indexing.  UNROLL independent 16-byte
-// loads are in flight per thread.
+// (VEC*t + j) % K: VEC running (value,index) pairs in registers, no dynamic indexing.  Four independent 16-byte loads
+// are in flight per thread at <= 48 registers: 4 resident CTAs per SM hide each other's reduction phases.
 template <typename T, int VEC>
-__global__ void decode_kernel(const T* __restrict__ hm, int H, int W, int K, double thr, int version,
-                              int32_t* __restrict__ out_idx, float* __restrict__ out_kp) {
+__global__ void __launch_bounds__(320, VEC == 8 ? 3 : 4) decode_kernel(const T* __restrict__ hm, int H, int W, int K, double thr, int version,
+                                                        int32_t* __restrict__ out_idx, float* __restrict__ out_kp) {
   extern __shared__ unsigned char s_raw[];
   const int S = 16 * K, t = threadIdx.x, b = blockIdx.y;  // blockDim = S rounded up to a warp multiple
-  const int cs = gridDim.x, rank = blockIdx.x;            // cluster = the gridDim.x CTAs of one sample
-  float* s_pv = reinterpret_cast<float*>(s_raw);          // [64] this CTA's per-joint maximum ...
-  int* s_pi = reinterpret_cast<int*>(s_raw) + 64;         // [64] ... and its flat element index (read by the peers)
-  float* s_val = reinterpret_cast<float*>(s_raw) + 128;   // [S*VEC]
-  int* s_idx = reinterpret_cast<int*>(s_raw) + 128 + S * VEC;   // [S*VEC]
+  const int split = gridDim.x, rank = blockIdx.x;
+  float* s_val = reinterpret_cast<float*>(s_raw);         // [S*VEC]
+  int* s_idx = reinterpret_cast<int*>(s_raw) + S * VEC;   // [S*VEC]
+  __shared__ int s_last;
   const int HWK = H * W * K;
-  const int nvec = HWK / VEC / cs;                        // vectors of this CTA's share
+  const int nvec = HWK / VEC / split;                     // vectors of this CTA's share
   const int v0 = rank * nvec;
   const T* base = hm + (size_t)b * HWK;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(out_idx + (size_t)b * K * 4);   // stride 2 per joint
+  int* counter = out_idx + (size_t)b * K * 4 + 2;
 
   float bv[VEC];
   int bi[VEC];
-  constexpr int UNROLL = 8;
+  constexpr int UNROLL = 4;
   // Fast path: a thread meets the elements of a slot in increasing index order, so "first maximum" is a strict
   // greater-than update (3-4 instructions per element) starting from (-inf, the slot's first index) -- the argmax of an
   // all -inf slot is its first element.  It is exact unless a NaN shows up (numpy: a NaN beats everything); any NaN
@@ -423,7 +420,7 @@ __global__ void decode_kernel(const T* __restrict__ hm, int H, int W, int K, dou
 
   const int warp = t >> 5, lane = t & 31, nwarp = blockDim.x >> 5;
   const int ncand = 16 * VEC;  // candidates per joint: c = k + K*m
-  for (int k = warp; k < K; k += nwarp) {   // this CTA's maximum of joint k
+  for (int k = warp; k < K; k += nwarp) {   // this CTA's maximum of joint k -> the sample's key
     float cv = -CUDART_INF_F;
     int ci = 0x7fffffff;
     for (int m = lane; m < ncand; m += 32) {
@@ -437,33 +434,25 @@ __global__ void decode_kernel(const T* __restrict__ hm, int H, int W, int K, dou
       const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
       if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
     }
-    if (lane == 0) { s_pv[k] = cv; s_pi[k] = ci; }
+    if (lane == 0) atomicMax(keys + 2 * k, decode_key(cv, ci));
   }
-  if (cs > 1) cluster_sync_all(); else __syncthreads();
+  __threadfence();
+  __syncthreads();
+  if (t == 0) s_last = atomicAdd(counter, 1) == split - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
 
-  // final step: joint k is handled by warp (k / cs) % nwarp of CTA k % cs
-  for (int k = rank + cs * warp; k < K; k += cs * nwarp) {
-    float cv = -CUDART_INF_F;
-    int ci = 0x7fffffff;
-    if (lane < cs) {
-      if (cs > 1) {
-        cv = ld_dsmem_f32(dsmem_addr(s_pv + k, (uint32_t)lane));
-        ci = ld_dsmem_s32(dsmem_addr(s_pi + k, (uint32_t)lane));
-      } else {
-        cv = s_pv[k]; ci = s_pi[k];
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
-      if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
-    }
+  // the last CTA of the sample: every share has merged its maxima
+  for (int k = warp; k < K; k += nwarp) {
+    const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(keys + 2 * k);
+    const int ci = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
     const int index = ci / K;  // flat pixel index (row-major)
     const int x = index % W;   // data_utils.py:121
     const int y = index / H;   // data_utils.py:122 (height; square maps only)
-    const float conf = cv;
     int pidx = 0;
+    float conf = 0.f;
+    if (lane == 31) conf = to_f32<T>(base[ci]);   // the element itself: exact bits (signed zero, NaN payload)
     if (version == 2) {        // data_utils.py:160-169: one lane per element of the clipped 3x3 window (parallel loads)
       const int x1 = max(x - 1, 0), x2 = min(x + 2, W), y1 = max(y - 1, 0), y2 = min(y + 2, H);
       const int pw = x2 - x1, ph = y2 - y1;
@@ -482,10 +471,12 @@ __global__ void decode_kernel(const T* __restrict__ hm, int H, int W, int K, dou
       }
       pidx = __shfl_sync(0xffffffffu, pbi, 0);
     }
+    conf = __shfl_sync(0xffffffffu, conf, 31);
+    __syncwarp();
     if (lane == 0) {
       const int px = pidx % 3, py = pidx / 3;  // always 3 (data_utils.py:168-169)
       int32_t* oi = out_idx + ((size_t)b * K + k) * 4;
-      oi[0] = index; oi[1] = x; oi[2] = y; oi[3] = pidx;
+      oi[0] = index; oi[1] = x; oi[2] = y; oi[3] = pidx;   // overwrites the key (and, for joint 0, the counter)
       float* ok = out_kp + ((size_t)b * K + k) * 3;
       // numpy >= 2 (NEP 50) compares the float32 confidence with float32(threshold); numpy 1.x
       // promoted to float64.  They differ only when conf == float32(thr) rounds above thr.
@@ -498,7 +489,6 @@ __global__ void decode_kernel(const T* __restrict__ hm, int H, int W, int K, dou
       }
     }
   }
-  if (cs > 1) cluster_sync_all();   // a CTA's shared memory must outlive the peers' reads of it
 }
 
 // ------------------------------------------------------------------------------------
@@ -697,31 +687,22 @@ extern "C" int hgb_decode(const void* heatmaps, int dtype, int B, int H, int W, 
   if (B == 0) return HGB_OK;
   HGB_CHECK_ARG(B <= 65535, "hgb_decode: batch exceeds the grid limit");
   const int threads = (16 * K + 31) / 32 * 32;
-  const size_t smem = 512 + (size_t)(16 * K) * vec * 8;
+  HGB_CHECK_ARG(threads <= 320, "hgb_decode: at most 20 joints per launch configuration");
+  const size_t smem = (size_t)(16 * K) * vec * 8;
   cudaStream_t st = (cudaStream_t)stream;
-  // cluster size: the largest of 8 / 4 / 2 / 1 whose share of a map is a whole number of 16-byte vectors and of pixels
-  // (K elements) -- 8 CTAs per sample while that is still less than ~4 waves of the chip, 4 otherwise
+  // CTAs per sample: shares must be a whole number of 16-byte vectors and of pixels (K elements); 8 shares while that is
+  // still less than ~4 waves of the chip, 4 otherwise (hgb_debug_set(24, n) overrides)
   const int64_t nvec = (int64_t)H * W * K / vec;
-  int cs = (int64_t)B * 8 <= 148 * 7 * 4 ? 8 : 4;
-  if (g_debug[24] > 0) cs = g_debug[24];
-  while (cs > 1 && (nvec % cs != 0 || (nvec / cs * vec) % K != 0 || nvec / cs < 16 * K)) cs >>= 1;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cs, B);
-  cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cs;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = cs > 1 ? 1 : 0;
+  int split = (int64_t)B * 8 <= 148 * 6 * 4 ? 8 : 4;
+  if (g_debug[24] > 0) split = g_debug[24];
+  while (split > 1 && (nvec % split != 0 || (nvec / split * vec) % K != 0 || nvec / split < 4 * 16 * K)) split >>= 1;
+  // keys + arrival counters live in out_idx (see decode_kernel)
+  HGB_CUDA(cudaMemsetAsync(out_idx, 0, (size_t)B * K * 4 * sizeof(int32_t), st));
   if (dtype == HGB_F32)
-    HGB_CUDA(cudaLaunchKernelEx(&cfg, decode_kernel<float, 4>, (const float*)heatmaps, H, W, K, conf_threshold, version, out_idx, out_kpts));
+    decode_kernel<float, 4><<<dim3(split, B), threads, smem, st>>>((const float*)heatmaps, H, W, K, conf_threshold, version, out_idx, out_kpts);
   else
-    HGB_CUDA(cudaLaunchKernelEx(&cfg, decode_kernel<__nv_bfloat16, 8>, (const __nv_bfloat16*)heatmaps, H, W, K, conf_threshold, version,
-                                out_idx, out_kpts));
+    decode_kernel<__nv_bfloat16, 8><<<dim3(split, B), threads, smem, st>>>((const __nv_bfloat16*)heatmaps, H, W, K, conf_threshold, version,
+                                                                        out_idx, out_kpts);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }

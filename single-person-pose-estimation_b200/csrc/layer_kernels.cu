@@ -48,13 +48,13 @@ __global__ void __launch_bounds__(256, 4) bn_apply_fwd_kernel(const bf16* __rest
                                                               bf16* __restrict__ out, const float* __restrict__ sums,
                                                               float* __restrict__ saved, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float* __restrict__ mm,
-                                                              float* __restrict__ mv, int M, int C, int training) {
+                                                              float* __restrict__ mv, int M, int M_stat, int C, int training) {
   pdl_trigger();
   pdl_wait();
   const int G = C >> 3, R = 256 / G;
   const int g = threadIdx.x % G, r0 = threadIdx.x / G;
   float sc[8], sh[8];
-  const float invM = 1.f / (float)M;
+  const float invM = 1.f / (float)M_stat;     // rows behind the sums (the global batch under sync-BN)
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = g * 8 + j;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256, 4) bn_apply_fwd_kernel(const bf16* __rest
     if (training && blockIdx.x == 0 && r0 == 0) {
       saved[c] = mean;
       saved[C + c] = rstd;
-      const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
+      const float unbiased = M_stat > 1 ? var * ((float)M_stat / (float)(M_stat - 1)) : var;
       mm[c] = mm[c] * kBnMomentum + mean * (1.f - kBnMomentum);
       mv[c] = mv[c] * kBnMomentum + unbiased * (1.f - kBnMomentum);
     }
@@ -110,16 +110,16 @@ __global__ void __launch_bounds__(256, 4) bn_apply_fwd_kernel(const bf16* __rest
 }
 
 int bn_apply_fwd(const bf16* y, const bf16* res, bf16* out, const float* sums, float* saved, const float* gamma,
-                 const float* beta, float* moving_mean, float* moving_var, int M, int C, int training, cudaStream_t st) {
+                 const float* beta, float* moving_mean, float* moving_var, int M, int M_stat, int C, int training, cudaStream_t st) {
   HGB_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "bn_apply: unsupported channel count %d", C);
   if (M == 0) return HGB_OK;
   // In inference the moving statistics are read-only, in training block 0 rewrites them after reading.
   if (res)
     launch_pdl(bn_apply_fwd_kernel<2, true>, dim3(row_blocks(M, C)), dim3(256), 0, st, y, res, out, sums, saved, gamma, beta,
-               moving_mean, moving_var, M, C, training);
+               moving_mean, moving_var, M, M_stat, C, training);
   else
     launch_pdl(bn_apply_fwd_kernel<4, false>, dim3(row_blocks(M, C)), dim3(256), 0, st, y, res, out, sums, saved, gamma, beta,
-               moving_mean, moving_var, M, C, training);
+               moving_mean, moving_var, M, M_stat, C, training);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -364,13 +364,13 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const bf16* __rest
                                                               bf16* __restrict__ dp, const float* __restrict__ bsums,
                                                               const float* __restrict__ saved, const float* __restrict__ gamma,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                              float* __restrict__ dbias, int M, int C) {
+                                                              float* __restrict__ dbias, int M, int M_stat, float pscale, int C) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float s_acc[];
   const int G = C >> 3, R = 256 / G;
   const int g = threadIdx.x % G, r0 = threadIdx.x / G;
-  const float invM = 1.f / (float)M;
+  const float invM = 1.f / (float)M_stat;     // rows behind the sums (the global batch under sync-BN)
   float cA[8], cB[8], cC[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -384,8 +384,8 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const bf16* __rest
     cB[j] = -k;
     cC[j] = k * mean - a * (sdz * invM);
     if (blockIdx.x == 0 && r0 == 0) {
-      dgamma[c] = sdzx;
-      dbeta[c] = sdz;
+      dgamma[c] = sdzx * pscale;     // pscale = 1 / ranks under sync-BN: every rank holds the GLOBAL sums and the
+      dbeta[c] = sdz * pscale;       // gradient bucket all-reduce adds the ranks up
     }
   }
   float acc[1][8];
@@ -429,11 +429,11 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const bf16* __rest
 }
 
 int bn_bwd_apply(const bf16* dz, const bf16* y, bf16* dp, const float* bsums, const float* saved, const float* gamma,
-                 float* dgamma, float* dbeta, float* dbias, int M, int C, cudaStream_t st) {
+                 float* dgamma, float* dbeta, float* dbias, int M, int M_stat, float pscale, int C, cudaStream_t st) {
   HGB_CHECK_ARG(C % 8 == 0 && 256 % (C / 8) == 0, "bn_bwd_apply: unsupported channel count %d", C);
   if (M == 0) return HGB_OK;
   launch_pdl(bn_bwd_apply_kernel, dim3(row_blocks(M, C, 8)), dim3(256), 2048 * sizeof(float), st, dz, y, dp, bsums, saved, gamma, dgamma, dbeta,
-                                                                           dbias, M, C);
+                                                                           dbias, M, M_stat, pscale, C);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }

@@ -10,9 +10,10 @@ typedef __nv_bfloat16 bf16;
 // BatchNormalization forward (model/hourglass.py:60,80,197-201; Keras defaults momentum .99, eps 1e-3)
 // out = (y - mean) * rstd * gamma + beta (+ res).  training: mean/var from `sums` (sum, sumsq over M rows,
 // produced by the conv epilogue); block 0 stores (mean, rstd) in `saved` and updates the moving
-// statistics (moving_var gets the unbiased batch variance, as TF's fused kernel does).
+// statistics (moving_var gets the unbiased batch variance, as TF's fused kernel does).  M = rows of this tensor,
+// M_stat = rows behind `sums` (= M, or the global batch under sync-BN).
 int bn_apply_fwd(const bf16* y, const bf16* res, bf16* out, const float* sums, float* saved, const float* gamma,
-                 const float* beta, float* moving_mean, float* moving_var, int M, int C, int training, cudaStream_t st);
+                 const float* beta, float* moving_mean, float* moving_var, int M, int M_stat, int C, int training, cudaStream_t st);
 
 // MaxPool2D 2x2/2 (hourglass.py:63,135,171-177) on [N][2h][2w][C] -> [N][h][w][C], and its gradient
 // (routed to the first maximum of each window in row-major order; accumulate=1 adds into dx).
@@ -29,7 +30,7 @@ int bn_bwd_reduce(const bf16* dz, const bf16* y, float* bsums, int M, int C, cud
 // pass 2: dp = [y > 0] * gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat));  dbias[c] += sum_rows dp;
 // block 0 also writes dgamma = sum dz*xhat, dbeta = sum dz.
 int bn_bwd_apply(const bf16* dz, const bf16* y, bf16* dp, const float* bsums, const float* saved, const float* gamma,
-                 float* dgamma, float* dbeta, float* dbias, int M, int C, cudaStream_t st);
+                 float* dgamma, float* dbeta, float* dbias, int M, int M_stat, float pscale, int C, cudaStream_t st);
 
 // Convs without BN: dp = relu ? g * [y > 0] : g (in place when dp == g; dp may be null when !relu),
 // dbias[c] += sum_rows dp for c < c_valid.

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "comm.cuh"
 #include "conv_gemm.cuh"
 #include "layer_kernels.cuh"
 
@@ -166,6 +167,12 @@ struct hgb_model {
   int bwd_unjoined_from = 1 << 30;   // first backward sequence index issued since the lanes were last joined into the caller
   bool lane_dirty[kNumLanes] = {false};   // lane has work the caller's stream has not been ordered after yet
   int num_sms = 0;
+
+  // ---- data parallelism (hgb_model_set_comm): gradient buckets are all-reduced over `comm`; with sync_bn the BatchNorm
+  // sums of every layer are all-reduced too, so N ranks compute exactly the single-device step of the concatenated batch
+  hgb_comm* comm = nullptr;
+  int sync_bn = 0;
+  int stat_ranks() const { return (comm && sync_bn) ? comm->nranks : 1; }
 
   // ---- build-time state
   size_t arena_cur = 0;
@@ -636,11 +643,15 @@ void op_access(const hgb_model* m, const Op& o, std::vector<Range>& r, std::vect
       if (o.flag & 0xffff) {
         const BNL& b = m->bns[(o.flag & 0xffff) - 1];
         add_arena(r, b.sums_off, 2 * (size_t)b.c * 4);
-        if (o.flag & 0x10000) add_arena(w, b.saved_off, 2 * (size_t)b.c * 4);
+        if (o.flag & 0x10000) {
+          add_arena(w, b.saved_off, 2 * (size_t)b.c * 4);
+          add_arena(w, b.sums_off, 2 * (size_t)b.c * 4);     // sync-BN: this launch all-reduces the sums in place first
+        }
       }
       break;
     case F_BN:
       add_act(m, r, o.a0); add_act(m, r, o.a1); add_act(m, w, o.a2);
+      add_arena(w, m->bns[o.bn].sums_off, 2 * (size_t)m->bns[o.bn].c * 4);   // (sync-BN all-reduces them in place)
       add_arena(r, m->bns[o.bn].sums_off, 2 * (size_t)m->bns[o.bn].c * 4);
       add_arena(w, m->bns[o.bn].saved_off, 2 * (size_t)m->bns[o.bn].c * 4);
       break;
@@ -655,6 +666,7 @@ void op_access(const hgb_model* m, const Op& o, std::vector<Range>& r, std::vect
       const BNL& b = m->bns[o.bn];
       add_act(m, r, o.a0); add_act(m, r, o.a1); add_act(m, w, o.a2);
       add_arena(r, b.bsums_off, 2 * (size_t)b.c * 4);
+      add_arena(w, b.bsums_off, 2 * (size_t)b.c * 4);        // (sync-BN all-reduces them in place)
       add_arena(r, b.saved_off, 2 * (size_t)b.c * 4);
       add_grad(w, b.gamma_off, b.c); add_grad(w, b.beta_off, b.c);
       add_grad(w, m->convs[o.conv].b_off, m->convs[o.conv].cout);
@@ -838,7 +850,11 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
         a.bn_in.gamma = m->p_params + b.gamma_off; a.bn_in.beta = m->p_params + b.beta_off;
         a.bn_in.moving_mean = m->p_params + b.mm_off; a.bn_in.moving_var = m->p_params + b.mv_off;
         a.bn_in.mode = training ? 0 : 1; a.bn_in.write = (o.flag & 0x10000) ? 1 : 0;
-        a.bn_in.M = in.n * in.h * in.w; a.bn_in.C = b.c;
+        a.bn_in.M = in.n * in.h * in.w * m->stat_ranks(); a.bn_in.C = b.c;
+        if (training && (o.flag & 0x10000) && m->stat_ranks() > 1) {   // sync-BN: global batch statistics
+          rc = comm_allreduce_sum_f32(m->comm, arena_f(m, b.sums_off), 2 * b.c, st);
+          if (rc) break;
+        }
       }
       if (o.flag & 0x20000) {   // inference: the BatchNorm that follows this conv is applied in the epilogue (fuse_inference_bn)
         const BNL& b = m->bns[o.bn];
@@ -852,9 +868,13 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
     case F_BN: {
       const BNL& b = m->bns[o.bn];
       const Act& y = m->acts[o.a0];
+      if (training && m->stat_ranks() > 1) {   // sync-BN: global batch statistics
+        rc = comm_allreduce_sum_f32(m->comm, arena_f(m, b.sums_off), 2 * b.c, st);
+        if (rc) break;
+      }
       rc = bn_apply_fwd(act_ptr(m, o.a0), act_ptr(m, o.a1), act_ptr(m, o.a2), arena_f(m, b.sums_off), arena_f(m, b.saved_off),
                         m->p_params + b.gamma_off, m->p_params + b.beta_off, m->p_params + b.mm_off, m->p_params + b.mv_off,
-                        y.n * y.h * y.w, b.c, training, st);
+                        y.n * y.h * y.w, y.n * y.h * y.w * m->stat_ranks(), b.c, training, st);
       break;
     }
     case F_POOL: {
@@ -883,9 +903,13 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
       const BNL& b = m->bns[o.bn];
       const ConvL& c = m->convs[o.conv];
       const Act& y = m->acts[o.a1];
+      if (m->stat_ranks() > 1) {   // sync-BN: global sums of dz and dz*y; dgamma / dbeta then come out identical on every
+        rc = comm_allreduce_sum_f32(m->comm, arena_f(m, b.bsums_off), 2 * b.c, st);   // rank and are pre-divided by the
+        if (rc) break;                                                                // world size (the bucket all-reduce sums them)
+      }
       rc = bn_bwd_apply(act_ptr(m, o.a0), act_ptr(m, o.a1), act_ptr(m, o.a2), arena_f(m, b.bsums_off), arena_f(m, b.saved_off),
                         m->p_params + b.gamma_off, m->p_grads + b.gamma_off, m->p_grads + b.beta_off, m->p_grads + c.b_off,
-                        y.n * y.h * y.w, b.c, st);
+                        y.n * y.h * y.w, y.n * y.h * y.w * m->stat_ranks(), 1.f / (float)m->stat_ranks(), b.c, st);
       break;
     }
     case B_WGRAD: {
@@ -1023,7 +1047,7 @@ int run_sequence(hgb_model* m, bool backward, int begin, int end, const float* i
   const std::vector<std::vector<Op>>& lists = backward ? m->bwd_ops : m->fwd_ops;
   if (begin >= end) return HGB_OK;
   auto op_at = [&](int k) -> const Op& { return lists[seq[k].seg][seq[k].idx]; };
-  if (hgb::g_debug[8] || m->prof_all) {
+  if (hgb::g_debug[8] || m->prof_all || m->stat_ranks() > 1) {   // (sync-BN interleaves collectives: one stream, plan order)
     for (int k = begin; k < end; ++k) {
       Op fused;
       const bool fz = !backward && fuse_inference_bn(m, op_at(k), k + 1 < end ? &op_at(k + 1) : nullptr, training, &fused);
@@ -1247,6 +1271,23 @@ extern "C" int hgb_model_backward_nojoin(hgb_model* m, int seg_lo, int seg_hi, v
   const int begin = m->bwd_seq_begin[seg_hi - 1];
   const int end = seg_lo == 0 ? (int)m->bwd_seq.size() : m->bwd_seq_begin[seg_lo - 1];
   return run_sequence(m, true, begin, end, nullptr, 1, (cudaStream_t)stream, /*join=*/hgb::g_debug[8] || m->prof_all);
+}
+
+// ---- data parallelism behind the ABI
+extern "C" int hgb_model_set_comm(hgb_model* m, hgb_comm* comm, int sync_bn) {
+  HGB_CHECK_ARG(m, "hgb_model_set_comm: null model");
+  m->comm = comm;
+  m->sync_bn = (comm && sync_bn) ? 1 : 0;
+  return HGB_OK;
+}
+
+extern "C" int hgb_grad_allreduce_bucket(hgb_model* m, int seg_lo, int seg_hi, void* stream) {
+  HGB_REQUIRE_READY(m);
+  HGB_CHECK_ARG(seg_lo >= 0 && seg_hi <= m->S + 1 && seg_lo < seg_hi, "hgb_grad_allreduce_bucket: bad segment range");
+  if (!m->comm || !m->p_grads) { set_error("hgb_grad_allreduce_bucket: no communicator (hgb_model_set_comm) or gradients bound"); return HGB_ERR_STATE; }
+  // segments own consecutive ranges of the flat gradient buffer: [seg_lo, seg_hi) is ONE contiguous bucket
+  const int64_t lo = m->seg_begin[seg_lo], hi = m->seg_end[seg_hi - 1];
+  return comm_allreduce_sum_f32(m->comm, m->p_grads + lo, hi - lo, (cudaStream_t)stream);
 }
 
 // order `stream` after everything issued on the lanes so far; is_caller != 0 marks the lanes as joined (the stream the

@@ -89,6 +89,7 @@ class _Plan:
         check(lib.hgb_model_bind(self.handle, _lib.BUF_ARENA, ptr(self.arena), nbytes))
         check(lib.hgb_model_sync_weights(self.handle, stream_ptr()))
         self.weights_version = model._weights_version
+        self.comm_key = None          # (communicator, sync_bn) attached to the handle
 
     def close(self):
         if self.handle:
@@ -442,12 +443,43 @@ class HourglassModel:
         inv = 1.0 / (gb * K) if self._loss_kind == 2 else 1.0 / (gb * h * w * K)
         losses = torch.zeros(self.num_stacks, dtype=torch.float64, device="cuda")
         st = stream_ptr()
+        if allreduce is not None and getattr(allreduce, "comm", None) is not None:
+            key = (allreduce.comm.value, allreduce.sync_bn)       # sync-BN all-reduces statistics in the forward pass already
+            if plan.comm_key != key:
+                check(lib.hgb_model_set_comm(plan.handle, allreduce.comm, int(allreduce.sync_bn)))
+                plan.comm_key = key
+        elif plan.comm_key is not None:
+            check(lib.hgb_model_set_comm(plan.handle, None, 0))
+            plan.comm_key = None
         check(lib.hgb_model_forward(plan.handle, ptr(images), 1, None, st))
         check(lib.hgb_model_loss(plan.handle, self._loss_kind, ptr(targets), inv, ptr(losses), st))
         nseg = lib.hgb_model_num_segments(plan.handle)
         world = 1
         if allreduce is None:
+            if plan.comm_key is not None:
+                check(lib.hgb_model_set_comm(plan.handle, None, 0))
+                plan.comm_key = None
             check(lib.hgb_model_backward(plan.handle, 0, nseg, st))
+        elif getattr(allreduce, "comm", None) is not None:
+            # the library's own communicator (NCCL): a few contiguous buckets, each all-reduced on a side stream as soon as
+            # its segments' backward has been issued (the main chain of the next group starts at once)
+            world = allreduce.world_size
+            key = (allreduce.comm.value, allreduce.sync_bn)
+            if plan.comm_key != key:
+                check(lib.hgb_model_set_comm(plan.handle, allreduce.comm, int(allreduce.sync_bn)))
+                plan.comm_key = key
+            comm = allreduce.comm_stream
+            for lo, hi in allreduce.bucket_groups(nseg):
+                if allreduce.sync_bn:      # statistics all-reduces share the communicator: everything in plan order on one stream
+                    check(lib.hgb_model_backward(plan.handle, lo, hi, st))
+                    check(lib.hgb_grad_allreduce_bucket(plan.handle, lo, hi, st))
+                    continue
+                check(lib.hgb_model_backward_nojoin(plan.handle, lo, hi, st))
+                check(lib.hgb_model_lanes_join(plan.handle, C.c_void_p(comm.cuda_stream), 0))
+                check(lib.hgb_grad_allreduce_bucket(plan.handle, lo, hi, C.c_void_p(comm.cuda_stream)))
+            if not allreduce.sync_bn:
+                check(lib.hgb_model_lanes_join(plan.handle, st, 1))
+                torch.cuda.current_stream().wait_stream(comm)
         else:
             world = allreduce.world_size
             off, cnt = C.c_int64(), C.c_int64()

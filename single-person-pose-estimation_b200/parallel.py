@@ -1,7 +1,9 @@
-"""Data parallelism: one process per GPU, gradients all-reduced per backward segment
-(front module, stack 0..S-1 = natural ~13 MB buckets) over torch.distributed (NCCL on NVLink),
-launched as soon as a segment's backward has been enqueued so the transfer overlaps the rest of
-the backward pass.  The reference has no distributed code; this is new.
+"""Data parallelism: one process per GPU.  The gradient buffer is all-reduced in a few contiguous buckets (groups of
+backward segments: stacks S-1.. down to the front module), each launched on a side stream as soon as its segments'
+backward has been enqueued, so the transfer overlaps the rest of the backward pass.  On GPUs the collective is issued by
+the library itself (hgb_comm_init / hgb_grad_allreduce_bucket: NCCL over NVLink, include/hgb200.h); torch.distributed
+only carries the 128-byte NCCL id and host-side scalars.  Without CUDA (gloo, the CPU tests of the bucket logic) the
+buckets go through torch.distributed.  The reference has no distributed code; this is new.
 """
 from __future__ import annotations
 
@@ -15,7 +17,7 @@ class GradAllReduce:
     The loss kernels already divide by the GLOBAL batch, so the summed buckets are the global-mean gradient; a caller
     that normalised by its local batch gets the remaining 1/world_size through Adam's grad_scale."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, native=None, sync_bn=False, buckets=3):
         import torch.distributed as dist
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
@@ -24,6 +26,49 @@ class GradAllReduce:
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self._pending = []
+        self.buckets = max(1, int(buckets))
+        self.sync_bn = bool(sync_bn)
+        self.comm = None                  # hgb_comm* (C ABI) when the collective is issued by the library
+        self.comm_stream = None
+        if native is None:
+            native = dist.get_backend(group) == "nccl"
+        if native:
+            self._init_native()
+        elif self.sync_bn:
+            raise ValueError("sync_bn needs the library's own communicator (NCCL)")
+
+    def _init_native(self):
+        """hgb_comm_unique_id on rank 0 -> 128 bytes broadcast over torch.distributed -> hgb_comm_init everywhere."""
+        import ctypes as C
+        import torch
+        from ._lib import check, lib
+        buf = (C.c_uint8 * 128)()
+        if self.rank == 0:
+            check(lib.hgb_comm_unique_id(buf, 128))
+        box = [bytes(buf)]
+        self.dist.broadcast_object_list(box, src=self.dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                                        group=self.group)
+        raw = (C.c_uint8 * 128).from_buffer_copy(box[0])
+        handle = C.c_void_p()
+        check(lib.hgb_comm_init(self.world_size, self.rank, raw, C.byref(handle)))
+        self.comm = handle
+        self.comm_stream = torch.cuda.Stream()
+
+    def close(self):
+        if self.comm is not None:
+            from ._lib import lib
+            import torch
+            torch.cuda.synchronize()
+            lib.hgb_comm_destroy(self.comm)
+            self.comm = None
+
+    def bucket_groups(self, nseg):
+        """Backward runs segments nseg-1 .. 0; consecutive segments share one contiguous gradient range.  -> [(lo, hi)] from
+        the top down, `buckets` groups of near-equal segment counts (fewer, larger all-reduces: launch latency and SM
+        contention with the backward kernels matter more than bucket size on NVSwitch)."""
+        n = min(self.buckets, nseg)
+        edges = [round(i * nseg / n) for i in range(n + 1)]
+        return [(edges[i], edges[i + 1]) for i in range(n - 1, -1, -1)]
 
     def __call__(self, bucket):
         if bucket.numel():
@@ -46,15 +91,18 @@ class GradAllReduce:
         return t.cpu().numpy()
 
 
-def enable(group=None):
-    """Make every subsequent train_on_batch / fit data-parallel over `group` (default: world)."""
+def enable(group=None, native=None, sync_bn=False, buckets=3):
+    """Make every subsequent train_on_batch / fit data-parallel over `group` (default: world).  sync_bn: all-reduce the
+    BatchNorm statistics too, so the N-rank step equals the single-device step on the concatenated batch."""
     global _CURRENT
-    _CURRENT = GradAllReduce(group)
+    _CURRENT = GradAllReduce(group, native=native, sync_bn=sync_bn, buckets=buckets)
     return _CURRENT
 
 
 def disable():
     global _CURRENT
+    if _CURRENT is not None:
+        _CURRENT.close()
     _CURRENT = None
 
 

@@ -4,7 +4,9 @@
 preallocated buffers), reported as achieved HBM GB/s of the ALGORITHMIC bytes:
   render : B*H*W*K*4 written          loss : read y_true + read y_pred + write grad (all fp32)
   decode : B*H*W*K*sizeof(elem) read
-Between launches a 256 MB buffer is rewritten so inputs never sit in the 126 MB L2.
+Between launches a 256 MB buffer is rewritten and a second one read back, so inputs never sit in the 126 MB L2 and
+the L2 is left CLEAN (after a pure write the cache holds ~100 MB of dirty lines whose write-back would be charged to
+the kernel under test: +35 % on a 285 MB launch).
     python tools_heatmap_bench.py [--json]"""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -17,13 +19,16 @@ def sweep(batches=(64, 256, 1024, 4096), sizes=(64, 128), iters=5):
     from hgb200._lib import lib, check, ptr, stream_ptr
     K = 17
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    flush2 = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    sink = torch.zeros((), dtype=torch.float32, device="cuda")
     rows = []
 
     def timed(fn):
         fn(); torch.cuda.synchronize()
         tot = 0.0
         for _ in range(iters):
-            flush.fill_(1.0)                      # evict the inputs from L2
+            flush.fill_(1.0)                      # evict the inputs from L2 ...
+            sink.add_(flush2.sum())               # ... and the dirty lines of that write (leaves clean lines behind)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record()
             torch.cuda.synchronize()
