@@ -10,6 +10,7 @@
 //   decode  : utilities/data_utils.py:100-183
 //   PCK     : eval.py:62-88 ; OKS: public COCO keypoint similarity (pycocotools computeOks)
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 #include <math_constants.h>
 
 namespace hgb {
@@ -298,17 +299,22 @@ struct DecLoad<float, 4> {
     const float4 v = __ldcs(reinterpret_cast<const float4*>(p));
     r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
   }
+  static __device__ __forceinline__ void unpack(const uint4& v, float (&r)[4]) {
+    r[0] = __uint_as_float(v.x); r[1] = __uint_as_float(v.y); r[2] = __uint_as_float(v.z); r[3] = __uint_as_float(v.w);
+  }
 };
 template <>
 struct DecLoad<__nv_bfloat16, 8> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&r)[8]) {
-    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p));
+  static __device__ __forceinline__ void unpack(const uint4& v, float (&r)[8]) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       r[2 * i] = __uint_as_float(w[i] << 16);
       r[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
     }
+  }
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&r)[8]) {
+    unpack(__ldcs(reinterpret_cast<const uint4*>(p)), r);
   }
 };
 
@@ -332,70 +338,103 @@ __device__ __forceinline__ unsigned long long decode_key(float v, int idx) {
   return ((unsigned long long)ord << 32) | (unsigned long long)(0xffffffffu - (uint32_t)idx);
 }
 
+// 1-D bulk copy global -> shared memory (TMA engine), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+constexpr int kDecStages = 4;   // bulk copies in flight per CTA
+constexpr int kDecIters = 4;    // 16-byte vectors per thread and chunk
+
 // `split` independent CTAs (16*K threads each) per sample: CTA r scans the r-th contiguous share of the map and merges its
 // per-joint maxima into the sample's keys with one 64-bit atomicMax per joint; the CTA that arrives last (a counter, the
 // threadfence-reduction pattern) finishes the sample: confidence, clipped 3x3 window, outputs.  The keys and the counter
 // live in out_idx itself (words 0-1 of every (sample, joint) row; word 2 of joint 0), zeroed by the launcher, so no
-// workspace is needed.  (One CTA per sample was a single ragged wave at batch 1024 -- every block loading, then every
-// block reducing -- at 0.54 / 0.35 of the HBM peak for f32 / bf16; a thread-block cluster per sample with a DSMEM
-// exchange measured worse still: 4-8 co-scheduled CTAs and two cluster barriers per 35-70 KB of loads.)
-// The vector stride VEC*16*K and the share size are multiples of K, so slot j of thread t always carries joint
-// (VEC*t + j) % K: VEC running (value,index) pairs in registers, no dynamic indexing.  Four independent 16-byte loads
-// are in flight per thread at <= 48 registers: 4 resident CTAs per SM hide each other's reduction phases.
+// workspace is needed.
+// The share is STREAMED THROUGH SHARED MEMORY by the TMA engine: a ring of kDecStages chunks of kDecIters*16*K vectors
+// (17 KB at K = 17), refilled by one thread with cp.async.bulk as soon as a chunk has been consumed.  With register loads
+// the bytes in flight are bounded by the register file (4 loads x 272 threads x 4 CTAs = 70 KB per SM, and none while a
+// CTA compares or reduces): one CTA per sample reached 0.54 / 0.35 of the HBM peak (f32 / bf16) at batch 1024, four
+// register-load CTAs per sample 0.57 / 0.28, a DSMEM cluster per sample less.  The ring keeps ~52 KB per CTA (3 CTAs per
+// SM) in flight regardless of what the threads are doing.
+// The vector stride VEC*16*K, the chunk and the share are multiples of K, so slot j of thread t always carries joint
+// (VEC*t + j) % K: VEC running (value,index) pairs in registers, no dynamic indexing.
 template <typename T, int VEC>
-__global__ void __launch_bounds__(320, VEC == 8 ? 3 : 4) decode_kernel(const T* __restrict__ hm, int H, int W, int K, double thr, int version,
-                                                        int32_t* __restrict__ out_idx, float* __restrict__ out_kp) {
-  extern __shared__ unsigned char s_raw[];
+__global__ void __launch_bounds__(320) decode_kernel(const T* __restrict__ hm, int H, int W, int K, double thr, int version,
+                                                     int32_t* __restrict__ out_idx, float* __restrict__ out_kp) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
   const int S = 16 * K, t = threadIdx.x, b = blockIdx.y;  // blockDim = S rounded up to a warp multiple
   const int split = gridDim.x, rank = blockIdx.x;
-  float* s_val = reinterpret_cast<float*>(s_raw);         // [S*VEC]
+  const int chunk_vec = kDecIters * S;
+  const uint32_t chunk_bytes = (uint32_t)chunk_vec * 16u;
+  const uint32_t ring = ptx::smem_u32(s_raw), bars = ring + kDecStages * chunk_bytes;
+  float* s_val = reinterpret_cast<float*>(s_raw);         // [S*VEC]  (aliases the ring once the share is consumed)
   int* s_idx = reinterpret_cast<int*>(s_raw) + S * VEC;   // [S*VEC]
   __shared__ int s_last;
   const int HWK = H * W * K;
   const int nvec = HWK / VEC / split;                     // vectors of this CTA's share
   const int v0 = rank * nvec;
+  const int nchunks = (nvec + chunk_vec - 1) / chunk_vec;
   const T* base = hm + (size_t)b * HWK;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(out_idx + (size_t)b * K * 4);   // stride 2 per joint
   int* counter = out_idx + (size_t)b * K * 4 + 2;
 
+  auto issue = [&](int c) {      // one thread: chunk c -> ring slot c % kDecStages
+    const int nv = min(chunk_vec, nvec - c * chunk_vec);
+    const uint32_t slot = (uint32_t)(c % kDecStages);
+    ptx::mbar_expect_tx(bars + 8u * slot, (uint32_t)nv * 16u);
+    bulk_load_1d(ring + slot * chunk_bytes, base + (size_t)(v0 + c * chunk_vec) * VEC, (uint32_t)nv * 16u, bars + 8u * slot);
+  };
+  if (t == 0) {
+    for (int i = 0; i < kDecStages; ++i) ptx::mbar_init(bars + 8u * i, 1);
+    ptx::fence_barrier_init();
+    for (int c = 0; c < kDecStages && c < nchunks; ++c) issue(c);
+  }
+  __syncthreads();
+
   float bv[VEC];
   int bi[VEC];
-  constexpr int UNROLL = 4;
   // Fast path: a thread meets the elements of a slot in increasing index order, so "first maximum" is a strict
   // greater-than update (3-4 instructions per element) starting from (-inf, the slot's first index) -- the argmax of an
   // all -inf slot is its first element.  It is exact unless a NaN shows up (numpy: a NaN beats everything); any NaN
-  // re-runs the CTA's share through the exact comparison below.
+  // re-runs the CTA's share through the exact comparison below (from global memory: the rare path).
   int nan_seen = 0;
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { bv[j] = -CUDART_INF_F; bi[j] = t < S ? (v0 + t) * VEC + j : 0x7fffffff; }
-  int v = t < S ? t : nvec;  // the padding threads of the last warp only help in the reduction
-  for (; v + (UNROLL - 1) * S < nvec; v += UNROLL * S) {
-    float r[UNROLL][VEC];
+  for (int c = 0; c < nchunks; ++c) {
+    const uint32_t slot = (uint32_t)(c % kDecStages);
+    ptx::mbar_wait(bars + 8u * slot, (uint32_t)(c / kDecStages) & 1u);
+    const int nv = min(chunk_vec, nvec - c * chunk_vec);
+    if (t < S) {
+      uint4 raw[kDecIters];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) DecLoad<T, VEC>::load(base + (size_t)(v0 + v + u * S) * VEC, r[u]);
+      for (int u = 0; u < kDecIters; ++u) {
+        const int vi = u * S + t;
+        raw[u] = make_uint4(0, 0, 0, 0);
+        if (vi < nv) raw[u] = *reinterpret_cast<const uint4*>(s_raw + slot * chunk_bytes + (size_t)vi * 16);
+      }
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int e0 = (v0 + v + u * S) * VEC;
+      for (int u = 0; u < kDecIters; ++u) {
+        const int vi = u * S + t;
+        if (vi < nv) {
+          float r[VEC];
+          DecLoad<T, VEC>::unpack(raw[u], r);
+          const int e0 = (v0 + c * chunk_vec + vi) * VEC;
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        const bool gt = r[u][j] > bv[j];
-        bv[j] = gt ? r[u][j] : bv[j];
-        bi[j] = gt ? e0 + j : bi[j];
-        nan_seen |= (r[u][j] != r[u][j]);
+          for (int j = 0; j < VEC; ++j) {
+            const bool gt = r[j] > bv[j];
+            bv[j] = gt ? r[j] : bv[j];
+            bi[j] = gt ? e0 + j : bi[j];
+            nan_seen |= (r[j] != r[j]);
+          }
+        }
       }
     }
+    __syncthreads();                                    // the chunk is consumed: its slot can be refilled
+    if (t == 0 && c + kDecStages < nchunks) issue(c + kDecStages);
   }
-  for (; v < nvec; v += S) {
-    float r[VEC];
-    DecLoad<T, VEC>::load(base + (size_t)(v0 + v) * VEC, r);
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const bool gt = r[j] > bv[j];
-      bv[j] = gt ? r[j] : bv[j];
-      bi[j] = gt ? (v0 + v) * VEC + j : bi[j];
-      nan_seen |= (r[j] != r[j]);
-    }
-  }
+  int v;
   if (__syncthreads_or(nan_seen)) {   // block-uniform: exact numpy order (NaN first, then value, then lower index)
 #pragma unroll
     for (int j = 0; j < VEC; ++j) { bv[j] = -CUDART_INF_F; bi[j] = 0x7fffffff; }
@@ -688,14 +727,26 @@ extern "C" int hgb_decode(const void* heatmaps, int dtype, int B, int H, int W, 
   HGB_CHECK_ARG(B <= 65535, "hgb_decode: batch exceeds the grid limit");
   const int threads = (16 * K + 31) / 32 * 32;
   HGB_CHECK_ARG(threads <= 320, "hgb_decode: at most 20 joints per launch configuration");
-  const size_t smem = (size_t)(16 * K) * vec * 8;
+  HGB_CHECK_ARG((((uintptr_t)heatmaps | (uintptr_t)out_idx) & 15) == 0, "hgb_decode: heatmaps / out_idx must be 16-byte aligned");
+  // ring of kDecStages chunks + their mbarriers; the (value, index) staging of the block reduction aliases the ring
+  const size_t ring = (size_t)kDecStages * kDecIters * (16 * K) * 16;
+  HGB_CHECK_ARG(ring >= (size_t)(16 * K) * vec * 8, "hgb_decode: staging does not fit the ring");
+  const size_t smem = ring + kDecStages * 8;
   cudaStream_t st = (cudaStream_t)stream;
-  // CTAs per sample: shares must be a whole number of 16-byte vectors and of pixels (K elements); 8 shares while that is
-  // still less than ~4 waves of the chip, 4 otherwise (hgb_debug_set(24, n) overrides)
+  static bool attr_done = false;
+  if (!attr_done) {
+    HGB_CUDA(cudaFuncSetAttribute(decode_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    HGB_CUDA(cudaFuncSetAttribute(decode_kernel<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_done = true;
+  }
+  HGB_CHECK_ARG(smem <= 100 * 1024, "hgb_decode: too many joints for the shared-memory ring");
+  // CTAs per sample: as few as give ~4 waves of 3 resident CTAs per SM (a whole map per CTA amortises the reduction best);
+  // shares must be a whole number of 16-byte vectors and of pixels (K elements).  hgb_debug_set(24, n) overrides.
   const int64_t nvec = (int64_t)H * W * K / vec;
-  int split = (int64_t)B * 8 <= 148 * 6 * 4 ? 8 : 4;
+  int split = 1;
+  while (split < 8 && (int64_t)B * split < 148 * 3 * 4) split <<= 1;
   if (g_debug[24] > 0) split = g_debug[24];
-  while (split > 1 && (nvec % split != 0 || (nvec / split * vec) % K != 0 || nvec / split < 4 * 16 * K)) split >>= 1;
+  while (split > 1 && (nvec % split != 0 || (nvec / split * vec) % K != 0)) split >>= 1;
   // keys + arrival counters live in out_idx (see decode_kernel)
   HGB_CUDA(cudaMemsetAsync(out_idx, 0, (size_t)B * K * 4 * sizeof(int32_t), st));
   if (dtype == HGB_F32)

@@ -166,6 +166,11 @@ class _Dataset:
             self._default = iter(self)
         return next(self._default)
 
+    def close(self):
+        if self._default is not None and hasattr(self._default, "close"):
+            self._default.close()
+        self._default = None
+
 
 # ------------------------------------------------------------------ prefetch (dataset_builder.py:46,54,65: .prefetch(AUTOTUNE))
 class Prefetcher:
@@ -220,7 +225,9 @@ class Prefetcher:
         if cuda:
             import torch
             torch.cuda.set_device(self._device)
-        stream = torch.cuda.Stream() if cuda else None
+        # highest priority (out-of-range values are clamped): the input kernels are short and must not queue behind the
+        # persistent CTAs of the training step, whose lanes run at raised priorities (csrc/model.cu ensure_lanes)
+        stream = torch.cuda.Stream(priority=-100) if cuda else None
         try:
             with (torch.cuda.stream(stream) if cuda else contextlib.nullcontext()):
                 for item in self._gen:
