@@ -53,7 +53,8 @@ int         hgb_version(void);
  *   14  no deferred BatchNorm (plan build)                             15  HALO tile threshold (default 4 x #SMs)
  *   16  one thread issues all output boxes                             17  no BatchNorm folding in inference
  *   18  PDL trigger at kernel start instead of after the last load     19  PDL also in the multi-lane backward pass
- *   20  CTA cap of side-lane weight gradients (default 64, -1 none)                                                     */
+ *   20  CTA cap of side-lane weight gradients (default 64, -1 none)    24  CTAs per sample in the decode kernel
+ *   25  N = 256 GEMM tiles always with 8 epilogue warps                26  no BatchNorm-backward fusion into 1x1 dgrads (plan build) */
 int         hgb_debug_set(int key, int value);
 
 /* ------------------------------------------------------------------------- */
@@ -285,6 +286,10 @@ int hgb_model_conv_input_bn(const hgb_model* m, int conv);
 int hgb_model_num_ops(const hgb_model* m, int seg, int backward);
 int hgb_model_op_info(const hgb_model* m, int seg, int backward, int index, int info[8]);
 int hgb_model_act_info(const hgb_model* m, int act, int64_t* arena_offset, int dims[4]);
+/* 1x1 B_DGRAD ops that carry the BatchNorm backward of their input gradient (the stand-alone bn_bwd_apply pass is fused into
+ * the GEMM's operand prologue: dz and y in, dp computed in shared memory, fed to the MMAs and stored for the weight gradient):
+ * out = {BatchNorm index, dz tensor, y tensor}; the dp tensor is the op's a0.  {-1,-1,-1} for every other op. */
+int hgb_model_op_fused_bn(const hgb_model* m, int seg, int backward, int index, int out[3]);
 int hgb_model_run_op(hgb_model* m, int seg, int backward, int index, const float* images, int training, void* stream);
 int hgb_model_conv_detail(const hgb_model* m, int conv, int info[8], int64_t offs[2]);
 int hgb_model_bn_detail(const hgb_model* m, int bn, int64_t offs[8]);
@@ -303,6 +308,7 @@ int hgb_model_profile_read(hgb_model* m, double* total_ms, int* launches, double
 int hgb_model_profile_all(hgb_model* m, int enable);
 int hgb_model_profile_count(const hgb_model* m);
 int hgb_model_profile_op(hgb_model* m, int i, int info[8], double* ms);
+int hgb_model_profile_op_fused(hgb_model* m, int i, int out[3]);   /* see hgb_model_op_fused_bn */
 
 /* Execution lanes.  Forward and backward run as a static schedule over several CUDA streams owned by the
  * handle (the skip bottleneck of every hourglass level beside the deeper sub-hourglass, weight gradients

@@ -81,6 +81,7 @@ PROTOTYPES = {
     "hgb_model_num_ops": (i32, [vp, i32, i32]),
     "hgb_model_op_info": (i32, [vp, i32, i32, i32, C.POINTER(i32 * 8)]),
     "hgb_model_act_info": (i32, [vp, i32, C.POINTER(i64), C.POINTER(i32 * 4)]),
+    "hgb_model_op_fused_bn": (i32, [vp, i32, i32, i32, C.POINTER(i32 * 3)]),
     "hgb_model_run_op": (i32, [vp, i32, i32, i32, vp, i32, vp]),
     "hgb_model_conv_detail": (i32, [vp, i32, C.POINTER(i32 * 8), C.POINTER(i64 * 2)]),
     "hgb_model_bn_detail": (i32, [vp, i32, C.POINTER(i64 * 8)]),
@@ -91,6 +92,7 @@ PROTOTYPES = {
     "hgb_model_profile_all": (i32, [vp, i32]),
     "hgb_model_profile_count": (i32, [vp]),
     "hgb_model_profile_op": (i32, [vp, i32, C.POINTER(i32 * 8), C.POINTER(f64)]),
+    "hgb_model_profile_op_fused": (i32, [vp, i32, C.POINTER(i32 * 3)]),
     "hgb_model_sched_count": (i32, [vp, i32]),
     "hgb_model_sched_op": (i32, [vp, i32, i32, C.POINTER(i32 * 4), C.POINTER(i32), C.POINTER(i32 * 16)]),
     "hgb_model_sched_access": (i32, [vp, i32, i32, i32, C.POINTER(i64)]),

@@ -53,6 +53,7 @@ struct GemmKernelParams {
   int res1_tma;               // res1 is fetched by TMA (tmR) into the staging buffer
   BnInput bn_in;              // gamma != null: normalise the A tile in shared memory before the MMAs read it
   BnInput bn_out;             // gamma != null (inference): scale/shift of the BatchNorm that follows, applied in the epilogue
+  BnBwdInput bn_bwd;          // gamma != null (BNB kernels): the A operand is BatchNorm-backward(dz, y), computed in shared memory
   int single_store;           // debug: one thread issues all output boxes (hgb_debug_set(16, 1))
   int late_trigger;           // programmatic dependent launch is released after the producer's last load
 };
@@ -145,6 +146,61 @@ __device__ __forceinline__ void bn_input_transform_box(uint32_t box, const float
   }
 }
 
+// Three coefficients per channel of the fused BatchNorm backward (same algebra as bn_bwd_apply_kernel):
+// dp = [y > 0] * (A*dz + B*y + C).  CTA 0 also writes dgamma / dbeta.
+__device__ __forceinline__ void bn_bwd_setup(const BnBwdInput& b, float* s_cA, float* s_cB, float* s_cC, int tid, int nthreads,
+                                             bool writer) {
+  const float invM = 1.f / (float)b.M_stat;
+  for (int c = tid; c < b.C; c += nthreads) {
+    const float mean = b.saved[c], rstd = b.saved[b.C + c];
+    const float sdz = b.bsums[c];
+    const float sdzx = rstd * (b.bsums[b.C + c] - mean * sdz);   // sum dz * xhat
+    const float a = b.gamma[c] * rstd;
+    const float k = a * rstd * (sdzx * invM);
+    s_cA[c] = a;
+    s_cB[c] = -k;
+    s_cC[c] = k * mean - a * (sdz * invM);
+    if (writer) {
+      b.dgamma[c] = sdzx * b.pscale;
+      b.dbeta[c] = sdz * b.pscale;
+    }
+  }
+}
+
+// dp = bf16([y > 0] * fma(A, dz, fma(B, y, C))) on one 128-pixel x 64-channel swizzled box pair (dz box rewritten in place,
+// y box read), by the 64 transform threads; acc += the values as rounded (bias gradient), packed fp32 pairs.
+__device__ __forceinline__ void bn_bwd_transform_box(uint32_t box_dz, uint32_t box_y, const float* s_cA, const float* s_cB,
+                                                     const float* s_cC, int ch0, int tw, uint64_t (&acc)[4]) {
+  const uint32_t c = (uint32_t)tw & 7u, r0 = (uint32_t)tw >> 3;          // chunk position, first row (0..7)
+  const int ch = ch0 + (int)((c ^ (r0 & 7u)) << 3);
+  uint64_t cA[4], cB[4], cC[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    cA[k] = pack_f32x2(__float_as_uint(s_cA[ch + 2 * k]), __float_as_uint(s_cA[ch + 2 * k + 1]));
+    cB[k] = pack_f32x2(__float_as_uint(s_cB[ch + 2 * k]), __float_as_uint(s_cB[ch + 2 * k + 1]));
+    cC[k] = pack_f32x2(__float_as_uint(s_cC[ch + 2 * k]), __float_as_uint(s_cC[ch + 2 * k + 1]));
+  }
+#pragma unroll 4
+  for (int j = 0; j < 16; ++j) {
+    const uint32_t off = (r0 + 8u * (uint32_t)j) * 128u + (c << 4);
+    uint32_t d[4], y[4], w[4];
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(box_dz + off));
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(y[0]), "=r"(y[1]), "=r"(y[2]), "=r"(y[3]) : "r"(box_y + off));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t d2 = pack_f32x2(d[k] << 16, d[k] & 0xffff0000u);
+      const uint64_t y2 = pack_f32x2(y[k] << 16, y[k] & 0xffff0000u);
+      const uint32_t t = cvt_bf16x2(fma_f32x2(cA[k], d2, fma_f32x2(cB[k], y2, cC[k])), false);
+      // ReLU sits between the conv and the BN (hourglass.py:196-201): the gradient passes where y > 0
+      const __nv_bfloat162 yb = *reinterpret_cast<const __nv_bfloat162*>(&y[k]);
+      const uint32_t m = __hgt2_mask(yb, __float2bfloat162_rn(0.f));
+      w[k] = t & m;
+      acc[k] = add_f32x2(acc[k], pack_f32x2(w[k] << 16, w[k] & 0xffff0000u));
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box_dz + off), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+  }
+}
+
 // Persistent: grid = min(#tile groups, #SMs); CTA i handles groups i, i+grid, ...  The TMA producer runs
 // ahead across group boundaries; the output tile is staged in swizzled smem and written with TMA bulk stores.
 //   TILES == 1: one 128-pixel tile per group, two TMEM accumulator stages (the MMAs of the next tile overlap
@@ -163,15 +219,22 @@ __device__ __forceinline__ void bn_input_transform_box(uint32_t box, const float
 //               HBM-bound 1x1 layers: their epilogue (TMEM drain, bias / ReLU / residual, staging, BatchNorm statistics:
 //               ~700 instructions per thread per tile) ran at IPC 0.3 per scheduler with two warps each and took 2.85 us
 //               per tile against 2.2 us of HBM time; four warps per scheduler hide the TMEM / shared-memory round trips.
-template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false, int EPI = 8>
+//   BNB        : 1x1 dgrad with the BatchNorm backward of its input gradient fused in (BnBwdInput): every stage carries
+//               the dz box and the y box; the transform warps turn the dz box into dp in place, hand it to the MMAs, and
+//               one of them stores it through tmDP (the weight gradient reads dp later).  A stage is recycled once the
+//               MMAs AND that bulk store have read it (empty barrier count 2).
+template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false, int EPI = 8, bool BNB = false>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ CUtensorMap tmC,
                                                                 const __grid_constant__ CUtensorMap tmR,
                                                                 const __grid_constant__ CUtensorMap tmY,
+                                                                const __grid_constant__ CUtensorMap tmZ,
+                                                                const __grid_constant__ CUtensorMap tmDP,
                                                                 const GemmKernelParams p) {
   constexpr int kBBytes = BLOCK_N * 128;
-  constexpr int kStageBytes = TILES * kABytes + kBBytes;
+  constexpr int kStageBytes = TILES * kABytes + kBBytes + (BNB ? kABytes : 0);   // BNB: + the y box behind the weights
+  static_assert(!BNB || (TILES == 1 && !HALO), "the fused BatchNorm backward is a 1x1 dgrad variant");
   constexpr int kAccStages = TILES == 1 ? 2 : 1;
   constexpr int kGemmThreads = gemm_threads(EPI), kEpiThreads = 32 * EPI;
   static_assert(EPI == 8 || EPI == 16, "two or four epilogue warps per TMEM lane quarter");
@@ -196,8 +259,13 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
   float* s_sc = s_bias + BLOCK_N;                             // [256] scale / [256] shift of a deferred input BatchNorm
   float* s_sh = s_sc + 256;
   float* s_osc = s_sh + 256;                                  // [256] / [256]: inference BatchNorm of the OUTPUT (epilogue)
-  float* s_osh = s_osc + 256;
-  float* s_stats = reinterpret_cast<float*>(smem);            // [row groups][2*BLOCK_N] = 16 KB, aliases pipeline stage 0: used only after the last tile
+  float* s_osh = s_osc + 256;                                 // (BNB: s_sc | s_sh | s_osc hold the coefficients A | B | C)
+  float* s_part = s_osh + 256;                                // BNB only: [8 row phases][4 channel blocks][64] bias-gradient partials
+  // [row groups][2*BLOCK_N] = 16 KB (32 KB with 16 epilogue warps), aliases pipeline stage 0: used only after the last tile.
+  // BNB: the y box of stage 0 (read by the transform warps only, long before the last accumulator is complete) -- the dz / dp
+  // box may still be being read by the last dp bulk store
+  float* s_stats = reinterpret_cast<float*>(smem + (BNB ? kABytes + kBBytes : 0));
+  static_assert(!BNB || EPI == 8, "the y box holds the 16 KB statistics scratch of 8 epilogue warps");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (p.M_total + kBlockM - 1) / kBlockM;
@@ -214,13 +282,14 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
     prefetch_tmap(&tmC);
     if (p.res1_tma) prefetch_tmap(&tmR);
     if (p.bn_y) prefetch_tmap(&tmY);
+    if (BNB) { prefetch_tmap(&tmZ); prefetch_tmap(&tmDP); }
     if (HALO) {
       for (int s = 0; s < kNumBars; ++s) {
         const bool tmem_empty = s >= 2 * kASlots + 2 * kBSlots + TILES && s < kNumBars - 1;
         mbar_init(bar0 + 8 * s, tmem_empty ? EPI : 1);
       }
     } else {
-      for (int s = 0; s < 2 * STAGES + 2; ++s) mbar_init(bar0 + 8 * s, 1);
+      for (int s = 0; s < 2 * STAGES + 2; ++s) mbar_init(bar0 + 8 * s, (BNB && s >= STAGES && s < 2 * STAGES) ? 2 : 1);   // BNB: empty = MMAs + dp store
       mbar_init(bar0 + 8 * (2 * STAGES + 2), EPI);  // tmem_empty: one arrival per epilogue warp
       mbar_init(bar0 + 8 * (2 * STAGES + 3), EPI);
       for (int s = 0; s < STAGES; ++s) mbar_init(bar0 + 8 * (2 * STAGES + 4 + s), 2);  // ready: two transform warps
@@ -235,10 +304,11 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
   if (threadIdx.x == 0) KT(1);
   pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
   if (threadIdx.x == 0) KT(2);
-  const bool xform = !HALO && TILES == 1 && p.bn_in.gamma != nullptr;
+  const bool xform = !BNB && !HALO && TILES == 1 && p.bn_in.gamma != nullptr;
   if (xform) bn_input_setup(p.bn_in, s_sc, s_sh, threadIdx.x, kGemmThreads, blockIdx.x == 0 && p.bn_in.write != 0);
-  const bool post_bn = !HALO && TILES == 1 && p.bn_out.gamma != nullptr;
+  const bool post_bn = !BNB && !HALO && TILES == 1 && p.bn_out.gamma != nullptr;
   if (post_bn) bn_input_setup(p.bn_out, s_osc, s_osh, threadIdx.x, kGemmThreads, false);
+  if (BNB) bn_bwd_setup(p.bn_bwd, s_sc, s_sh, s_osc, threadIdx.x, kGemmThreads, blockIdx.x == 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -353,6 +423,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
 #pragma unroll
           for (int t = 0; t < TILES; ++t)
             tma_load_4d(sa + t * kABytes, &tmA, full0 + 8 * s, cb * 64, dx, y0[t] + dy, n0[t]);
+          if (BNB) tma_load_4d(sa + kABytes + kBBytes, &tmZ, full0 + 8 * s, cb * 64, 0, y0[0], n0[0]);
         }
       }
     }
@@ -372,7 +443,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
         for (int kb = 0; kb < p.nkb; ++kb, ++kbt) {
           const int s = kbt % STAGES;
           const uint32_t ph = (kbt / STAGES) & 1;
-          mbar_wait((xform ? ready0 : full0) + 8 * s, ph);
+          mbar_wait(((xform || BNB) ? ready0 : full0) + 8 * s, ph);
           tc_fence_after();
           if (kbt == 0) KT(4);
           const uint32_t sa = base + s * kStageBytes;
@@ -396,7 +467,56 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
     // 128-pixel x 64-channel box of a stage, z = bf16(y * scale + shift) is applied in place; the MMA warp waits
     // for `ready` instead of `full`.  Zero-filled rows past the end of the tensor become `shift`: they only reach
     // accumulator rows that the store clips and the statistics skip.
-    if (xform) {
+    if constexpr (BNB) {
+      // fused BatchNorm backward: dz box (+ y box) -> dp box, in place; MMAs and the dp store read it from there
+      const int tw = threadIdx.x - 64;
+      uint64_t acc[4][4];          // [channel block][packed pair]: bias-gradient partial sums of this thread's 8 channels
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[i][k] = 0ull;
+      int kbt = 0, pend = -1;      // pend: stage whose dp store was issued last; its smem read is awaited one box later
+      for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
+        const int p0 = grp * kBlockM;
+        const int n0 = p0 / p.HW;
+        const int y0 = (p0 - n0 * p.HW) / p.W;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {          // 1x1: one k-block per 64-channel block, at most 4 (static acc index)
+          if (kb >= p.nkb) break;
+          const int s = kbt % STAGES;
+          mbar_wait(full0 + 8 * s, (kbt / STAGES) & 1);
+          const uint32_t sa = base + s * kStageBytes;
+          bn_bwd_transform_box(sa, sa + kABytes + kBBytes, s_sc, s_sh, s_osc, kb * 64, tw, acc[kb]);
+          fence_proxy_async();   // generic-proxy writes -> visible to the tensor core and to the bulk store
+          asm volatile("bar.sync 2, 64;" ::: "memory");   // both transform warps are done with the box
+          if (lane == 0) mbar_arrive(ready0 + 8 * s);
+          if (tw == 0) {
+            tma_store_4d(&tmDP, sa, kb * 64, 0, y0, n0);
+            tma_store_commit();
+            if (pend >= 0) { tma_store_wait_read1(); mbar_arrive(empty0 + 8 * pend); }
+            pend = s;
+          }
+          ++kbt;
+        }
+      }
+      if (tw == 0 && pend >= 0) { tma_store_wait_read(); mbar_arrive(empty0 + 8 * pend); }
+      // bias gradient: park the partials by (row phase, channel block), one thread per channel adds the 8 row phases up
+      const uint32_t cpos = (uint32_t)tw & 7u, r0 = (uint32_t)tw >> 3;
+      const int lch = (int)((cpos ^ r0) << 3);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float* d = s_part + ((int)r0 * 4 + i) * 64 + lch;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) unpack_f32x2(acc[i][k], d[2 * k], d[2 * k + 1]);
+      }
+      asm volatile("bar.sync 2, 64;" ::: "memory");
+      for (int i = tw; i < p.cblk * 64 && i < p.bn_bwd.C; i += 64) {
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += s_part[(r * 4 + (i >> 6)) * 64 + (i & 63)];
+        atomicAdd(p.bn_bwd.dbias + i, t);
+      }
+    } else if (xform) {
       const int tw = threadIdx.x - 64;
       int kbt = 0;
       for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
@@ -1145,18 +1265,20 @@ int conv_gemm_block_n(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 
 
 static int g_num_sms = 0;
 
-template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false, int EPI = 8>
+template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false, int EPI = 8, bool BNB = false>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
-                         const CUtensorMap& tmY, const GemmKernelParams& kp, int tiles_m, int max_ctas, cudaStream_t st) {
-  constexpr int ring = HALO ? (TILES + 1) * kABytes + 6 * BLOCK_N * 128 : STAGES * (TILES * kABytes + BLOCK_N * 128);
+                         const CUtensorMap& tmY, const GemmKernelParams& kp, int tiles_m, int max_ctas, cudaStream_t st,
+                         const CUtensorMap* tmZ = nullptr, const CUtensorMap* tmDP = nullptr) {
+  constexpr int ring = HALO ? (TILES + 1) * kABytes + 6 * BLOCK_N * 128
+                            : STAGES * (TILES * kABytes + BLOCK_N * 128 + (BNB ? kABytes : 0));
   constexpr int nbars = HALO ? 2 * (TILES + 1) + 12 + 2 * TILES + 1 : 3 * STAGES + 5;
   constexpr int smem = ring + OUT_BUFS * (BLOCK_N / 64) * kABytes + (nbars * 8 + 15) / 16 * 16 + 16 + BLOCK_N * 4 +
-                       (TILES == 1 ? 4 * 256 * 4 : 0) + 1024;   // input / output BatchNorm scale+shift only for the 1x1 variants
+                       (TILES == 1 ? 4 * 256 * 4 : 0) + (BNB ? 8 * 4 * 64 * 4 : 0) + 1024;   // BatchNorm scale+shift tables only for the 1x1 variants
   static_assert(ring >= (EPI == 16 ? 32 : 16) * 1024, "stats scratch (16 / 32 KB) aliases the pipeline stages");
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    HGB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS, HALO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HGB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS, HALO, EPI, BNB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
   if (!g_num_sms) {
@@ -1167,13 +1289,20 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   const int groups = (tiles_m + TILES - 1) / TILES;
   int grid = groups < g_num_sms ? groups : g_num_sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  HGB_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS, HALO, EPI>, dim3(grid), dim3(gemm_threads(EPI)), smem, st, tmA, tmB, tmC, tmR, tmY, kp));
+  HGB_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS, HALO, EPI, BNB>, dim3(grid), dim3(gemm_threads(EPI)), smem, st, tmA, tmB,
+                      tmC, tmR, tmY, tmZ ? *tmZ : tmC, tmDP ? *tmDP : tmC, kp));
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
 
+bool conv_gemm_supports_bn_bwd(int ksize, int Cin, int Cout) {
+  // Cin = channels of dz / y / dp (K of the dgrad GEMM, at most 4 blocks of 64), Cout = the dgrad's output channels
+  return ksize == 1 && Cin % 64 == 0 && Cin <= 256 && (Cout == 128 || Cout == 256);
+}
+
 int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap* tmR,
-                     const CUtensorMap* tmY, const ConvGemmArgs& a, cudaStream_t st) {
+                     const CUtensorMap* tmY, const ConvGemmArgs& a, cudaStream_t st, const CUtensorMap* tmZ,
+                     const CUtensorMap* tmDP) {
   HGB_CHECK_ARG(a.ksize == 1 || a.ksize == 3, "conv_gemm: kernel size must be 1 or 3");
   HGB_CHECK_ARG(a.Cin % 64 == 0 && a.Cin > 0, "conv_gemm: Cin must be a multiple of 64 (got %d)", a.Cin);
   HGB_CHECK_ARG(a.Cout % 64 == 0 && a.Cout > 0, "conv_gemm: Cout must be a multiple of 64 (got %d)", a.Cout);
@@ -1196,6 +1325,10 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   kp.single_store = g_debug[16];
   kp.late_trigger = !g_debug[18];   // default on: forward pass at batch 32 9.55 -> 8.93 ms (hgb_debug_set(18, 1) = trigger at kernel start)
   kp.bn_out = a.bn_out;
+  kp.bn_bwd = a.bn_bwd;
+  HGB_CHECK_ARG(a.bn_bwd.gamma == nullptr || (conv_gemm_supports_bn_bwd(a.ksize, a.Cin, a.Cout) && a.bn_bwd.C == a.Cin && tmZ && tmDP &&
+                                              a.bn_in.gamma == nullptr && a.bn_out.gamma == nullptr),
+                "conv_gemm: the fused BatchNorm backward needs a 1x1 dgrad with <= 256 input and 128 / 256 output channels");
   HGB_CHECK_ARG(a.bn_out.gamma == nullptr || (a.ksize == 1 && a.bn_out.C == a.Cout && a.Cout <= 256 && a.bn_out.mode == 1),
                 "conv_gemm: an output BatchNorm needs a 1x1 convolution with Cout <= 256 in inference mode");
   HGB_CHECK_ARG(a.bn_in.gamma == nullptr || (a.ksize == 1 && a.bn_in.C == a.Cin && a.Cin <= 256),
@@ -1220,15 +1353,21 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   const int halo_min = g_debug[15] > 0 ? g_debug[15] : 4 * g_num_sms;
   const bool halo = kp.tap3 && !g_debug[5] && tiles_m >= halo_min && !g_debug[12] && a.W <= 64 && rpt >= 2 &&
                     a.H % (4 * rpt) == 0 && a.Cout == 128;
+  if (a.bn_bwd.gamma) {   // 1x1 dgrad with the BatchNorm backward fused in
+    if (a.Cout == 128) return launch_gemm_t<128, 3, 1, 2, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
+    return launch_gemm_t<256, 2, 1, 1, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
+  }
   if (halo) return launch_gemm_t<128, 1, 4, 1, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
   switch (conv_gemm_block_n(a.Cout)) {
     case 64: return ws ? launch_gemm_t<64, 2, 4, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
                        : launch_gemm_t<64, 6, 1, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
     case 128: return ws ? launch_gemm_t<128, 2, 4, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
                         : launch_gemm_t<128, 4, 1, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
-    default:   // 64 KB staging: single.  16 epilogue warps (hgb_debug_set(25, 1): the 8-warp variant)
-      return g_debug[25] ? launch_gemm_t<256, 3, 1, 1>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
-                         : launch_gemm_t<256, 3, 1, 1, false, 16>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
+    default:   // 64 KB staging: single.  16 epilogue warps only where they measured faster (A/B on B200, batch 256 @64x64:
+      // dgrad with TMA residual + BatchNorm statistics 382 vs 399 us; plain forward tiles 171 vs 167 us: those are bound
+      // by shared-memory traffic -- 448 KB per tile -- not by epilogue issue slots).  hgb_debug_set(25, 1) = always 8.
+      return (g_debug[25] || !(kp.res1_tma && a.bn_y)) ? launch_gemm_t<256, 3, 1, 1>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
+                                                       : launch_gemm_t<256, 3, 1, 1, false, 16>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
   }
 }
 

@@ -32,6 +32,23 @@ struct BnInput {
   int write = 0, M = 0, C = 0;
 };
 
+// BatchNorm BACKWARD applied to the A operand of a 1x1 dgrad inside the kernel (fused bn_bwd_apply): the kernel loads the
+// dz tile and the y tile of the BatchNorm that follows the convolution, computes
+//     dp = [y > 0] * (A*dz + B*y + C)          (the three-coefficient form of layer_kernels.cu, bit-identical)
+// in shared memory, feeds it to the MMAs, stores it (the weight gradient reads it) and accumulates the bias gradient.
+// One read of dp and one launch disappear per BatchNorm (the stand-alone pass moved r dz + r y + w dp, the GEMM r dp).
+struct BnBwdInput {
+  const float* bsums = nullptr;   // [2C] sum dz, sum dz*y
+  const float* saved = nullptr;   // [2C] mean, rstd
+  const float* gamma = nullptr;   // non-null enables the fusion
+  float* dgamma = nullptr;        // [C] written by CTA 0
+  float* dbeta = nullptr;
+  float* dbias = nullptr;         // [C] += column sums of dp (as rounded to bf16)
+  int M_stat = 0;                 // rows behind the sums (global batch under sync-BN)
+  float pscale = 1.f;             // 1 / ranks under sync-BN (dgamma / dbeta are identical on every rank)
+  int C = 0;
+};
+
 struct ConvGemmArgs {
   int N, H, W, Cin, Cout;   // Cout = channels actually stored (multiple of 32)
   int ksize;                // 1 or 3
@@ -47,14 +64,19 @@ struct ConvGemmArgs {
   int max_ctas = 0;         // > 0: cap of the persistent grid (side lanes leave SMs to the main chain)
   BnInput bn_in;            // 1x1 only
   BnInput bn_out;           // 1x1 only, inference: out = BN(relu(conv + bias)) (+ residuals) straight from the accumulator
+  BnBwdInput bn_bwd;        // 1x1 dgrad only: the input map (tmA) is dz; tmZ = y of that BatchNorm, tmDP = where dp is stored
 };
 // tmA: activation map of the input; tmB: weight matrix [>=Cout rows][ksize^2*Cin], box rows = block_n
 int conv_gemm_block_n(int Cout);
 // tmC: activation map of the output tensor (the epilogue writes the tile with TMA bulk stores)
 // tmR: activation map of res1 (or null): the residual tile is then fetched by TMA into the staging buffer
 // tmY: activation map of bn_y (or null): used to prefetch its tiles into L2 ahead of the statistics pass
+// tmZ / tmDP: activation maps of the BatchNorm's y tensor and of the dp tensor when a.bn_bwd is enabled (else null)
 int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap* tmR,
-                     const CUtensorMap* tmY, const ConvGemmArgs& a, cudaStream_t st);
+                     const CUtensorMap* tmY, const ConvGemmArgs& a, cudaStream_t st, const CUtensorMap* tmZ = nullptr,
+                     const CUtensorMap* tmDP = nullptr);
+// whether launch_conv_gemm can run the fused BatchNorm-backward prologue for this shape
+bool conv_gemm_supports_bn_bwd(int ksize, int Cin, int Cout);
 
 struct WgradArgs {
   int N, H, W, Cin, Cout;

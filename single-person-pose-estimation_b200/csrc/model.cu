@@ -79,6 +79,9 @@ struct Op {
   int a0 = -1, a1 = -1, a2 = -1, a3 = -1;
   int flag = 0;
   int lane = -1;   // execution lane (CUDA stream); -1 = the lane current at emission
+  // B_DGRAD with the BatchNorm backward of its input gradient fused in (the stand-alone B_BN_APPLY is gone): the GEMM
+  // reads dz = act fz and y = act fy of BatchNorm fbn, computes dp in shared memory and stores it into a0
+  int fbn = -1, fz = -1, fy = -1;
 };
 
 // Execution lanes.  The hourglass is not a chain: the skip ("short") bottleneck of every level is independent
@@ -610,6 +613,33 @@ int build(hgb_model* m) {
       ops.swap(out);
     }
   }
+  // fuse each BatchNorm-backward apply into the 1x1 dgrad GEMM that consumes its dp (APPLY, DGRAD adjacent in the list;
+  // the weight gradient, which also reads dp, comes after the dgrad): the GEMM's transform warps compute dp from dz and y in
+  // shared memory and store it on the side, so the stand-alone pass (r dz, r y, w dp) and the GEMM's own read of dp
+  // collapse into r dz, r y, w dp.  3x3 dgrads (strip reuse) and the front module's projected-skip blocks keep the pass.
+  if (cfg.training && !hgb::g_debug[26]) {
+    for (auto& ops : m->bwd_ops) {
+      std::vector<Op> out;
+      for (size_t i = 0; i < ops.size(); ++i) {
+        const Op& o = ops[i];
+        if (o.type == B_BN_APPLY && i + 1 < ops.size()) {
+          const Op& d = ops[i + 1];
+          const ConvL& c = m->convs[o.conv];
+          if (d.type == B_DGRAD && d.conv == o.conv && d.a0 == o.a2 && d.lane == o.lane && d.fbn < 0 &&
+              conv_gemm_supports_bn_bwd(c.ksize, c.cout_pad, c.cin_pad) && c.cout_pad == m->bns[o.bn].c &&
+              m->acts[o.a0].off != m->acts[o.a2].off) {
+            Op f = d;
+            f.fbn = o.bn; f.fz = o.a0; f.fy = o.a1;
+            out.push_back(f);
+            ++i;
+            continue;
+          }
+        }
+        out.push_back(o);
+      }
+      ops.swap(out);
+    }
+  }
   // relocate the non-trainable parameters behind the trainable region
   for (auto& p : m->params)
     if (!p.trainable) p.off += m->train_floats;
@@ -681,6 +711,15 @@ void op_access(const hgb_model* m, const Op& o, std::vector<Range>& r, std::vect
     }
     case B_DGRAD:
       add_act(m, r, o.a0); add_act(m, r, o.a2); add_act(m, r, o.a3); add_act(m, w, o.a1);
+      if (o.fbn >= 0) {   // fused BatchNorm backward: dz and y in, dp (a0) out, plus everything B_BN_APPLY touches
+        const BNL& b = m->bns[o.fbn];
+        add_act(m, r, o.fz); add_act(m, r, o.fy); add_act(m, w, o.a0);
+        add_arena(r, b.bsums_off, 2 * (size_t)b.c * 4);
+        add_arena(w, b.bsums_off, 2 * (size_t)b.c * 4);        // (sync-BN all-reduces them in place)
+        add_arena(r, b.saved_off, 2 * (size_t)b.c * 4);
+        add_grad(w, b.gamma_off, b.c); add_grad(w, b.beta_off, b.c);
+        add_grad(w, m->convs[o.conv].b_off, m->convs[o.conv].cout);
+      }
       if (o.bn >= 0) {
         add_act(m, r, o.flag - 1);
         add_arena(w, m->bns[o.bn].bsums_off, 2 * (size_t)m->bns[o.bn].c * 4);
@@ -946,6 +985,20 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
       a.stats = o.bn >= 0 ? arena_f(m, m->bns[o.bn].bsums_off) : nullptr;
       a.bn_y = o.bn >= 0 ? act_ptr(m, o.flag - 1) : nullptr;
       a.max_ctas = side_lane_ctas(m, o);
+      if (o.fbn >= 0) {   // BatchNorm backward fused into the operand prologue: the input map is dz, dp is stored on the side
+        const BNL& b = m->bns[o.fbn];
+        if (m->stat_ranks() > 1) {   // sync-BN: global sums of dz and dz*y (see B_BN_APPLY)
+          rc = comm_allreduce_sum_f32(m->comm, arena_f(m, b.bsums_off), 2 * b.c, st);
+          if (rc) break;
+        }
+        a.bn_bwd.bsums = arena_f(m, b.bsums_off); a.bn_bwd.saved = arena_f(m, b.saved_off);
+        a.bn_bwd.gamma = m->p_params + b.gamma_off;
+        a.bn_bwd.dgamma = m->p_grads + b.gamma_off; a.bn_bwd.dbeta = m->p_grads + b.beta_off; a.bn_bwd.dbias = m->p_grads + c.b_off;
+        a.bn_bwd.M_stat = dp.n * dp.h * dp.w * m->stat_ranks(); a.bn_bwd.pscale = 1.f / (float)m->stat_ranks(); a.bn_bwd.C = b.c;
+        rc = launch_conv_gemm(m->acts[o.fz].tmap, c.tm_wd, out.tmap, o.a2 >= 0 ? &m->acts[o.a2].tmap : nullptr,
+                              o.bn >= 0 ? &m->acts[o.flag - 1].tmap : nullptr, a, st, &m->acts[o.fy].tmap, &dp.tmap);
+        break;
+      }
       rc = launch_conv_gemm(dp.tmap, c.tm_wd, out.tmap, o.a2 >= 0 ? &m->acts[o.a2].tmap : nullptr,
                             o.bn >= 0 ? &m->acts[o.flag - 1].tmap : nullptr, a, st);
       break;
@@ -1352,6 +1405,15 @@ extern "C" int hgb_model_op_info(const hgb_model* m, int seg, int backward, int 
   info[7] = o.flag;
   return HGB_OK;
 }
+// B_DGRAD ops with the BatchNorm backward fused in: out = {BatchNorm index, dz act, y act} (the dp tensor is the op's a0), or
+// {-1, -1, -1} for every other op
+extern "C" int hgb_model_op_fused_bn(const hgb_model* m, int seg, int backward, int index, int out[3]) {
+  HGB_CHECK_ARG(seg >= 0 && seg <= m->S, "hgb_model_op_fused_bn: bad segment");
+  const std::vector<Op>& v = backward ? m->bwd_ops[seg] : m->fwd_ops[seg];
+  HGB_CHECK_ARG(index >= 0 && index < (int)v.size(), "hgb_model_op_fused_bn: index out of range");
+  out[0] = v[index].fbn; out[1] = v[index].fz; out[2] = v[index].fy;
+  return HGB_OK;
+}
 extern "C" int hgb_model_act_info(const hgb_model* m, int act, int64_t* arena_offset, int dims[4]) {
   HGB_CHECK_ARG(act >= 0 && act < (int)m->acts.size(), "hgb_model_act_info: index out of range");
   const Act& a = m->acts[act];
@@ -1459,6 +1521,13 @@ extern "C" int hgb_model_profile_op(hgb_model* m, int i, int info[8], double* ms
   float t = 0;
   HGB_CUDA(cudaEventElapsedTime(&t, m->prof_ev[2 * i], m->prof_ev[2 * i + 1]));
   *ms = t;
+  return HGB_OK;
+}
+
+// {BatchNorm, dz act, y act} of profiled op i when it is a dgrad with the BatchNorm backward fused in, else -1s
+extern "C" int hgb_model_profile_op_fused(hgb_model* m, int i, int out[3]) {
+  HGB_CHECK_ARG(i >= 0 && i < (int)m->prof_ops.size(), "hgb_model_profile_op_fused: index");
+  out[0] = m->prof_ops[i].fbn; out[1] = m->prof_ops[i].fz; out[2] = m->prof_ops[i].fy;
   return HGB_OK;
 }
 

@@ -197,6 +197,10 @@ class Prefetcher:
             pass
         self._thread = threading.Thread(target=self._run, name="hgb200-prefetch", daemon=True)
         self._thread.start()
+        import atexit
+        import weakref
+        ref = weakref.ref(self)
+        atexit.register(lambda: ref() is not None and ref().close())
 
     @staticmethod
     def _tensors(item):
@@ -264,8 +268,23 @@ class Prefetcher:
         return item
 
     def close(self):
+        """Stop the worker and wait for it: a daemon thread killed inside the decoder at interpreter exit would take the
+        process down with it."""
         self._stop = True
         self._done = True
+        try:
+            while True:
+                self._q.get_nowait()          # unblock a worker waiting for queue space
+        except Exception:
+            pass
+        if self._thread.is_alive() and self._thread is not __import__("threading").current_thread():
+            self._thread.join(timeout=10.0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def __del__(self):
         self._stop = True

@@ -28,7 +28,7 @@ class PlanInfo:
         lib.hgb_model_conv_detail(self.h, i, C.byref(self._cinfo), C.byref(self._coffs))
         return dict(zip(("ksize", "taps", "cin", "cout", "cin_pad", "cout_pad", "relu", "has_dgrad"), self._cinfo))
 
-    def classify(self, info):
+    def classify(self, info, fused_bn=False):
         """info = the 8 ints of hgb_model_op_info -> (class key, flops, bytes, selector) where selector =
         (op_type, k, cin, cout, h) as hgb_model_profile_conv takes it."""
         ty, conv, bn, a0, a1, a2, a3, flag = info
@@ -43,9 +43,12 @@ class PlanInfo:
                 byt = 2.0 * (M * (c["cin_pad"] + c["cout_pad"]) + el(a2) + el(a3))
             elif ty == 8:
                 byt = 2.0 * M * (c["cin_pad"] + c["cout_pad"])
-            else:
-                byt = 2.0 * (M * (c["cin_pad"] + c["cout_pad"]) + el(a2) + el(a3) + (el(flag - 1) if bn >= 0 else 0))
+            else:   # dgrad: dp in, dx out, residuals, the y of a fused BatchNorm-backward REDUCTION; with the BatchNorm-backward
+                #        APPLY fused in: dz and y in, dp out instead of dp in
+                byt = 2.0 * (M * (c["cin_pad"] + c["cout_pad"] * (3 if fused_bn else 1)) + el(a2) + el(a3) + (el(flag - 1) if bn >= 0 else 0))
             key = f"{name} k{c['ksize']} {c['cin']}->{c['cout']} @{hh}"
+            if ty == 9 and fused_bn:
+                key += " +bnapply"
             if ty == 9 and bn >= 0:
                 key += " +bnstats"
             if ty == 9 and (a2 >= 0 or a3 >= 0):
@@ -90,12 +93,13 @@ def bound_of(flops, byt):
 def summarize(plan_handle, num_classes=17):
     """After a step run under hgb_model_profile_all: {class: dict(launches, ms, flops, bytes, selector)} and the total ms."""
     pi = PlanInfo(plan_handle, num_classes)
-    info, ms = (C.c_int * 8)(), C.c_double()
+    info, ms, fb = (C.c_int * 8)(), C.c_double(), (C.c_int * 3)()
     agg, tot = {}, 0.0
     for i in range(lib.hgb_model_profile_count(plan_handle)):
         if lib.hgb_model_profile_op(plan_handle, i, C.byref(info), C.byref(ms)):
             continue
-        key, flops, byt, sel = pi.classify(tuple(info))
+        lib.hgb_model_profile_op_fused(plan_handle, i, C.byref(fb))
+        key, flops, byt, sel = pi.classify(tuple(info), fused_bn=fb[0] >= 0)
         r = agg.setdefault(key, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0, selector=sel))
         r["launches"] += 1
         r["ms"] += ms.value

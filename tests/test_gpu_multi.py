@@ -55,7 +55,7 @@ def _worker(rank, world, port, q, sync_bn):
     out = model.train_on_batch(images[sl], targets[sl])
     torch.cuda.synchronize()
     # trainable weights only: the BN moving averages legitimately differ between replicas with per-replica statistics
-    q.put((rank, out, model._grads.cpu().numpy(), model._adam_m.cpu().numpy(), model._params[:model._train_floats].cpu().numpy()))
+    q.put((rank, out, model._grads.cpu().numpy(), model._adam_m.cpu().numpy(), model._params[:model._train_floats - 256].cpu().numpy()))   # (the gradient buffer carries 256 floats of padding)
     hgb200.parallel.disable()
     dist.destroy_process_group()
 

@@ -243,6 +243,7 @@ def test_replay_every_op(S, B):
     chk(lib.hgb_model_loss(R.h, R.model._loss_kind, ptr(R.targets), 1.0 / (B * 64 * 64 * 17), ptr(losses), sp()))
     torch.cuda.synchronize()
     fused_reduces = [0]
+    fused_applies = [0]
     for seg in range(S, -1, -1):
         for i, (ty, ci, bi, a0, a1, a2, a3, flag) in R.ops(seg, 1):
             if ty == B_BN_REDUCE:
@@ -303,12 +304,43 @@ def test_replay_every_op(S, B):
                 assert R.cos(ty, got, ref) > 0.999, f"wgrad conv {ci}: cosine"
             elif ty == B_DGRAD:
                 c = R.conv(ci)
-                dp = R.act(a0).float()[..., :c["cout"]].clone()
+                fb = (C.c_int * 3)()
+                chk(lib.hgb_model_op_fused_bn(R.h, seg, 1, i, C.byref(fb)))
+                fused_bn = fb[0] >= 0     # the BatchNorm backward of this conv's output gradient runs inside the GEMM
+                if fused_bn:
+                    fbd = R.bn(fb[0])
+                    Cf = fbd["c"]
+                    dz_f, y_f = R.act(fb[1]).float().reshape(-1, Cf).clone(), R.act(fb[2]).float().reshape(-1, Cf)
+                    db0 = R.grads[c["b_off"]:c["b_off"] + Cf].clone()
+                    R.act(a0).zero_()     # dp is an OUTPUT of the fused op
+                else:
+                    dp = R.act(a0).float()[..., :c["cout"]].clone()
                 res = [R.act(a).float().clone() for a in (a2, a3) if a >= 0]
                 bnd = R.bn(bi) if bi >= 0 else None      # fused BatchNorm-backward reduction of the consumer BN
                 s0 = R.arena_f32(bnd["bsums"], 2 * bnd["c"]).clone() if bnd else None
                 R.run(seg, 1, i)
                 out = R.act(a1).float()
+                if fused_bn:     # same checks as the stand-alone B_BN_APPLY op
+                    dp_dev = R.act(a0).float()
+                    dpf = dp_dev.reshape(-1, Cf)
+                    saved = R.arena_f32(fbd["saved"], 2 * Cf)
+                    mean, rstd = saved[:Cf], saved[Cf:]
+                    g = R.params[fbd["gamma"]:fbd["gamma"] + Cf]
+                    xh = (y_f - mean) * rstd
+                    Mr = y_f.shape[0]
+                    sdz, sdzx = dz_f.sum(0), (dz_f * xh).sum(0)
+                    ref_dp = torch.where(y_f > 0, g * rstd * (dz_f - sdz / Mr - xh * sdzx / Mr), torch.zeros_like(y_f))
+                    e = R.rel(dpf, ref_dp)
+                    R.note(B_BN_APPLY, e)
+                    assert e <= 1.5e-2, f"fused bn_bwd {fb[0]}: {e}"
+                    assert R.cos(B_BN_APPLY, dpf, ref_dp) > 0.999, f"fused bn_bwd {fb[0]}: cosine"
+                    scale = max(sdzx.abs().max().item(), sdz.abs().max().item(), 1e-20)
+                    assert (R.grads[fbd["gamma"]:fbd["gamma"] + Cf] - sdzx).abs().max().item() <= 5e-3 * max(scale, (dz_f * xh).abs().sum(0).max().item())
+                    assert (R.grads[fbd["beta"]:fbd["beta"] + Cf] - sdz).abs().max().item() <= 5e-3 * max(scale, dz_f.abs().sum(0).max().item())
+                    dbias = R.grads[c["b_off"]:c["b_off"] + Cf] - db0
+                    assert (dbias - dpf.sum(0)).abs().max().item() <= 2e-3 * max(dpf.abs().sum(0).max().item(), 1e-20)
+                    fused_applies[0] += 1
+                    dp = dp_dev[..., :c["cout"]].clone()
                 if bnd:
                     Cc = bnd["c"]
                     dzf, yf = out.reshape(-1, Cc), R.act(flag - 1).float().reshape(-1, Cc)
@@ -378,6 +410,8 @@ def test_replay_every_op(S, B):
     assert all(v > 0.999 for v in R.low_cos.values())
     assert {"F_CONV", "F_BN", "B_BN_APPLY", "B_WGRAD", "B_DGRAD"} <= set(R.low_cos)
     n_bneck = 3 + 15 * S
+    print("BatchNorm-backward applies fused into 1x1 dgrad GEMMs:", fused_applies[0])
+    assert fused_applies[0] >= 2 * 15 * S          # BN3 and BN1 of every hourglass bottleneck (+ the heads)
     assert fused_reduces[0] > n_bneck
     print("convolutions / weight gradients with a deferred input BatchNorm:", deferred[0], "statistic writers:", writers[0])
     assert deferred[0] >= 2 * n_bneck and writers[0] >= n_bneck
