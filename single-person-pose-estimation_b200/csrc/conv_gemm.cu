@@ -1297,7 +1297,9 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
 
 bool conv_gemm_supports_bn_bwd(int ksize, int Cin, int Cout) {
   // Cin = channels of dz / y / dp (K of the dgrad GEMM, at most 4 blocks of 64), Cout = the dgrad's output channels
-  return ksize == 1 && Cin % 64 == 0 && Cin <= 256 && (Cout == 128 || Cout == 256);
+  // (256 -> 256, the head convolution, is excluded: its stages are 64 KB, only two fit, and the fused kernel measured
+  //  690 us against 248 + 256 us for the two-pass form at batch 256)
+  return ksize == 1 && Cin % 64 == 0 && Cin <= 256 && (Cout == 128 || (Cout == 256 && Cin <= 128));
 }
 
 int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap* tmR,
