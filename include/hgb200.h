@@ -54,7 +54,8 @@ int         hgb_version(void);
  *   16  one thread issues all output boxes                             17  no BatchNorm folding in inference
  *   18  PDL trigger at kernel start instead of after the last load     19  PDL also in the multi-lane backward pass
  *   20  CTA cap of side-lane weight gradients (default 64, -1 none)    24  CTAs per sample in the decode kernel
- *   25  N = 256 GEMM tiles always with 8 epilogue warps                26  no BatchNorm-backward fusion into 1x1 dgrads (plan build) */
+ *   25  N = 256 GEMM tiles always with 8 epilogue warps                26  no BatchNorm-backward fusion into 1x1 dgrads (plan build)
+ *   27  no programmatic dependent launch exception for small ops                                                        */
 int         hgb_debug_set(int key, int value);
 
 /* ------------------------------------------------------------------------- */

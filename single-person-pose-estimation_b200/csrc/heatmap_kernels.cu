@@ -344,199 +344,188 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-constexpr int kDecStages = 4;   // bulk copies in flight per CTA
-constexpr int kDecIters = 4;    // 16-byte vectors per thread and chunk
+constexpr int kDecStages = 4;   // bulk copies in flight per CTA (default; hgb_debug_set(28, ...) varies ring geometry)
 
-// Work unit = one of `split` contiguous shares of one sample's map.  The kernel is PERSISTENT: grid = 2 CTAs per SM
-// (16*K threads each), CTA i takes units i, i + grid, ...  A unit's per-joint maxima are merged into the sample's keys with
-// one 64-bit atomicMax per joint; the unit that arrives last (a counter, the threadfence-reduction pattern) finishes the
-// sample: confidence, clipped 3x3 window, outputs.  The keys and the counter live in out_idx itself (words 0-1 of every
-// (sample, joint) row; word 2 of joint 0), zeroed by the launcher, so no workspace is needed.
-// The data is STREAMED THROUGH SHARED MEMORY by the TMA engine: a ring of kDecStages chunks of kDecIters*16*K vectors
-// (17 KB at K = 17), refilled by one thread with cp.async.bulk as soon as a chunk has been consumed -- across unit
-// boundaries, so the loads of the next unit are in flight while this one is reduced and merged.  History (B200, batch 1024,
-// 64x64x17, f32 / bf16, fraction of the measured HBM peak): one CTA per sample with register loads 0.54 / 0.35 (a single
-// ragged wave: every block loading, then every block reducing); four register-load CTAs per sample 0.57 / 0.28 (bytes in
-// flight bounded by the register file); a DSMEM cluster per sample: less; one TMA ring per non-persistent CTA 0.59 / 0.32
-// (a fixed ~28 us of ramp and tail: the reduction of every CTA ran with its own ring empty).
+// `split` independent CTAs (16*K threads each) per sample: CTA r scans the r-th contiguous share of the map and merges its
+// per-joint maxima into the sample's keys with one 64-bit atomicMax per joint; the CTA that arrives last (a counter, the
+// threadfence-reduction pattern) finishes the sample: confidence, clipped 3x3 window, outputs.  The keys and the counter
+// live in out_idx itself (words 0-1 of every (sample, joint) row; word 2 of joint 0), zeroed by the launcher, so no
+// workspace is needed.
+// The share is STREAMED THROUGH SHARED MEMORY by the TMA engine: a ring of kDecStages chunks of kDecIters*16*K vectors
+// (17 KB at K = 17), refilled by one thread with cp.async.bulk as soon as a chunk has been consumed.  With register loads
+// the bytes in flight are bounded by the register file (4 loads x 272 threads x 4 CTAs = 70 KB per SM, and none while a
+// CTA compares or reduces): one CTA per sample reached 0.54 / 0.35 of the HBM peak (f32 / bf16) at batch 1024, four
+// register-load CTAs per sample 0.57 / 0.28, a DSMEM cluster per sample less.  The ring keeps ~52 KB per CTA (3 CTAs per
+// SM) in flight regardless of what the threads are doing: 0.59 / 0.32 at batch 1024, 0.84 / 0.50 at batch 4096, 0.93-1.05 /
+// 0.62-0.77 at 128x128.  (A persistent variant -- 2 CTAs per SM looping over units, the ring running ahead across unit
+// boundaries -- measured WORSE, 0.46 / 0.24 at batch 1024: fewer resident CTAs, same per-chunk barrier cost.)
 // The vector stride VEC*16*K, the chunk and the share are multiples of K, so slot j of thread t always carries joint
 // (VEC*t + j) % K: VEC running (value,index) pairs in registers, no dynamic indexing.
-template <typename T, int VEC>
-__global__ void __launch_bounds__(320) decode_kernel(const T* __restrict__ hm, int B, int H, int W, int K, int split, double thr,
-                                                     int version, int32_t* __restrict__ out_idx, float* __restrict__ out_kp) {
+template <typename T, int VEC, int kDecIters>
+__global__ void __launch_bounds__(320) decode_kernel(const T* __restrict__ hm, int H, int W, int K, double thr, int version,
+                                                     int32_t* __restrict__ out_idx, float* __restrict__ out_kp, int stages) {
   extern __shared__ __align__(128) unsigned char s_raw[];
-  const int S = 16 * K, t = threadIdx.x;                  // blockDim = S rounded up to a warp multiple
+  const int S = 16 * K, t = threadIdx.x, b = blockIdx.y;  // blockDim = S rounded up to a warp multiple
+  const int split = gridDim.x, rank = blockIdx.x;
   const int chunk_vec = kDecIters * S;
   const uint32_t chunk_bytes = (uint32_t)chunk_vec * 16u;
-  const uint32_t ring = ptx::smem_u32(s_raw), bars = ring + kDecStages * chunk_bytes;
-  float* s_val = reinterpret_cast<float*>(s_raw + kDecStages * chunk_bytes + 64);   // [S*VEC]
-  int* s_idx = reinterpret_cast<int*>(s_val) + S * VEC;                             // [S*VEC]
+  const uint32_t ring = ptx::smem_u32(s_raw), bars = ring + (uint32_t)stages * chunk_bytes;
+  float* s_val = reinterpret_cast<float*>(s_raw);         // [S*VEC]  (aliases the ring once the share is consumed)
+  int* s_idx = reinterpret_cast<int*>(s_raw) + S * VEC;   // [S*VEC]
   __shared__ int s_last;
   const int HWK = H * W * K;
-  const int nvec = HWK / VEC / split;                     // vectors per unit
-  const int nc = (nvec + chunk_vec - 1) / chunk_vec;      // chunks per unit
-  const int units = B * split, G = gridDim.x;
-  const int my_units = (units - (int)blockIdx.x + G - 1) / G;
-  const int Q = my_units * nc;                            // chunks this CTA streams
+  const int nvec = HWK / VEC / split;                     // vectors of this CTA's share
+  const int v0 = rank * nvec;
+  const int nchunks = (nvec + chunk_vec - 1) / chunk_vec;
+  const T* base = hm + (size_t)b * HWK;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(out_idx + (size_t)b * K * 4);   // stride 2 per joint
+  int* counter = out_idx + (size_t)b * K * 4 + 2;
 
-  auto issue = [&](int q) {      // one thread: q-th chunk of this CTA -> ring slot q % kDecStages
-    const int ui = q / nc, c = q - ui * nc;
-    const int u = (int)blockIdx.x + ui * G;
-    const int b = u / split, rank = u - b * split;
+  auto issue = [&](int c) {      // one thread: chunk c -> ring slot c % kDecStages
     const int nv = min(chunk_vec, nvec - c * chunk_vec);
-    const uint32_t slot = (uint32_t)(q % kDecStages);
+    const uint32_t slot = (uint32_t)(c % stages);
     ptx::mbar_expect_tx(bars + 8u * slot, (uint32_t)nv * 16u);
-    bulk_load_1d(ring + slot * chunk_bytes, hm + (size_t)b * HWK + (size_t)(rank * nvec + c * chunk_vec) * VEC, (uint32_t)nv * 16u,
-                 bars + 8u * slot);
+    bulk_load_1d(ring + slot * chunk_bytes, base + (size_t)(v0 + c * chunk_vec) * VEC, (uint32_t)nv * 16u, bars + 8u * slot);
   };
   if (t == 0) {
-    for (int i = 0; i < kDecStages; ++i) ptx::mbar_init(bars + 8u * i, 1);
+    for (int i = 0; i < stages; ++i) ptx::mbar_init(bars + 8u * i, 1);
     ptx::fence_barrier_init();
-    for (int q = 0; q < kDecStages && q < Q; ++q) issue(q);
+    for (int c = 0; c < stages && c < nchunks; ++c) issue(c);
+  }
+  __syncthreads();
+
+  float bv[VEC];
+  int bi[VEC];
+  // Fast path: a thread meets the elements of a slot in increasing index order, so "first maximum" is a strict
+  // greater-than update (3-4 instructions per element) starting from (-inf, the slot's first index) -- the argmax of an
+  // all -inf slot is its first element.  It is exact unless a NaN shows up (numpy: a NaN beats everything); any NaN
+  // re-runs the CTA's share through the exact comparison below (from global memory: the rare path).
+  int nan_seen = 0;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { bv[j] = -CUDART_INF_F; bi[j] = t < S ? (v0 + t) * VEC + j : 0x7fffffff; }
+  for (int c = 0; c < nchunks; ++c) {
+    const uint32_t slot = (uint32_t)(c % stages);
+    ptx::mbar_wait(bars + 8u * slot, (uint32_t)(c / stages) & 1u);
+    const int nv = min(chunk_vec, nvec - c * chunk_vec);
+    if (t < S) {
+      uint4 raw[kDecIters];
+#pragma unroll
+      for (int u = 0; u < kDecIters; ++u) {
+        const int vi = u * S + t;
+        raw[u] = make_uint4(0, 0, 0, 0);
+        if (vi < nv) raw[u] = *reinterpret_cast<const uint4*>(s_raw + slot * chunk_bytes + (size_t)vi * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < kDecIters; ++u) {
+        const int vi = u * S + t;
+        if (vi < nv) {
+          float r[VEC];
+          DecLoad<T, VEC>::unpack(raw[u], r);
+          const int e0 = (v0 + c * chunk_vec + vi) * VEC;
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            const bool gt = r[j] > bv[j];
+            bv[j] = gt ? r[j] : bv[j];
+            bi[j] = gt ? e0 + j : bi[j];
+            nan_seen |= (r[j] != r[j]);
+          }
+        }
+      }
+    }
+    __syncthreads();                                    // the chunk is consumed: its slot can be refilled
+    if (t == 0 && c + stages < nchunks) issue(c + stages);
+  }
+  int v;
+  if (__syncthreads_or(nan_seen)) {   // block-uniform: exact numpy order (NaN first, then value, then lower index)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { bv[j] = -CUDART_INF_F; bi[j] = 0x7fffffff; }
+    for (v = t < S ? t : nvec; v < nvec; v += S) {
+      float r[VEC];
+      DecLoad<T, VEC>::load(base + (size_t)(v0 + v) * VEC, r);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int e = (v0 + v) * VEC + j;
+        if (better(r[j], e, bv[j], bi[j])) { bv[j] = r[j]; bi[j] = e; }
+      }
+    }
+  }
+  if (t < S) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      s_val[t * VEC + j] = bv[j];
+      s_idx[t * VEC + j] = bi[j];
+    }
   }
   __syncthreads();
 
   const int warp = t >> 5, lane = t & 31, nwarp = blockDim.x >> 5;
-  int q = 0;
-  for (int ui = 0; ui < my_units; ++ui) {
-    const int u = (int)blockIdx.x + ui * G;
-    const int b = u / split, rank = u - b * split;
-    const int v0 = rank * nvec;
-    const T* base = hm + (size_t)b * HWK;
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(out_idx + (size_t)b * K * 4);   // stride 2 per joint
-    int* counter = out_idx + (size_t)b * K * 4 + 2;
+  const int ncand = 16 * VEC;  // candidates per joint: c = k + K*m
+  for (int k = warp; k < K; k += nwarp) {   // this CTA's maximum of joint k -> the sample's key
+    float cv = -CUDART_INF_F;
+    int ci = 0x7fffffff;
+    for (int m = lane; m < ncand; m += 32) {
+      const float a = s_val[k + K * m];
+      const int ia = s_idx[k + K * m];
+      if (better(a, ia, cv, ci)) { cv = a; ci = ia; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+      if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
+    }
+    if (lane == 0) atomicMax(keys + 2 * k, decode_key(cv, ci));
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) s_last = atomicAdd(counter, 1) == split - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
 
-    float bv[VEC];
-    int bi[VEC];
-    // Fast path: a thread meets the elements of a slot in increasing index order, so "first maximum" is a strict
-    // greater-than update (3-4 instructions per element) starting from (-inf, the slot's first index) -- the argmax of an
-    // all -inf slot is its first element.  It is exact unless a NaN shows up (numpy: a NaN beats everything); any NaN
-    // re-runs the unit through the exact comparison below (from global memory: the rare path).
-    int nan_seen = 0;
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) { bv[j] = -CUDART_INF_F; bi[j] = t < S ? (v0 + t) * VEC + j : 0x7fffffff; }
-    for (int c = 0; c < nc; ++c, ++q) {
-      const uint32_t slot = (uint32_t)(q % kDecStages);
-      ptx::mbar_wait(bars + 8u * slot, (uint32_t)(q / kDecStages) & 1u);
-      const int nv = min(chunk_vec, nvec - c * chunk_vec);
-      if (t < S) {
-        uint4 raw[kDecIters];
-#pragma unroll
-        for (int i = 0; i < kDecIters; ++i) {
-          const int vi = i * S + t;
-          raw[i] = make_uint4(0, 0, 0, 0);
-          if (vi < nv) raw[i] = *reinterpret_cast<const uint4*>(s_raw + slot * chunk_bytes + (size_t)vi * 16);
-        }
-#pragma unroll
-        for (int i = 0; i < kDecIters; ++i) {
-          const int vi = i * S + t;
-          if (vi < nv) {
-            float r[VEC];
-            DecLoad<T, VEC>::unpack(raw[i], r);
-            const int e0 = (v0 + c * chunk_vec + vi) * VEC;
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-              const bool gt = r[j] > bv[j];
-              bv[j] = gt ? r[j] : bv[j];
-              bi[j] = gt ? e0 + j : bi[j];
-              nan_seen |= (r[j] != r[j]);
-            }
-          }
-        }
+  // the last CTA of the sample: every share has merged its maxima
+  for (int k = warp; k < K; k += nwarp) {
+    const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(keys + 2 * k);
+    const int ci = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+    const int index = ci / K;  // flat pixel index (row-major)
+    const int x = index % W;   // data_utils.py:121
+    const int y = index / H;   // data_utils.py:122 (height; square maps only)
+    int pidx = 0;
+    float conf = 0.f;
+    if (lane == 31) conf = to_f32<T>(base[ci]);   // the element itself: exact bits (signed zero, NaN payload)
+    if (version == 2) {        // data_utils.py:160-169: one lane per element of the clipped 3x3 window (parallel loads)
+      const int x1 = max(x - 1, 0), x2 = min(x + 2, W), y1 = max(y - 1, 0), y2 = min(y + 2, H);
+      const int pw = x2 - x1, ph = y2 - y1;
+      float pb = -CUDART_INF_F;
+      int pbi = 0x7fffffff;
+      if (lane < pw * ph) {
+        const int r = lane / pw, c = lane - r * pw;
+        pb = (r == 1 && c == 1) ? 0.f : to_f32<T>(base[((size_t)(y1 + r) * W + (x1 + c)) * K + k]);   // :166 reads as 0
+        pbi = lane;
       }
-      __syncthreads();                                    // the chunk is consumed: its slot can be refilled
-      if (t == 0 && q + kDecStages < Q) issue(q + kDecStages);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, pb, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, pbi, o);
+        if (better(ov, oi, pb, pbi)) { pb = ov; pbi = oi; }
+      }
+      pidx = __shfl_sync(0xffffffffu, pbi, 0);
     }
-    if (__syncthreads_or(nan_seen)) {   // block-uniform: exact numpy order (NaN first, then value, then lower index)
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) { bv[j] = -CUDART_INF_F; bi[j] = 0x7fffffff; }
-      for (int v = t < S ? t : nvec; v < nvec; v += S) {
-        float r[VEC];
-        DecLoad<T, VEC>::load(base + (size_t)(v0 + v) * VEC, r);
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          const int e = (v0 + v) * VEC + j;
-          if (better(r[j], e, bv[j], bi[j])) { bv[j] = r[j]; bi[j] = e; }
-        }
-      }
-    }
-    if (t < S) {
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        s_val[t * VEC + j] = bv[j];
-        s_idx[t * VEC + j] = bi[j];
-      }
-    }
-    __syncthreads();
-
-    const int ncand = 16 * VEC;  // candidates per joint: c = k + K*m
-    for (int k = warp; k < K; k += nwarp) {   // this unit's maximum of joint k -> the sample's key
-      float cv = -CUDART_INF_F;
-      int ci = 0x7fffffff;
-      for (int m = lane; m < ncand; m += 32) {
-        const float a = s_val[k + K * m];
-        const int ia = s_idx[k + K * m];
-        if (better(a, ia, cv, ci)) { cv = a; ci = ia; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
-        if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
-      }
-      if (lane == 0) atomicMax(keys + 2 * k, decode_key(cv, ci));
-    }
-    __threadfence();
-    __syncthreads();
-    if (t == 0) s_last = atomicAdd(counter, 1) == split - 1;
-    __syncthreads();
-    if (!s_last) continue;      // block-uniform
-    __threadfence();
-
-    // the last unit of the sample: every share has merged its maxima
-    for (int k = warp; k < K; k += nwarp) {
-      const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(keys + 2 * k);
-      const int ci = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
-      const int index = ci / K;  // flat pixel index (row-major)
-      const int x = index % W;   // data_utils.py:121
-      const int y = index / H;   // data_utils.py:122 (height; square maps only)
-      int pidx = 0;
-      float conf = 0.f;
-      if (lane == 31) conf = to_f32<T>(base[ci]);   // the element itself: exact bits (signed zero, NaN payload)
-      if (version == 2) {        // data_utils.py:160-169: one lane per element of the clipped 3x3 window (parallel loads)
-        const int x1 = max(x - 1, 0), x2 = min(x + 2, W), y1 = max(y - 1, 0), y2 = min(y + 2, H);
-        const int pw = x2 - x1, ph = y2 - y1;
-        float pb = -CUDART_INF_F;
-        int pbi = 0x7fffffff;
-        if (lane < pw * ph) {
-          const int r = lane / pw, c = lane - r * pw;
-          pb = (r == 1 && c == 1) ? 0.f : to_f32<T>(base[((size_t)(y1 + r) * W + (x1 + c)) * K + k]);   // :166 reads as 0
-          pbi = lane;
-        }
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, pb, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, pbi, o);
-          if (better(ov, oi, pb, pbi)) { pb = ov; pbi = oi; }
-        }
-        pidx = __shfl_sync(0xffffffffu, pbi, 0);
-      }
-      conf = __shfl_sync(0xffffffffu, conf, 31);
-      __syncwarp();
-      if (lane == 0) {
-        const int px = pidx % 3, py = pidx / 3;  // always 3 (data_utils.py:168-169)
-        int32_t* oi = out_idx + ((size_t)b * K + k) * 4;
-        oi[0] = index; oi[1] = x; oi[2] = y; oi[3] = pidx;   // overwrites the key (and, for joint 0, the counter)
-        float* ok = out_kp + ((size_t)b * K + k) * 3;
-        // numpy >= 2 (NEP 50) compares the float32 confidence with float32(threshold); numpy 1.x
-        // promoted to float64.  They differ only when conf == float32(thr) rounds above thr.
-        if (conf > (float)thr) {
-          ok[0] = (float)x + 0.25f * (float)px;
-          ok[1] = (float)y + 0.25f * (float)py;
-          ok[2] = conf;
-        } else {
-          ok[0] = 0.f; ok[1] = 0.f; ok[2] = 0.f;
-        }
+    conf = __shfl_sync(0xffffffffu, conf, 31);
+    __syncwarp();
+    if (lane == 0) {
+      const int px = pidx % 3, py = pidx / 3;  // always 3 (data_utils.py:168-169)
+      int32_t* oi = out_idx + ((size_t)b * K + k) * 4;
+      oi[0] = index; oi[1] = x; oi[2] = y; oi[3] = pidx;   // overwrites the key (and, for joint 0, the counter)
+      float* ok = out_kp + ((size_t)b * K + k) * 3;
+      // numpy >= 2 (NEP 50) compares the float32 confidence with float32(threshold); numpy 1.x
+      // promoted to float64.  They differ only when conf == float32(thr) rounds above thr.
+      if (conf > (float)thr) {
+        ok[0] = (float)x + 0.25f * (float)px;
+        ok[1] = (float)y + 0.25f * (float)py;
+        ok[2] = conf;
+      } else {
+        ok[0] = 0.f; ok[1] = 0.f; ok[2] = 0.f;
       }
     }
   }
@@ -736,36 +725,44 @@ extern "C" int hgb_decode(const void* heatmaps, int dtype, int B, int H, int W, 
   HGB_CHECK_ARG(((int64_t)H * W * K) % vec == 0, "hgb_decode: H*W*K must be a multiple of %d", vec);
   HGB_CHECK_ARG((int64_t)H * W * K < (1ll << 31), "hgb_decode: map too large");
   if (B == 0) return HGB_OK;
+  HGB_CHECK_ARG(B <= 65535, "hgb_decode: batch exceeds the grid limit");
   const int threads = (16 * K + 31) / 32 * 32;
   HGB_CHECK_ARG(threads <= 320, "hgb_decode: at most 20 joints per launch configuration");
   HGB_CHECK_ARG((((uintptr_t)heatmaps | (uintptr_t)out_idx) & 15) == 0, "hgb_decode: heatmaps / out_idx must be 16-byte aligned");
-  // ring of kDecStages chunks + their mbarriers + the (value, index) staging of the block reduction
-  const size_t ring = (size_t)kDecStages * kDecIters * (16 * K) * 16;
-  const size_t smem = ring + 64 + (size_t)(16 * K) * vec * 8;
+  // ring of `stages` chunks of `iters` vectors per thread + their mbarriers; the (value, index) staging of the block
+  // reduction aliases the ring.  hgb_debug_set(28, 10 * stages + iters) varies the geometry (iters 4 or 8).
+  int stages = kDecStages, iters = 4;
+  if (g_debug[28] > 0) { stages = g_debug[28] / 10; iters = g_debug[28] % 10; }
+  HGB_CHECK_ARG(stages >= 2 && stages <= 8 && (iters == 4 || iters == 8), "hgb_decode: ring geometry");
+  const size_t ring = (size_t)stages * iters * (16 * K) * 16;
+  HGB_CHECK_ARG(ring >= (size_t)(16 * K) * vec * 8, "hgb_decode: staging does not fit the ring");
+  const size_t smem = ring + stages * 8;
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_done = false;
   if (!attr_done) {
-    HGB_CUDA(cudaFuncSetAttribute(decode_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-    HGB_CUDA(cudaFuncSetAttribute(decode_kernel<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    HGB_CUDA(cudaFuncSetAttribute(decode_kernel<float, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    HGB_CUDA(cudaFuncSetAttribute(decode_kernel<__nv_bfloat16, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    HGB_CUDA(cudaFuncSetAttribute(decode_kernel<float, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    HGB_CUDA(cudaFuncSetAttribute(decode_kernel<__nv_bfloat16, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
-  HGB_CHECK_ARG(smem <= 110 * 1024, "hgb_decode: too many joints for the shared-memory ring");
-  // units per sample: as few as give every persistent CTA several units (a whole map per unit amortises the reduction
-  // best); shares must be a whole number of 16-byte vectors and of pixels (K elements).  hgb_debug_set(24, n) overrides.
+  HGB_CHECK_ARG(smem <= 200 * 1024, "hgb_decode: too many joints for the shared-memory ring");
+  // CTAs per sample: as few as give ~4 waves of 3 resident CTAs per SM (a whole map per CTA amortises the reduction best);
+  // shares must be a whole number of 16-byte vectors and of pixels (K elements).  hgb_debug_set(24, n) overrides.
   const int64_t nvec = (int64_t)H * W * K / vec;
   int split = 1;
-  while (split < 8 && (int64_t)B * split < 2048) split <<= 1;
+  while (split < 8 && (int64_t)B * split < 148 * 3 * 4) split <<= 1;
   if (g_debug[24] > 0) split = g_debug[24];
   while (split > 1 && (nvec % split != 0 || (nvec / split * vec) % K != 0)) split >>= 1;
-  const int64_t units = (int64_t)B * split;
-  const int grid = (int)(units < 2 * 148 ? units : 2 * 148);
   // keys + arrival counters live in out_idx (see decode_kernel)
   HGB_CUDA(cudaMemsetAsync(out_idx, 0, (size_t)B * K * 4 * sizeof(int32_t), st));
-  if (dtype == HGB_F32)
-    decode_kernel<float, 4><<<grid, threads, smem, st>>>((const float*)heatmaps, B, H, W, K, split, conf_threshold, version, out_idx, out_kpts);
-  else
-    decode_kernel<__nv_bfloat16, 8><<<grid, threads, smem, st>>>((const __nv_bfloat16*)heatmaps, B, H, W, K, split, conf_threshold, version,
-                                                                 out_idx, out_kpts);
+  if (dtype == HGB_F32) {
+    if (iters == 4) decode_kernel<float, 4, 4><<<dim3(split, B), threads, smem, st>>>((const float*)heatmaps, H, W, K, conf_threshold, version, out_idx, out_kpts, stages);
+    else decode_kernel<float, 4, 8><<<dim3(split, B), threads, smem, st>>>((const float*)heatmaps, H, W, K, conf_threshold, version, out_idx, out_kpts, stages);
+  } else {
+    if (iters == 4) decode_kernel<__nv_bfloat16, 8, 4><<<dim3(split, B), threads, smem, st>>>((const __nv_bfloat16*)heatmaps, H, W, K, conf_threshold, version, out_idx, out_kpts, stages);
+    else decode_kernel<__nv_bfloat16, 8, 8><<<dim3(split, B), threads, smem, st>>>((const __nv_bfloat16*)heatmaps, H, W, K, conf_threshold, version, out_idx, out_kpts, stages);
+  }
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }

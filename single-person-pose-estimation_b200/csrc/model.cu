@@ -836,7 +836,17 @@ int run_op(hgb_model* m, const Op& o, const float* images, int training, cudaStr
   // With the lanes active, an early-launched dependent CTA parks on an SM (holding ~200 KB of shared memory) until its
   // predecessor finishes and keeps the OTHER lanes' kernels off that SM: measured -1.7 % in the backward pass, where the
   // side lanes carry a third of the work, so there it stays off.
-  hgb::g_debug[6] = hgb::g_debug[7] == 1 ? 0 : hgb::g_debug[7] == 2 ? 1 : (m->B > 64 || (m->pdl_suppressed && !hgb::g_debug[19]));
+  // Small ops are the exception to both rules: a kernel of at most one wave of 128-pixel tiles never fills the chip, so an
+  // early-launched dependent parks on an SM nobody else wants, and what it hides (launch latency, mbarrier / TMEM / descriptor
+  // set-up: about half of a 7-10 us kernel at the 16x16, 8x8 and 4x4 levels) is what those levels are made of.
+  // hgb_debug_set(27, 1) restores the batch / pass rule for every op.
+  bool small_op = false;
+  if (!hgb::g_debug[27] && o.a0 >= 0) {
+    const Act& t0 = m->acts[o.a0];
+    small_op = (int64_t)t0.n * t0.h * t0.w <= (int64_t)128 * 148;
+  }
+  hgb::g_debug[6] = hgb::g_debug[7] == 1 ? 0 : hgb::g_debug[7] == 2 ? 1
+                  : small_op ? 0 : (m->B > 64 || (m->pdl_suppressed && !hgb::g_debug[19]));
   bool timed = false;
   if (m->prof_all) {
     timed = m->prof_used + 2 <= m->prof_ev.size();
