@@ -302,6 +302,7 @@ struct DecLoad<float, 4> {
   static __device__ __forceinline__ void unpack(const uint4& v, float (&r)[4]) {
     r[0] = __uint_as_float(v.x); r[1] = __uint_as_float(v.y); r[2] = __uint_as_float(v.z); r[3] = __uint_as_float(v.w);
   }
+  static __device__ __forceinline__ uint4 neg_inf() { return make_uint4(0xff800000u, 0xff800000u, 0xff800000u, 0xff800000u); }
 };
 template <>
 struct DecLoad<__nv_bfloat16, 8> {
@@ -316,6 +317,7 @@ struct DecLoad<__nv_bfloat16, 8> {
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&r)[8]) {
     unpack(__ldcs(reinterpret_cast<const uint4*>(p)), r);
   }
+  static __device__ __forceinline__ uint4 neg_inf() { return make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u); }
 };
 
 template <typename T>
@@ -344,7 +346,7 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-constexpr int kDecStages = 4;   // bulk copies in flight per CTA (default; hgb_debug_set(28, ...) varies ring geometry)
+constexpr int kDecStages = 2;   // bulk copies in flight per CTA (default; hgb_debug_set(28, ...) varies ring geometry)
 
 // `split` independent CTAs (16*K threads each) per sample: CTA r scans the r-th contiguous share of the map and merges its
 // per-joint maxima into the sample's keys with one 64-bit atomicMax per joint; the CTA that arrives last (a counter, the
@@ -396,11 +398,17 @@ __global__ void __launch_bounds__(320) decode_kernel(const T* __restrict__ hm, i
 
   float bv[VEC];
   int bi[VEC];
-  // Fast path: a thread meets the elements of a slot in increasing index order, so "first maximum" is a strict
-  // greater-than update (3-4 instructions per element) starting from (-inf, the slot's first index) -- the argmax of an
-  // all -inf slot is its first element.  It is exact unless a NaN shows up (numpy: a NaN beats everything); any NaN
-  // re-runs the CTA's share through the exact comparison below (from global memory: the rare path).
-  int nan_seen = 0;
+  // Fast path.  ncu on the first ring version: 18 thread-instructions per element (compare + two selects + index add + NaN
+  // test on EVERY element), issue slots 48 % busy -- instruction-bound at 0.59 of the HBM peak.  Now the common case costs
+  // ~3: a thread takes G vectors of a chunk at a time (16 values per slot group), forms the per-slot maximum with fmaxf,
+  // and only when that beats the slot's running maximum (rare once the maximum has settled) looks for the FIRST vector that
+  // holds it -- vectors arrive in increasing index order, so "first maximum" is a strict greater-than against the running
+  // value.  NaN / Inf are caught by one fused multiply-add per vector group: sum * 0 is NaN iff some value was NaN or
+  // infinite (numpy: a NaN beats everything; an all -inf slot keeps its first element) and sends the CTA's share through
+  // the exact comparison below (from global memory: the rare path).
+  constexpr int G = 16 / VEC;             // vectors per group: 4 (f32) / 2 (bf16)
+  static_assert(kDecIters % G == 0, "chunk = whole vector groups per thread");
+  float nanacc = 0.f;
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { bv[j] = -CUDART_INF_F; bi[j] = t < S ? (v0 + t) * VEC + j : 0x7fffffff; }
   for (int c = 0; c < nchunks; ++c) {
@@ -412,22 +420,32 @@ __global__ void __launch_bounds__(320) decode_kernel(const T* __restrict__ hm, i
 #pragma unroll
       for (int u = 0; u < kDecIters; ++u) {
         const int vi = u * S + t;
-        raw[u] = make_uint4(0, 0, 0, 0);
-        if (vi < nv) raw[u] = *reinterpret_cast<const uint4*>(s_raw + slot * chunk_bytes + (size_t)vi * 16);
+        raw[u] = vi < nv ? *reinterpret_cast<const uint4*>(s_raw + slot * chunk_bytes + (size_t)vi * 16) : DecLoad<T, VEC>::neg_inf();
       }
 #pragma unroll
-      for (int u = 0; u < kDecIters; ++u) {
-        const int vi = u * S + t;
-        if (vi < nv) {
-          float r[VEC];
-          DecLoad<T, VEC>::unpack(raw[u], r);
-          const int e0 = (v0 + c * chunk_vec + vi) * VEC;
+      for (int g0 = 0; g0 < kDecIters; g0 += G) {
+        float r[G][VEC];
+        float sum = 0.f;
 #pragma unroll
-          for (int j = 0; j < VEC; ++j) {
-            const bool gt = r[j] > bv[j];
-            bv[j] = gt ? r[j] : bv[j];
-            bi[j] = gt ? e0 + j : bi[j];
-            nan_seen |= (r[j] != r[j]);
+        for (int u = 0; u < G; ++u) {
+          DecLoad<T, VEC>::unpack(raw[g0 + u], r[u]);
+          if (g0 * S + u * S + t < nv) {               // (padding vectors of a ragged last chunk hold -inf: not a NaN signal)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) sum += r[u][j];
+          }
+        }
+        nanacc = fmaf(sum, 0.f, nanacc);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float m = r[0][j];
+#pragma unroll
+          for (int u = 1; u < G; ++u) m = fmaxf(m, r[u][j]);
+          if (m > bv[j]) {                              // rare: find the first vector of the group that holds the maximum
+            int uf = G - 1;
+#pragma unroll
+            for (int u = G - 2; u >= 0; --u) uf = (r[u][j] == m) ? u : uf;
+            bv[j] = m;
+            bi[j] = (v0 + c * chunk_vec + (g0 + uf) * S + t) * VEC + j;
           }
         }
       }
@@ -435,6 +453,7 @@ __global__ void __launch_bounds__(320) decode_kernel(const T* __restrict__ hm, i
     __syncthreads();                                    // the chunk is consumed: its slot can be refilled
     if (t == 0 && c + stages < nchunks) issue(c + stages);
   }
+  const int nan_seen = nanacc != nanacc;
   int v;
   if (__syncthreads_or(nan_seen)) {   // block-uniform: exact numpy order (NaN first, then value, then lower index)
 #pragma unroll
@@ -474,9 +493,11 @@ __global__ void __launch_bounds__(320) decode_kernel(const T* __restrict__ hm, i
       const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
       if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
     }
-    if (lane == 0) atomicMax(keys + 2 * k, decode_key(cv, ci));
+    if (lane == 0) {
+      atomicMax(keys + 2 * k, decode_key(cv, ci));
+      __threadfence();       // the key must be visible before this CTA's arrival is counted
+    }
   }
-  __threadfence();
   __syncthreads();
   if (t == 0) s_last = atomicAdd(counter, 1) == split - 1;
   __syncthreads();
@@ -731,7 +752,7 @@ extern "C" int hgb_decode(const void* heatmaps, int dtype, int B, int H, int W, 
   HGB_CHECK_ARG((((uintptr_t)heatmaps | (uintptr_t)out_idx) & 15) == 0, "hgb_decode: heatmaps / out_idx must be 16-byte aligned");
   // ring of `stages` chunks of `iters` vectors per thread + their mbarriers; the (value, index) staging of the block
   // reduction aliases the ring.  hgb_debug_set(28, 10 * stages + iters) varies the geometry (iters 4 or 8).
-  int stages = kDecStages, iters = 4;
+  int stages = kDecStages, iters = 8;      // A/B on B200 (tools_decode_ab.py): 2 x 35 KB beat 4 x 17 KB and every larger ring
   if (g_debug[28] > 0) { stages = g_debug[28] / 10; iters = g_debug[28] % 10; }
   HGB_CHECK_ARG(stages >= 2 && stages <= 8 && (iters == 4 || iters == 8), "hgb_decode: ring geometry");
   const size_t ring = (size_t)stages * iters * (16 * K) * 16;
@@ -747,11 +768,12 @@ extern "C" int hgb_decode(const void* heatmaps, int dtype, int B, int H, int W, 
     attr_done = true;
   }
   HGB_CHECK_ARG(smem <= 200 * 1024, "hgb_decode: too many joints for the shared-memory ring");
-  // CTAs per sample: as few as give ~4 waves of 3 resident CTAs per SM (a whole map per CTA amortises the reduction best);
-  // shares must be a whole number of 16-byte vectors and of pixels (K elements).  hgb_debug_set(24, n) overrides.
+  // CTAs per sample: one whole map per CTA amortises the reduction and the key merge best (A/B: split 1 >= split 2 > 4 > 8
+  // at batch 1024 and 4096); small batches are split so that every SM still gets its 3 resident CTAs.  Shares must be a
+  // whole number of 16-byte vectors and of pixels (K elements).  hgb_debug_set(24, n) overrides.
   const int64_t nvec = (int64_t)H * W * K / vec;
   int split = 1;
-  while (split < 8 && (int64_t)B * split < 148 * 3 * 4) split <<= 1;
+  while (split < 8 && (int64_t)B * split < 148 * 3) split <<= 1;
   if (g_debug[24] > 0) split = g_debug[24];
   while (split > 1 && (nvec % split != 0 || (nvec / split * vec) % K != 0)) split >>= 1;
   // keys + arrival counters live in out_idx (see decode_kernel)

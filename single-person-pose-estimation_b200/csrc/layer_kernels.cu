@@ -292,7 +292,7 @@ int upsample_add_bwd(const bf16* dout, bf16* dlow, int N, int h, int w, int C, c
 // threads contending per address it cost several microseconds per block.)
 template <int NSTAT>
 __device__ __forceinline__ void block_channel_flush(float (&acc)[NSTAT][8], float* s_acc /*[R*NSTAT*C]*/, float* const* dst,
-                                                    int C, int g, int c_valid) {
+                                                    int C, int g, int c_valid, float* dst2 = nullptr) {
   const int G = C >> 3, R = 256 / G, r0 = threadIdx.x / G;
 #pragma unroll
   for (int s = 0; s < NSTAT; ++s) {
@@ -307,6 +307,7 @@ __device__ __forceinline__ void block_channel_flush(float (&acc)[NSTAT][8], floa
       float t = 0.f;
       for (int r = 0; r < R; ++r) t += s_acc[(size_t)r * NSTAT * C + i];
       atomicAdd(dst[s] + c, t);
+      if (dst2) atomicAdd(dst2 + c, t);      // a second consumer of the same column sums (statistic 0 only callers)
     }
   }
 }
@@ -440,7 +441,7 @@ int bn_bwd_apply(const bf16* dz, const bf16* y, bf16* dp, const float* bsums, co
 
 __global__ void __launch_bounds__(256) relu_mask_colsum_kernel(const bf16* __restrict__ gsrc, const bf16* __restrict__ y,
                                                                bf16* __restrict__ dp, float* __restrict__ dbias, int M, int C,
-                                                               int c_valid, int relu) {
+                                                               int c_valid, int relu, float* __restrict__ dbias2) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float s_acc[];
@@ -464,14 +465,15 @@ __global__ void __launch_bounds__(256) relu_mask_colsum_kernel(const bf16* __res
     for (int j = 0; j < 8; ++j) acc[0][j] += d[j];
   }
   float* dst[1] = {dbias};
-  block_channel_flush<1>(acc, s_acc, dst, C, g, c_valid);
+  block_channel_flush<1>(acc, s_acc, dst, C, g, c_valid, dbias2);
 }
 
 int relu_mask_colsum(const bf16* g, const bf16* y, bf16* dp, float* dbias, int M, int C, int c_valid, int relu,
-                     cudaStream_t st) {
+                     cudaStream_t st, float* dbias2) {
   HGB_CHECK_ARG(C % 8 == 0 && 256 % (C / 8) == 0, "relu_mask_colsum: unsupported channel count %d", C);
   if (M == 0) return HGB_OK;
-  launch_pdl(relu_mask_colsum_kernel, dim3(row_blocks(M, C, 8)), dim3(256), 2048 * sizeof(float), st, g, y, dp, dbias, M, C, c_valid, relu);
+  launch_pdl(relu_mask_colsum_kernel, dim3(row_blocks(M, C, 8)), dim3(256), 2048 * sizeof(float), st, g, y, dp, dbias, M, C, c_valid, relu,
+             dbias2);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }

@@ -34,8 +34,9 @@ int bn_bwd_apply(const bf16* dz, const bf16* y, bf16* dp, const float* bsums, co
 
 // Convs without BN: dp = relu ? g * [y > 0] : g (in place when dp == g; dp may be null when !relu),
 // dbias[c] += sum_rows dp for c < c_valid.
+// dbias2 (optional): a second bias gradient that receives the same column sums.
 int relu_mask_colsum(const bf16* g, const bf16* y, bf16* dp, float* dbias, int M, int C, int c_valid, int relu,
-                     cudaStream_t st);
+                     cudaStream_t st, float* dbias2 = nullptr);
 
 // Prediction head (hourglass.py:83): logits [M][ldl] bf16 (first K valid) -> heat [M][K] f32 = act(logits) and
 // pbf [M][64] bf16 (act value, zero in the padding channels) for the re-injection conv (hourglass.py:88).

@@ -391,7 +391,15 @@ struct hgb_model {
     if (dgrad_out >= 0) {
       o.type = B_DGRAD; o.conv = conv; o.a0 = dp; o.a1 = dgrad_out; o.a2 = res1; emit_b(o);
     }
-    o = Op(); o.type = B_COLSUM; o.conv = conv; o.a0 = dp; o.lane = leaf_lane(); emit_b(o);
+    // bias gradient = column sums of dp.  conv_1x1_2 and conv_1x1_3 of a stack see the SAME gradient tensor (the three-way
+    // Add of hourglass.py:91): one pass writes both bias gradients (a1 = the second convolution)
+    bool merged = false;
+    for (auto it = bwd_ops[cur_seg].rbegin(); it != bwd_ops[cur_seg].rend() && !merged; ++it)
+      if (it->type == B_COLSUM && it->a0 == dp && it->a1 < 0 && convs[it->conv].cout == convs[conv].cout && !hgb::g_debug[29]) {
+        it->a1 = conv;
+        merged = true;
+      }
+    if (!merged) { o = Op(); o.type = B_COLSUM; o.conv = conv; o.a0 = dp; o.lane = leaf_lane(); emit_b(o); }
     emit_wgrad(conv, dp, x_in);
   }
 };
@@ -729,7 +737,10 @@ void op_access(const hgb_model* m, const Op& o, std::vector<Range>& r, std::vect
       add_act(m, r, o.a0); add_act(m, r, o.a1); add_act(m, w, o.a0);
       add_grad(w, m->convs[o.conv].b_off, m->convs[o.conv].cout);
       break;
-    case B_COLSUM: add_act(m, r, o.a0); add_grad(w, m->convs[o.conv].b_off, m->convs[o.conv].cout); break;
+    case B_COLSUM:
+      add_act(m, r, o.a0); add_grad(w, m->convs[o.conv].b_off, m->convs[o.conv].cout);
+      if (o.a1 >= 0) add_grad(w, m->convs[o.a1].b_off, m->convs[o.a1].cout);   // a1: a second convolution with the same gradient
+      break;
     case B_POOL: add_act(m, r, o.a0); add_act(m, r, o.a1); if (o.flag) add_act(m, r, o.a2); add_act(m, w, o.a2); break;
     case B_UPADD: add_act(m, r, o.a0); add_act(m, w, o.a1); break;
     case B_HEAD:
@@ -1023,7 +1034,8 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
     case B_COLSUM: {
       const ConvL& c = m->convs[o.conv];
       const Act& g = m->acts[o.a0];
-      rc = relu_mask_colsum(act_ptr(m, o.a0), nullptr, nullptr, m->p_grads + c.b_off, g.n * g.h * g.w, g.c, c.cout, 0, st);
+      rc = relu_mask_colsum(act_ptr(m, o.a0), nullptr, nullptr, m->p_grads + c.b_off, g.n * g.h * g.w, g.c, c.cout, 0, st,
+                            o.a1 >= 0 ? m->p_grads + m->convs[o.a1].b_off : nullptr);
       break;
     }
     case B_POOL: {

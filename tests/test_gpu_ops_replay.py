@@ -244,6 +244,7 @@ def test_replay_every_op(S, B):
     torch.cuda.synchronize()
     fused_reduces = [0]
     fused_applies = [0]
+    shared_colsums = [0]
     for seg in range(S, -1, -1):
         for i, (ty, ci, bi, a0, a1, a2, a3, flag) in R.ops(seg, 1):
             if ty == B_BN_REDUCE:
@@ -364,6 +365,9 @@ def test_replay_every_op(S, B):
                 c = R.conv(ci)
                 g0 = R.act(a0).clone()
                 db0 = R.grads[c["b_off"]:c["b_off"] + c["cout"]].clone()
+                if ty == B_COLSUM and a1 >= 0:
+                    c2 = R.conv(a1)
+                    db2 = R.grads[c2["b_off"]:c2["b_off"] + c2["cout"]].clone()
                 R.run(seg, 1, i)
                 g1 = R.act(a0)
                 if ty == B_RELU_MASK:
@@ -375,6 +379,10 @@ def test_replay_every_op(S, B):
                 dbias = R.grads[c["b_off"]:c["b_off"] + c["cout"]] - db0
                 denom = max(g1.float().abs().reshape(-1, g1.shape[-1]).sum(0).max().item(), 1e-20)
                 assert (dbias - col).abs().max().item() <= 2e-3 * denom
+                if ty == B_COLSUM and a1 >= 0:     # a second convolution fed by the same gradient (hourglass.py:91) shares the pass
+                    c2 = R.conv(a1)
+                    assert (R.grads[c2["b_off"]:c2["b_off"] + c2["cout"]] - db2 - col).abs().max().item() <= 2e-3 * denom
+                    shared_colsums[0] += 1
             elif ty == B_POOL:
                 x, gy = R.act(a0).float(), R.act(a1).float()
                 old = R.act(a2).float().clone()
@@ -410,7 +418,8 @@ def test_replay_every_op(S, B):
     assert all(v > 0.999 for v in R.low_cos.values())
     assert {"F_CONV", "F_BN", "B_BN_APPLY", "B_WGRAD", "B_DGRAD"} <= set(R.low_cos)
     n_bneck = 3 + 15 * S
-    print("BatchNorm-backward applies fused into 1x1 dgrad GEMMs:", fused_applies[0])
+    print("BatchNorm-backward applies fused into 1x1 dgrad GEMMs:", fused_applies[0], " shared bias-gradient passes:", shared_colsums[0])
+    assert shared_colsums[0] == S - 1
     assert fused_applies[0] >= 2 * 15 * S          # BN3 and BN1 of every hourglass bottleneck (+ the heads)
     assert fused_reduces[0] > n_bneck
     print("convolutions / weight gradients with a deferred input BatchNorm:", deferred[0], "statistic writers:", writers[0])
