@@ -223,7 +223,15 @@ __device__ __forceinline__ void bn_bwd_transform_box(uint32_t box_dz, uint32_t b
 //               the dz box and the y box; the transform warps turn the dz box into dp in place, hand it to the MMAs, and
 //               one of them stores it through tmDP (the weight gradient reads dp later).  A stage is recycled once the
 //               MMAs AND that bulk store have read it (empty barrier count 2).
-template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false, int EPI = 8, bool BNB = false>
+//   CTA2       : HALO only: a cluster of two CTAs (one TPC) runs every MMA as tcgen05.mma.cta_group::2 with M = 256.  CTA r keeps
+//               its own four tiles (own strip ring, own accumulators in its own TMEM, own epilogue) and HALF of every
+//               weight box (64 of the 128 output channels); the leader's single thread issues the MMAs for both SMs.  Every
+//               weight half is read from shared memory once and reaches both tensor cores, so the operand reads per SM drop
+//               from 128 to 96 B/clk -- the port that pinned the one-CTA kernel at 55 % tensor-pipe utilisation (ncu).
+//               Barriers: TMA loads of both CTAs count their bytes on the LEADER's full barriers; tcgen05.commit
+//               multicasts to the empty / accumulator-full barriers of both CTAs; the epilogue warps of both CTAs arrive on
+//               the leader's accumulator-empty barriers.
+template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false, int EPI = 8, bool BNB = false, bool CTA2 = false>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ CUtensorMap tmC,
@@ -232,8 +240,9 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
                                                                 const __grid_constant__ CUtensorMap tmZ,
                                                                 const __grid_constant__ CUtensorMap tmDP,
                                                                 const GemmKernelParams p) {
-  constexpr int kBBytes = BLOCK_N * 128;
+  constexpr int kBBytes = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 128;                  // CTA2: this CTA's half of the weight box
   constexpr int kStageBytes = TILES * kABytes + kBBytes + (BNB ? kABytes : 0);   // BNB: + the y box behind the weights
+  static_assert(!CTA2 || HALO, "CTA pairs are implemented for the strip-reuse 3x3 kernel");
   static_assert(!BNB || (TILES == 1 && !HALO), "the fused BatchNorm backward is a 1x1 dgrad variant");
   constexpr int kAccStages = TILES == 1 ? 2 : 1;
   constexpr int kGemmThreads = gemm_threads(EPI), kEpiThreads = 32 * EPI;
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
     if (HALO) {
       for (int s = 0; s < kNumBars; ++s) {
         const bool tmem_empty = s >= 2 * kASlots + 2 * kBSlots + TILES && s < kNumBars - 1;
-        mbar_init(bar0 + 8 * s, tmem_empty ? EPI : 1);
+        mbar_init(bar0 + 8 * s, tmem_empty ? (CTA2 ? 2 * EPI : EPI) : 1);   // CTA2: the epilogue warps of both CTAs arrive on the leader's
       }
     } else {
       for (int s = 0; s < 2 * STAGES + 2; ++s) mbar_init(bar0 + 8 * s, (BNB && s >= STAGES && s < 2 * STAGES) ? 2 : 1);   // BNB: empty = MMAs + dp store
@@ -298,8 +307,13 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), kAccStages * TILES * BLOCK_N);
-    tmem_relinquish();
+    if (CTA2) {
+      tmem_alloc_pair(smem_u32(tmem_slot), kAccStages * TILES * BLOCK_N);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(smem_u32(tmem_slot), kAccStages * TILES * BLOCK_N);
+      tmem_relinquish();
+    }
   }
   if (threadIdx.x == 0) KT(1);
   pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
@@ -311,6 +325,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
   if (BNB) bn_bwd_setup(p.bn_bwd, s_sc, s_sh, s_osc, threadIdx.x, kGemmThreads, blockIdx.x == 0);
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_arrive_wait();   // the peer's barriers are initialised before anything is signalled across the pair
   tc_fence_after();
   if (threadIdx.x == 0) KT(3);
   // the bias is needed by the epilogue only: its (cold) load overlaps the first TMA loads instead of delaying them
@@ -329,8 +344,11 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
   const uint32_t ringB = base + kASlots * kABytes;
   const int rpt = kBlockM / p.W;   // image rows per tile
 
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
   if (HALO && warp == 0) {
     if (lane == 0) {
+      // CTA2: bytes of both CTAs are counted on the leader's full barriers (its producer expects twice the bytes)
+      const uint32_t lfullA = CTA2 ? mapa_u32(fullA, 0) : fullA, lfullB = CTA2 ? mapa_u32(fullB, 0) : fullB;
       int sc = 0;   // running strip counter
       for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
         const int p0 = grp * TILES * kBlockM;
@@ -345,22 +363,32 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
           for (int dyi = 0; dyi < 3; ++dyi) {   // the three weight boxes of this column of taps
             const int slot = set * 3 + dyi;
             mbar_wait(emptyB + 8 * slot, bph ^ 1);
-            mbar_expect_tx(fullB + 8 * slot, kBBytes);
-            tma_load_2d(ringB + slot * kBBytes, &tmB, fullB + 8 * slot, ((dyi * 3 + dxi) * p.cblk + cb) * 64, 0);
+            if (CTA2) {
+              if (rank == 0) mbar_expect_tx(fullB + 8 * slot, 2 * kBBytes);
+              tma_load_2d_pair(ringB + slot * kBBytes, &tmB, lfullB + 8 * slot, ((dyi * 3 + dxi) * p.cblk + cb) * 64, (int)rank * (BLOCK_N / 2));
+            } else {
+              mbar_expect_tx(fullB + 8 * slot, kBBytes);
+              tma_load_2d(ringB + slot * kBBytes, &tmB, fullB + 8 * slot, ((dyi * 3 + dxi) * p.cblk + cb) * 64, 0);
+            }
           }
 #pragma unroll
           for (int j = 0; j < kASlots; ++j) {   // strip rows y0 - 1 ... y0 + TILES * rpt (+ slack), shifted by dx
             mbar_wait(emptyA + 8 * j, aph ^ 1);
-            mbar_expect_tx(fullA + 8 * j, kABytes);
-            tma_load_4d(base + j * kABytes, &tmA, fullA + 8 * j, cb * 64, dx, y0 - 1 + j * rpt, n0);
+            if (CTA2) {
+              if (rank == 0) mbar_expect_tx(fullA + 8 * j, 2 * kABytes);
+              tma_load_4d_pair(base + j * kABytes, &tmA, lfullA + 8 * j, cb * 64, dx, y0 - 1 + j * rpt, n0);
+            } else {
+              mbar_expect_tx(fullA + 8 * j, kABytes);
+              tma_load_4d(base + j * kABytes, &tmA, fullA + 8 * j, cb * 64, dx, y0 - 1 + j * rpt, n0);
+            }
           }
         }
       }
     }
     if (p.late_trigger) pdl_trigger();
   } else if (HALO && warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+    if (lane == 0 && rank == 0) {   // CTA2: the leader's thread issues the M = 256 MMAs of the pair
+      constexpr uint32_t idesc = make_idesc_bf16(CTA2 ? 2 * kBlockM : kBlockM, BLOCK_N, 0, 0);
       const uint32_t row_bytes = (uint32_t)p.W * 128u;
       int sc = 0, lt = 0;
       for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x, ++lt) {
@@ -382,16 +410,19 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
               const uint64_t adesc = make_smem_desc_sw128(base + (uint32_t)(t * rpt + dy + 1) * row_bytes, 16, 1024);
               const uint64_t bdesc = make_smem_desc_sw128(ringB + (set * 3 + dyi) * kBBytes, 16, 1024);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_base + (uint32_t)(t * BLOCK_N), adesc + 2 * k, bdesc + 2 * k, idesc, (st | dyi | k) != 0);
+              for (int k = 0; k < 4; ++k) {
+                if (CTA2) umma_bf16_pair(tmem_base + (uint32_t)(t * BLOCK_N), adesc + 2 * k, bdesc + 2 * k, idesc, (st | dyi | k) != 0);
+                else umma_bf16(tmem_base + (uint32_t)(t * BLOCK_N), adesc + 2 * k, bdesc + 2 * k, idesc, (st | dyi | k) != 0);
+              }
             }
-            umma_commit(emptyA + 8 * t);              // later tiles start at box t + 1
+            auto commit = [&](uint32_t bar) { if (CTA2) umma_commit_pair(bar); else umma_commit(bar); };
+            commit(emptyA + 8 * t);              // later tiles start at box t + 1
             if (t == TILES - 1) {
-              umma_commit(emptyA + 8 * TILES);
+              commit(emptyA + 8 * TILES);
 #pragma unroll
-              for (int dyi = 0; dyi < 3; ++dyi) umma_commit(emptyB + 8 * (set * 3 + dyi));
+              for (int dyi = 0; dyi < 3; ++dyi) commit(emptyB + 8 * (set * 3 + dyi));
             }
-            if (st == nst - 1) umma_commit(tfull0 + 8 * t);   // accumulator of tile t complete
+            if (st == nst - 1) commit(tfull0 + 8 * t);   // accumulator of tile t complete
           }
         }
       }
@@ -751,7 +782,10 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
       if (HALO || t == TILES - 1 || tile + 1 >= num_tiles) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8 * (HALO ? t : acc));
+        if (lane == 0) {
+          if (CTA2) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * t, 0));   // the leader issues the pair's MMAs
+          else mbar_arrive(tempty0 + 8 * (HALO ? t : acc));
+        }
       }
       fence_proxy_async();                            // generic-proxy smem writes -> visible to the TMA engine
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // the eight epilogue warps: tile fully staged
@@ -875,9 +909,11 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_arrive_wait();   // both CTAs are done with the pair's tensor memory and with each other's barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kAccStages * TILES * BLOCK_N);
+    if (CTA2) tmem_dealloc_pair(tmem_base, kAccStages * TILES * BLOCK_N);
+    else tmem_dealloc(tmem_base, kAccStages * TILES * BLOCK_N);
   }
   if (threadIdx.x == 32) KT(12);
 }
@@ -1265,11 +1301,11 @@ int conv_gemm_block_n(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 
 
 static int g_num_sms = 0;
 
-template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false, int EPI = 8, bool BNB = false>
+template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false, int EPI = 8, bool BNB = false, bool CTA2 = false>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                          const CUtensorMap& tmY, const GemmKernelParams& kp, int tiles_m, int max_ctas, cudaStream_t st,
                          const CUtensorMap* tmZ = nullptr, const CUtensorMap* tmDP = nullptr) {
-  constexpr int ring = HALO ? (TILES + 1) * kABytes + 6 * BLOCK_N * 128
+  constexpr int ring = HALO ? (TILES + 1) * kABytes + 6 * (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 128
                             : STAGES * (TILES * kABytes + BLOCK_N * 128 + (BNB ? kABytes : 0));
   constexpr int nbars = HALO ? 2 * (TILES + 1) + 12 + 2 * TILES + 1 : 3 * STAGES + 5;
   constexpr int smem = ring + OUT_BUFS * (BLOCK_N / 64) * kABytes + (nbars * 8 + 15) / 16 * 16 + 16 + BLOCK_N * 4 +
@@ -1278,7 +1314,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    HGB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS, HALO, EPI, BNB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HGB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS, HALO, EPI, BNB, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
   if (!g_num_sms) {
@@ -1289,8 +1325,9 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   const int groups = (tiles_m + TILES - 1) / TILES;
   int grid = groups < g_num_sms ? groups : g_num_sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  HGB_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS, HALO, EPI, BNB>, dim3(grid), dim3(gemm_threads(EPI)), smem, st, tmA, tmB,
-                      tmC, tmR, tmY, tmZ ? *tmZ : tmC, tmDP ? *tmDP : tmC, kp));
+  if (CTA2) grid &= ~1;     // whole CTA pairs (the caller guarantees an even number of groups: both CTAs of a pair loop alike)
+  HGB_CUDA(launch_pdl_cluster(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS, HALO, EPI, BNB, CTA2>, dim3(grid), dim3(gemm_threads(EPI)), smem,
+                              st, CTA2 ? 2 : 1, tmA, tmB, tmC, tmR, tmY, tmZ ? *tmZ : tmC, tmDP ? *tmDP : tmC, kp));
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -1304,7 +1341,7 @@ bool conv_gemm_supports_bn_bwd(int ksize, int Cin, int Cout) {
 
 int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap* tmR,
                      const CUtensorMap* tmY, const ConvGemmArgs& a, cudaStream_t st, const CUtensorMap* tmZ,
-                     const CUtensorMap* tmDP) {
+                     const CUtensorMap* tmDP, const CUtensorMap* tmB64) {
   HGB_CHECK_ARG(a.ksize == 1 || a.ksize == 3, "conv_gemm: kernel size must be 1 or 3");
   HGB_CHECK_ARG(a.Cin % 64 == 0 && a.Cin > 0, "conv_gemm: Cin must be a multiple of 64 (got %d)", a.Cin);
   HGB_CHECK_ARG(a.Cout % 64 == 0 && a.Cout > 0, "conv_gemm: Cout must be a multiple of 64 (got %d)", a.Cout);
@@ -1359,6 +1396,10 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     if (a.Cout == 128) return launch_gemm_t<128, 3, 1, 2, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
     return launch_gemm_t<256, 2, 1, 1, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
   }
+  // CTA pairs (tcgen05.mma.cta_group::2) when the weight map with 64-row boxes is available and the groups pair up: with an
+  // even number of groups and an even grid both CTAs of a pair always run the same number of iterations
+  if (halo && tmB64 && !g_debug[30] && (tiles_m % 8) == 0 && g_num_sms % 2 == 0 && (a.max_ctas <= 0 || a.max_ctas >= 2))
+    return launch_gemm_t<128, 1, 4, 1, true, 8, false, true>(tmA, *tmB64, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
   if (halo) return launch_gemm_t<128, 1, 4, 1, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
   switch (conv_gemm_block_n(a.Cout)) {
     case 64: return ws ? launch_gemm_t<64, 2, 4, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
@@ -1489,7 +1530,13 @@ extern "C" int hgb_conv_gemm(const void* in, const void* w, const float* bias, c
     rc = make_tmap_act(&tmR, res1, N, H, W, ldc);
     if (rc) return rc;
   }
-  return launch_conv_gemm(tmA, tmB, tmC, res1 ? &tmR : nullptr, nullptr, a, (cudaStream_t)stream);
+  CUtensorMap tmB64;
+  const bool pair_ok = ksize == 3 && Cout == 128;
+  if (pair_ok) {
+    rc = make_tmap_mat(&tmB64, w, Cout, ksize * ksize * Cin, 64);
+    if (rc) return rc;
+  }
+  return launch_conv_gemm(tmA, tmB, tmC, res1 ? &tmR : nullptr, nullptr, a, (cudaStream_t)stream, nullptr, nullptr, pair_ok ? &tmB64 : nullptr);
 }
 
 #ifdef HGB_KTIME

@@ -74,7 +74,8 @@ int conv_gemm_block_n(int Cout);
 // tmZ / tmDP: activation maps of the BatchNorm's y tensor and of the dp tensor when a.bn_bwd is enabled (else null)
 int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap* tmR,
                      const CUtensorMap* tmY, const ConvGemmArgs& a, cudaStream_t st, const CUtensorMap* tmZ = nullptr,
-                     const CUtensorMap* tmDP = nullptr);
+                     const CUtensorMap* tmDP = nullptr, const CUtensorMap* tmB64 = nullptr);
+// tmB64: the same weight matrix with 64-row boxes (3x3, 128 output channels): enables the CTA-pair (cta_group::2) kernel
 // whether launch_conv_gemm can run the fused BatchNorm-backward prologue for this shape
 bool conv_gemm_supports_bn_bwd(int ksize, int Cin, int Cout);
 

@@ -479,35 +479,8 @@ __global__ void __launch_bounds__(320) decode_kernel(const T* __restrict__ hm, i
 
   const int warp = t >> 5, lane = t & 31, nwarp = blockDim.x >> 5;
   const int ncand = 16 * VEC;  // candidates per joint: c = k + K*m
-  for (int k = warp; k < K; k += nwarp) {   // this CTA's maximum of joint k -> the sample's key
-    float cv = -CUDART_INF_F;
-    int ci = 0x7fffffff;
-    for (int m = lane; m < ncand; m += 32) {
-      const float a = s_val[k + K * m];
-      const int ia = s_idx[k + K * m];
-      if (better(a, ia, cv, ci)) { cv = a; ci = ia; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
-      if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
-    }
-    if (lane == 0) {
-      atomicMax(keys + 2 * k, decode_key(cv, ci));
-      __threadfence();       // the key must be visible before this CTA's arrival is counted
-    }
-  }
-  __syncthreads();
-  if (t == 0) s_last = atomicAdd(counter, 1) == split - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-
-  // the last CTA of the sample: every share has merged its maxima
-  for (int k = warp; k < K; k += nwarp) {
-    const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(keys + 2 * k);
-    const int ci = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+  // confidence, clipped 3x3 window and outputs of joint k from its argmax element ci (whole warp)
+  auto finish = [&](int k, int ci) {
     const int index = ci / K;  // flat pixel index (row-major)
     const int x = index % W;   // data_utils.py:121
     const int y = index / H;   // data_utils.py:122 (height; square maps only)
@@ -537,7 +510,7 @@ __global__ void __launch_bounds__(320) decode_kernel(const T* __restrict__ hm, i
     if (lane == 0) {
       const int px = pidx % 3, py = pidx / 3;  // always 3 (data_utils.py:168-169)
       int32_t* oi = out_idx + ((size_t)b * K + k) * 4;
-      oi[0] = index; oi[1] = x; oi[2] = y; oi[3] = pidx;   // overwrites the key (and, for joint 0, the counter)
+      oi[0] = index; oi[1] = x; oi[2] = y; oi[3] = pidx;   // (split > 1: overwrites the key and, for joint 0, the counter)
       float* ok = out_kp + ((size_t)b * K + k) * 3;
       // numpy >= 2 (NEP 50) compares the float32 confidence with float32(threshold); numpy 1.x
       // promoted to float64.  They differ only when conf == float32(thr) rounds above thr.
@@ -549,6 +522,38 @@ __global__ void __launch_bounds__(320) decode_kernel(const T* __restrict__ hm, i
         ok[0] = 0.f; ok[1] = 0.f; ok[2] = 0.f;
       }
     }
+  };
+  for (int k = warp; k < K; k += nwarp) {   // this CTA's maximum of joint k
+    float cv = -CUDART_INF_F;
+    int ci = 0x7fffffff;
+    for (int m = lane; m < ncand; m += 32) {
+      const float a = s_val[k + K * m];
+      const int ia = s_idx[k + K * m];
+      if (better(a, ia, cv, ci)) { cv = a; ci = ia; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+      if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
+    }
+    if (split == 1) {          // the CTA saw the whole map: no merge, no keys, no counter
+      finish(k, ci);
+    } else if (lane == 0) {
+      atomicMax(keys + 2 * k, decode_key(cv, ci));
+      __threadfence();       // the key must be visible before this CTA's arrival is counted
+    }
+  }
+  if (split == 1) return;
+  __syncthreads();
+  if (t == 0) s_last = atomicAdd(counter, 1) == split - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // the last CTA of the sample: every share has merged its maxima
+  for (int k = warp; k < K; k += nwarp) {
+    const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(keys + 2 * k);
+    finish(k, (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull)));
   }
 }
 
@@ -776,8 +781,8 @@ extern "C" int hgb_decode(const void* heatmaps, int dtype, int B, int H, int W, 
   while (split < 8 && (int64_t)B * split < 148 * 3) split <<= 1;
   if (g_debug[24] > 0) split = g_debug[24];
   while (split > 1 && (nvec % split != 0 || (nvec / split * vec) % K != 0)) split >>= 1;
-  // keys + arrival counters live in out_idx (see decode_kernel)
-  HGB_CUDA(cudaMemsetAsync(out_idx, 0, (size_t)B * K * 4 * sizeof(int32_t), st));
+  // keys + arrival counters live in out_idx (see decode_kernel); a whole map per CTA needs neither
+  if (split > 1) HGB_CUDA(cudaMemsetAsync(out_idx, 0, (size_t)B * K * 4 * sizeof(int32_t), st));
   if (dtype == HGB_F32) {
     if (iters == 4) decode_kernel<float, 4, 4><<<dim3(split, B), threads, smem, st>>>((const float*)heatmaps, H, W, K, conf_threshold, version, out_idx, out_kpts, stages);
     else decode_kernel<float, 4, 8><<<dim3(split, B), threads, smem, st>>>((const float*)heatmaps, H, W, K, conf_threshold, version, out_idx, out_kpts, stages);

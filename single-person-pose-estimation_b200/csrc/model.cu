@@ -47,6 +47,8 @@ struct ConvL {
   size_t wf_off, wd_off;
   bool has_wd;
   CUtensorMap tm_wf, tm_wd;
+  CUtensorMap tm_wf64, tm_wd64;   // 64-row boxes of the same operands: halves of a CTA pair (3x3, 128 -> 128)
+  bool has_w64 = false;
   double flops;
   int seg;
   int y_act = -1, in_act = -1, z_act = -1, in_bn = -1;
@@ -824,6 +826,13 @@ int build_maps(hgb_model* m) {
       rc = make_tmap_mat(&c.tm_wd, m->p_arena + c.wd_off, c.cin_pad, c.taps * c.cout_pad, conv_gemm_block_n(c.cin_pad));
       if (rc) return rc;
     }
+    c.has_w64 = c.ksize == 3 && c.cout_pad == 128 && c.cin_pad == 128 && c.has_wd;
+    if (c.has_w64) {
+      rc = make_tmap_mat(&c.tm_wf64, m->p_arena + c.wf_off, c.cout_pad, c.taps * c.cin_pad, 64);
+      if (rc) return rc;
+      rc = make_tmap_mat(&c.tm_wd64, m->p_arena + c.wd_off, c.cin_pad, c.taps * c.cout_pad, 64);
+      if (rc) return rc;
+    }
   }
   // weight-refresh table
   std::vector<WeightSyncEntry> tab(m->convs.size());
@@ -922,7 +931,8 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
         a.bn_out.moving_mean = m->p_params + b.mm_off; a.bn_out.moving_var = m->p_params + b.mv_off;
         a.bn_out.mode = 1; a.bn_out.M = in.n * in.h * in.w; a.bn_out.C = b.c;
       }
-      rc = launch_conv_gemm(in.tmap, c.tm_wf, out.tmap, o.a2 >= 0 ? &m->acts[o.a2].tmap : nullptr, nullptr, a, st);
+      rc = launch_conv_gemm(in.tmap, c.tm_wf, out.tmap, o.a2 >= 0 ? &m->acts[o.a2].tmap : nullptr, nullptr, a, st, nullptr, nullptr,
+                            c.has_w64 ? &c.tm_wf64 : nullptr);
       break;
     }
     case F_BN: {
@@ -1021,7 +1031,7 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
         break;
       }
       rc = launch_conv_gemm(dp.tmap, c.tm_wd, out.tmap, o.a2 >= 0 ? &m->acts[o.a2].tmap : nullptr,
-                            o.bn >= 0 ? &m->acts[o.flag - 1].tmap : nullptr, a, st);
+                            o.bn >= 0 ? &m->acts[o.flag - 1].tmap : nullptr, a, st, nullptr, nullptr, c.has_w64 ? &c.tm_wd64 : nullptr);
       break;
     }
     case B_RELU_MASK: {
