@@ -56,7 +56,7 @@ int         hgb_version(void);
  *   20  CTA cap of side-lane weight gradients (default 64, -1 none)    24  CTAs per sample in the decode kernel
  *   25  N = 256 GEMM tiles always with 8 epilogue warps                26  no BatchNorm-backward fusion into 1x1 dgrads (plan build)
  *   27  no programmatic dependent launch exception for small ops       28  decode ring geometry (10 * stages + vectors / thread)
- *   29  no shared bias-gradient pass of conv_1x1_2 / conv_1x1_3 (plan)  30  no CTA pairs (cta_group::2) in the 3x3 strip kernel      */
+ *   29  no shared bias-gradient pass of conv_1x1_2 / conv_1x1_3 (plan)  30  1: CTA pairs (cta_group::2) in the 3x3 strip kernel     */
 int         hgb_debug_set(int key, int value);
 
 /* ------------------------------------------------------------------------- */

@@ -1396,9 +1396,12 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     if (a.Cout == 128) return launch_gemm_t<128, 3, 1, 2, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
     return launch_gemm_t<256, 2, 1, 1, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
   }
-  // CTA pairs (tcgen05.mma.cta_group::2) when the weight map with 64-row boxes is available and the groups pair up: with an
-  // even number of groups and an even grid both CTAs of a pair always run the same number of iterations
-  if (halo && tmB64 && !g_debug[30] && (tiles_m % 8) == 0 && g_num_sms % 2 == 0 && (a.max_ctas <= 0 || a.max_ctas >= 2))
+  // CTA pairs (tcgen05.mma.cta_group::2), OPT-IN with hgb_debug_set(30, 1): parity-green (tests/test_gpu_conv.py and the
+  // batch-80 replay run it) but measured SLOWER than the one-CTA strip kernel on B200 at batch 256 -- forward 64x64 297.7 vs
+  // 260.1 us, dgrad 331.8 vs 299.0 us, 32x32 94.9 vs 84.0 us (profiles/r02_ops_ab_cta_pairs.txt) -- so the one-CTA kernel
+  // stays the default.  Needs the weight map with 64-row boxes and an even number of groups (with an even grid both CTAs of
+  // a pair then run the same number of iterations).
+  if (halo && tmB64 && g_debug[30] == 1 && (tiles_m % 8) == 0 && g_num_sms % 2 == 0 && (a.max_ctas <= 0 || a.max_ctas >= 2))
     return launch_gemm_t<128, 1, 4, 1, true, 8, false, true>(tmA, *tmB64, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
   if (halo) return launch_gemm_t<128, 1, 4, 1, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
   switch (conv_gemm_block_n(a.Cout)) {

@@ -101,6 +101,34 @@ def test_conv_dgrad_mirrored_taps(ops, torch, N, H, C):
     assert (y.float() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("N,H,tap_sign", [(40, 64, 1), (152, 32, 1), (38, 64, -1), (150, 32, -1)])
+def test_conv3x3_cta_pairs_opt_in(ops, torch, N, H, tap_sign):
+    """The cta_group::2 variant of the strip-reuse 3x3 kernel (hgb_debug_set(30, 1): two CTAs of one TPC, M = 256 MMAs,
+    half of every weight box per CTA) against fp32 torch, forward and mirrored-tap dgrad with a residual, and bit-identical
+    to the default one-CTA kernel (same MMA order per accumulator, same epilogue)."""
+    import hgb200
+    lib = hgb200._lib.lib
+    C = 128
+    x = _rand(torch, (N, H, H, C), 21)
+    w = _rand(torch, (C, 9 * C), 22, scale=(9 * C) ** -0.5)
+    bias = torch.randn(C, device="cuda") * 0.1 if tap_sign == 1 else None
+    res = _rand(torch, (N, H, H, C), 23) if tap_sign == -1 else None
+    stats1, stats2 = torch.zeros(2 * C, device="cuda"), torch.zeros(2 * C, device="cuda")
+    y_one = ops.conv_gemm(x, w, bias=bias, res1=res, ksize=3, relu=tap_sign == 1, tap_sign=tap_sign, stats=stats1)
+    try:
+        lib.hgb_debug_set(30, 1)
+        y_pair = ops.conv_gemm(x, w, bias=bias, res1=res, ksize=3, relu=tap_sign == 1, tap_sign=tap_sign, stats=stats2)
+        torch.cuda.synchronize()
+    finally:
+        lib.hgb_debug_set(30, 0)
+    ref = _ref_conv(torch, x, w, bias, 3, tap_sign == 1, flip=tap_sign == -1)
+    if res is not None:
+        ref = ref + res.float()
+    assert (y_pair.float() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+    assert torch.equal(y_pair, y_one)
+    np.testing.assert_allclose(stats2.cpu().numpy(), stats1.cpu().numpy(), rtol=1e-4, atol=1e-2)
+
+
 WG_CASES = [
     (2, 64, 128, 128, 3),
     (2, 64, 256, 128, 1),
