@@ -186,6 +186,8 @@ typedef struct {
   int activation;     /* predict_activation: 0 linear, 1 sigmoid */
   int batch;          /* per-device batch the execution plan is built for */
   int training;       /* 1: plan keeps activations and allocates the backward pass */
+  int mobile;         /* 1: bottleneck_block_mobile (model/hourglass.py:9-11,209-231): every convolution of a bottleneck is a
+                         SeparableConv2D = depthwise k x k (per-channel stencil kernel) + pointwise 1x1 (the tcgen05 GEMM) */
 } hgb_model_config;
 
 /* buffers the caller allocates and binds */
@@ -284,7 +286,8 @@ int hgb_model_conv_input_bn(const hgb_model* m, int conv);
 
 /* plan introspection and single-op stepping: lets a test replay EVERY op of the real execution plan
  * (forward and backward) against an fp32 reference computed from the device's own input tensors.
- * op info = {type, conv, bn, a0, a1, a2, a3, flag}; see csrc/model.cu (OpType) for the roles. */
+ * op info = {type, conv, bn, a0, a1, a2, a3, flag}; see csrc/model.cu (OpType) for the roles.  Types 15-17 (mobile variant):
+ * depthwise forward / input gradient / weight gradient, `conv` = index for hgb_model_dw_detail. */
 int hgb_model_num_ops(const hgb_model* m, int seg, int backward);
 int hgb_model_op_info(const hgb_model* m, int seg, int backward, int index, int info[8]);
 int hgb_model_act_info(const hgb_model* m, int act, int64_t* arena_offset, int dims[4]);
@@ -295,6 +298,7 @@ int hgb_model_op_fused_bn(const hgb_model* m, int seg, int backward, int index, 
 int hgb_model_run_op(hgb_model* m, int seg, int backward, int index, const float* images, int training, void* stream);
 int hgb_model_conv_detail(const hgb_model* m, int conv, int info[8], int64_t offs[2]);
 int hgb_model_bn_detail(const hgb_model* m, int bn, int64_t offs[8]);
+int hgb_model_dw_detail(const hgb_model* m, int dw, int info[4], int64_t* w_off);   /* mobile: depthwise stage {k, c, h, w} */
 int hgb_model_head_buffers(const hgb_model* m, int stack, int64_t offs[2]);
 int hgb_model_begin_step(hgb_model* m, void* stream);
 

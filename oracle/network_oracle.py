@@ -1,7 +1,7 @@
 """fp32 CPU restatement of the reference network, losses-on-outputs and Keras Adam --
 TEST INFRASTRUCTURE ONLY (imported by tests/, __graft_entry__.smoke() and bench.py's CPU legs).
 
-Follows model/hourglass.py:5-206 line by line, with the Keras defaults the reference relies on
+Follows model/hourglass.py:5-231 line by line (mobile=True: the SeparableConv2D bottleneck of :209-231), with the Keras defaults the reference relies on
 (SURVEY.md section 7 appendix): Conv2D use_bias, 'same' padding (TF: extra pixel after),
 activation inside the conv, BatchNormalization(momentum .99, eps 1e-3) in training mode
 (biased batch variance) or inference mode (moving statistics), MaxPool2D 2x2/2,
@@ -34,7 +34,8 @@ BN_MOMENTUM = 0.99
 class _Builder:
     """Walks model/hourglass.py once; in 'spec' mode it records parameter names/shapes, in 'run' mode it computes."""
 
-    def __init__(self, params=None, training=True, update_moving=False, emulate_bf16=False):
+    def __init__(self, params=None, training=True, update_moving=False, emulate_bf16=False, mobile=False):
+        self.mobile = mobile              # bottleneck_block_mobile instead of bottleneck_block (hourglass.py:9-11)
         self.params = params
         self.training = training
         self.update_moving = update_moving
@@ -70,6 +71,25 @@ class _Builder:
         y = self.q(y)                      # the conv epilogue stores bf16 (logits included)
         if activation == "sigmoid":
             y = torch.sigmoid(y)           # fp32 heat map computed from the stored logits
+        self.taps[name] = y
+        return y
+
+    def sepconv(self, x, name, k, cin, cout, activation):
+        """SeparableConv2D (hourglass.py:216-226): depthwise k x k 'same' (depth_multiplier 1, no bias, no activation), then
+        pointwise 1x1 + bias + activation.  Keras variables: depthwise_kernel (k,k,cin,1), pointwise_kernel (1,1,cin,cout), bias."""
+        if self.params is None:
+            self.spec[name + "/depthwise_kernel"] = (k, k, cin, 1)
+            self.spec[name + "/pointwise_kernel"] = (1, 1, cin, cout)
+            self.spec[name + "/bias"] = (cout,)
+            return x
+        dw = self.params[name + "/depthwise_kernel"].permute(2, 3, 0, 1)       # (k,k,cin,1) -> (cin,1,k,k); fp32 on the device too
+        t = self.q(F.conv2d(x, dw, None, padding=k // 2, groups=cin))          # the stencil kernel stores bf16
+        w = self.q(self.params[name + "/pointwise_kernel"]).permute(3, 2, 0, 1)
+        y = F.conv2d(t, w, self.params[name + "/bias"])
+        if activation == "relu":
+            y = torch.relu(y)
+        y = self.q(y)
+        self.taps[name + "/depthwise"] = t
         self.taps[name] = y
         return y
 
@@ -115,14 +135,15 @@ class _Builder:
 
     # ---- blocks (hourglass.py:184-206, 160-181, 127-157, 71-93, 54-68)
     def bottleneck(self, x, cin, cout, name):
+        conv = self.sepconv if self.mobile else self.conv      # hourglass.py:209-231 vs :184-206: same wiring, other layer class
         skip = x
         if cin != cout:
-            skip = self.conv(x, name + "_skip", 1, cin, cout, "relu")
-        y = self.conv(x, name + "_conv_1x1_1", 1, cin, cout // 2, "relu")
+            skip = conv(x, name + "_skip", 1, cin, cout, "relu")
+        y = conv(x, name + "_conv_1x1_1", 1, cin, cout // 2, "relu")
         y = self.bn(y, cout // 2)
-        y = self.conv(y, name + "_conv_3x3_2", 3, cout // 2, cout // 2, "relu")
+        y = conv(y, name + "_conv_3x3_2", 3, cout // 2, cout // 2, "relu")
         y = self.bn(y, cout // 2)
-        y = self.conv(y, name + "_conv_1x1_3", 1, cout // 2, cout, "relu")
+        y = conv(y, name + "_conv_1x1_3", 1, cout // 2, cout, "relu")
         y = self.bn(y, cout, residual=skip if self.params is not None else None)  # Add (hourglass.py:204)
         return y if self.params is not None else x
 
@@ -171,9 +192,9 @@ class _Builder:
         return outs
 
 
-def param_spec(num_classes=17, num_stacks=1, num_channels=256):
+def param_spec(num_classes=17, num_stacks=1, num_channels=256, mobile=False):
     """OrderedDict name -> shape in Keras creation order (kernels HWIO)."""
-    b = _Builder(None)
+    b = _Builder(None, mobile=mobile)
     b.model(None, num_classes, num_stacks, num_channels, "sigmoid")
     return b.spec
 
@@ -190,7 +211,7 @@ def init_params(spec, seed=2, perturb_bn=False):
     rng = np.random.default_rng(seed)
     out = OrderedDict()
     for name, shape in spec.items():
-        if name.endswith("/kernel"):
+        if name.endswith("kernel"):       # kernel / depthwise_kernel / pointwise_kernel: glorot_uniform over Keras' fans
             k1, k2, cin, cout = shape
             limit = np.sqrt(6.0 / (k1 * k2 * cin + k1 * k2 * cout))
             out[name] = rng.uniform(-limit, limit, size=shape).astype(np.float32)
@@ -217,13 +238,13 @@ def _fp32_exact(device):
 
 
 def forward(params_np, images_nhwc, num_classes, num_stacks, num_channels, activation="sigmoid", training=True,
-            requires_grad=False, update_moving=False, return_taps=False, emulate_bf16=False, device="cpu"):
+            requires_grad=False, update_moving=False, return_taps=False, emulate_bf16=False, device="cpu", mobile=False):
     """images (B,H,W,3) f32 -> list of S tensors (B,h,w,K) f32 (NHWC).  Returns (outputs, torch params)."""
     _fp32_exact(device)
     params = OrderedDict((k, torch.tensor(v, dtype=torch.float32, device=device, requires_grad=requires_grad and "moving_" not in k))
                          for k, v in params_np.items())
     x = torch.as_tensor(np.asarray(images_nhwc), dtype=torch.float32).to(device).permute(0, 3, 1, 2)
-    b = _Builder(params, training=training, update_moving=update_moving, emulate_bf16=emulate_bf16)
+    b = _Builder(params, training=training, update_moving=update_moving, emulate_bf16=emulate_bf16, mobile=mobile)
     outs = b.model(x, num_classes, num_stacks, num_channels, activation)
     outs = [o.permute(0, 2, 3, 1) for o in outs]
     if return_taps:
@@ -251,10 +272,10 @@ def torch_loss(kind, y_true, y_pred):
 
 
 def loss_and_grads(params_np, images, y_true, kind, num_classes, num_stacks, num_channels, activation="sigmoid",
-                   emulate_bf16=False, device="cpu"):
+                   emulate_bf16=False, device="cpu", mobile=False):
     """Training-mode forward, sum of per-stack losses (Keras compile with one loss fn), backward."""
     outs, params = forward(params_np, images, num_classes, num_stacks, num_channels, activation, training=True,
-                           requires_grad=True, emulate_bf16=emulate_bf16, device=device)
+                           requires_grad=True, emulate_bf16=emulate_bf16, device=device, mobile=mobile)
     t = torch.as_tensor(np.asarray(y_true), dtype=torch.float32).to(device)
     losses = [torch_loss(kind, t, o) for o in outs]
     total = sum(losses)

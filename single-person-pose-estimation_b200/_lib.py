@@ -21,7 +21,7 @@ vp, i32, i64, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_double
 
 class ModelConfig(C.Structure):
     _fields_ = [("num_classes", i32), ("num_stacks", i32), ("num_channels", i32), ("in_h", i32), ("in_w", i32),
-                ("activation", i32), ("batch", i32), ("training", i32)]
+                ("activation", i32), ("batch", i32), ("training", i32), ("mobile", i32)]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check every symbol of hgb200.h is exported
@@ -84,6 +84,7 @@ PROTOTYPES = {
     "hgb_model_op_fused_bn": (i32, [vp, i32, i32, i32, C.POINTER(i32 * 3)]),
     "hgb_model_run_op": (i32, [vp, i32, i32, i32, vp, i32, vp]),
     "hgb_model_conv_detail": (i32, [vp, i32, C.POINTER(i32 * 8), C.POINTER(i64 * 2)]),
+    "hgb_model_dw_detail": (i32, [vp, i32, C.POINTER(i32 * 4), C.POINTER(i64)]),
     "hgb_model_bn_detail": (i32, [vp, i32, C.POINTER(i64 * 8)]),
     "hgb_model_head_buffers": (i32, [vp, i32, C.POINTER(i64 * 2)]),
     "hgb_model_begin_step": (i32, [vp, vp]),

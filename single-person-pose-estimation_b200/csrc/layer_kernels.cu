@@ -3,6 +3,8 @@
 // All are HBM-bound streaming kernels: one thread owns 8 consecutive channels (one 16-byte access)
 // of a row; per-channel reductions are accumulated in registers over the thread's rows, combined in
 // shared memory and flushed with one atomic per channel per block.
+#include <algorithm>
+
 #include "layer_kernels.cuh"
 
 namespace hgb {
@@ -474,6 +476,147 @@ int relu_mask_colsum(const bf16* g, const bf16* y, bf16* dp, float* dbias, int M
   if (M == 0) return HGB_OK;
   launch_pdl(relu_mask_colsum_kernel, dim3(row_blocks(M, C, 8)), dim3(256), 2048 * sizeof(float), st, g, y, dp, dbias, M, C, c_valid, relu,
              dbias2);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+// ---------------------------------------------------------------------------------- depthwise convolution (mobile variant)
+// SeparableConv2D of bottleneck_block_mobile (model/hourglass.py:209-231) = depthwise k x k 'same' convolution (one filter per
+// channel, no bias, no activation) followed by a pointwise 1x1 convolution (bias + activation), which runs on the tcgen05 GEMM
+// like every other 1x1 layer.  The depthwise half is a per-channel stencil: HBM-bound, one thread per (pixel, 8 channels).
+//   forward  : out[p][c] = sum_tap x[p + tap][c] * w[tap][c]                  (fp32 weights, fp32 accumulate, bf16 out)
+//   backward : dx[p][c]  = sum_tap dy[p - tap][c] * w[tap][c] (+ residuals)   = the same stencil with mirrored taps (flip)
+//   weights  : dw[tap][c] += sum_p dy[p][c] * x[p + tap][c]
+template <int KS>
+__global__ void __launch_bounds__(256) dwconv_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const bf16* __restrict__ res1,
+                                                     const bf16* __restrict__ res2, bf16* __restrict__ out, int64_t total, int H, int W, int G,
+                                                     int flip) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int R = KS / 2;
+  const int C = G * 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    int64_t pix = i / G;
+    const int px = (int)(pix % W);
+    pix /= W;
+    const int py = (int)(pix % H);
+    const int64_t n = pix / H;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+      const int yy = py + ky - R;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) {
+        const int xx = px + kx - R;
+        if (xx < 0 || xx >= W) continue;
+        float v[8];
+        unpack8(ld16(x + ((n * H + yy) * W + xx) * C + g * 8), v);
+        const int tap = flip ? (KS - 1 - ky) * KS + (KS - 1 - kx) : ky * KS + kx;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (size_t)tap * C + g * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (size_t)tap * C + g * 8) + 1);
+        acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]); acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
+        acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]); acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+      }
+    }
+    if (res1) {
+      float q[8];
+      unpack8(*reinterpret_cast<const uint4*>(res1 + (size_t)i * 8), q);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += q[j];
+    }
+    if (res2) {
+      float q[8];
+      unpack8(*reinterpret_cast<const uint4*>(res2 + (size_t)i * 8), q);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += q[j];
+    }
+    st16(out + (size_t)i * 8, pack8(acc));
+  }
+}
+
+int dwconv(const bf16* x, const float* w, const bf16* res1, const bf16* res2, bf16* out, int N, int H, int W, int C, int ksize, int flip,
+           cudaStream_t st) {
+  HGB_CHECK_ARG(C % 8 == 0 && (ksize == 1 || ksize == 3), "dwconv: C %% 8 and a 1x1 or 3x3 kernel required");
+  const int64_t total = (int64_t)N * H * W * (C / 8);
+  if (total == 0) return HGB_OK;
+  if (ksize == 1)
+    launch_pdl(dwconv_kernel<1>, dim3(flat_blocks(total)), dim3(256), 0, st, x, w, res1, res2, out, total, H, W, C / 8, flip);
+  else
+    launch_pdl(dwconv_kernel<3>, dim3(flat_blocks(total)), dim3(256), 0, st, x, w, res1, res2, out, total, H, W, C / 8, flip);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
+// dw[tap][c] += sum over pixels of dy[p][c] * x[p + tap][c].  Thread = (8 channels, a strided set of pixel rows); per-thread
+// partial sums for all taps in registers, combined per block through shared memory, one global reduction per (tap, channel).
+template <int KS>
+__global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw,
+                                                           int N, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float s_acc[];       // [R][KS*KS][C]
+  constexpr int T = KS * KS, Rd = KS / 2;
+  const int G = C >> 3, R = 256 / G;
+  const int g = threadIdx.x % G, r0 = threadIdx.x / G;
+  float acc[T][8];
+#pragma unroll
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  const int64_t M = (int64_t)N * H * W;
+  for (int64_t p = (int64_t)blockIdx.x * R + r0; p < M; p += (int64_t)gridDim.x * R) {
+    const int px = (int)(p % W), py = (int)((p / W) % H);
+    float d[8];
+    unpack8(ld16(dy + p * C + g * 8), d);
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+      const int yy = py + ky - Rd;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) {
+        const int xx = px + kx - Rd;
+        if (xx < 0 || xx >= W) continue;
+        float v[8];
+        unpack8(ld16(x + (p + (int64_t)(ky - Rd) * W + (kx - Rd)) * C + g * 8), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[ky * KS + kx][j] = fmaf(d[j], v[j], acc[ky * KS + kx][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    float4* dst = reinterpret_cast<float4*>(s_acc + ((size_t)r0 * T + t) * C + g * 8);
+    dst[0] = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+    dst[1] = make_float4(acc[t][4], acc[t][5], acc[t][6], acc[t][7]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * C; i += blockDim.x) {
+    float t = 0.f;
+    for (int r = 0; r < R; ++r) t += s_acc[(size_t)r * T * C + i];
+    atomicAdd(dw + i, t);
+  }
+}
+
+int dwconv_wgrad(const bf16* x, const bf16* dy, float* dw, int N, int H, int W, int C, int ksize, cudaStream_t st) {
+  HGB_CHECK_ARG(C % 8 == 0 && 256 % (C / 8) == 0 && (ksize == 1 || ksize == 3), "dwconv_wgrad: unsupported shape");
+  const int64_t M = (int64_t)N * H * W;
+  if (M == 0) return HGB_OK;
+  const int taps = ksize * ksize;
+  const size_t smem = (size_t)256 * 8 * taps * sizeof(float);      // R * T * C floats = 256 threads x 8 channels x T
+  int blocks = (int)std::min<int64_t>(148 * 2, (M + 63) / 64);
+  if (blocks < 1) blocks = 1;
+  if (ksize == 1) {
+    launch_pdl(dwconv_wgrad_kernel<1>, dim3(blocks), dim3(256), smem, st, x, dy, dw, N, H, W, C);
+  } else {
+    static bool attr_done = false;
+    if (!attr_done) {
+      HGB_CUDA(cudaFuncSetAttribute(dwconv_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_done = true;
+    }
+    launch_pdl(dwconv_wgrad_kernel<3>, dim3(blocks), dim3(256), smem, st, x, dy, dw, N, H, W, C);
+  }
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }

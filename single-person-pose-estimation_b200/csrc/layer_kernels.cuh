@@ -38,6 +38,12 @@ int bn_bwd_apply(const bf16* dz, const bf16* y, bf16* dp, const float* bsums, co
 int relu_mask_colsum(const bf16* g, const bf16* y, bf16* dp, float* dbias, int M, int C, int c_valid, int relu,
                      cudaStream_t st, float* dbias2 = nullptr);
 
+// Depthwise half of SeparableConv2D (bottleneck_block_mobile, hourglass.py:209-231): out = dw_conv(x, w) (+res1 +res2);
+// w fp32 [k*k][C] (tap-major); flip = mirrored taps (the input gradient of the same layer).  And its weight gradient.
+int dwconv(const bf16* x, const float* w, const bf16* res1, const bf16* res2, bf16* out, int N, int H, int W, int C, int ksize, int flip,
+           cudaStream_t st);
+int dwconv_wgrad(const bf16* x, const bf16* dy, float* dw, int N, int H, int W, int C, int ksize, cudaStream_t st);
+
 // Prediction head (hourglass.py:83): logits [M][ldl] bf16 (first K valid) -> heat [M][K] f32 = act(logits) and
 // pbf [M][64] bf16 (act value, zero in the padding channels) for the re-injection conv (hourglass.py:88).
 int head_act_fwd(const bf16* logits, int ldl, float* heat, bf16* pbf, int M, int K, int sigmoid, cudaStream_t st);

@@ -52,6 +52,15 @@ struct ConvL {
   double flops;
   int seg;
   int y_act = -1, in_act = -1, z_act = -1, in_bn = -1;
+  int dw = -1;          // mobile: index of the depthwise stage that feeds this (pointwise) convolution
+};
+
+// depthwise stage of a SeparableConv2D (mobile bottleneck): per-channel k x k stencil, fp32 weights [k*k][c], no bias
+struct DwL {
+  std::string name;
+  int k, c, h, w;
+  int64_t w_off;        // float offset into the parameter buffer
+  int in_act, out_act;
 };
 
 struct BNL {
@@ -72,7 +81,8 @@ struct ParamT {
 
 enum OpType {
   F_IM2COL, F_CONV, F_BN, F_POOL, F_UPADD, F_HEAD,
-  B_BN_REDUCE, B_BN_APPLY, B_WGRAD, B_DGRAD, B_RELU_MASK, B_COLSUM, B_POOL, B_UPADD, B_HEAD
+  B_BN_REDUCE, B_BN_APPLY, B_WGRAD, B_DGRAD, B_RELU_MASK, B_COLSUM, B_POOL, B_UPADD, B_HEAD,
+  F_DW, B_DW_DGRAD, B_DW_WGRAD      // mobile variant: depthwise stencil (conv = index into dws)
 };
 
 struct Op {
@@ -95,7 +105,7 @@ constexpr int kLaneMain = 0;    // the critical chain: down path, bottom, merges
 constexpr int kLaneWgrad = 1;   // weight / bias gradients of the main chain
 constexpr int kLaneShort0 = 2;  // + level (f1, f2, f4, f8): the skip bottleneck of that level
 constexpr int kNumLanes = 6;
-constexpr int kScratchKinds = 4;                  // dp3 | dz(mid) | dp(mid, conv2) | dp(mid, conv1)
+constexpr int kScratchKinds = 8;                  // dp3 | dz(mid) | dp(mid, conv2) | dp(mid, conv1) | mobile: dt of conv3 / conv2 / conv1 / skip
 constexpr int kScratchSets = 2 + 4;               // main chain ping-pong + one per skip lane
 
 struct Range { int space; size_t lo, hi; };       // space 0: arena bytes, 1: gradient buffer (floats)
@@ -131,6 +141,7 @@ struct hgb_model {
 
   std::vector<Act> acts;
   std::vector<ConvL> convs;
+  std::vector<DwL> dws;
   std::vector<BNL> bns;
   std::vector<ParamT> params;
   std::vector<std::vector<Op>> fwd_ops, bwd_ops;  // per segment
@@ -224,7 +235,8 @@ struct hgb_model {
     return p.off;
   }
 
-  int add_conv(const std::string& name, int in_act, int real_k, int real_cin, int cout, int relu, bool need_dgrad) {
+  int add_conv(const std::string& name, int in_act, int real_k, int real_cin, int cout, int relu, bool need_dgrad,
+               const char* kernel_leaf = "/kernel") {
     const Act& in = acts[in_act];
     ConvL c;
     c.name = name;
@@ -236,7 +248,7 @@ struct hgb_model {
     c.relu = relu;
     c.h = in.h; c.w = in.w;
     const int64_t kd[4] = {real_k, real_k, real_cin, cout};
-    c.w_off = add_param(name + "/kernel", 4, kd, 1);
+    c.w_off = add_param(name + kernel_leaf, 4, kd, 1);
     const int64_t bd[1] = {cout};
     c.b_off = add_param(name + "/bias", 1, bd, 1);
     c.wf_off = arena_alloc((size_t)c.cout_pad * c.taps * c.cin_pad * 2);
@@ -269,8 +281,26 @@ struct hgb_model {
 
   // conv (+ReLU) [+ BN] -> returns the tensor the next layer consumes; y/z report both stages
   int conv_unit(const std::string& name, int in_act, int real_k, int real_cin, int cout, int relu, bool bn, bool need_dgrad,
-                int bn_res, int* conv_idx, int* bn_idx, int* y_act, int res1 = -1, int res2 = -1, bool defer_bn = false) {
-    const int ci = add_conv(name, in_act, real_k, real_cin, cout, relu, need_dgrad);
+                int bn_res, int* conv_idx, int* bn_idx, int* y_act, int res1 = -1, int res2 = -1, bool defer_bn = false,
+                bool separable = false) {
+    int dwi = -1;
+    if (separable) {
+      // SeparableConv2D (hourglass.py:218-226): depthwise k x k on the input channels, then the pointwise 1x1 (bias, activation).
+      // Keras variable order: depthwise_kernel (k,k,cin,1), pointwise_kernel (1,1,cin,cout), bias.
+      DwL d;
+      d.name = name; d.k = real_k; d.c = acts[in_act].c; d.h = acts[in_act].h; d.w = acts[in_act].w;
+      const int64_t kd[4] = {real_k, real_k, real_cin, 1};
+      d.w_off = add_param(name + "/depthwise_kernel", 4, kd, 1);
+      d.in_act = in_act;
+      d.out_act = new_act(acts[in_act].n, d.h, d.w, d.c);
+      dws.push_back(d);
+      dwi = (int)dws.size() - 1;
+      Op o; o.type = F_DW; o.conv = dwi; o.a0 = in_act; o.a1 = d.out_act; emit_f(o);
+      in_act = d.out_act;
+      real_k = 1;
+    }
+    const int ci = add_conv(name, in_act, real_k, real_cin, cout, relu, need_dgrad, separable ? "/pointwise_kernel" : "/kernel");
+    convs[ci].dw = dwi;
     const Act in = acts[in_act];
     const int y = new_act(in.n, in.h, in.w, convs[ci].cout_pad);
     Op o;
@@ -310,14 +340,15 @@ struct hgb_model {
     r.x = x;
     r.skip_conv = -1; r.s_act = -1;
     int skip = x;
+    const bool sep = cfg.mobile != 0;   // bottleneck_block_mobile: every convolution of the block is a SeparableConv2D
     if (cin != cout) {
-      skip = conv_unit(name + "_skip", x, 1, cin, cout, 1, false, true, -1, &r.skip_conv, nullptr, nullptr);
+      skip = conv_unit(name + "_skip", x, 1, cin, cout, 1, false, true, -1, &r.skip_conv, nullptr, nullptr, -1, -1, false, sep);
       r.s_act = skip;
     }
-    r.z1 = conv_unit(name + "_conv_1x1_1", x, 1, cin, cout / 2, 1, true, true, -1, &r.c1, &r.bn1, &r.y1);
+    r.z1 = conv_unit(name + "_conv_1x1_1", x, 1, cin, cout / 2, 1, true, true, -1, &r.c1, &r.bn1, &r.y1, -1, -1, false, sep);
     r.z2 = conv_unit(name + "_conv_3x3_2", r.z1, 3, cout / 2, cout / 2, 1, true, true, -1, &r.c2, &r.bn2, &r.y2, -1, -1,
-                     /*defer_bn=*/true);   // only consumer: the 1x1 conv_1x1_3
-    r.out = conv_unit(name + "_conv_1x1_3", r.z2, 1, cout / 2, cout, 1, true, true, skip, &r.c3, &r.bn3, &r.y3);
+                     /*defer_bn=*/!sep, sep);   // only consumer: the 1x1 conv_1x1_3 (a depthwise stage cannot normalise its operand)
+    r.out = conv_unit(name + "_conv_1x1_3", r.z2, 1, cout / 2, cout, 1, true, true, skip, &r.c3, &r.bn3, &r.y3, -1, -1, false, sep);
     return r;
   }
   int pool(int x) {
@@ -342,10 +373,29 @@ struct hgb_model {
     grad_max = std::max(grad_max, grad_cur);
     return alias_act(n, h, w, c, off);
   }
-  void bn_conv_bwd(int bn, int conv, int dz, int y, int dp, int x_in, int dgrad_out, int res1, int res2) {
+  // mobile: the gradient of a separable convolution passes through its depthwise stage: the pointwise dgrad writes dt (gradient
+  // wrt the depthwise output, scratch `kind`), the depthwise stencil with mirrored taps turns it into the input gradient
+  // (+ residuals), and the depthwise weights get their own reduction.  Returns true when it handled the dgrad / wgrad pair.
+  bool separable_bwd(int conv, int dp, int dgrad_out, int res1, int res2, int kind) {
+    const int dwi = convs[conv].dw;
+    if (dwi < 0) return false;
+    const DwL& d = dws[dwi];
+    const Act t = acts[d.out_act];
+    const int dt = scratch_act(kind, t.n, t.h, t.w, t.c);
+    Op o;
+    o.type = B_DGRAD; o.conv = conv; o.a0 = dp; o.a1 = dt; emit_b(o);
+    emit_wgrad(conv, dp, d.out_act);
+    if (dgrad_out >= 0) {
+      o = Op(); o.type = B_DW_DGRAD; o.conv = dwi; o.a0 = dt; o.a1 = dgrad_out; o.a2 = res1; o.a3 = res2; emit_b(o);
+    }
+    o = Op(); o.type = B_DW_WGRAD; o.conv = dwi; o.a0 = dt; o.a1 = d.in_act; o.lane = leaf_lane(); emit_b(o);
+    return true;
+  }
+  void bn_conv_bwd(int bn, int conv, int dz, int y, int dp, int x_in, int dgrad_out, int res1, int res2, int dt_kind = 4) {
     Op o;
     o = Op(); o.type = B_BN_REDUCE; o.bn = bn; o.a0 = dz; o.a1 = y; emit_b(o);
     o = Op(); o.type = B_BN_APPLY; o.bn = bn; o.conv = conv; o.a0 = dz; o.a1 = y; o.a2 = dp; emit_b(o);
+    if (separable_bwd(conv, dp, dgrad_out, res1, res2, dt_kind)) return;
     // the dgrad continues the chain; the weight gradient is a leaf of the backward graph (side lane)
     const bool wfirst = hgb::g_debug[10] != 0;
     if (wfirst) emit_wgrad(conv, dp, x_in);
@@ -373,19 +423,30 @@ struct hgb_model {
     const int dzm = scratch_act(1, o.n, o.h, o.w, cmid);
     const int dpm = scratch_act(2, o.n, o.h, o.w, cmid);
     const int dpm1 = scratch_act(3, o.n, o.h, o.w, cmid);
-    bn_conv_bwd(r.bn3, r.c3, g_out, r.y3, dp3, r.z2, dzm, -1, -1);
-    bn_conv_bwd(r.bn2, r.c2, dzm, r.y2, dpm, r.z1, dzm, -1, -1);
+    bn_conv_bwd(r.bn3, r.c3, g_out, r.y3, dp3, r.z2, dzm, -1, -1, 4);
+    bn_conv_bwd(r.bn2, r.c2, dzm, r.y2, dpm, r.z1, dzm, -1, -1, 5);
     if (r.skip_conv >= 0) {
-      bn_conv_bwd(r.bn1, r.c1, dzm, r.y1, dpm1, r.x, -1, -1, -1);
-      Op m;
-      m.type = B_RELU_MASK; m.conv = r.skip_conv; m.a0 = g_out; m.a1 = r.s_act; m.flag = 1; emit_b(m);
-      if (g_x >= 0) {
-        m = Op(); m.type = B_DGRAD; m.conv = r.skip_conv; m.a0 = g_out; m.a1 = g_x; m.a2 = extra; emit_b(m);
-        m = Op(); m.type = B_DGRAD; m.conv = r.c1; m.a0 = dpm1; m.a1 = g_x; m.a2 = g_x; emit_b(m);
+      const bool sep = convs[r.c1].dw >= 0;
+      if (sep) {
+        // mobile: both branches end in a depthwise stage; the skip's input gradient is written first, conv_1x1_1's is added to it
+        Op m;
+        m = Op(); m.type = B_BN_REDUCE; m.bn = r.bn1; m.a0 = dzm; m.a1 = r.y1; emit_b(m);
+        m = Op(); m.type = B_BN_APPLY; m.bn = r.bn1; m.conv = r.c1; m.a0 = dzm; m.a1 = r.y1; m.a2 = dpm1; emit_b(m);
+        m = Op(); m.type = B_RELU_MASK; m.conv = r.skip_conv; m.a0 = g_out; m.a1 = r.s_act; m.flag = 1; emit_b(m);
+        separable_bwd(r.skip_conv, g_out, g_x, extra, -1, 7);
+        separable_bwd(r.c1, dpm1, g_x, g_x >= 0 ? g_x : -1, -1, 6);
+      } else {
+        bn_conv_bwd(r.bn1, r.c1, dzm, r.y1, dpm1, r.x, -1, -1, -1);
+        Op m;
+        m.type = B_RELU_MASK; m.conv = r.skip_conv; m.a0 = g_out; m.a1 = r.s_act; m.flag = 1; emit_b(m);
+        if (g_x >= 0) {
+          m = Op(); m.type = B_DGRAD; m.conv = r.skip_conv; m.a0 = g_out; m.a1 = g_x; m.a2 = extra; emit_b(m);
+          m = Op(); m.type = B_DGRAD; m.conv = r.c1; m.a0 = dpm1; m.a1 = g_x; m.a2 = g_x; emit_b(m);
+        }
+        emit_wgrad(r.skip_conv, g_out, r.x);
       }
-      emit_wgrad(r.skip_conv, g_out, r.x);
     } else {
-      bn_conv_bwd(r.bn1, r.c1, dzm, r.y1, dpm1, r.x, g_x, g_out, extra);
+      bn_conv_bwd(r.bn1, r.c1, dzm, r.y1, dpm1, r.x, g_x, g_out, extra, 6);
     }
   }
   void linear_conv_bwd(int conv, int dp, int x_in, int dgrad_out, int res1) {
@@ -609,7 +670,8 @@ int build(hgb_model* m) {
           for (int i = (int)out.size() - 1; i >= 0 && w < 0; --i) {
             const Op& q = out[i];
             const int written = q.type == B_DGRAD ? q.a1 : q.type == B_POOL ? q.a2 : q.type == B_UPADD ? q.a1
-                              : q.type == B_BN_APPLY ? q.a2 : q.type == B_RELU_MASK ? q.a0 : q.type == B_HEAD ? q.a1 : -1;
+                              : q.type == B_BN_APPLY ? q.a2 : q.type == B_RELU_MASK ? q.a0 : q.type == B_HEAD ? q.a1
+                              : q.type == B_DW_DGRAD ? q.a1 : -1;
             if (written >= 0 && (written == o.a0 || m->acts[written].off == m->acts[o.a0].off)) w = i;
           }
           if (w >= 0 && out[w].type == B_DGRAD && out[w].a1 == o.a0 && out[w].bn < 0) {
@@ -750,6 +812,14 @@ void op_access(const hgb_model* m, const Op& o, std::vector<Range>& r, std::vect
       add_arena(r, m->heat_off[o.flag], hm_bytes);
       if (m->cfg.training) add_arena(r, m->dldp_off[o.flag], hm_bytes);
       break;
+    case F_DW: add_act(m, r, o.a0); add_act(m, w, o.a1); break;
+    case B_DW_DGRAD: add_act(m, r, o.a0); add_act(m, r, o.a2); add_act(m, r, o.a3); add_act(m, w, o.a1); break;
+    case B_DW_WGRAD: {
+      const DwL& d = m->dws[o.conv];
+      add_act(m, r, o.a0); add_act(m, r, o.a1);
+      add_grad(w, d.w_off, (int64_t)d.k * d.k * d.c);
+      break;
+    }
   }
 }
 
@@ -1064,6 +1134,24 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
                         gl.n * gl.h * gl.w, m->K, m->cfg.activation, st);
       break;
     }
+    case F_DW: {
+      const DwL& d = m->dws[o.conv];
+      const Act& x = m->acts[o.a0];
+      rc = dwconv(act_ptr(m, o.a0), m->p_params + d.w_off, nullptr, nullptr, act_ptr(m, o.a1), x.n, x.h, x.w, x.c, d.k, 0, st);
+      break;
+    }
+    case B_DW_DGRAD: {
+      const DwL& d = m->dws[o.conv];
+      const Act& g = m->acts[o.a0];
+      rc = dwconv(act_ptr(m, o.a0), m->p_params + d.w_off, act_ptr(m, o.a2), act_ptr(m, o.a3), act_ptr(m, o.a1), g.n, g.h, g.w, g.c, d.k, 1, st);
+      break;
+    }
+    case B_DW_WGRAD: {
+      const DwL& d = m->dws[o.conv];
+      const Act& g = m->acts[o.a0];
+      rc = dwconv_wgrad(act_ptr(m, o.a1), act_ptr(m, o.a0), m->p_grads + d.w_off, g.n, g.h, g.w, g.c, d.k, st);
+      break;
+    }
   }
   if (rc == HGB_OK) ++m->launches;
   return rc;
@@ -1185,6 +1273,7 @@ extern "C" int hgb_model_create(const hgb_model_config* cfg, int device, hgb_mod
                 "hgb_model_create: input must be square, a power of two in [64,256] (got %dx%d)", cfg->in_h, cfg->in_w);
   HGB_CHECK_ARG(cfg->activation == 0 || cfg->activation == 1, "hgb_model_create: activation must be 0 (linear) or 1 (sigmoid)");
   HGB_CHECK_ARG(cfg->batch >= 1, "hgb_model_create: batch must be >= 1");
+  HGB_CHECK_ARG(cfg->mobile == 0 || cfg->mobile == 1, "hgb_model_create: mobile must be 0 or 1 (got %d)", cfg->mobile);
   HGB_CHECK_ARG(((int64_t)cfg->in_h / 4) * (cfg->in_w / 4) * cfg->num_classes % 4 == 0, "hgb_model_create: heat map size");
   hgb_model* m = new hgb_model();
   m->cfg = *cfg;
@@ -1467,6 +1556,14 @@ extern "C" int hgb_model_conv_detail(const hgb_model* m, int conv, int info[8], 
   info[0] = c.ksize; info[1] = c.taps; info[2] = c.cin; info[3] = c.cout; info[4] = c.cin_pad; info[5] = c.cout_pad;
   info[6] = c.relu; info[7] = c.has_wd;
   offs[0] = c.w_off; offs[1] = c.b_off;
+  return HGB_OK;
+}
+// depthwise stage `dw` of the mobile variant: info = {k, channels, h, w}; *w_off = float offset of its [k*k][c] weights
+extern "C" int hgb_model_dw_detail(const hgb_model* m, int dw, int info[4], int64_t* w_off) {
+  HGB_CHECK_ARG(dw >= 0 && dw < (int)m->dws.size(), "hgb_model_dw_detail: index out of range");
+  const DwL& d = m->dws[dw];
+  info[0] = d.k; info[1] = d.c; info[2] = d.h; info[3] = d.w;
+  if (w_off) *w_off = d.w_off;
   return HGB_OK;
 }
 // offs: channels, gamma, beta, moving_mean, moving_var (floats into params), sums, bsums, saved (bytes into arena)

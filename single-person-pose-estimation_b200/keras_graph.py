@@ -35,8 +35,8 @@ class Layer:
 class _Builder:
     """Creates layers the way the reference's calls do, with Keras' per-class name counters (reset by K.clear_session, :7)."""
 
-    def __init__(self):
-        self.layers, self.counters = [], defaultdict(int)
+    def __init__(self, mobile=False):
+        self.layers, self.counters, self.mobile = [], defaultdict(int), mobile
 
     def _auto(self, base):
         k = self.counters[base]
@@ -54,6 +54,12 @@ class _Builder:
     def conv(self, x, filters, k, name):
         return self._add(Layer(name, "Conv2D", [x], [("kernel", (k, k, x.channels, filters)), ("bias", (filters,))], filters))
 
+    def sepconv(self, x, filters, k, name):
+        # SeparableConv2D (model/hourglass.py:216-226): variables depthwise_kernel, pointwise_kernel, bias in that order
+        return self._add(Layer(name, "SeparableConv2D", [x], [("depthwise_kernel", (k, k, x.channels, 1)),
+                                                               ("pointwise_kernel", (1, 1, x.channels, filters)),
+                                                               ("bias", (filters,))], filters))
+
     def bn(self, x):
         c = x.channels
         return self._add(Layer(self._auto("batch_normalization"), "BatchNormalization", [x],
@@ -68,18 +74,19 @@ class _Builder:
     def add(self, xs, name=None):
         return self._add(Layer(name or self._auto("add"), "Add", xs, [], xs[0].channels))
 
-    # model/hourglass.py:184-206
+    # model/hourglass.py:184-206 (bottleneck_block) / :209-231 (bottleneck_block_mobile)
     def bottleneck(self, x, out, name):
-        skip = x if x.channels == out else self.conv(x, out, 1, name + "_skip")
-        y = self.bn(self.conv(x, out // 2, 1, name + "_conv_1x1_1"))
-        y = self.bn(self.conv(y, out // 2, 3, name + "_conv_3x3_2"))
-        y = self.bn(self.conv(y, out, 1, name + "_conv_1x1_3"))
+        conv = self.sepconv if self.mobile else self.conv
+        skip = x if x.channels == out else conv(x, out, 1, name + "_skip")
+        y = self.bn(conv(x, out // 2, 1, name + "_conv_1x1_1"))
+        y = self.bn(conv(y, out // 2, 3, name + "_conv_3x3_2"))
+        y = self.bn(conv(y, out, 1, name + "_conv_1x1_3"))
         return self.add([skip, y], name + "_add")
 
 
-def build_hourglass_graph(num_classes=17, num_stacks=1, num_channels=256, in_channels=3):
+def build_hourglass_graph(num_classes=17, num_stacks=1, num_channels=256, in_channels=3, mobile=False):
     """-> (layers in creation order, output layers).  Mirrors create_hourglass_model (model/hourglass.py:5-32)."""
-    b = _Builder()
+    b = _Builder(mobile)
     c = num_channels
     x = b.input(in_channels)
     # front module (:54-68)
@@ -156,10 +163,10 @@ def model_layers(outputs):
     return ordered
 
 
-def checkpoint_keys(num_classes=17, num_stacks=1, num_channels=256):
+def checkpoint_keys(num_classes=17, num_stacks=1, num_channels=256, mobile=False):
     """OrderedDict {'<layer name>/<attr>' (the names of hgb_model's parameter table) ->
     'layer_with_weights-<N>/<attr>/.ATTRIBUTES/VARIABLE_VALUE'} in `model.layers` order."""
-    _layers, outputs = build_hourglass_graph(num_classes, num_stacks, num_channels)
+    _layers, outputs = build_hourglass_graph(num_classes, num_stacks, num_channels, mobile=mobile)
     keys, n = OrderedDict(), 0
     for layer in model_layers(outputs):
         if not layer.weights:

@@ -18,6 +18,7 @@ from .. import _lib
 from .._lib import check, lib, ptr, stream_ptr
 
 _ACTIVATIONS = {"linear": 0, None: 0, "sigmoid": 1}
+_GEMM_KERNELS = ("/kernel", "/pointwise_kernel")     # stored OHWI in the flat parameter buffer
 
 
 class Adam:
@@ -74,7 +75,7 @@ class _Plan:
     def __init__(self, model, batch, training):
         torch = _lib.require_cuda()
         cfg = _lib.ModelConfig(model.num_classes, model.num_stacks, model.num_channels, model.input_shape[0],
-                               model.input_shape[1], model._act, int(batch), int(bool(training)))
+                               model.input_shape[1], model._act, int(batch), int(bool(training)), int(model.mobile))
         self.handle = C.c_void_p()
         check(lib.hgb_model_create(C.byref(cfg), torch.cuda.current_device(), C.byref(self.handle)))
         self.batch, self.training = int(batch), bool(training)
@@ -106,7 +107,8 @@ class _Plan:
 class HourglassModel:
     """What `create_hourglass_model` returns (stands in for the keras.Model of hourglass.py:25)."""
 
-    def __init__(self, num_classes, num_stacks, num_channels, input_shape, predict_activation, seed=None):
+    def __init__(self, num_classes, num_stacks, num_channels, input_shape, predict_activation, seed=None, mobile=False):
+        self.mobile = bool(mobile)      # bottleneck_block_mobile (model/hourglass.py:9-11): SeparableConv2D bottlenecks
         if predict_activation not in _ACTIVATIONS:
             raise ValueError(f"predict_activation must be 'sigmoid' or 'linear', got {predict_activation!r}")
         self.num_classes, self.num_stacks, self.num_channels = int(num_classes), int(num_stacks), int(num_channels)
@@ -126,7 +128,7 @@ class HourglassModel:
         self._comm_stream = None
         # a host-only handle: parameter table and counts (no GPU needed)
         cfg = _lib.ModelConfig(self.num_classes, self.num_stacks, self.num_channels, self.input_shape[0],
-                               self.input_shape[1], self._act, 1, 0)
+                               self.input_shape[1], self._act, 1, 0, int(self.mobile))
         h = C.c_void_p()
         check(lib.hgb_model_create(C.byref(cfg), 0, C.byref(h)))
         try:
@@ -166,7 +168,7 @@ class HourglassModel:
         rng = np.random.default_rng(seed)
         out = OrderedDict()
         for name, (shape, _off, _tr) in self._table.items():
-            if name.endswith("/kernel"):
+            if name.endswith("kernel"):     # kernel | depthwise_kernel (k,k,cin,1) | pointwise_kernel (1,1,cin,cout)
                 k1, k2, cin, cout = shape
                 limit = np.sqrt(6.0 / (k1 * k2 * (cin + cout)))
                 out[name] = rng.uniform(-limit, limit, size=shape).astype(np.float32)
@@ -183,8 +185,8 @@ class HourglassModel:
             a = np.asarray(weights[name], np.float32)
             if a.shape != tuple(shape):
                 raise ValueError(f"{name}: expected shape {tuple(shape)}, got {a.shape}")
-            if name.endswith("/kernel"):
-                a = a.transpose(3, 0, 1, 2)  # HWIO -> OHWI: the K-major GEMM operand
+            if name.endswith(_GEMM_KERNELS):
+                a = a.transpose(3, 0, 1, 2)  # HWIO -> OHWI: the K-major GEMM operand (depthwise kernels stay [k][k][c])
             flat[off:off + a.size] = a.reshape(-1)
         return flat
 
@@ -193,7 +195,7 @@ class HourglassModel:
         for name, (shape, off, _tr) in self._table.items():
             n = int(np.prod(shape))
             a = flat[off:off + n]
-            if name.endswith("/kernel"):
+            if name.endswith(_GEMM_KERNELS):
                 k1, k2, cin, cout = shape
                 a = a.reshape(cout, k1, k2, cin).transpose(1, 2, 3, 0)
             out[name] = np.array(a.reshape(shape), np.float32)
@@ -640,10 +642,7 @@ class HourglassModel:
 
 def create_hourglass_model(num_classes, num_stacks, num_channels, input_shape, predict_activation, mobile=False):
     """Same signature and console output as the reference (model/hourglass.py:5-32)."""
-    if mobile:
-        raise NotImplementedError("mobile=True (SeparableConv2D bottleneck, hourglass.py:209-231) is outside the "
-                                  "B200 hot path; only the standard residual bottleneck is implemented")
-    model = HourglassModel(num_classes, num_stacks, num_channels, input_shape, predict_activation)
+    model = HourglassModel(num_classes, num_stacks, num_channels, input_shape, predict_activation, mobile=mobile)
     print(f'''Created Hourglass model:
     1. {num_stacks} stacks.
     2. {model.count_params()} parameters. Call model.get_summary() for more detail.

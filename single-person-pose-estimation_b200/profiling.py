@@ -10,7 +10,7 @@ import ctypes as C
 from ._lib import lib
 
 OP_NAMES = ["F_IM2COL", "F_CONV", "F_BN", "F_POOL", "F_UPADD", "F_HEAD", "B_BN_REDUCE", "B_BN_APPLY", "B_WGRAD", "B_DGRAD",
-            "B_RELU_MASK", "B_COLSUM", "B_POOL", "B_UPADD", "B_HEAD"]
+            "B_RELU_MASK", "B_COLSUM", "B_POOL", "B_UPADD", "B_HEAD", "F_DW", "B_DW_DGRAD", "B_DW_WGRAD"]
 RIDGE_FLOP_PER_BYTE = 212.0     # measured bf16 peak / measured HBM bandwidth
 
 
@@ -79,6 +79,8 @@ class PlanInfo:
             byt = 2.0 * (el(a0) + el(a1) + el(a2) * (2 if flag else 1))
         elif ty == 13:
             byt = 2.0 * (el(a0) + el(a1))
+        elif ty in (15, 16, 17):   # mobile variant, depthwise stencil: tensor in, tensor out (+ residuals) / two tensors in
+            byt = 2.0 * (el(a0) + el(a1) + (el(a2) + el(a3) if ty == 16 else 0))
         else:            # B_HEAD: loss gradient + heat map (fp32), re-injection gradient in, logits gradient out
             n, hh, ww, cc = self.act(a1)
             M = n * hh * ww

@@ -338,7 +338,7 @@ def parse_object_graph(blob):
 
 # ------------------------------------------------------------------ Keras weights <-> checkpoint
 def _layer_weights(model):
-    keys = keras_graph.checkpoint_keys(model.num_classes, model.num_stacks, model.num_channels)
+    keys = keras_graph.checkpoint_keys(model.num_classes, model.num_stacks, model.num_channels, mobile=getattr(model, "mobile", False))
     if set(keys) != set(model._table):
         raise RuntimeError("keras_graph and the library's parameter table disagree on the weight names")
     layers = OrderedDict()

@@ -62,6 +62,80 @@ def test_layer_names_shapes_and_order_match_independent_restatement():
     assert t["hg0_conv_1x1_3/kernel"][0] == (1, 1, 17, 256)
 
 
+def _separable_bottleneck_params(cin, cout):
+    """bottleneck_block_mobile (model/hourglass.py:209-231) counted by hand: SeparableConv2D(k, cin -> f) owns a depthwise
+    kernel k*k*cin, a pointwise kernel cin*f and a bias f; BatchNormalization owns 4 vectors (2 trainable)."""
+    sep = lambda k, ci, f: k * k * ci + ci * f + f
+    mid = cout // 2
+    train = sep(1, cin, mid) + sep(3, mid, mid) + sep(1, mid, cout) + 2 * (mid + mid + cout)
+    if cin != cout:
+        train += sep(1, cin, cout)
+    return train, 2 * (mid + mid + cout)
+
+
+@pytest.mark.parametrize("stacks", [1, 2, 8])
+def test_mobile_variant_parameter_table(stacks):
+    """mobile=True (model/hourglass.py:9-11): every bottleneck is a SeparableConv2D block; the stem, the heads and the
+    re-injection convolutions stay Conv2D.  The reference saved no summary of this variant, so the counts are pinned by a
+    closed form written from the layer definitions, the names / order by the oracle's independent walk and the Keras
+    checkpoint keys by keras_graph."""
+    import hgb200
+    from hgb200 import keras_graph
+    from oracle import network_oracle as norc
+    C, K = 256, 17
+    m = hgb200.HourglassModel(K, stacks, C, (256, 256, 3), "sigmoid", mobile=True)
+    tr, non = 7 * 7 * 3 * 64 + 64 + 2 * 64, 2 * 64                                   # stem Conv2D + BN
+    for cin, cout in ((64, C // 2), (C // 2, C // 2), (C // 2, C)):                  # front bottlenecks
+        a, b = _separable_bottleneck_params(cin, cout)
+        tr, non = tr + a, non + b
+    a, b = _separable_bottleneck_params(C, C)
+    for s in range(stacks):
+        tr, non = tr + 15 * a, non + 15 * b                                          # 4 down, 3 bottom, 4 short, 4 merged
+        tr, non = tr + C * C + C + 2 * C, non + 2 * C                                # head conv + BN
+        tr += C * K + K                                                              # predict
+        if s + 1 < stacks:
+            tr += C * C + C + K * C + C                                              # re-injection pair (pruned on the last stack)
+    assert (m.trainable_count, m.count_params()) == (tr, tr + non)
+    spec = norc.param_spec(K, stacks, C, mobile=True)
+    assert list(m._table) == list(spec) and all(tuple(m._table[k][0]) == tuple(spec[k]) for k in spec)
+    t = m._table
+    assert t["hg0_downsample_f1_conv_3x3_2/depthwise_kernel"][0] == (3, 3, 128, 1)
+    assert t["hg0_downsample_f1_conv_3x3_2/pointwise_kernel"][0] == (1, 1, 128, 128)
+    assert t["front_bottleneck_1_skip/depthwise_kernel"][0] == (1, 1, 64, 1)
+    assert "hg0_conv_1x1_1/kernel" in t and "front_conv_1x1_1/kernel" in t           # not separable
+    names = list(t)
+    i = names.index("hg0_downsample_f1_conv_1x1_1/depthwise_kernel")
+    assert names[i + 1:i + 3] == ["hg0_downsample_f1_conv_1x1_1/pointwise_kernel", "hg0_downsample_f1_conv_1x1_1/bias"]
+    keys = keras_graph.checkpoint_keys(K, stacks, C, mobile=True)
+    assert set(keys) == set(t)
+    assert keys["front_bottleneck_1_skip/depthwise_kernel"].endswith("/depthwise_kernel/.ATTRIBUTES/VARIABLE_VALUE")
+    # a standard model's count is untouched by the switch
+    assert hgb200.HourglassModel(K, 1, C, (256, 256, 3), "sigmoid").count_params() == 3659665
+
+
+def test_mobile_weights_pack_and_checkpoint_roundtrip(tmp_path):
+    """depthwise kernels are stored [k][k][c] (no transpose), pointwise kernels OHWI like every GEMM operand; a TF-format
+    checkpoint written from one mobile model loads into another by Keras key."""
+    import hgb200
+    a = hgb200.HourglassModel(17, 1, 256, (256, 256, 3), "sigmoid", seed=3, mobile=True)
+    w = a.get_weights_dict()
+    flat = a._pack(w)
+    name = "hg0_downsample_f2_conv_3x3_2"
+    off = a._table[name + "/depthwise_kernel"][1]
+    assert np.array_equal(flat[off:off + 9 * 128].reshape(3, 3, 128), w[name + "/depthwise_kernel"][..., 0])
+    off = a._table[name + "/pointwise_kernel"][1]
+    assert np.array_equal(flat[off:off + 128 * 128].reshape(128, 128), w[name + "/pointwise_kernel"][0, 0].T)
+    back = a._unpack(flat)
+    assert all(np.array_equal(back[n], w[n]) for n in w)
+    a.save_weights(str(tmp_path / "mob.ckpt"))
+    b = hgb200.HourglassModel(17, 1, 256, (256, 256, 3), "sigmoid", seed=4, mobile=True)
+    b.load_weights(str(tmp_path / "mob.ckpt"))
+    wb = b.get_weights_dict()
+    assert all(np.array_equal(wb[n], w[n]) for n in w)
+    with pytest.raises(Exception):      # a standard model does not accept the mobile checkpoint
+        hgb200.HourglassModel(17, 1, 256, (256, 256, 3), "sigmoid").load_weights(str(tmp_path / "mob.ckpt"))
+
+
 def test_weight_pack_roundtrip_and_keras_init():
     import hgb200
     m = hgb200.HourglassModel(17, 1, 256, (256, 256, 3), "sigmoid", seed=0)
@@ -85,8 +159,8 @@ def test_model_factory_contract(capsys):
     out = capsys.readouterr().out
     assert "2 stacks" in out and "7034530 parameters" in out
     assert m.output_names == ["hg0_conv_1x1_predict", "hg1_conv_1x1_predict"]
-    with pytest.raises(NotImplementedError):
-        hgb200.create_hourglass_model(17, 1, 256, (256, 256, 3), "sigmoid", mobile=True)
+    mob = hgb200.create_hourglass_model(17, 1, 256, (256, 256, 3), "sigmoid", mobile=True)
+    assert mob.mobile and f"{mob.count_params()} parameters" in capsys.readouterr().out
     with pytest.raises(ValueError):
         hgb200.create_hourglass_model(17, 1, 256, (256, 256, 3), "tanh")
 

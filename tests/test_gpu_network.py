@@ -86,20 +86,20 @@ def _tame(weights, factor=0.05):
     gradients become comparable across implementations (this checks the WIRING of the backward plan)."""
     last_conv = None
     for name in weights:
-        if name.endswith("/kernel"):
-            last_conv = name[:-7]
+        if name.endswith("/kernel") or name.endswith("/pointwise_kernel"):
+            last_conv = name.rsplit("/", 1)[0]
         elif name.endswith("/gamma") and last_conv is not None and last_conv.endswith("_conv_1x1_3") and "sample" in last_conv + "bottleneck" and ("bottleneck" in last_conv or "sample" in last_conv):
             weights[name] = (weights[name] * factor).astype(np.float32)
     return weights
 
 
-def _run_train_case(hgb, torch, S, B, kind, perturb=True, layerwise=True, tame=False, loss_tol=2e-2):
+def _run_train_case(hgb, torch, S, B, kind, perturb=True, layerwise=True, tame=False, loss_tol=2e-2, mobile=False):
     images, targets = _inputs(B)
-    spec = norc.param_spec(17, S, 256)
+    spec = norc.param_spec(17, S, 256, mobile=mobile)
     weights = norc.init_params(spec, seed=2, perturb_bn=perturb)
     if tame:
         weights = _tame(weights)
-    model = hgb.HourglassModel(17, S, 256, (256, 256, 3), "sigmoid")
+    model = hgb.HourglassModel(17, S, 256, (256, 256, 3), "sigmoid", mobile=mobile)
     model.set_weights_dict(weights)
     model.compile(optimizer=hgb.Adam(1e-3), loss=kind)
 
@@ -114,8 +114,8 @@ def _run_train_case(hgb, torch, S, B, kind, perturb=True, layerwise=True, tame=F
     chk(lib.hgb_model_backward(plan.handle, 0, S + 1, hgb._lib.stream_ptr()))
     torch.cuda.synchronize()
 
-    f_outs, f_losses, f_grads = norc.loss_and_grads(weights, images, targets, kind, 17, S, 256)                 # fp32
-    e_outs, e_losses, e_grads = norc.loss_and_grads(weights, images, targets, kind, 17, S, 256, emulate_bf16=True)
+    f_outs, f_losses, f_grads = norc.loss_and_grads(weights, images, targets, kind, 17, S, 256, mobile=mobile)  # fp32
+    e_outs, e_losses, e_grads = norc.loss_and_grads(weights, images, targets, kind, 17, S, 256, emulate_bf16=True, mobile=mobile)
 
     def l2(a, b):
         return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30))

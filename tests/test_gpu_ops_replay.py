@@ -24,18 +24,18 @@ from tests.test_gpu_network import _inputs
 pytestmark = pytest.mark.gpu
 
 (F_IM2COL, F_CONV, F_BN, F_POOL, F_UPADD, F_HEAD, B_BN_REDUCE, B_BN_APPLY, B_WGRAD, B_DGRAD, B_RELU_MASK, B_COLSUM,
- B_POOL, B_UPADD, B_HEAD) = range(15)
+ B_POOL, B_UPADD, B_HEAD, F_DW, B_DW_DGRAD, B_DW_WGRAD) = range(18)
 NAMES = ["F_IM2COL", "F_CONV", "F_BN", "F_POOL", "F_UPADD", "F_HEAD", "B_BN_REDUCE", "B_BN_APPLY", "B_WGRAD", "B_DGRAD",
-         "B_RELU_MASK", "B_COLSUM", "B_POOL", "B_UPADD", "B_HEAD"]
+         "B_RELU_MASK", "B_COLSUM", "B_POOL", "B_UPADD", "B_HEAD", "F_DW", "B_DW_DGRAD", "B_DW_WGRAD"]
 
 
 class Replay:
-    def __init__(self, hgb, torch, S, B, kind="weighted_mse"):
+    def __init__(self, hgb, torch, S, B, kind="weighted_mse", mobile=False):
         self.hgb, self.torch, self.S, self.B = hgb, torch, S, B
         self.lib, self.chk = hgb._lib.lib, hgb._lib.check
         images, targets = _inputs(B)
-        weights = norc.init_params(norc.param_spec(17, S, 256), seed=7, perturb_bn=True)
-        self.model = hgb.HourglassModel(17, S, 256, (256, 256, 3), "sigmoid")
+        weights = norc.init_params(norc.param_spec(17, S, 256, mobile=mobile), seed=7, perturb_bn=True)
+        self.model = hgb.HourglassModel(17, S, 256, (256, 256, 3), "sigmoid", mobile=mobile)
         self.model.set_weights_dict(weights)
         self.model.compile(optimizer=hgb.Adam(1e-3), loss=kind)
         self.plan = self.model._plan(B, True)
@@ -64,6 +64,19 @@ class Replay:
         d = dict(zip(("ksize", "taps", "cin", "cout", "cin_pad", "cout_pad", "relu", "has_dgrad"), info))
         d["w_off"], d["b_off"] = offs[0], offs[1]
         return d
+
+    def dw(self, di):
+        """depthwise stage of a SeparableConv2D (mobile variant): fp32 weights [k][k][c]."""
+        info, off = (C.c_int * 4)(), C.c_int64()
+        self.chk(self.lib.hgb_model_dw_detail(self.h, di, C.byref(info), C.byref(off)))
+        d = dict(zip(("k", "c", "h", "w"), info))
+        d["w_off"] = off.value
+        return d
+
+    def dw_weight(self, d):
+        """(c,1,k,k) fp32: the torch depthwise (groups = c) layout of the [k][k][c] device weights."""
+        n = d["k"] * d["k"] * d["c"]
+        return self.params[d["w_off"]:d["w_off"] + n].view(d["k"], d["k"], d["c"]).permute(2, 0, 1).unsqueeze(1).contiguous()
 
     def bn(self, bi):
         offs = (C.c_int64 * 8)()
@@ -124,14 +137,16 @@ def _unwindows(v, N, H, W, Cc):
     return v.view(N, H // 2, W // 2, 2, 2, Cc).permute(0, 1, 3, 2, 4, 5).reshape(N, H, W, Cc)
 
 
-@pytest.mark.parametrize("S,B", [(2, 3), (1, 80)])
-def test_replay_every_op(S, B):
+@pytest.mark.parametrize("S,B,mobile", [(2, 3, False), (1, 80, False), (2, 5, True)])
+def test_replay_every_op(S, B, mobile):
+    """mobile=True replays the SeparableConv2D plan (model/hourglass.py:209-231): depthwise stencil forward / input gradient
+    (mirrored taps, fused residual adds) / weight gradient next to the pointwise GEMMs."""
     import hgb200 as hgb
     import torch
     import torch.nn.functional as F
     torch.backends.cudnn.allow_tf32 = False          # the reference of every op is plain fp32
     torch.backends.cuda.matmul.allow_tf32 = False
-    R = Replay(hgb, torch, S, B)
+    R = Replay(hgb, torch, S, B, mobile=mobile)
     lib, chk, ptr, sp = R.lib, R.chk, hgb._lib.ptr, hgb._lib.stream_ptr
     chk(lib.hgb_model_begin_step(R.h, sp()))
     torch.cuda.synchronize()
@@ -216,6 +231,16 @@ def test_replay_every_op(S, B):
                 M = y.numel() // Cc
                 torch.testing.assert_close(R.params[b["mm"]:b["mm"] + Cc], 0.99 * mm0 + 0.01 * mean, rtol=1e-4, atol=1e-5)
                 torch.testing.assert_close(R.params[b["mv"]:b["mv"] + Cc], 0.99 * mv0 + 0.01 * var * M / (M - 1), rtol=1e-3, atol=1e-5)
+            elif ty == F_DW:
+                d = R.dw(ci)
+                x = R.act(a0).float()
+                R.run(seg, 0, i)
+                ref = F.conv2d(x.permute(0, 3, 1, 2), R.dw_weight(d), padding=d["k"] // 2, groups=d["c"]).permute(0, 2, 3, 1)
+                out = R.act(a1).float()
+                e = R.rel(out, ref)
+                R.note(ty, e)
+                assert e <= 1e-2, f"depthwise {ci}: {e}"
+                assert R.cos(ty, out, ref) > 0.999, f"depthwise {ci}: cosine"
             elif ty == F_POOL:
                 R.run(seg, 0, i)
                 x, out = R.act(a0), R.act(a1)
@@ -361,6 +386,35 @@ def test_replay_every_op(S, B):
                 assert R.cos(ty, out[..., :c["cin"]], ref) > 0.999, f"dgrad conv {ci}: cosine"
                 if out.shape[-1] > c["cin"] and not res:
                     assert out[..., c["cin"]:].abs().max().item() == 0
+            elif ty == B_DW_DGRAD:
+                d = R.dw(ci)
+                dt = R.act(a0).float()
+                res = [R.act(a).float().clone() for a in (a2, a3) if a >= 0]      # may alias the output (in-place add)
+                R.run(seg, 1, i)
+                xz = torch.zeros((dt.shape[0], d["c"], dt.shape[1], dt.shape[2]), device="cuda", requires_grad=True)
+                F.conv2d(xz, R.dw_weight(d), padding=d["k"] // 2, groups=d["c"]).backward(dt.permute(0, 3, 1, 2))
+                ref = xz.grad.permute(0, 2, 3, 1)
+                for r in res:
+                    ref = ref + r
+                out = R.act(a1).float()
+                e = R.rel(out, ref)
+                R.note(ty, e)
+                assert e <= 1e-2, f"depthwise dgrad {ci}: {e}"
+                assert R.cos(ty, out, ref) > 0.999, f"depthwise dgrad {ci}: cosine"
+            elif ty == B_DW_WGRAD:
+                d = R.dw(ci)
+                n = d["k"] * d["k"] * d["c"]
+                g0 = R.grads[d["w_off"]:d["w_off"] + n].clone()
+                R.run(seg, 1, i)
+                dt, x = R.act(a0).float(), R.act(a1).float()
+                w = torch.zeros((d["c"], 1, d["k"], d["k"]), device="cuda", requires_grad=True)
+                F.conv2d(x.permute(0, 3, 1, 2), w, padding=d["k"] // 2, groups=d["c"]).backward(dt.permute(0, 3, 1, 2))
+                ref = w.grad.squeeze(1).permute(1, 2, 0).reshape(-1)               # -> [k][k][c]
+                got = R.grads[d["w_off"]:d["w_off"] + n] - g0
+                e = R.rel(got, ref)
+                R.note(ty, e)
+                assert e <= 3e-3, f"depthwise wgrad {ci}: {e}"
+                assert R.cos(ty, got, ref) > 0.999, f"depthwise wgrad {ci}: cosine"
             elif ty in (B_RELU_MASK, B_COLSUM):
                 c = R.conv(ci)
                 g0 = R.act(a0).clone()
@@ -420,10 +474,15 @@ def test_replay_every_op(S, B):
     n_bneck = 3 + 15 * S
     print("BatchNorm-backward applies fused into 1x1 dgrad GEMMs:", fused_applies[0], " shared bias-gradient passes:", shared_colsums[0])
     assert shared_colsums[0] == S - 1
-    assert fused_applies[0] >= 2 * 15 * S          # BN3 and BN1 of every hourglass bottleneck (+ the heads)
-    assert fused_reduces[0] > n_bneck
     print("convolutions / weight gradients with a deferred input BatchNorm:", deferred[0], "statistic writers:", writers[0])
-    assert deferred[0] >= 2 * n_bneck and writers[0] >= n_bneck
+    if mobile:      # every pointwise GEMM is a 1x1: all three BatchNorm-backward applies of a bottleneck fuse; only the head BN defers
+        assert {"F_DW", "B_DW_DGRAD", "B_DW_WGRAD"} <= set(R.low_cos)
+        assert fused_applies[0] >= 3 * 15 * S
+        assert deferred[0] >= 2 * S and writers[0] >= S
+    else:
+        assert fused_applies[0] >= 2 * 15 * S          # BN3 and BN1 of every hourglass bottleneck (+ the heads)
+        assert fused_reduces[0] > n_bneck
+        assert deferred[0] >= 2 * n_bneck and writers[0] >= n_bneck
 
     # the stepped run and one whole training step see the same loss (gradients are not compared end to
     # end: fp32 atomics ordering differs between two runs and a random-init hourglass in training mode
