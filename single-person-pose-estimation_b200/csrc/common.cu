@@ -4,7 +4,7 @@
 namespace hgb {
 
 static thread_local char t_err[1024] = "";
-int g_debug[32] = {0};
+int g_debug[48] = {0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -18,7 +18,7 @@ void set_error(const char* fmt, ...) {
 extern "C" const char* hgb_last_error(void) { return hgb::t_err; }
 extern "C" int hgb_version(void) { return 100; }
 extern "C" int hgb_debug_set(int key, int value) {
-  if (key < 0 || key >= 32) {
+  if (key < 0 || key >= 48) {
     hgb::set_error("hgb_debug_set: unknown key %d", key);
     return HGB_ERR_INVALID;
   }

@@ -43,7 +43,7 @@ void set_error(const char* fmt, ...);
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-extern int g_debug[32];
+extern int g_debug[48];
 
 // Programmatic dependent launch: every kernel of the training step is launched with
 // programmaticStreamSerialization, calls pdl_trigger() first thing and pdl_wait() before its first

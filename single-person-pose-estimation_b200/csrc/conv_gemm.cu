@@ -56,6 +56,7 @@ struct GemmKernelParams {
   BnBwdInput bn_bwd;          // gamma != null (BNB kernels): the A operand is BatchNorm-backward(dz, y), computed in shared memory
   int single_store;           // debug: one thread issues all output boxes (hgb_debug_set(16, 1))
   int late_trigger;           // programmatic dependent launch is released after the producer's last load
+  int a_prefetch;             // 1x1 only: the producer pulls the A (and y) boxes of the tile `a_prefetch` rounds ahead into L2
 };
 
 template <int OFF>
@@ -228,8 +229,9 @@ __device__ __forceinline__ void bn_bwd_transform_box(uint32_t box_dz, uint32_t b
 //               it last has drained.  2 * BLOCK_N / 64 boxes = plain double buffering.  The N = 256 tiles cannot afford that
 //               (128 KB): with exactly 4 boxes every tile waited for its predecessor's 64 KB store to leave shared memory before
 //               it could stage (or TMA-fetch its residual tile) -- ncu: 41 % of the epilogue warps' samples on that wait, 3.1 us
-//               per tile against 2.2 us of HBM time -- so they run 2 pipeline stages and 7 boxes (5 with the fused BatchNorm
-//               backward): every store gets more than a tile period to drain.
+//               per tile against 2.2 us of HBM time.  A 7-box ring (with 2 pipeline stages; 5 boxes with the fused BatchNorm
+//               backward) gives every store more than a tile period to drain -- built, parity-green, and measured SLOWER than
+//               the 4-box / 3-stage geometry (see launch_conv_gemm), so it is opt-in: hgb_debug_set(31, 1).
 //   CTA2       : HALO only: a cluster of two CTAs (one TPC) runs every MMA as tcgen05.mma.cta_group::2 with M = 256.  CTA r keeps
 //               its own four tiles (own strip ring, own accumulators in its own TMEM, own epilogue) and HALF of every
 //               weight box (64 of the 128 output channels); the leader's single thread issues the MMAs for both SMs.  Every
@@ -445,6 +447,18 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
           const int p0 = (grp * TILES + t) * kBlockM;
           n0[t] = p0 / p.HW;
           y0[t] = (p0 - n0[t] * p.HW) / p.W;
+        }
+        if (TILES == 1 && p.a_prefetch > 0) {
+          // two-stage rings keep the TMA loads only one tile ahead of the MMAs: HBM latency is hidden by an L2 prefetch of
+          // the operand boxes a few rounds ahead instead (the loads then hit L2)
+          const int gp = grp + p.a_prefetch * (int)gridDim.x;
+          if (gp < num_groups) {
+            const int pp = gp * kBlockM, nn = pp / p.HW, yy = (pp - nn * p.HW) / p.W;
+            for (int cb = 0; cb < p.cblk; ++cb) {
+              tma_prefetch_4d(&tmA, cb * 64, 0, yy, nn);
+              if (BNB) tma_prefetch_4d(&tmZ, cb * 64, 0, yy, nn);
+            }
+          }
         }
         for (int kb = 0; kb < p.nkb; ++kb, ++kbt) {
           const int s = kbt % STAGES;
@@ -1391,6 +1405,8 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   kp.late_trigger = !g_debug[18];   // default on: forward pass at batch 32 9.55 -> 8.93 ms (hgb_debug_set(18, 1) = trigger at kernel start)
   kp.bn_out = a.bn_out;
   kp.bn_bwd = a.bn_bwd;
+  // L2 prefetch distance of the 1x1 N = 256 kernels (two pipeline stages): hgb_debug_set(33, n) = n rounds, -1 = off
+  kp.a_prefetch = (a.ksize == 1 && a.Cout > 128 && g_debug[31]) ? (g_debug[33] ? (g_debug[33] < 0 ? 0 : g_debug[33]) : 1) : 0;
   HGB_CHECK_ARG(a.bn_bwd.gamma == nullptr || (conv_gemm_supports_bn_bwd(a.ksize, a.Cin, a.Cout) && a.bn_bwd.C == a.Cin && tmZ && tmDP &&
                                               a.bn_in.gamma == nullptr && a.bn_out.gamma == nullptr),
                 "conv_gemm: the fused BatchNorm backward needs a 1x1 dgrad with <= 256 input and 128 / 256 output channels");
@@ -1420,9 +1436,10 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
                     a.H % (4 * rpt) == 0 && a.Cout == 128;
   if (a.bn_bwd.gamma) {   // 1x1 dgrad with the BatchNorm backward fused in
     if (a.Cout == 128) return launch_gemm_t<128, 3, 1, 4, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
-    // N = 256: 2 stages of 64 KB (dz | weights | y) + 5 staging boxes; hgb_debug_set(31, 1) = the 4-box form
-    if (g_debug[31]) return launch_gemm_t<256, 2, 1, 4, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
-    return launch_gemm_t<256, 2, 1, 5, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
+    // N = 256: 2 stages of 64 KB (dz | weights | y) + 4 staging boxes; hgb_debug_set(31, 1) = a 5-box ring (measured slower:
+    // 638 vs 568 us at batch 256, profiles/r02_ops_ab_staging_ring.txt)
+    if (g_debug[31]) return launch_gemm_t<256, 2, 1, 5, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
+    return launch_gemm_t<256, 2, 1, 4, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
   }
   // CTA pairs (tcgen05.mma.cta_group::2), OPT-IN with hgb_debug_set(30, 1): parity-green (tests/test_gpu_conv.py and the
   // batch-80 replay run it) but measured SLOWER than the one-CTA strip kernel on B200 at batch 256 -- forward 64x64 297.7 vs
@@ -1440,8 +1457,12 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     default:   // 64 KB staging: single.  16 epilogue warps only where they measured faster (A/B on B200, batch 256 @64x64:
       // dgrad with TMA residual + BatchNorm statistics 382 vs 399 us; plain forward tiles 171 vs 167 us: those are bound
       // by shared-memory traffic -- 448 KB per tile -- not by epilogue issue slots).  hgb_debug_set(25, 1) = always 8.
-      // hgb_debug_set(31, 1) = the round-1 geometry (3 stages, 4 staging boxes) for A/B runs; default: 2 stages + a 7-box ring
-      if (g_debug[31])
+      // hgb_debug_set(31, 1) = 2 pipeline stages + a 7-box staging ring (+ L2 prefetch of the operand boxes, knob 33), OPT-IN:
+      // every store then has 1.75 tile periods to drain, but the loads run only one tile ahead, and it measured SLOWER on B200
+      // at batch 256 (128->256: 154 vs 145 us, 256->256: 247 vs 207 us stand-alone; in the step 239 vs 226 us) -- the wait on
+      // the previous tile's store that ncu attributes 41 % of the epilogue samples to is not the bound: HBM is (5.5 of the
+      // 5.65 TB/s a 1 read : 2 write stream reaches on this part, tools_cuda/membench.cu)
+      if (!g_debug[31])
         return (g_debug[25] || !(kp.res1_tma && a.bn_y)) ? launch_gemm_t<256, 3, 1, 4>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
                                                          : launch_gemm_t<256, 3, 1, 4, false, 16>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
       return (g_debug[25] || !(kp.res1_tma && a.bn_y)) ? launch_gemm_t<256, 2, 1, 7>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
