@@ -66,9 +66,15 @@ class GradAllReduce:
         """Backward runs segments nseg-1 .. 0; consecutive segments share one contiguous gradient range.  -> [(lo, hi)] from
         the top down, `buckets` groups of near-equal segment counts (fewer, larger all-reduces: launch latency and SM
         contention with the backward kernels matter more than bucket size on NVSwitch)."""
-        n = min(self.buckets, nseg)
-        edges = [round(i * nseg / n) for i in range(n + 1)]
-        return [(edges[i], edges[i + 1]) for i in range(n - 1, -1, -1)]
+        import os
+        env = os.environ.get("HGB_DP_BUCKET_EDGES")       # e.g. "0,1,5,9": explicit segment edges (A/B runs)
+        if env:
+            edges = sorted({int(v) for v in env.split(",")} | {0, nseg})
+            edges = [e for e in edges if 0 <= e <= nseg]
+        else:
+            n = min(self.buckets, nseg)
+            edges = [round(i * nseg / n) for i in range(n + 1)]
+        return [(edges[i], edges[i + 1]) for i in range(len(edges) - 2, -1, -1)]
 
     def __call__(self, bucket):
         if bucket.numel():
