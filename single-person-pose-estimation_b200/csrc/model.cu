@@ -104,7 +104,11 @@ struct Op {
 constexpr int kLaneMain = 0;    // the critical chain: down path, bottom, merges, heads
 constexpr int kLaneWgrad = 1;   // weight / bias gradients of the main chain
 constexpr int kLaneShort0 = 2;  // + level (f1, f2, f4, f8): the skip bottleneck of that level
-constexpr int kNumLanes = 6;
+constexpr int kLaneWgradX = 6;  // + i: extra weight-gradient lanes (leaf ops of the main chain are dealt round-robin)
+constexpr int kMaxWgradLanes = 3;
+constexpr int kNumLanes = 6 + kMaxWgradLanes - 1;
+inline bool is_skip_lane(int l) { return l >= kLaneShort0 && l < kLaneShort0 + 4; }
+inline bool is_wgrad_lane(int l) { return l == kLaneWgrad || l >= kLaneWgradX; }
 constexpr int kScratchKinds = 8;                  // dp3 | dz(mid) | dp(mid, conv2) | dp(mid, conv1) | mobile: dt of conv3 / conv2 / conv1 / skip
 constexpr int kScratchSets = 2 + 4;               // main chain ping-pong + one per skip lane
 
@@ -277,7 +281,14 @@ struct hgb_model {
   void emit_f(Op o) { if (o.lane < 0) o.lane = cur_lane; fwd_ops[cur_seg].push_back(o); }
   void emit_b(Op o) { if (o.lane < 0) o.lane = cur_lane; bwd_ops[cur_seg].push_back(o); }
   // weight / bias gradients are leaves: the main chain hands them to its side lane
-  int leaf_lane() const { return cur_lane == kLaneMain ? kLaneWgrad : cur_lane; }
+  // (the leaf ops of the main chain are independent of each other: dealt round-robin over `wgrad_lanes` streams, so the short,
+  //  latency-bound weight gradients of the low-resolution levels overlap instead of queueing behind one another)
+  int wgrad_lanes = 1, leaf_rr = 0;
+  int leaf_lane() {
+    if (cur_lane != kLaneMain) return cur_lane;
+    const int i = leaf_rr++ % wgrad_lanes;
+    return i == 0 ? kLaneWgrad : kLaneWgradX + i - 1;
+  }
 
   // conv (+ReLU) [+ BN] -> returns the tensor the next layer consumes; y/z report both stages
   int conv_unit(const std::string& name, int in_act, int real_k, int real_cin, int cout, int relu, bool bn, bool need_dgrad,
@@ -474,6 +485,8 @@ int build(hgb_model* m) {
   const int B = cfg.batch, C = cfg.num_channels, S = cfg.num_stacks;
   m->fwd_ops.assign(S + 1, {});
   m->bwd_ops.assign(S + 1, {});
+  // weight-gradient lanes: hgb_debug_set(35, n) before the plan is created, n = 1..3 (0 = the default for this batch)
+  m->wgrad_lanes = hgb::g_debug[35] > 0 ? std::min(hgb::g_debug[35], kMaxWgradLanes) : 1;
   m->seg_begin.assign(S + 1, 0);
   m->seg_end.assign(S + 1, 0);
 
@@ -579,7 +592,7 @@ int build(hgb_model* m) {
           if (m->scratch_bytes[i]) m->scratch_off[i] = m->arena_alloc(m->scratch_bytes[i]);
         m->grad_base = m->arena_alloc(m->grad_max);
       }
-      m->cur_lane = kLaneMain; m->cur_set = 0; m->main_set = 0;
+      m->cur_lane = kLaneMain; m->cur_set = 0; m->main_set = 0; m->leaf_rr = 0;
       for (int s = S - 1; s >= 0; --s) {
         m->cur_seg = 1 + s;
         m->grad_cur = 0;
@@ -959,7 +972,7 @@ int run_op(hgb_model* m, const Op& o, const float* images, int training, cudaStr
 
 // persistent GEMMs of the skip lanes leave a few SMs free so the main chain's small kernels never queue behind them
 inline int side_lane_ctas(const hgb_model* m, const Op& o) {
-  if (o.lane < kLaneShort0 || !m->lanes_ready || hgb::g_debug[8] || m->prof_all) return 0;
+  if (!is_skip_lane(o.lane) || !m->lanes_ready || hgb::g_debug[8] || m->prof_all) return 0;
   const int reserve = hgb::g_debug[9] > 0 ? hgb::g_debug[9] : 20;
   return m->num_sms > 2 * reserve ? m->num_sms - reserve : 0;
 }
@@ -1061,10 +1074,12 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
       a.Cin_valid = c.cin; a.Cout_valid = c.cout;
       a.dw = m->p_grads + c.w_off;
       // On its side lane a weight gradient is never urgent, but its CTAs are long-lived and cannot be preempted: filling the
-      // chip with them makes every main-chain kernel wait for an SM.  64 CTAs (of 148 SMs) measured best at every batch
-      // size (batch 256: -3.4 % step time, batch 32: -2.2 %); hgb_debug_set(20, n) overrides, -1 = no cap.
+      // chip with them makes every main-chain kernel wait for an SM.  64 CTAs (of 148 SMs) measured best at batch 64 and above
+      // (batch 256: -3.4 % step time); at batch 32 the weight-gradient lane itself is close to the critical path (cap 16: 36 ms,
+      // 64: 25.5 ms, 96: 24.9 ms, none: 25.1 ms; profiles/r02_lane_caps.txt) and gets 96.  Dealing the leaf ops over two or
+      // three streams (hgb_debug_set(35, n)) measured no better.  hgb_debug_set(20, n) overrides, -1 = no cap.
       if (m->lanes_ready && !hgb::g_debug[8] && !m->prof_all && o.lane != kLaneMain)
-        a.max_ctas = hgb::g_debug[20] > 0 ? hgb::g_debug[20] : (hgb::g_debug[20] < 0 ? 0 : 64);
+        a.max_ctas = hgb::g_debug[20] > 0 ? hgb::g_debug[20] : (hgb::g_debug[20] < 0 ? 0 : (m->B <= 48 ? 96 : 64));
       if (o.bn >= 0) {   // x = BatchNorm(o.bn)(source tensor), rebuilt from the saved statistics
         const BNL& b = m->bns[o.bn];
         a.bn_in.saved = arena_f(m, b.saved_off);
@@ -1166,7 +1181,7 @@ int ensure_lanes(hgb_model* m) {
   HGB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = numerically smallest = highest priority
   for (int l = 0; l < kNumLanes; ++l) {
     int pr = l == kLaneMain ? hi : hi + 1;
-    if (l == kLaneWgrad && hgb::g_debug[21]) pr = hi + 1 + hgb::g_debug[21];   // experiment: weight gradients below the skip lanes
+    if (is_wgrad_lane(l) && hgb::g_debug[21]) pr = hi + 1 + hgb::g_debug[21];   // experiment: weight gradients below the skip lanes
     if (pr > lo) pr = lo;
     HGB_CUDA(cudaStreamCreateWithPriority(&m->lane_stream[l], cudaStreamNonBlocking, pr));
     HGB_CUDA(cudaEventCreateWithFlags(&m->join_ev[l], cudaEventDisableTiming));

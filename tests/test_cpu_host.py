@@ -325,20 +325,27 @@ def _conflict(a, b):
     return False
 
 
-@pytest.mark.parametrize("backward", [0, 1])
-def test_lane_schedule_orders_every_conflicting_pair(backward):
+@pytest.mark.parametrize("backward,wgrad_lanes", [(0, 0), (1, 0), (1, 1), (1, 3)])
+def test_lane_schedule_orders_every_conflicting_pair(backward, wgrad_lanes):
     """The multi-stream schedule (csrc/model.cu build_sequence) must order every pair of ops whose byte ranges
-    conflict: replay the dependencies as vector clocks and check all pairs of a 2-stack training plan."""
+    conflict: replay the dependencies as vector clocks and check all pairs of a 2-stack training plan -- with the default
+    number of weight-gradient lanes and with the leaf ops dealt over one and three streams (hgb_debug_set(35, n))."""
     import ctypes as C
     import hgb200
     from hgb200._lib import lib, check, ModelConfig
     cfg = ModelConfig(17, 2, 256, 256, 256, 1, 4, 1)
     h = C.c_void_p()
-    check(lib.hgb_model_create(C.byref(cfg), 0, C.byref(h)))
+    check(lib.hgb_debug_set(35, wgrad_lanes))
+    try:
+        check(lib.hgb_model_create(C.byref(cfg), 0, C.byref(h)))
+    finally:
+        check(lib.hgb_debug_set(35, 0))
     try:
         ops = _read_schedule(h, backward)
     finally:
         lib.hgb_model_destroy(h)
+    if wgrad_lanes == 3:
+        assert {o["lane"] for o in ops} >= {1, 6, 7}, "the extra weight-gradient lanes are not used"
     n = len(ops)
     lanes = sorted({o["lane"] for o in ops})
     assert len(lanes) >= 5, "skip lanes / weight-gradient lane missing from the plan"
