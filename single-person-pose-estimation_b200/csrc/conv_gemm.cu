@@ -645,6 +645,19 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
       // issuing all boxes delayed its whole warp -- and with it the tile -- by 0.35 us at N = 256)
       wait_slots(0, 0);
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");     // slots of phase 0 free; everybody past the previous tile's statistics
+      // BatchNorm-backward statistics (dgrad): this thread's rows of y are pulled into L1 NOW (no registers: the kernel sits at
+      // its 168-register cap) -- an L2 round trip that used to sit, fully exposed, between the bulk store of this tile and the
+      // TMEM loads of the next (the statistics cost 1.4 us per tile in the 3x3 dgrad)
+      if (kRowsPer <= 8 && p.stats && p.bn_y && sch * 8 < p.Cout) {
+        int rows_h = p.M_total - p0;
+        if (rows_h > kBlockM) rows_h = kBlockM;
+#pragma unroll
+        for (int i = 0; i < (kRowsPer <= 8 ? kRowsPer : 1); ++i) {
+          const int r = rg * kRowsPer + i;
+          if (r < rows_h)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint4*>(p.bn_y + (size_t)(p0 + r) * p.ldc) + sch));
+        }
+      }
       if (p.bn_y && et == 32) {
         // BatchNorm-backward statistics stream y from global memory: pull the NEXT tile's boxes into L2 now
         // (and this tile's, the first time) so those loads are L2 hits when the statistics pass issues them
@@ -807,6 +820,16 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
           tmem_ld_32x32(t0, va);
           if (two) tmem_ld_32x32(t0 + 64u, vb);
           tmem_ld_wait();
+          if (kPhases == 1 && (HALO || t == TILES - 1 || tile + 1 >= num_tiles)) {
+            // the whole accumulator is in registers: hand it back before staging, not after (the MMA warp of a strip kernel
+            // needs accumulator t of the next group long before the epilogue is through with tiles 0..t-1)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CTA2) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * t, 0));   // the leader issues the pair's MMAs
+              else mbar_arrive(tempty0 + 8 * (HALO ? t : acc));
+            }
+          }
           stage_chunk(va, g0);
           if (two) stage_chunk(vb, g0 + 1);
         } else {
@@ -820,7 +843,8 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
           }
         }
         // last phase: the accumulator stage is fully read, hand it back to the MMA warp
-        if ((ph == kPhases - 1 || (g0 + kPerPhase) * 64 >= p.Cout) && (HALO || t == TILES - 1 || tile + 1 >= num_tiles)) {
+        if (!(EPI == 8 && kPhases == 1) && (ph == kPhases - 1 || (g0 + kPerPhase) * 64 >= p.Cout) &&
+            (HALO || t == TILES - 1 || tile + 1 >= num_tiles)) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -1404,6 +1428,7 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   kp.tap_sign = a.tap_sign;
   kp.Cout = a.Cout; kp.ldc = a.ldc; kp.relu = a.relu;
   kp.bias = a.bias; kp.res1 = a.res1; kp.res2 = a.res2; kp.out = a.out; kp.stats = a.stats;
+  if (g_debug[37]) kp.stats = nullptr;      // TIMING EXPERIMENTS ONLY: drop the BatchNorm statistics of the epilogue (wrong results)
   kp.bn_y = a.bn_y;
   kp.bn_in = a.bn_in;
   kp.single_store = g_debug[16];
