@@ -1484,17 +1484,20 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
                        : launch_gemm_t<64, 6, 1, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
     case 128: return ws ? launch_gemm_t<128, 2, 4, 4>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
                         : launch_gemm_t<128, 4, 1, 4>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
-    default:   // 64 KB staging: single.  16 epilogue warps only where they measured faster (A/B on B200, batch 256 @64x64:
-      // dgrad with TMA residual + BatchNorm statistics 382 vs 399 us; plain forward tiles 171 vs 167 us: those are bound
-      // by shared-memory traffic -- 448 KB per tile -- not by epilogue issue slots).  hgb_debug_set(25, 1) = always 8.
+    default:   // 64 KB staging: single.
       // hgb_debug_set(31, 1) = 2 pipeline stages + a 7-box staging ring (+ L2 prefetch of the operand boxes, knob 33), OPT-IN:
       // every store then has 1.75 tile periods to drain, but the loads run only one tile ahead, and it measured SLOWER on B200
       // at batch 256 (128->256: 154 vs 145 us, 256->256: 247 vs 207 us stand-alone; in the step 239 vs 226 us) -- the wait on
       // the previous tile's store that ncu attributes 41 % of the epilogue samples to is not the bound: HBM is (5.5 of the
       // 5.65 TB/s a 1 read : 2 write stream reaches on this part, tools_cuda/membench.cu)
-      if (!g_debug[31])
-        return (g_debug[25] || !(kp.res1_tma && a.bn_y)) ? launch_gemm_t<256, 3, 1, 4>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
-                                                         : launch_gemm_t<256, 3, 1, 4, false, 16>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
+      if (!g_debug[31]) {
+        // 16 epilogue warps whenever the epilogue carries BatchNorm statistics (their pass over the staged tile is shared by
+        // twice the threads): 128->256 forward 235 -> 212 us, 256->256 dgrad 359 -> 303 us at batch 256; plain tiles measured
+        // no gain (171 vs 167 us).  hgb_debug_set(25, 1) = always 8, 2 = the round-1 rule (TMA residual + dgrad statistics only)
+        const bool epi16 = g_debug[25] == 1 ? false : g_debug[25] == 2 ? (kp.res1_tma && a.bn_y) : kp.stats != nullptr;
+        return !epi16 ? launch_gemm_t<256, 3, 1, 4>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
+                      : launch_gemm_t<256, 3, 1, 4, false, 16>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
+      }
       return (g_debug[25] || !(kp.res1_tma && a.bn_y)) ? launch_gemm_t<256, 2, 1, 7>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
                                                        : launch_gemm_t<256, 2, 1, 7, false, 16>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
   }
