@@ -281,10 +281,10 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
   float* s_osh = s_osc + 256;                                 // (BNB: s_sc | s_sh | s_osc hold the coefficients A | B | C)
   float* s_part = s_osh + 256;                                // BNB only: [8 row phases][4 channel blocks][64] bias-gradient partials
   // [row groups][2*BLOCK_N] = 16 KB (32 KB with 16 epilogue warps), aliases pipeline stage 0: used only after the last tile.
-  // BNB: the y box of stage 0 (read by the transform warps only, long before the last accumulator is complete) -- the dz / dp
-  // box may still be being read by the last dp bulk store
-  float* s_stats = reinterpret_cast<float*>(smem + (BNB ? kABytes + kBBytes : 0));
-  static_assert(!BNB || EPI == 8, "the y box holds the 16 KB statistics scratch of 8 epilogue warps");
+  // BNB: the staging boxes instead (the pipeline stages may still be being read by the last dp bulk store), once the last
+  // output store has read them
+  float* s_stats = reinterpret_cast<float*>(smem + (BNB ? kRingBytes : 0));
+  static_assert(!BNB || kOutBytes >= (EPI == 16 ? 32 : 16) * 1024, "statistics scratch in the staging boxes");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (p.M_total + kBlockM - 1) / kBlockM;
@@ -943,6 +943,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
     if (et == 0) KT(9);
     if (store_box >= 0) tma_store_wait_read();        // smem must stay valid until the last bulk store has read it
     if (et == 0) KT(10);
+    if (BNB && p.stats) asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // the scratch is the staging boxes: every store has read them
     if (p.stats) {
       // the pipeline stages are idle now: stage 0 doubles as the cross-thread reduction scratch.  Every thread
       // parks its 16 partial sums, then one thread per channel adds the row groups up -- no shared-memory float
@@ -1469,6 +1470,9 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     // N = 256: 2 stages of 64 KB (dz | weights | y) + 4 staging boxes; hgb_debug_set(31, 1) = a 5-box ring (measured slower:
     // 638 vs 568 us at batch 256, profiles/r02_ops_ab_staging_ring.txt)
     if (g_debug[31]) return launch_gemm_t<256, 2, 1, 5, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
+    // 16 epilogue warps when the epilogue also carries the next BatchNorm's statistics (hgb_debug_set(38, 1) = never, 2 = always)
+    if (g_debug[38] == 2 || (g_debug[38] == 0 && kp.stats))
+      return launch_gemm_t<256, 2, 1, 4, false, 16, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
     return launch_gemm_t<256, 2, 1, 4, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
   }
   // CTA pairs (tcgen05.mma.cta_group::2), OPT-IN with hgb_debug_set(30, 1): parity-green (tests/test_gpu_conv.py and the
