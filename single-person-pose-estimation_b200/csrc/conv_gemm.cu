@@ -56,7 +56,7 @@ struct GemmKernelParams {
   BnBwdInput bn_bwd;          // gamma != null (BNB kernels): the A operand is BatchNorm-backward(dz, y), computed in shared memory
   int single_store;           // debug: one thread issues all output boxes (hgb_debug_set(16, 1))
   int late_trigger;           // programmatic dependent launch is released after the producer's last load
-  int a_prefetch;             // 1x1 only: the producer pulls the A (and y) boxes of the tile `a_prefetch` rounds ahead into L2
+  int early_release;          // the epilogue hands the accumulator back right after its last TMEM load (0: after staging)
 };
 
 template <int OFF>
@@ -224,14 +224,6 @@ __device__ __forceinline__ void bn_bwd_transform_box(uint32_t box_dz, uint32_t b
 //               the dz box and the y box; the transform warps turn the dz box into dp in place, hand it to the MMAs, and
 //               one of them stores it through tmDP (the weight gradient reads dp later).  A stage is recycled once the
 //               MMAs AND that bulk store have read it (empty barrier count 2).
-//   OUT_BOXES  : epilogue staging = a RING of 128-pixel x 64-channel boxes (16 KB each); a tile takes BLOCK_N / 64 consecutive
-//               slots.  Boxes are staged and bulk-stored in pairs ("phases"), and a slot is rewritten only when the store that read
-//               it last has drained.  2 * BLOCK_N / 64 boxes = plain double buffering.  The N = 256 tiles cannot afford that
-//               (128 KB): with exactly 4 boxes every tile waited for its predecessor's 64 KB store to leave shared memory before
-//               it could stage (or TMA-fetch its residual tile) -- ncu: 41 % of the epilogue warps' samples on that wait, 3.1 us
-//               per tile against 2.2 us of HBM time.  A 7-box ring (with 2 pipeline stages; 5 boxes with the fused BatchNorm
-//               backward) gives every store more than a tile period to drain -- built, parity-green, and measured SLOWER than
-//               the 4-box / 3-stage geometry (see launch_conv_gemm), so it is opt-in: hgb_debug_set(31, 1).
 //   CTA2       : HALO only: a cluster of two CTAs (one TPC) runs every MMA as tcgen05.mma.cta_group::2 with M = 256.  CTA r keeps
 //               its own four tiles (own strip ring, own accumulators in its own TMEM, own epilogue) and HALF of every
 //               weight box (64 of the 128 output channels); the leader's single thread issues the MMAs for both SMs.  Every
@@ -240,7 +232,7 @@ __device__ __forceinline__ void bn_bwd_transform_box(uint32_t box_dz, uint32_t b
 //               Barriers: TMA loads of both CTAs count their bytes on the LEADER's full barriers; tcgen05.commit
 //               multicasts to the empty / accumulator-full barriers of both CTAs; the epilogue warps of both CTAs arrive on
 //               the leader's accumulator-empty barriers.
-template <int BLOCK_N, int STAGES, int TILES, int OUT_BOXES, bool HALO = false, int EPI = 8, bool BNB = false, bool CTA2 = false>
+template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false, int EPI = 8, bool BNB = false, bool CTA2 = false>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ CUtensorMap tmC,
@@ -257,8 +249,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
   constexpr int kGemmThreads = gemm_threads(EPI), kEpiThreads = 32 * EPI;
   static_assert(EPI == 8 || EPI == 16, "two or four epilogue warps per TMEM lane quarter");
   static_assert(kAccStages * TILES * BLOCK_N <= 512, "TMEM columns");
-  constexpr int kOutBytes = OUT_BOXES * kABytes;              // the staging ring
-  static_assert(OUT_BOXES >= BLOCK_N / 64 && OUT_BOXES <= 2 * (BLOCK_N / 64), "staging ring: one to two tiles");
+  constexpr int kOutBytes = (BLOCK_N / 64) * kABytes;
   constexpr int kASlots = TILES + 1, kBSlots = 6;             // HALO: strip boxes | two sets of three weight boxes
   constexpr int kRingBytes = HALO ? kASlots * kABytes + kBSlots * kBBytes : STAGES * kStageBytes;
   // full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | residual
@@ -270,9 +261,9 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // 128-byte swizzle atoms need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t outbase = base + kRingBytes;                 // OUT_BOXES epilogue staging boxes (1024-aligned)
-  const uint32_t bar0 = outbase + kOutBytes;
-  uint8_t* tail = smem + kRingBytes + kOutBytes + (kNumBars * 8 + 15) / 16 * 16;   // 16-byte aligned
+  const uint32_t outbase = base + kRingBytes;                 // OUT_BUFS epilogue staging buffers (1024-aligned)
+  const uint32_t bar0 = outbase + OUT_BUFS * kOutBytes;
+  uint8_t* tail = smem + kRingBytes + OUT_BUFS * kOutBytes + (kNumBars * 8 + 15) / 16 * 16;   // 16-byte aligned
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail);
   float* s_bias = reinterpret_cast<float*>(tail + 16);        // [BLOCK_N]
   float* s_sc = s_bias + BLOCK_N;                             // [256] scale / [256] shift of a deferred input BatchNorm
@@ -281,10 +272,11 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
   float* s_osh = s_osc + 256;                                 // (BNB: s_sc | s_sh | s_osc hold the coefficients A | B | C)
   float* s_part = s_osh + 256;                                // BNB only: [8 row phases][4 channel blocks][64] bias-gradient partials
   // [row groups][2*BLOCK_N] = 16 KB (32 KB with 16 epilogue warps), aliases pipeline stage 0: used only after the last tile.
-  // BNB: the staging boxes instead (the pipeline stages may still be being read by the last dp bulk store), once the last
-  // output store has read them
+  // BNB: the y box of stage 0 (read by the transform warps only, long before the last accumulator is complete) -- the dz / dp
+  // box may still be being read by the last dp bulk store
+  // (round 2) BNB: the output staging buffer instead, once the last output store has read it -- 32 KB with 16 epilogue warps
   float* s_stats = reinterpret_cast<float*>(smem + (BNB ? kRingBytes : 0));
-  static_assert(!BNB || kOutBytes >= (EPI == 16 ? 32 : 16) * 1024, "statistics scratch in the staging boxes");
+  static_assert(!BNB || OUT_BUFS * kOutBytes >= (EPI == 16 ? 32 : 16) * 1024, "statistics scratch in the staging buffer");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (p.M_total + kBlockM - 1) / kBlockM;
@@ -448,18 +440,6 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
           n0[t] = p0 / p.HW;
           y0[t] = (p0 - n0[t] * p.HW) / p.W;
         }
-        if (TILES == 1 && p.a_prefetch > 0) {
-          // two-stage rings keep the TMA loads only one tile ahead of the MMAs: HBM latency is hidden by an L2 prefetch of
-          // the operand boxes a few rounds ahead instead (the loads then hit L2)
-          const int gp = grp + p.a_prefetch * (int)gridDim.x;
-          if (gp < num_groups) {
-            const int pp = gp * kBlockM, nn = pp / p.HW, yy = (pp - nn * p.HW) / p.W;
-            for (int cb = 0; cb < p.cblk; ++cb) {
-              tma_prefetch_4d(&tmA, cb * 64, 0, yy, nn);
-              if (BNB) tma_prefetch_4d(&tmZ, cb * 64, 0, yy, nn);
-            }
-          }
-        }
         for (int kb = 0; kb < p.nkb; ++kb, ++kbt) {
           const int s = kbt % STAGES;
           const uint32_t ph = (kbt / STAGES) & 1;
@@ -592,23 +572,20 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
     const int gsel = ew >> 3;                        // 0 when EPI == 8
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 128;                // 0 .. kEpiThreads-1
-    // lane 0 of every (EPI / 4)-th epilogue warp issues (and tracks, as its own bulk groups: one per tile) the store of
-    // output box 0, 1, 2, 3 of every tile
+    // lane 0 of every (EPI / 4)-th epilogue warp issues (and tracks) the bulk store of output box 0, 1, 2, 3
     constexpr int kWarpsPerBox = EPI / 4;
-    constexpr int kBoxes = BLOCK_N / 64;
-    constexpr int kPhases = kBoxes > 2 ? kBoxes / 2 : 1;     // boxes are staged and stored in pairs
-    constexpr int kPerPhase = kBoxes / kPhases;
-    const int store_box = (lane == 0 && ew % kWarpsPerBox == 0 && ew / kWarpsPerBox < kBoxes) ? ew / kWarpsPerBox : -1;
+    const int store_box = p.single_store ? (et == 0 ? 0 : -1)
+                        : (lane == 0 && ew % kWarpsPerBox == 0 && ew / kWarpsPerBox < BLOCK_N / 64) ? ew / kWarpsPerBox : -1;
     // BN statistics: thread -> (16-byte chunk = 8 channels, group of kRowsPer pixel rows) of the staged tile
     constexpr int kChunks = BLOCK_N / 8;
     constexpr int kRowsPer = kBlockM / (kEpiThreads / kChunks);   // 16 / 8 / 4 rows for N = 256 / 128 / 64
     const int sch = et % kChunks, rg = et / kChunks;
+    const uint32_t st_boxoff = (uint32_t)(sch >> 3) * kABytes;
     const uint32_t st_chunk = (uint32_t)(sch & 7);
     uint64_t sa2[4], sq2[4];   // packed fp32 pairs: per-channel sum and second statistic of this thread's rows
 #pragma unroll
     for (int j = 0; j < 4; ++j) { sa2[j] = 0ull; sq2[j] = 0ull; }
-    int lt = 0, rt = 0, nt = 0;   // groups / residual phases / tiles processed by this CTA
-    int slot_base = 0;            // ring slot of box 0 of the current tile = (nt * kBoxes) % OUT_BOXES
+    int lt = 0, rt = 0, nt = 0;   // groups / residual tiles / tiles processed by this CTA
     for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x, ++lt) {
       const int acc = HALO ? 0 : lt % kAccStages;
       const uint32_t aph = HALO ? (lt & 1) : (lt / kAccStages) & 1;
@@ -617,51 +594,23 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
       const int tile = grp * TILES + t;
       if (tile >= num_tiles) break;      // uniform over the CTA
       const uint32_t acc_col = (uint32_t)((acc * TILES + t) * BLOCK_N);
-      auto box_addr = [&](int g) -> uint32_t {          // staging box g of this tile
-        int sl = slot_base + g;
-        if (sl >= OUT_BOXES) sl -= OUT_BOXES;
-        return outbase + (uint32_t)sl * kABytes;
-      };
-      // Before phase `ph` of this tile overwrites its slots, the bulk stores that read them last must have drained.  The
-      // thread that issued such a store waits on its own bulk groups ("at most `allowed` younger groups still pending");
-      // everybody else learns it through the barrier that follows.  `done_ph`: phases of THIS tile already stored.
-      auto wait_slots = [&](int ph, int done_ph) {
-        if (store_box < 0) return;
-#pragma unroll
-        for (int i = 0; i < kPerPhase; ++i) {
-          const int prev = nt * kBoxes + ph * kPerPhase + i - OUT_BOXES;      // sequence number of the slot's previous box
-          if (prev >= 0 && prev % kBoxes == store_box) {
-            const int committed = nt + (store_box / kPerPhase < done_ph ? 1 : 0);
-            if (committed - (prev / kBoxes + 1) >= 1) tma_store_wait_read1(); else tma_store_wait_read();
-          }
-        }
-      };
+      const uint32_t out0 = outbase + (uint32_t)(nt & (OUT_BUFS - 1)) * kOutBytes;   // staging buffers alternate tile by tile
+      const uint32_t st_box = out0 + st_boxoff;
+      ++nt;
       const int p0 = tile * kBlockM;
       const int pix = p0 + row;
       const bool row_ok = pix < p.M_total;
-      const int n0t = p0 / p.HW;
-      const int y0t = (p0 - n0t * p.HW) / p.W;
+      // the bulk store issued two tiles ago must be done reading this staging buffer (the previous tile's
+      // store may still be draining from the other one); then the residual tile (if any) is fetched into
+      // it while this tile's MMAs may still be running
       // (box g of every tile is stored by lane 0 of epilogue warp 2g, which also owns that bulk group: one thread
       // issuing all boxes delayed its whole warp -- and with it the tile -- by 0.35 us at N = 256)
-      wait_slots(0, 0);
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");     // slots of phase 0 free; everybody past the previous tile's statistics
-      // BatchNorm-backward statistics (dgrad): this thread's rows of y are pulled into L1 NOW (no registers: the kernel sits at
-      // its 168-register cap) -- an L2 round trip that used to sit, fully exposed, between the bulk store of this tile and the
-      // TMEM loads of the next (the statistics cost 1.4 us per tile in the 3x3 dgrad)
-      if (kRowsPer <= 8 && p.stats && p.bn_y && sch * 8 < p.Cout) {
-        int rows_h = p.M_total - p0;
-        if (rows_h > kBlockM) rows_h = kBlockM;
-#pragma unroll
-        for (int i = 0; i < (kRowsPer <= 8 ? kRowsPer : 1); ++i) {
-          const int r = rg * kRowsPer + i;
-          if (r < rows_h)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint4*>(p.bn_y + (size_t)(p0 + r) * p.ldc) + sch));
-        }
-      }
+      if (store_box >= 0) { if (OUT_BUFS == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       if (p.bn_y && et == 32) {
         // BatchNorm-backward statistics stream y from global memory: pull the NEXT tile's boxes into L2 now
         // (and this tile's, the first time) so those loads are L2 hits when the statistics pass issues them
-        for (int ahead = (nt == 0 ? 0 : 1); ahead <= 1; ++ahead) {
+        for (int ahead = (nt == 1 ? 0 : 1); ahead <= 1; ++ahead) {
           const int tl = (ahead == 0) ? tile : ((t + 1 < TILES && tile + 1 < num_tiles) ? tile + 1 : (grp + (int)gridDim.x) * TILES);
           if (tl < num_tiles) {
             const int pp = tl * kBlockM, nn = pp / p.HW, yy0 = (pp - nn * p.HW) / p.W;
@@ -672,7 +621,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
       }
       if (p.res1_tma && et == 64) {
         // same for the residual tile: the NEXT tile's boxes travel HBM -> L2 while this tile is processed, so the
-        // TMA fetch into the staging boxes at the top of the next tile is an L2 hit
+        // TMA fetch into the (single) staging buffer at the top of the next tile is an L2 hit
         const int tl = (t + 1 < TILES && tile + 1 < num_tiles) ? tile + 1 : (grp + (int)gridDim.x) * TILES;
         if (tl < num_tiles) {
           const int pp = tl * kBlockM, nn = pp / p.HW, yy0 = (pp - nn * p.HW) / p.W;
@@ -680,13 +629,30 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
             if (g * 64 < p.Cout) tma_prefetch_4d(&tmR, g * 64, 0, yy0, nn);
         }
       }
+      if (p.res1_tma) {
+        if (et == 0) {
+          const int n0 = p0 / p.HW;
+          const int y0 = (p0 - n0 * p.HW) / p.W;
+          int nbox = 0;
+          for (int g = 0; g < BLOCK_N / 64; ++g) nbox += (g * 64 < p.Cout);
+          mbar_expect_tx(resbar, nbox * kABytes);
+          for (int g = 0; g < BLOCK_N / 64; ++g)
+            if (g * 64 < p.Cout) tma_load_4d(out0 + (uint32_t)g * kABytes, &tmR, resbar, g * 64, 0, y0, n0);
+        }
+      }
+      if (et == 0 && (nt == 4 || nt == 5)) KT(13 + (nt - 4) * 5);
+      mbar_wait(tfull0 + 8 * (HALO ? t : acc), aph);
+      tc_fence_after();
+      if (et == 0 && nt == 1) KT(6);
+      if (et == 0 && (nt == 4 || nt == 5)) KT(14 + (nt - 4) * 5);
+      if (p.res1_tma) { mbar_wait(resbar, rt & 1); ++rt; }
       // one 32-column chunk of this thread's row: bias / ReLU / residuals -> bf16 -> swizzled staging box
       auto stage_chunk = [&](const uint32_t (&v)[32], int g) {
         const int n0c = g * 64 + hsel * 32;
         const size_t off = (size_t)pix * p.ldc + n0c;
         // staging: 128-pixel x 64-channel boxes in the 128-byte-swizzled layout TMA expects
         // (16-byte chunk index XOR (row mod 8)); a TMA-fetched residual sits at the very same addresses
-        const uint32_t box = box_addr(g) + (uint32_t)row * 128u;
+        const uint32_t box = out0 + (uint32_t)g * kABytes + (uint32_t)row * 128u;
         if (!p.res1 && !p.res2 && !post_bn) {
           // no residual: bias on packed fp32 pairs, ReLU on the packed bf16 pairs -- 3 instructions per 2 channels
           // the 32 bias values of the chunk are fetched up front (8 x 16 bytes, broadcast): issued back to back, their
@@ -788,83 +754,64 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
                        : "memory");
         }
       };
+      constexpr int kBoxes = BLOCK_N / 64;
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CTA2) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * t, 0));   // the leader issues the pair's MMAs
+          else mbar_arrive(tempty0 + 8 * (HALO ? t : acc));
+        }
+      };
+      const bool last_read = HALO || t == TILES - 1 || tile + 1 >= num_tiles;   // this tile ends the accumulator stage's use
+      if constexpr (EPI == 8) {
+        // two chunks per TMEM round trip: the second load is in flight while the first is converted
 #pragma unroll 1
-      for (int ph = 0; ph < kPhases; ++ph) {
-        const int g0 = ph * kPerPhase;
-        if (g0 * 64 >= p.Cout) {     // (Cout is a multiple of 64: whole boxes; a phase without boxes still keeps the barrier count)
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-          if (store_box >= 0 && store_box / kPerPhase == ph) tma_store_commit();
-          continue;
-        }
-        if (p.res1_tma && et == 0) {
-          // the residual boxes of this phase are fetched into the staging boxes while this tile's MMAs may still be running
-          int nbox = 0;
-          for (int i = 0; i < kPerPhase; ++i) nbox += ((g0 + i) * 64 < p.Cout);
-          mbar_expect_tx(resbar, nbox * kABytes);
-          for (int i = 0; i < kPerPhase; ++i)
-            if ((g0 + i) * 64 < p.Cout) tma_load_4d(box_addr(g0 + i), &tmR, resbar, (g0 + i) * 64, 0, y0t, n0t);
-        }
-        if (ph == 0) {
-          if (et == 0 && (nt == 3 || nt == 4)) KT(13 + (nt - 3) * 5);
-          mbar_wait(tfull0 + 8 * (HALO ? t : acc), aph);
-          tc_fence_after();
-          if (et == 0 && nt == 0) KT(6);
-          if (et == 0 && (nt == 3 || nt == 4)) KT(14 + (nt - 3) * 5);
-        }
-        if (p.res1_tma) { mbar_wait(resbar, rt & 1); ++rt; }
-        if constexpr (EPI == 8) {
-          // two chunks per TMEM round trip: the second load is in flight while the first is converted
-          const bool two = kPerPhase > 1 && (g0 + 1) * 64 < p.Cout;
+        for (int g = 0; g < kBoxes; g += 2) {
+          if (g * 64 >= p.Cout) break;  // warp-uniform (Cout is a multiple of 64: whole boxes)
+          const bool two = kBoxes > 1 && (g + 1) * 64 < p.Cout;
           uint32_t va[32], vb[32];
-          const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(g0 * 64 + hsel * 32);
+          const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(g * 64 + hsel * 32);
           tmem_ld_32x32(t0, va);
           if (two) tmem_ld_32x32(t0 + 64u, vb);
           tmem_ld_wait();
-          if (kPhases == 1 && (HALO || t == TILES - 1 || tile + 1 >= num_tiles)) {
-            // the whole accumulator is in registers: hand it back before staging, not after (the MMA warp of a strip kernel
-            // needs accumulator t of the next group long before the epilogue is through with tiles 0..t-1)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (CTA2) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * t, 0));   // the leader issues the pair's MMAs
-              else mbar_arrive(tempty0 + 8 * (HALO ? t : acc));
-            }
-          }
-          stage_chunk(va, g0);
-          if (two) stage_chunk(vb, g0 + 1);
-        } else {
-          // four warps per scheduler: one chunk at a time (96 registers), the other warps hide the TMEM round trip
-          const int g = g0 + gsel;
-          if (g < kBoxes && g * 64 < p.Cout) {
-            uint32_t va[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(g * 64 + hsel * 32), va);
-            tmem_ld_wait();
-            stage_chunk(va, g);
-          }
+          // The last columns of the accumulator are in registers: hand it back BEFORE staging, not after.  The four
+          // accumulators of a strip-kernel group complete together, and the MMA warp needs accumulator t of the NEXT group
+          // after t/6 of a tile time -- long before the epilogue is through with tiles 0..t-1 (forward 3x3 284 -> 257 us).
+          if (p.early_release && last_read && (g + 2 >= kBoxes || (g + 2) * 64 >= p.Cout)) release_acc();
+          stage_chunk(va, g);
+          if (two) stage_chunk(vb, g + 1);
         }
-        // last phase: the accumulator stage is fully read, hand it back to the MMA warp
-        if (!(EPI == 8 && kPhases == 1) && (ph == kPhases - 1 || (g0 + kPerPhase) * 64 >= p.Cout) &&
-            (HALO || t == TILES - 1 || tile + 1 >= num_tiles)) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (CTA2) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * t, 0));   // the leader issues the pair's MMAs
-            else mbar_arrive(tempty0 + 8 * (HALO ? t : acc));
-          }
+        if (!p.early_release && last_read) release_acc();
+      } else {
+        // four warps per scheduler: one chunk at a time (96 registers), the other warps hide the TMEM round trip
+#pragma unroll 1
+        for (int g = gsel; g < kBoxes; g += 2) {
+          if (g * 64 >= p.Cout) break;
+          uint32_t va[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(g * 64 + hsel * 32), va);
+          tmem_ld_wait();
+          stage_chunk(va, g);
         }
-        if (ph + 1 < kPhases) wait_slots(ph + 1, ph);    // (the next phase's slots: their stores were issued a tile ago)
-        fence_proxy_async();                            // generic-proxy smem writes -> visible to the TMA engine
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // the epilogue warps: phase fully staged, next slots free
-        if (et == 0 && nt == 0 && ph == kPhases - 1) KT(7);
-        if (et == 0 && (nt == 3 || nt == 4) && ph == kPhases - 1) KT(15 + (nt - 3) * 5);
-        if (store_box >= 0 && store_box / kPerPhase == ph) {
-          if (store_box * 64 < p.Cout) tma_store_4d(&tmC, box_addr(store_box), store_box * 64, 0, y0t, n0t);
-          tma_store_commit();
-        }
+        if (last_read) release_acc();
       }
-      if (et == 0 && nt == 0) KT(8);
-      if (et == 0 && (nt == 3 || nt == 4)) KT(16 + (nt - 3) * 5);
-      const uint32_t st_box = box_addr(sch >> 3);
+      fence_proxy_async();                            // generic-proxy smem writes -> visible to the TMA engine
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // the eight epilogue warps: tile fully staged
+      if (et == 0 && nt == 1) KT(7);
+      if (et == 0 && (nt == 4 || nt == 5)) KT(15 + (nt - 4) * 5);
+      if (store_box >= 0) {
+        const int n0 = p0 / p.HW;
+        const int y0 = (p0 - n0 * p.HW) / p.W;
+        if (p.single_store) {
+          for (int g = 0; g < BLOCK_N / 64; ++g)
+            if (g * 64 < p.Cout) tma_store_4d(&tmC, out0 + (uint32_t)g * kABytes, g * 64, 0, y0, n0);
+        } else if (store_box * 64 < p.Cout) {
+          tma_store_4d(&tmC, out0 + (uint32_t)store_box * kABytes, store_box * 64, 0, y0, n0);
+        }
+        tma_store_commit();
+        if (et == 0 && nt == 1) KT(8);
+        if (et == 0 && (nt == 4 || nt == 5)) KT(16 + (nt - 4) * 5);
+      }
       if (p.stats && sch * 8 < p.Cout) {
         // per-channel sums of the values as stored (bf16), read back from the staged tile with one 16-byte
         // shared load per pixel row (a warp covers whole rows: conflict-free); second statistic is either
@@ -934,16 +881,13 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
           }
         }
       }
-      if (et == 0 && (nt == 3 || nt == 4)) KT(17 + (nt - 3) * 5);
-      ++nt;
-      slot_base += kBoxes;
-      if (slot_base >= OUT_BOXES) slot_base -= OUT_BOXES;
+      if (et == 0 && (nt == 4 || nt == 5)) KT(17 + (nt - 4) * 5);
       }  // tiles of the group
     }
     if (et == 0) KT(9);
     if (store_box >= 0) tma_store_wait_read();        // smem must stay valid until the last bulk store has read it
     if (et == 0) KT(10);
-    if (BNB && p.stats) asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // the scratch is the staging boxes: every store has read them
+    if (BNB && p.stats) asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // the scratch is the staging buffer: every store has read it
     if (p.stats) {
       // the pipeline stages are idle now: stage 0 doubles as the cross-thread reduction scratch.  Every thread
       // parks its 16 partial sums, then one thread per channel adds the row groups up -- no shared-memory float
@@ -1371,20 +1315,20 @@ int conv_gemm_block_n(int Cout) { return Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 
 
 static int g_num_sms = 0;
 
-template <int BLOCK_N, int STAGES, int TILES, int OUT_BOXES, bool HALO = false, int EPI = 8, bool BNB = false, bool CTA2 = false>
+template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false, int EPI = 8, bool BNB = false, bool CTA2 = false>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                          const CUtensorMap& tmY, const GemmKernelParams& kp, int tiles_m, int max_ctas, cudaStream_t st,
                          const CUtensorMap* tmZ = nullptr, const CUtensorMap* tmDP = nullptr) {
   constexpr int ring = HALO ? (TILES + 1) * kABytes + 6 * (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 128
                             : STAGES * (TILES * kABytes + BLOCK_N * 128 + (BNB ? kABytes : 0));
   constexpr int nbars = HALO ? 2 * (TILES + 1) + 12 + 2 * TILES + 1 : 3 * STAGES + 5;
-  constexpr int smem = ring + OUT_BOXES * kABytes + (nbars * 8 + 15) / 16 * 16 + 16 + BLOCK_N * 4 +
+  constexpr int smem = ring + OUT_BUFS * (BLOCK_N / 64) * kABytes + (nbars * 8 + 15) / 16 * 16 + 16 + BLOCK_N * 4 +
                        (TILES == 1 ? 4 * 256 * 4 : 0) + (BNB ? 8 * 4 * 64 * 4 : 0) + 1024;   // BatchNorm scale+shift tables only for the 1x1 variants
   static_assert(ring >= (EPI == 16 ? 32 : 16) * 1024, "stats scratch (16 / 32 KB) aliases the pipeline stages");
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    HGB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BOXES, HALO, EPI, BNB, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HGB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS, HALO, EPI, BNB, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
   if (!g_num_sms) {
@@ -1396,7 +1340,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   int grid = groups < g_num_sms ? groups : g_num_sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (CTA2) grid &= ~1;     // whole CTA pairs (the caller guarantees an even number of groups: both CTAs of a pair loop alike)
-  HGB_CUDA(launch_pdl_cluster(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BOXES, HALO, EPI, BNB, CTA2>, dim3(grid), dim3(gemm_threads(EPI)), smem,
+  HGB_CUDA(launch_pdl_cluster(conv_gemm_kernel<BLOCK_N, STAGES, TILES, OUT_BUFS, HALO, EPI, BNB, CTA2>, dim3(grid), dim3(gemm_threads(EPI)), smem,
                               st, CTA2 ? 2 : 1, tmA, tmB, tmC, tmR, tmY, tmZ ? *tmZ : tmC, tmDP ? *tmDP : tmC, kp));
   HGB_LAUNCH_CHECK();
   return HGB_OK;
@@ -1430,14 +1374,13 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   kp.Cout = a.Cout; kp.ldc = a.ldc; kp.relu = a.relu;
   kp.bias = a.bias; kp.res1 = a.res1; kp.res2 = a.res2; kp.out = a.out; kp.stats = a.stats;
   if (g_debug[37]) kp.stats = nullptr;      // TIMING EXPERIMENTS ONLY: drop the BatchNorm statistics of the epilogue (wrong results)
+  kp.early_release = !g_debug[39];
   kp.bn_y = a.bn_y;
   kp.bn_in = a.bn_in;
   kp.single_store = g_debug[16];
   kp.late_trigger = !g_debug[18];   // default on: forward pass at batch 32 9.55 -> 8.93 ms (hgb_debug_set(18, 1) = trigger at kernel start)
   kp.bn_out = a.bn_out;
   kp.bn_bwd = a.bn_bwd;
-  // L2 prefetch distance of the 1x1 N = 256 kernels (two pipeline stages): hgb_debug_set(33, n) = n rounds, -1 = off
-  kp.a_prefetch = (a.ksize == 1 && a.Cout > 128 && g_debug[31]) ? (g_debug[33] ? (g_debug[33] < 0 ? 0 : g_debug[33]) : 1) : 0;
   HGB_CHECK_ARG(a.bn_bwd.gamma == nullptr || (conv_gemm_supports_bn_bwd(a.ksize, a.Cin, a.Cout) && a.bn_bwd.C == a.Cin && tmZ && tmDP &&
                                               a.bn_in.gamma == nullptr && a.bn_out.gamma == nullptr),
                 "conv_gemm: the fused BatchNorm backward needs a 1x1 dgrad with <= 256 input and 128 / 256 output channels");
@@ -1466,14 +1409,12 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   const bool halo = kp.tap3 && !g_debug[5] && tiles_m >= halo_min && !g_debug[12] && a.W <= 64 && rpt >= 2 &&
                     a.H % (4 * rpt) == 0 && a.Cout == 128;
   if (a.bn_bwd.gamma) {   // 1x1 dgrad with the BatchNorm backward fused in
-    if (a.Cout == 128) return launch_gemm_t<128, 3, 1, 4, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
-    // N = 256: 2 stages of 64 KB (dz | weights | y) + 4 staging boxes; hgb_debug_set(31, 1) = a 5-box ring (measured slower:
-    // 638 vs 568 us at batch 256, profiles/r02_ops_ab_staging_ring.txt)
-    if (g_debug[31]) return launch_gemm_t<256, 2, 1, 5, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
-    // 16 epilogue warps when the epilogue also carries the next BatchNorm's statistics (hgb_debug_set(38, 1) = never, 2 = always)
+    if (a.Cout == 128) return launch_gemm_t<128, 3, 1, 2, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
+    // 16 epilogue warps when the epilogue also carries the next BatchNorm's statistics (569 -> 525 us at batch 256);
+    // hgb_debug_set(38, 1) = never, 2 = always
     if (g_debug[38] == 2 || (g_debug[38] == 0 && kp.stats))
-      return launch_gemm_t<256, 2, 1, 4, false, 16, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
-    return launch_gemm_t<256, 2, 1, 4, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
+      return launch_gemm_t<256, 2, 1, 1, false, 16, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
+    return launch_gemm_t<256, 2, 1, 1, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
   }
   // CTA pairs (tcgen05.mma.cta_group::2), OPT-IN with hgb_debug_set(30, 1): parity-green (tests/test_gpu_conv.py and the
   // batch-80 replay run it) but measured SLOWER than the one-CTA strip kernel on B200 at batch 256 -- forward 64x64 297.7 vs
@@ -1481,29 +1422,24 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   // stays the default.  Needs the weight map with 64-row boxes and an even number of groups (with an even grid both CTAs of
   // a pair then run the same number of iterations).
   if (halo && tmB64 && g_debug[30] == 1 && (tiles_m % 8) == 0 && g_num_sms % 2 == 0 && (a.max_ctas <= 0 || a.max_ctas >= 2))
-    return launch_gemm_t<128, 1, 4, 2, true, 8, false, true>(tmA, *tmB64, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
-  if (halo) return launch_gemm_t<128, 1, 4, 2, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
+    return launch_gemm_t<128, 1, 4, 1, true, 8, false, true>(tmA, *tmB64, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
+  // (16 epilogue warps measured slower in the strip kernel: forward 277 vs 257 us, dgrad 308 vs 294 us)
+  if (halo) return launch_gemm_t<128, 1, 4, 1, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
   switch (conv_gemm_block_n(a.Cout)) {
     case 64: return ws ? launch_gemm_t<64, 2, 4, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
                        : launch_gemm_t<64, 6, 1, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
-    case 128: return ws ? launch_gemm_t<128, 2, 4, 4>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
-                        : launch_gemm_t<128, 4, 1, 4>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
-    default:   // 64 KB staging: single.
-      // hgb_debug_set(31, 1) = 2 pipeline stages + a 7-box staging ring (+ L2 prefetch of the operand boxes, knob 33), OPT-IN:
-      // every store then has 1.75 tile periods to drain, but the loads run only one tile ahead, and it measured SLOWER on B200
-      // at batch 256 (128->256: 154 vs 145 us, 256->256: 247 vs 207 us stand-alone; in the step 239 vs 226 us) -- the wait on
-      // the previous tile's store that ncu attributes 41 % of the epilogue samples to is not the bound: HBM is (5.5 of the
-      // 5.65 TB/s a 1 read : 2 write stream reaches on this part, tools_cuda/membench.cu)
-      if (!g_debug[31]) {
-        // 16 epilogue warps whenever the epilogue carries BatchNorm statistics (their pass over the staged tile is shared by
-        // twice the threads): 128->256 forward 235 -> 212 us, 256->256 dgrad 359 -> 303 us at batch 256; plain tiles measured
-        // no gain (171 vs 167 us).  hgb_debug_set(25, 1) = always 8, 2 = the round-1 rule (TMA residual + dgrad statistics only)
+    case 128: return ws ? launch_gemm_t<128, 2, 4, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
+                        : launch_gemm_t<128, 4, 1, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
+    default:   // 64 KB staging: single.  16 epilogue warps only where they measured faster (A/B on B200, batch 256 @64x64:
+      // dgrad with TMA residual + BatchNorm statistics 382 vs 399 us; plain forward tiles 171 vs 167 us: those are bound
+      // by shared-memory traffic -- 448 KB per tile -- not by epilogue issue slots).  hgb_debug_set(25, 1) = always 8.
+      // (round 2) 16 warps whenever the epilogue carries BatchNorm statistics -- their pass over the staged tile is shared by
+      // twice the threads: 128->256 forward 235 -> 212 us, 256->256 dgrad 359 -> 303 us.  hgb_debug_set(25, 2) = the round-1 rule.
+      {
         const bool epi16 = g_debug[25] == 1 ? false : g_debug[25] == 2 ? (kp.res1_tma && a.bn_y) : kp.stats != nullptr;
-        return !epi16 ? launch_gemm_t<256, 3, 1, 4>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
-                      : launch_gemm_t<256, 3, 1, 4, false, 16>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
+        return !epi16 ? launch_gemm_t<256, 3, 1, 1>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
+                      : launch_gemm_t<256, 3, 1, 1, false, 16>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
       }
-      return (g_debug[25] || !(kp.res1_tma && a.bn_y)) ? launch_gemm_t<256, 2, 1, 7>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
-                                                       : launch_gemm_t<256, 2, 1, 7, false, 16>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
   }
 }
 
