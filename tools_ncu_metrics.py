@@ -15,7 +15,8 @@ REPORTS = {   # op class (hgb200/profiling.py naming) -> report
     "B_DGRAD k3 128->128 @64 +bnstats": "r02_conv3x3_dgrad_b256_halo.ncu-rep",
     "B_WGRAD k3 128->128 @64": "r02_conv3x3_wgrad3_b256.ncu-rep",
     "B_WGRAD k1 256->256 @64": "r02_wgrad_k1_256to256.ncu-rep",
-    "F_CONV k1 128->256 @64": "r02_fconv_k1_128to256.ncu-rep",
+    "F_CONV k1 128->256 @64": "r02_fconv_k1_128to256_bn_stats.ncu-rep",
+    "F_CONV k1 128->256 @64 (plain: no input BatchNorm, no statistics; round-2 start)": "r02_fconv_k1_128to256.ncu-rep",
     "B_DGRAD k1 256->128 @64 +bnapply +bnstats +res": "r02_dgrad_k1_256to128_bnb.ncu-rep",
     "decode_v2 f32 64x64 batch 1024": "r02_decode_f32_b1024_final.ncu-rep",
 }

@@ -27,6 +27,7 @@ ap.add_argument("--stacks", type=int, default=1)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--fused-stats", type=int, default=-1, help="B_DGRAD only: 1 = must carry a fused BN reduction, 0 = must not")
 ap.add_argument("--debug", default="")
+ap.add_argument("--input-bn", type=int, default=-1, help="F_CONV only: 1 = must read a deferred input BatchNorm (conv_1x1_3), 0 = must not")
 ap.add_argument("--ab", default="", help="key=value: time every op a second time with this debug knob set (A/B in one process)")
 ap.add_argument("--specs", default="", help="several ops in one process: TYPE:k:cin:cout:h[:fused] separated by commas "
                                             "(non-conv ops: TYPE:0:0:C:h); inputs are those left behind by one full step")
@@ -66,6 +67,8 @@ def matches(info):
         ok = cinfo[0] == a.k and cinfo[2] == a.cin and cinfo[3] == a.cout and dims[1] == a.h
         if ok and want == 9 and a.fused_stats >= 0:
             ok = (bn >= 0) == bool(a.fused_stats)
+        if ok and want == 1 and a.input_bn >= 0:
+            ok = bool(info[7] & 0xffff) == bool(a.input_bn)
         return ok
     lib.hgb_model_act_info(h, a0, C.byref(off), C.byref(dims))
     return dims[1] == a.h and (a.c == 0 or dims[3] == a.c)
