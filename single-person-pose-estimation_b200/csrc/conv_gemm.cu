@@ -34,6 +34,9 @@ constexpr int kThreads = 192;       // 3x3 wgrad kernel: TMA warp, MMA warp, 4 e
 constexpr int kWgradThreads = 256;  // wgrad kernel: + 2 operand-transform warps (deferred BatchNorm)
 // forward/dgrad kernel: warp 0 TMA, warp 1 MMA, warps 2-3 operand transform, then EPI (8 or 16) epilogue warps
 __host__ __device__ constexpr int gemm_threads(int epi) { return 128 + 32 * epi; }
+#ifndef HGB_REGSPLIT
+#define HGB_REGSPLIT 1
+#endif
 constexpr float kBnEpsIn = 1e-3f;       // Keras BatchNormalization defaults (as in layer_kernels.cu)
 constexpr float kBnMomentumIn = 0.99f;
 
@@ -57,6 +60,7 @@ struct GemmKernelParams {
   int single_store;           // debug: one thread issues all output boxes (hgb_debug_set(16, 1))
   int late_trigger;           // programmatic dependent launch is released after the producer's last load
   int early_release;          // the epilogue hands the accumulator back right after its last TMEM load (0: after staging)
+  int hoist_y;                // dgrad statistics: the first batch of y rows is loaded at the top of the tile (0: inside the statistics pass)
 };
 
 template <int OFF>
@@ -347,6 +351,15 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
   const int rpt = kBlockM / p.W;   // image rows per tile
 
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  // Register re-partitioning (8 epilogue warps: 384 threads x 168 registers at launch).  The epilogue is the only
+  // register-hungry role -- 64 accumulator values, 32 bias values and the statistics registers live at once -- and 168 was not
+  // enough to also keep the dgrad statistics' y rows in flight across the TMEM loads (they spilled, and the hoist cost more
+  // than it hid).  The producer / MMA / transform warp group hands registers back, the two epilogue warp groups take them.
+  constexpr bool kRegSplit = EPI == 8 && HGB_REGSPLIT != 0;
+  constexpr int kRegsLow = (BNB || HALO) ? 104 : 72, kRegsHigh = (BNB || HALO) ? 200 : 216;
+  static_assert(128 * kRegsLow + 256 * kRegsHigh <= 384 * 168, "register re-partitioning must fit the launch allocation");
+  if (warp < 4) {      // warp group 0: producer, MMA issuer, two operand-transform warps
+  if constexpr (kRegSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLow));
   if (HALO && warp == 0) {
     if (lane == 0) {
       // CTA2: bytes of both CTAs are counted on the leader's full barriers (its producer expects twice the bytes)
@@ -495,7 +508,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
         if (lt == 3 || lt == 4) KT(25 + (lt - 3) * 3);
       }
     }
-  } else if (warp < 4) {
+  } else {
     // ---------------- operand transform (deferred BatchNorm of the input): as soon as TMA has delivered the
     // 128-pixel x 64-channel box of a stage, z = bf16(y * scale + shift) is applied in place; the MMA warp waits
     // for `ready` instead of `full`.  Zero-filled rows past the end of the tensor become `shift`: they only reach
@@ -563,7 +576,9 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
         }
       }
     }
+  }
   } else {
+    if constexpr (kRegSplit) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsHigh));
     // ---------------- epilogue: EPI warps; TMEM lane quarter = warp % 4.  The EPI / 4 warps of a quarter split every
     // 64-channel box into its two 32-column halves (hsel) and, with 16 warps, the boxes into even and odd ones (gsel)
     const int q = warp & 3;
@@ -607,6 +622,22 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
       // issuing all boxes delayed its whole warp -- and with it the tile -- by 0.35 us at N = 256)
       if (store_box >= 0) { if (OUT_BUFS == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      // BatchNorm-backward statistics (dgrad): the first batch of this thread's y rows is requested NOW; the L2 round trip used
+      // to start only inside the statistics pass, fully exposed once per tile (needs the re-partitioned registers)
+      constexpr int kStatBatch = kRowsPer < 8 ? kRowsPer : (EPI == 16 ? 4 : 8);   // rows in flight per thread (bounds register use)
+      constexpr bool kHoistY = kRegSplit;
+      uint4 yh[kHoistY ? kStatBatch : 1];
+      const bool hoist = kHoistY && p.hoist_y && p.bn_y && p.stats && sch * 8 < p.Cout;
+      if (hoist) {
+        int rows_h = p.M_total - p0;
+        if (rows_h > kBlockM) rows_h = kBlockM;
+#pragma unroll
+        for (int i = 0; i < (kHoistY ? kStatBatch : 1); ++i) {
+          const int r = rg * kRowsPer + i;
+          yh[i] = make_uint4(0, 0, 0, 0);
+          if (r < rows_h) yh[i] = __ldg(reinterpret_cast<const uint4*>(p.bn_y + (size_t)(p0 + r) * p.ldc) + sch);
+        }
+      }
       if (p.bn_y && et == 32) {
         // BatchNorm-backward statistics stream y from global memory: pull the NEXT tile's boxes into L2 now
         // (and this tile's, the first time) so those loads are L2 hits when the statistics pass issues them
@@ -820,16 +851,21 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
         // (channel 2i in the low lane, 2i+1 in the high lane: exactly the two halves of a bf16x2 word).
         int rows = p.M_total - p0;
         if (rows > kBlockM) rows = kBlockM;
-        constexpr int kBatch = kRowsPer < 8 ? kRowsPer : (EPI == 16 ? 4 : 8);   // rows in flight per thread (bounds register use)
+        constexpr int kBatch = kStatBatch;
 #pragma unroll 1
         for (int rb = rg * kRowsPer; rb < (rg + 1) * kRowsPer; rb += kBatch) {
           uint4 vv[kBatch], yy[kBatch];
           if (p.bn_y) {
+            if (kHoistY && hoist && rb == rg * kRowsPer) {
 #pragma unroll
-            for (int i = 0; i < kBatch; ++i) {
-              const int r = rb + i;
-              yy[i] = make_uint4(0, 0, 0, 0);
-              if (r < rows) yy[i] = __ldg(reinterpret_cast<const uint4*>(p.bn_y + (size_t)(p0 + r) * p.ldc) + sch);
+              for (int i = 0; i < kBatch; ++i) yy[i] = yh[kHoistY ? i : 0];
+            } else {
+#pragma unroll
+              for (int i = 0; i < kBatch; ++i) {
+                const int r = rb + i;
+                yy[i] = make_uint4(0, 0, 0, 0);
+                if (r < rows) yy[i] = __ldg(reinterpret_cast<const uint4*>(p.bn_y + (size_t)(p0 + r) * p.ldc) + sch);
+              }
             }
           }
 #pragma unroll
@@ -1375,6 +1411,7 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   kp.bias = a.bias; kp.res1 = a.res1; kp.res2 = a.res2; kp.out = a.out; kp.stats = a.stats;
   if (g_debug[37]) kp.stats = nullptr;      // TIMING EXPERIMENTS ONLY: drop the BatchNorm statistics of the epilogue (wrong results)
   kp.early_release = !g_debug[39];
+  kp.hoist_y = !g_debug[41];
   kp.bn_y = a.bn_y;
   kp.bn_in = a.bn_in;
   kp.single_store = g_debug[16];
