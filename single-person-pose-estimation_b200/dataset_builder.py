@@ -286,9 +286,6 @@ class Prefetcher:
         except Exception:
             pass
 
-    def __del__(self):
-        self._stop = True
-
 
 # ------------------------------------------------------------------ the TFRecord-backed builder (dataset_builder.py:10-66)
 class DatasetBuilder:

@@ -1,4 +1,4 @@
-"""Debug aid (not a pytest): per-layer isolation of the CUDA forward pass.
+"""Debug aid (NOT a pytest; lives under tests/ because it imports the oracle, which only test infrastructure may do): per-layer isolation of the CUDA forward pass.
 For every conv: recompute it in fp32 torch FROM THE DEVICE'S OWN INPUT and compare with the device
 output (isolated error), next to the error accumulated against the fp32 oracle."""
 import ctypes as C
