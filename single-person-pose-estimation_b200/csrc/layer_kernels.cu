@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(256, 4) bn_apply_fwd_kernel(const bf16* __rest
                                                               bf16* __restrict__ out, const float* __restrict__ sums,
                                                               float* __restrict__ saved, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float* __restrict__ mm,
-                                                              float* __restrict__ mv, int M, int M_stat, int C, int training) {
+                                                              float* __restrict__ mv, int M, int M_stat, int C, int training,
+                                                              const bf16* __restrict__ up, int lw, int lh) {
   pdl_trigger();
   pdl_wait();
   const int G = C >> 3, R = 256 / G;
@@ -104,6 +105,13 @@ __global__ void __launch_bounds__(256, 4) bn_apply_fwd_kernel(const bf16* __rest
           unpack8(vr[u], q);
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] += q[j];
+          if (up) {     // + UpSampling2D(nearest 2x) of the lower level: pixel (n, y, x) reads (n, y/2, x/2); W = 1<<lw, H = 1<<lh
+            const int x = r & ((1 << lw) - 1), t = r >> lw, y = t & ((1 << lh) - 1), n = t >> lh;
+            const size_t lr = ((((size_t)n << (lh - 1)) + (size_t)(y >> 1)) << (lw - 1)) + (size_t)(x >> 1);
+            unpack8(ld16(up + lr * C + g * 8), q);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += q[j];
+          }
         }
         st16(out + (size_t)r * C + g * 8, pack8(f));
       }
@@ -112,16 +120,24 @@ __global__ void __launch_bounds__(256, 4) bn_apply_fwd_kernel(const bf16* __rest
 }
 
 int bn_apply_fwd(const bf16* y, const bf16* res, bf16* out, const float* sums, float* saved, const float* gamma,
-                 const float* beta, float* moving_mean, float* moving_var, int M, int M_stat, int C, int training, cudaStream_t st) {
+                 const float* beta, float* moving_mean, float* moving_var, int M, int M_stat, int C, int training, cudaStream_t st,
+                 const bf16* up, int H, int W) {
   HGB_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "bn_apply: unsupported channel count %d", C);
   if (M == 0) return HGB_OK;
+  int lw = 0, lh = 0;
+  if (up) {
+    HGB_CHECK_ARG(res && H >= 2 && W >= 2 && (H & (H - 1)) == 0 && (W & (W - 1)) == 0 && M % (H * W) == 0,
+                  "bn_apply: the fused upsample-add needs a residual and power-of-two maps (got %dx%d)", H, W);
+    while ((1 << lw) < W) ++lw;
+    while ((1 << lh) < H) ++lh;
+  }
   // In inference the moving statistics are read-only, in training block 0 rewrites them after reading.
   if (res)
     launch_pdl(bn_apply_fwd_kernel<2, true>, dim3(row_blocks(M, C)), dim3(256), 0, st, y, res, out, sums, saved, gamma, beta,
-               moving_mean, moving_var, M, M_stat, C, training);
+               moving_mean, moving_var, M, M_stat, C, training, up, lw, lh);
   else
     launch_pdl(bn_apply_fwd_kernel<4, false>, dim3(row_blocks(M, C)), dim3(256), 0, st, y, res, out, sums, saved, gamma, beta,
-               moving_mean, moving_var, M, M_stat, C, training);
+               moving_mean, moving_var, M, M_stat, C, training, (const bf16*)nullptr, 0, 0);
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }

@@ -13,7 +13,8 @@ typedef __nv_bfloat16 bf16;
 // statistics (moving_var gets the unbiased batch variance, as TF's fused kernel does).  M = rows of this tensor,
 // M_stat = rows behind `sums` (= M, or the global batch under sync-BN).
 int bn_apply_fwd(const bf16* y, const bf16* res, bf16* out, const float* sums, float* saved, const float* gamma,
-                 const float* beta, float* moving_mean, float* moving_var, int M, int M_stat, int C, int training, cudaStream_t st);
+                 const float* beta, float* moving_mean, float* moving_var, int M, int M_stat, int C, int training, cudaStream_t st,
+                 const bf16* up = nullptr, int H = 0, int W = 0);   // up: + UpSampling2D(2x, nearest) of a [N][H/2][W/2][C] tensor
 
 // MaxPool2D 2x2/2 (hourglass.py:63,135,171-177) on [N][2h][2w][C] -> [N][h][w][C], and its gradient
 // (routed to the first maximum of each window in row-major order; accumulate=1 adds into dx).

@@ -532,8 +532,22 @@ int build(hgb_model* m) {
       m->cur_lane = kLaneMain;
       const Act sa = m->acts[r.shortb[u].out];
       r.up_low[u] = cur;
-      r.up_a[u] = m->new_act(sa.n, sa.h, sa.w, sa.c);
-      Op o; o.type = F_UPADD; o.a0 = r.shortb[u].out; o.a1 = cur; o.a2 = r.up_a[u]; m->emit_f(o);
+      Op* last = m->fwd_ops[m->cur_seg].empty() ? nullptr : &m->fwd_ops[m->cur_seg].back();
+      // (batch 256: 147.9 -> 146.5 ms per step.  At batch 32 the step is latency-bound and the folded kernel sits on the critical
+      //  path behind the deep levels, where the stand-alone merge was shorter: 24.97 vs 25.13 ms -- so only above batch 48;
+      //  hgb_debug_set(42, 2) forces it)
+      const bool fold_upadd = hgb::g_debug[42] == 2 || (hgb::g_debug[42] == 0 && cfg.batch > 48);
+      if (fold_upadd && last && last->type == F_BN && last->a2 == r.shortb[u].out && last->a1 >= 0 && last->a3 < 0) {
+        // UpSampling2D + Add (hourglass.py:152-154) folded into the skip bottleneck's closing BatchNorm: that kernel already
+        // reads y3 and the skip and writes the block output -- it now adds the upsampled lower level too and writes the MERGE
+        // input; the block's own output is never stored (nothing reads it: its backward pass needs y3 only).  One write and one
+        // read of a 256-channel tensor less per level and stack than the stand-alone merge kernel (hgb_debug_set(42, 1)).
+        last->a3 = cur;
+        r.up_a[u] = r.shortb[u].out;
+      } else {
+        r.up_a[u] = m->new_act(sa.n, sa.h, sa.w, sa.c);
+        Op o; o.type = F_UPADD; o.a0 = r.shortb[u].out; o.a1 = cur; o.a2 = r.up_a[u]; m->emit_f(o);
+      }
       r.merged[u] = m->bottleneck(r.up_a[u], C, nm + "_merged");
       cur = r.merged[u].out;
     }
@@ -765,7 +779,7 @@ void op_access(const hgb_model* m, const Op& o, std::vector<Range>& r, std::vect
       }
       break;
     case F_BN:
-      add_act(m, r, o.a0); add_act(m, r, o.a1); add_act(m, w, o.a2);
+      add_act(m, r, o.a0); add_act(m, r, o.a1); add_act(m, r, o.a3); add_act(m, w, o.a2);
       add_arena(w, m->bns[o.bn].sums_off, 2 * (size_t)m->bns[o.bn].c * 4);   // (sync-BN all-reduces them in place)
       add_arena(r, m->bns[o.bn].sums_off, 2 * (size_t)m->bns[o.bn].c * 4);
       add_arena(w, m->bns[o.bn].saved_off, 2 * (size_t)m->bns[o.bn].c * 4);
@@ -1027,7 +1041,7 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
       }
       rc = bn_apply_fwd(act_ptr(m, o.a0), act_ptr(m, o.a1), act_ptr(m, o.a2), arena_f(m, b.sums_off), arena_f(m, b.saved_off),
                         m->p_params + b.gamma_off, m->p_params + b.beta_off, m->p_params + b.mm_off, m->p_params + b.mv_off,
-                        y.n * y.h * y.w, y.n * y.h * y.w * m->stat_ranks(), b.c, training, st);
+                        y.n * y.h * y.w, y.n * y.h * y.w * m->stat_ranks(), b.c, training, st, act_ptr(m, o.a3), y.h, y.w);
       break;
     }
     case F_POOL: {
@@ -1206,6 +1220,7 @@ int ensure_lanes(hgb_model* m) {
 bool fuse_inference_bn(const hgb_model* m, const Op& conv, const Op* next, int training, Op* fused) {
   if (training || hgb::g_debug[17] || !next || conv.type != F_CONV || next->type != F_BN || conv.bn < 0 || next->bn != conv.bn) return false;
   if (m->convs[conv.conv].ksize != 1 || conv.a2 >= 0 || conv.a3 >= 0 || next->a0 != conv.a1 || conv.lane != next->lane) return false;
+  if (next->a3 >= 0) return false;     // the BatchNorm also adds the upsampled lower level: a job for its own kernel
   *fused = conv;
   fused->a1 = next->a2;      // write the BN's output tensor
   fused->a2 = next->a1;      // + the BN's residual (identity / projected skip)

@@ -59,8 +59,8 @@ class PlanInfo:
         hm = 4.0 * M * self.K
         if ty == 0:      # stem patches: fp32 image in, bf16 patches out
             byt = 4.0 * n * (2 * hh) * (2 * ww) * 3 + 2.0 * el(a0)
-        elif ty == 2:
-            byt = 2.0 * (el(a0) + el(a1) + el(a2))
+        elif ty == 2:    # y in, residual in, output out (+ the lower level of a fused upsample-add merge: a3)
+            byt = 2.0 * (el(a0) + el(a1) + el(a2) + el(a3))
         elif ty == 3:
             byt = 2.0 * (el(a0) + el(a1))
         elif ty == 4:
@@ -85,7 +85,10 @@ class PlanInfo:
             n, hh, ww, cc = self.act(a1)
             M = n * hh * ww
             byt = 2.0 * 4.0 * M * self.K + 2.0 * (el(a0) + el(a1))
-        return f"{name} C{cc} @{hh}", 0.0, byt, (ty, 0, 0, cc, hh)
+        key = f"{name} C{cc} @{hh}"
+        if ty == 2 and a3 >= 0:
+            key += " +upadd"
+        return key, 0.0, byt, (ty, 0, 0, cc, hh)
 
 
 def bound_of(flops, byt):

@@ -152,7 +152,7 @@ def test_replay_every_op(S, B, mobile):
     torch.cuda.synchronize()
     bf = torch.bfloat16
 
-    deferred, writers = [0], [0]
+    deferred, writers, fused_upadds = [0], [0], [0]
     # ------------------------------------------------------------------ forward
     for seg in range(S + 1):
         for i, (ty, ci, bi, a0, a1, a2, a3, flag) in R.ops(seg, 0):
@@ -213,6 +213,10 @@ def test_replay_every_op(S, B, mobile):
                 Cc = b["c"]
                 y = R.act(a0).float()
                 res = R.act(a1).float() if a1 >= 0 else 0.0
+                if a3 >= 0:      # UpSampling2D(2x) + Add of the lower level folded into the skip bottleneck's closing BatchNorm
+                    lo = R.act(a3).float()
+                    res = res + lo.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+                    fused_upadds[0] += 1
                 mm0 = R.params[b["mm"]:b["mm"] + Cc].clone()
                 mv0 = R.params[b["mv"]:b["mv"] + Cc].clone()
                 R.run(seg, 0, i)
@@ -474,7 +478,9 @@ def test_replay_every_op(S, B, mobile):
     n_bneck = 3 + 15 * S
     print("BatchNorm-backward applies fused into 1x1 dgrad GEMMs:", fused_applies[0], " shared bias-gradient passes:", shared_colsums[0])
     assert shared_colsums[0] == S - 1
-    print("convolutions / weight gradients with a deferred input BatchNorm:", deferred[0], "statistic writers:", writers[0])
+    print("convolutions / weight gradients with a deferred input BatchNorm:", deferred[0], "statistic writers:", writers[0],
+          " upsample-add merges folded into a BatchNorm:", fused_upadds[0])
+    assert fused_upadds[0] == (4 * S if B > 48 else 0)      # every level of every stack (hourglass.py:143-157), large batches only
     if mobile:      # every pointwise GEMM is a 1x1: all three BatchNorm-backward applies of a bottleneck fuse; only the head BN defers
         assert {"F_DW", "B_DW_DGRAD", "B_DW_WGRAD"} <= set(R.low_cos)
         assert fused_applies[0] >= 3 * 15 * S
