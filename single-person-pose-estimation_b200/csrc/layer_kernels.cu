@@ -119,6 +119,109 @@ __global__ void __launch_bounds__(256, 4) bn_apply_fwd_kernel(const bf16* __rest
   }
 }
 
+// BatchNorm (+ residual) AND the MaxPool2D 2x2/2 that follows it (hourglass.py:63,135,171-177) in one pass: a thread owns a 2x2
+// window of pixels (8 channels), writes the four normalised pixels and their maximum.  The maximum is taken over the bf16 values
+// as stored, so the pooled tensor is bit-identical to what maxpool_fwd_kernel computes from `out`; what disappears is that
+// kernel's re-read of `out`.  W = 1 << lw, H = 1 << lh.
+template <bool RES>
+__global__ void __launch_bounds__(256, 3) bn_apply_pool_fwd_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res,
+                                                                   bf16* __restrict__ out, bf16* __restrict__ pooled,
+                                                                   const float* __restrict__ sums, float* __restrict__ saved,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   float* __restrict__ mm, float* __restrict__ mv, int M, int M_stat,
+                                                                   int C, int training, int lw, int lh) {
+  pdl_trigger();
+  pdl_wait();
+  const int G = C >> 3, R = 256 / G;
+  const int g = threadIdx.x % G, r0 = threadIdx.x / G;
+  float sc[8], sh[8];
+  const float invM = 1.f / (float)M_stat;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    float mean, var;
+    if (training) {
+      mean = sums[c] * invM;
+      var = fmaxf(sums[C + c] * invM - mean * mean, 0.f);
+    } else {
+      mean = mm[c];
+      var = mv[c];
+    }
+    const float rstd = rsqrtf(var + kBnEps);
+    sc[j] = gamma[c] * rstd;
+    sh[j] = beta[c] - mean * sc[j];
+    if (training && blockIdx.x == 0 && r0 == 0) {
+      saved[c] = mean;
+      saved[C + c] = rstd;
+      const float unbiased = M_stat > 1 ? var * ((float)M_stat / (float)(M_stat - 1)) : var;
+      mm[c] = mm[c] * kBnMomentum + mean * (1.f - kBnMomentum);
+      mv[c] = mv[c] * kBnMomentum + unbiased * (1.f - kBnMomentum);
+    }
+  }
+  const int W = 1 << lw, windows = M >> 2;
+  for (int wi = blockIdx.x * R + r0; wi < windows; wi += gridDim.x * R) {
+    const int xo = wi & ((W >> 1) - 1), t = wi >> (lw - 1), yo = t & ((1 << (lh - 1)) - 1), n = t >> (lh - 1);
+    const size_t base = ((((size_t)n << lh) + (size_t)(2 * yo)) << lw) + (size_t)(2 * xo);
+    const size_t rows[4] = {base, base + 1, base + W, base + W + 1};
+    uint4 vy[4], vr[RES ? 4 : 1];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      vy[u] = ld16(y + rows[u] * C + g * 8);
+      if (RES) vr[u] = ld16(res + rows[u] * C + g * 8);
+    }
+    uint4 mx = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(vy[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = f[j] * sc[j] + sh[j];
+      if (RES) {
+        float q[8];
+        unpack8(vr[u], q);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += q[j];
+      }
+      const uint4 o = pack8(f);
+      st16(out + rows[u] * C + g * 8, o);
+      if (u == 0) {
+        mx = o;
+      } else {
+        const uint32_t a[4] = {mx.x, mx.y, mx.z, mx.w}, b[4] = {o.x, o.y, o.z, o.w};
+        uint32_t m4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const __nv_bfloat162 h = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a[k]), *reinterpret_cast<const __nv_bfloat162*>(&b[k]));
+          m4[k] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        mx = make_uint4(m4[0], m4[1], m4[2], m4[3]);
+      }
+    }
+    st16(pooled + (size_t)wi * C + g * 8, mx);
+  }
+}
+
+int bn_apply_pool_fwd(const bf16* y, const bf16* res, bf16* out, bf16* pooled, const float* sums, float* saved, const float* gamma,
+                      const float* beta, float* moving_mean, float* moving_var, int M, int M_stat, int C, int H, int W, int training,
+                      cudaStream_t st) {
+  HGB_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "bn_apply_pool: unsupported channel count %d", C);
+  HGB_CHECK_ARG(H >= 2 && W >= 2 && (H & (H - 1)) == 0 && (W & (W - 1)) == 0 && M % (H * W) == 0,
+                "bn_apply_pool: power-of-two maps required (got %dx%d)", H, W);
+  if (M == 0) return HGB_OK;
+  int lw = 0, lh = 0;
+  while ((1 << lw) < W) ++lw;
+  while ((1 << lh) < H) ++lh;
+  const int blocks = row_blocks(M / 4, C, 1);
+  if (res)
+    launch_pdl(bn_apply_pool_fwd_kernel<true>, dim3(blocks), dim3(256), 0, st, y, res, out, pooled, sums, saved, gamma, beta,
+               moving_mean, moving_var, M, M_stat, C, training, lw, lh);
+  else
+    launch_pdl(bn_apply_pool_fwd_kernel<false>, dim3(blocks), dim3(256), 0, st, y, res, out, pooled, sums, saved, gamma, beta,
+               moving_mean, moving_var, M, M_stat, C, training, lw, lh);
+  HGB_LAUNCH_CHECK();
+  return HGB_OK;
+}
+
 int bn_apply_fwd(const bf16* y, const bf16* res, bf16* out, const float* sums, float* saved, const float* gamma,
                  const float* beta, float* moving_mean, float* moving_var, int M, int M_stat, int C, int training, cudaStream_t st,
                  const bf16* up, int H, int W) {

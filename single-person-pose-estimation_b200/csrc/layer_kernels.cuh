@@ -12,6 +12,10 @@ typedef __nv_bfloat16 bf16;
 // produced by the conv epilogue); block 0 stores (mean, rstd) in `saved` and updates the moving
 // statistics (moving_var gets the unbiased batch variance, as TF's fused kernel does).  M = rows of this tensor,
 // M_stat = rows behind `sums` (= M, or the global batch under sync-BN).
+// the same + the MaxPool2D 2x2/2 of the output (pooled: [N][H/2][W/2][C]), bit-identical to maxpool_fwd on `out`
+int bn_apply_pool_fwd(const bf16* y, const bf16* res, bf16* out, bf16* pooled, const float* sums, float* saved, const float* gamma,
+                      const float* beta, float* moving_mean, float* moving_var, int M, int M_stat, int C, int H, int W, int training,
+                      cudaStream_t st);
 int bn_apply_fwd(const bf16* y, const bf16* res, bf16* out, const float* sums, float* saved, const float* gamma,
                  const float* beta, float* moving_mean, float* moving_var, int M, int M_stat, int C, int training, cudaStream_t st,
                  const bf16* up = nullptr, int H = 0, int W = 0);   // up: + UpSampling2D(2x, nearest) of a [N][H/2][W/2][C] tensor

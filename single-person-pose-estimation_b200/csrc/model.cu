@@ -365,6 +365,16 @@ struct hgb_model {
   int pool(int x) {
     const Act a = acts[x];
     const int o = new_act(a.n, a.h / 2, a.w / 2, a.c);
+    // MaxPool2D folded into the BatchNorm that produces its input (same lane, the op emitted last): that kernel writes the
+    // pooled tensor next to its output (F_BN flag bit 0: a3 is the pooled OUTPUT) and the pool kernel's re-read of a whole
+    // 256-channel tensor disappears, together with one launch on the main chain.  hgb_debug_set(43, 1) keeps the pool kernel.
+    Op* last = fwd_ops[cur_seg].empty() ? nullptr : &fwd_ops[cur_seg].back();
+    if (!hgb::g_debug[43] && last && last->type == F_BN && last->a2 == x && last->a3 < 0 && last->lane == cur_lane &&
+        (a.h & (a.h - 1)) == 0 && (a.w & (a.w - 1)) == 0 && a.h >= 2 && a.w >= 2) {
+      last->a3 = o;
+      last->flag |= 1;
+      return o;
+    }
     Op p;
     p.type = F_POOL; p.a0 = x; p.a1 = o;
     emit_f(p);
@@ -779,7 +789,7 @@ void op_access(const hgb_model* m, const Op& o, std::vector<Range>& r, std::vect
       }
       break;
     case F_BN:
-      add_act(m, r, o.a0); add_act(m, r, o.a1); add_act(m, r, o.a3); add_act(m, w, o.a2);
+      add_act(m, r, o.a0); add_act(m, r, o.a1); add_act(m, (o.flag & 1) ? w : r, o.a3); add_act(m, w, o.a2);
       add_arena(w, m->bns[o.bn].sums_off, 2 * (size_t)m->bns[o.bn].c * 4);   // (sync-BN all-reduces them in place)
       add_arena(r, m->bns[o.bn].sums_off, 2 * (size_t)m->bns[o.bn].c * 4);
       add_arena(w, m->bns[o.bn].saved_off, 2 * (size_t)m->bns[o.bn].c * 4);
@@ -1038,6 +1048,12 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
       if (training && m->stat_ranks() > 1) {   // sync-BN: global batch statistics
         rc = comm_allreduce_sum_f32(m->comm, arena_f(m, b.sums_off), 2 * b.c, st);
         if (rc) break;
+      }
+      if (o.flag & 1) {     // + the MaxPool2D of the output
+        rc = bn_apply_pool_fwd(act_ptr(m, o.a0), act_ptr(m, o.a1), act_ptr(m, o.a2), act_ptr(m, o.a3), arena_f(m, b.sums_off),
+                               arena_f(m, b.saved_off), m->p_params + b.gamma_off, m->p_params + b.beta_off, m->p_params + b.mm_off,
+                               m->p_params + b.mv_off, y.n * y.h * y.w, y.n * y.h * y.w * m->stat_ranks(), b.c, y.h, y.w, training, st);
+        break;
       }
       rc = bn_apply_fwd(act_ptr(m, o.a0), act_ptr(m, o.a1), act_ptr(m, o.a2), arena_f(m, b.sums_off), arena_f(m, b.saved_off),
                         m->p_params + b.gamma_off, m->p_params + b.beta_off, m->p_params + b.mm_off, m->p_params + b.mv_off,

@@ -87,7 +87,7 @@ class PlanInfo:
             byt = 2.0 * 4.0 * M * self.K + 2.0 * (el(a0) + el(a1))
         key = f"{name} C{cc} @{hh}"
         if ty == 2 and a3 >= 0:
-            key += " +upadd"
+            key += " +pool" if flag & 1 else " +upadd"
         return key, 0.0, byt, (ty, 0, 0, cc, hh)
 
 

@@ -152,7 +152,7 @@ def test_replay_every_op(S, B, mobile):
     torch.cuda.synchronize()
     bf = torch.bfloat16
 
-    deferred, writers, fused_upadds = [0], [0], [0]
+    deferred, writers, fused_upadds, fused_pools = [0], [0], [0], [0]
     # ------------------------------------------------------------------ forward
     for seg in range(S + 1):
         for i, (ty, ci, bi, a0, a1, a2, a3, flag) in R.ops(seg, 0):
@@ -213,7 +213,7 @@ def test_replay_every_op(S, B, mobile):
                 Cc = b["c"]
                 y = R.act(a0).float()
                 res = R.act(a1).float() if a1 >= 0 else 0.0
-                if a3 >= 0:      # UpSampling2D(2x) + Add of the lower level folded into the skip bottleneck's closing BatchNorm
+                if a3 >= 0 and not (flag & 1):      # UpSampling2D(2x) + Add of the lower level folded into the skip bottleneck's closing BatchNorm
                     lo = R.act(a3).float()
                     res = res + lo.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
                     fused_upadds[0] += 1
@@ -229,6 +229,9 @@ def test_replay_every_op(S, B, mobile):
                 R.note(ty, e)
                 assert e <= 1e-2, f"bn {bi}: {e}"
                 assert R.cos(ty, out, ref) > 0.999, f"bn {bi}: cosine"
+                if a3 >= 0 and (flag & 1):     # MaxPool2D folded in: bit-identical to pooling the stored output
+                    assert torch.equal(R.act(a3), _windows(R.act(a2).float()).max(dim=-2).values.to(bf))
+                    fused_pools[0] += 1
                 saved = R.arena_f32(b["saved"], 2 * Cc)
                 torch.testing.assert_close(saved[:Cc], mean, rtol=1e-3, atol=1e-4)
                 torch.testing.assert_close(saved[Cc:], torch.rsqrt(var + 1e-3), rtol=2e-3, atol=1e-4)
@@ -480,6 +483,8 @@ def test_replay_every_op(S, B, mobile):
     assert shared_colsums[0] == S - 1
     print("convolutions / weight gradients with a deferred input BatchNorm:", deferred[0], "statistic writers:", writers[0],
           " upsample-add merges folded into a BatchNorm:", fused_upadds[0])
+    print("max-pools folded into the BatchNorm in front of them:", fused_pools[0])
+    assert fused_pools[0] == 1 + 4 * S         # the front module's pool + four per stack (hourglass.py:63,135,171-177)
     assert fused_upadds[0] == (4 * S if B > 48 else 0)      # every level of every stack (hourglass.py:143-157), large batches only
     if mobile:      # every pointwise GEMM is a 1x1: all three BatchNorm-backward applies of a bottleneck fuse; only the head BN defers
         assert {"F_DW", "B_DW_DGRAD", "B_DW_WGRAD"} <= set(R.low_cos)
