@@ -548,6 +548,93 @@ class HourglassModel:
             per = ar.sum_host(per)
         return [float(per.sum())] + [float(v) for v in per]
 
+    def train_on_keypoints_stream(self, batches):
+        """Pipelined train_on_keypoints over an iterable of host (images, kps_x, kps_y, kps_v) batches: a generator that
+        yields, in order, exactly what train_on_keypoints returns for each batch.
+
+        The reference ends its input pipelines with `.prefetch(AUTOTUNE)` (dataset_builder.py:46,54) and Keras' fit keeps
+        the device one step ahead of the host; this is the same overlap, stated explicitly: batch i+1 travels host->device
+        on a copy stream (two device slots) while step i computes, and step i's losses come back through a pinned buffer
+        that is read only after step i+1 has been enqueued, so neither the PCIe copy nor the host's launch work for the
+        next step sits between two steps.  Every batch is still copied host->device and every loss device->host; results
+        are identical to calling train_on_keypoints per batch (same kernels, same order on the compute stream)."""
+        torch = _lib.require_cuda()
+        from .. import ops
+        from ..parallel import current_allreduce
+        ar = current_allreduce()
+        h, w, _k = self.heatmap_shape
+        compute = torch.cuda.current_stream()
+        if getattr(self, "_h2d_stream", None) is None:
+            self._h2d_stream = torch.cuda.Stream(priority=-1)
+        copy = self._h2d_stream
+        slots = [dict(bufs=None, uploaded=torch.cuda.Event(), consumed=None, loss_ready=torch.cuda.Event(),
+                      host_loss=torch.empty(self.num_stacks, dtype=torch.float64).pin_memory()) for _ in range(2)]
+
+        def as_host(a, dtype):
+            if isinstance(a, torch.Tensor):
+                return a if a.dtype == dtype else a.to(dtype)
+            return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype={torch.float32: np.float32, torch.int32: np.int32}[dtype])))
+
+        def upload(batch, s):
+            src = [as_host(batch[0], torch.float32), as_host(batch[1], torch.float32), as_host(batch[2], torch.float32),
+                   as_host(batch[3], torch.int32)]
+            if src[0].dim() != 4 or tuple(src[0].shape[1:]) != self.input_shape:
+                raise ValueError(f"images must be (B,{self.input_shape[0]},{self.input_shape[1]},3), got {tuple(src[0].shape)}")
+            sl = slots[s]
+            if sl["bufs"] is None or any(b.shape != t.shape for b, t in zip(sl["bufs"], src)):
+                sl["bufs"] = [torch.empty(t.shape, dtype=t.dtype, device="cuda") for t in src]
+                sl["consumed"] = torch.cuda.Event()      # the allocator may hand back blocks the compute stream still reads
+                sl["consumed"].record(compute)
+            with torch.cuda.stream(copy):
+                if sl["consumed"] is not None:
+                    copy.wait_event(sl["consumed"])      # the step that last read this slot has been enqueued and must finish
+                for b, t in zip(sl["bufs"], src):
+                    b.copy_(t, non_blocking=True)
+                sl["uploaded"].record(copy)
+            sl["src"] = src      # keeps the host tensors alive until the copy has run
+
+        def finish(s):
+            sl = slots[s]
+            sl["loss_ready"].synchronize()
+            per = sl["host_loss"].numpy().copy()
+            if ar and sl["reduce_on_host"]:
+                per = ar.sum_host(per)
+            return [float(per.sum())] + [float(v) for v in per]
+
+        it = iter(batches)
+        try:
+            upload(next(it), 0)
+        except StopIteration:
+            return
+        i, pending, more = 0, None, True
+        while more:
+            s = i & 1
+            try:
+                upload(next(it), s ^ 1)
+            except StopIteration:
+                more = False
+            sl = slots[s]
+            compute.wait_event(sl["uploaded"])
+            x, kx, ky, kv = sl["bufs"]
+            y = ops.render_targets(kx, ky, kv, h, w)
+            gb = x.shape[0] * (ar.world_size if ar else 1)
+            losses = self.train_step_device(x, y, global_batch=gb, allreduce=ar)
+            sl["consumed"] = torch.cuda.Event()
+            sl["consumed"].record(compute)
+            sl["reduce_on_host"] = False
+            if ar:       # per-shard losses carry 1/global_batch: the global loss is their sum (device-side when the group is NCCL)
+                if ar.dist.get_backend(ar.group) == "nccl":
+                    ar.dist.all_reduce(losses, op=ar.dist.ReduceOp.SUM, group=ar.group)
+                else:
+                    sl["reduce_on_host"] = True
+            sl["host_loss"].copy_(losses, non_blocking=True)
+            sl["loss_ready"].record(compute)
+            if pending is not None:
+                yield finish(pending)
+            pending = s
+            i += 1
+        yield finish(pending)
+
     def test_on_batch(self, x, y):
         from .. import ops
         from ..parallel import current_allreduce

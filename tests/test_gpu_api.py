@@ -176,3 +176,37 @@ def test_tf_checkpoint_round_trip_keeps_training_state(hgb, tmp_path):
     assert b._pending_opt is None and b.optimizer.iterations == a.optimizer.iterations == 4
     # same state, same batch: what is left is the run-to-run noise of a batch-4 training-mode forward (2.6e-3 here)
     assert np.isfinite(lb[0]) and abs(la[0] - lb[0]) <= 5e-2 * abs(la[0]), (la, lb)
+
+
+def test_train_on_keypoints_stream_equals_per_batch_calls(hgb):
+    """The pipelined generator (copy of batch i+1 under step i, losses read one step late) returns, in order, what
+    train_on_keypoints returns for the same batches on an identically initialised model (same kernels in the same order).
+    The tolerance is measured, not chosen: two synchronous runs differ by the fp32 reduction order of the statistics /
+    weight-gradient atomics, and the pipelined run must stay within a small multiple of that spread.  The batches differ
+    strongly in their visible-keypoint count, so a slot mix-up would show as a loss from the wrong batch."""
+    import torch
+    rng = np.random.default_rng(5)
+    batches = []
+    for i, b in enumerate((4, 4, 4, 2, 4)):        # a shape change in the middle re-allocates a slot
+        kv = np.zeros((b, 17), np.int32)
+        kv[:, :3 * i + 1] = 2                       # 1, 4, 7, 10, 13 visible joints: the weighted loss scales with them
+        batches.append((torch.from_numpy(rng.random((b, 256, 256, 3), dtype=np.float32)).pin_memory(),
+                        rng.uniform(4, 60, (b, 17)).astype(np.float32), rng.uniform(4, 60, (b, 17)).astype(np.float32), kv))
+    outs = []
+    for mode in ("sync", "sync", "stream"):
+        model = hgb.HourglassModel(17, 2, 256, (256, 256, 3), "sigmoid", seed=3)
+        model.compile(optimizer=hgb.Adam(1e-3), loss=hgb.loss.weighted_mse)
+        if mode == "sync":
+            outs.append(np.array([model.train_on_keypoints(*b) for b in batches]))
+        else:
+            outs.append(np.array(list(model.train_on_keypoints_stream(iter(batches)))))
+            assert list(model.train_on_keypoints_stream(iter([]))) == []
+        assert model.optimizer.iterations == len(batches)
+    a, b, c = outs
+    assert c.shape == (len(batches), 3)
+    floor = np.abs(a - b) / np.abs(a)
+    err = np.abs(c - a) / np.abs(a)
+    print("sync vs sync:", floor.max(axis=1), " stream vs sync:", err.max(axis=1), " losses:", a[:, 0])
+    assert np.all(np.abs(np.diff(a[:, 0])) / a[:-1, 0] > 0.05), "batches must be told apart by their loss"
+    assert err[0].max() <= max(10 * floor[0].max(), 1e-5)                # same weights, same batch
+    assert np.all(err.max(axis=1) <= np.maximum(10 * floor.max(axis=1), 2e-3))      # trajectories stay together
