@@ -245,6 +245,32 @@ int bn_apply_fwd(const bf16* y, const bf16* res, bf16* out, const float* sums, f
   return HGB_OK;
 }
 
+// Block-level combine of per-thread 8-channel partials: every thread parks its partial sums in shared memory
+// ([row group][stat][channel], 2048 floats per statistic for any C), one thread per channel adds the row groups up and
+// issues one global reduction.  (Shared-memory float atomicAdd compiles to a compare-and-swap spin loop: with R
+// threads contending per address it cost several microseconds per block.)
+template <int NSTAT>
+__device__ __forceinline__ void block_channel_flush(float (&acc)[NSTAT][8], float* s_acc /*[R*NSTAT*C]*/, float* const* dst,
+                                                    int C, int g, int c_valid, float* dst2 = nullptr) {
+  const int G = C >> 3, R = 256 / G, r0 = threadIdx.x / G;
+#pragma unroll
+  for (int s = 0; s < NSTAT; ++s) {
+    float4* d = reinterpret_cast<float4*>(s_acc + ((size_t)r0 * NSTAT + s) * C + g * 8);
+    d[0] = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
+    d[1] = make_float4(acc[s][4], acc[s][5], acc[s][6], acc[s][7]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NSTAT * C; i += blockDim.x) {
+    const int s = i / C, c = i - s * C;
+    if (dst[s] && c < c_valid) {
+      float t = 0.f;
+      for (int r = 0; r < R; ++r) t += s_acc[(size_t)r * NSTAT * C + i];
+      atomicAdd(dst[s] + c, t);
+      if (dst2) atomicAdd(dst2 + c, t);      // a second consumer of the same column sums (statistic 0 only callers)
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------- max-pool
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int64_t total,
                                                           int h, int w, int G) {
@@ -270,11 +296,20 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const bf16* __restrict
   }
 }
 
+// STATS: the gradient this kernel writes is the dz of a BatchNorm (the closing one of the bottleneck below the pool): its
+// backward statistics sum(dz), sum(dz * y) are accumulated here, over the values as stored (bf16), instead of by a
+// bn_bwd_reduce pass that would read the tensor again.  A thread keeps one channel group for all its windows
+// (256 % G == 0 and the grid stride is a multiple of 256), so the partial sums live in registers.
+template <bool STATS>
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
                                                           bf16* __restrict__ dx, int64_t total, int h, int w, int G,
-                                                          int accumulate) {
+                                                          int accumulate, const bf16* __restrict__ ybn, float* __restrict__ bsums) {
   pdl_trigger();
   pdl_wait();
+  extern __shared__ float s_acc[];
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(i % G);
     int64_t pix = i / G;
@@ -286,8 +321,13 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const bf16* __restrict
     const size_t base = (((size_t)n * 2 * h + 2 * oy) * 2 * w + 2 * ox) * C + g * 8;
     const size_t offs[4] = {base, base + C, base + 2 * w * C, base + 2 * w * C + C};
     float v[4][8], gy[8];
+    uint4 yv[STATS ? 4 : 1];
 #pragma unroll
     for (int q = 0; q < 4; ++q) unpack8(ld16(x + offs[q]), v[q]);
+    if (STATS) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) yv[q] = ld16(ybn + offs[q]);
+    }
     unpack8(ld16(dy + (size_t)i * 8), gy);
     float o[4][8];
 #pragma unroll
@@ -308,8 +348,21 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const bf16* __restrict
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[q][j] += old[j];
       }
-      st16(dx + offs[q], pack8(o[q]));
+      const uint4 packed = pack8(o[q]);
+      st16(dx + offs[q], packed);
+      if (STATS) {
+        float d[8], yy[8];
+        unpack8(packed, d);
+        unpack8(yv[q], yy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[0][j] += d[j]; acc[1][j] += d[j] * yy[j]; }
+      }
     }
+  }
+  if (STATS) {
+    const int C = G * 8;
+    float* dst[2] = {bsums, bsums + C};
+    block_channel_flush<2>(acc, s_acc, dst, C, threadIdx.x % G, C);
   }
 }
 
@@ -327,11 +380,19 @@ int maxpool_fwd(const bf16* x, bf16* out, int N, int h, int w, int C, cudaStream
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
-int maxpool_bwd(const bf16* x, const bf16* dy, bf16* dx, int N, int h, int w, int C, int accumulate, cudaStream_t st) {
+int maxpool_bwd(const bf16* x, const bf16* dy, bf16* dx, int N, int h, int w, int C, int accumulate, cudaStream_t st,
+                const bf16* ybn, float* bsums) {
   HGB_CHECK_ARG(C % 8 == 0, "maxpool: C %% 8");
   const int64_t total = (int64_t)N * h * w * (C / 8);
   if (total == 0) return HGB_OK;
-  launch_pdl(maxpool_bwd_kernel, dim3(flat_blocks(total)), dim3(256), 0, st, x, dy, dx, total, h, w, C / 8, accumulate);
+  if (ybn) {
+    HGB_CHECK_ARG(256 % (C / 8) == 0 && C <= 2048, "maxpool_bwd: statistics need a channel count that divides 2048 (got %d)", C);
+    launch_pdl(maxpool_bwd_kernel<true>, dim3(flat_blocks(total)), dim3(256), 2 * 2048 * sizeof(float), st, x, dy, dx, total, h, w,
+               C / 8, accumulate, ybn, bsums);
+  } else {
+    launch_pdl(maxpool_bwd_kernel<false>, dim3(flat_blocks(total)), dim3(256), 0, st, x, dy, dx, total, h, w, C / 8, accumulate,
+               ybn, bsums);
+  }
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
@@ -365,10 +426,17 @@ __global__ void __launch_bounds__(256) upsample_add_fwd_kernel(const bf16* __res
   }
 }
 
+// STATS: as in maxpool_bwd_kernel -- dlow is the dz of the BatchNorm that closes the merged bottleneck one level down
+template <bool STATS>
 __global__ void __launch_bounds__(256) upsample_add_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dlow,
-                                                               int64_t total, int h, int w, int G) {
+                                                               int64_t total, int h, int w, int G, const bf16* __restrict__ ybn,
+                                                               float* __restrict__ bsums) {
   pdl_trigger();
   pdl_wait();
+  extern __shared__ float s_acc[];
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(i % G);
     int64_t pix = i / G;
@@ -379,13 +447,28 @@ __global__ void __launch_bounds__(256) upsample_add_bwd_kernel(const bf16* __res
     const size_t C = (size_t)G * 8;
     const size_t base = (((size_t)n * 2 * h + 2 * oy) * 2 * w + 2 * ox) * C + g * 8;
     float a[8], b[8], c[8], d[8];
+    uint4 yv = make_uint4(0, 0, 0, 0);
+    if (STATS) yv = ld16(ybn + (size_t)i * 8);
     unpack8(ld16(dout + base), a);
     unpack8(ld16(dout + base + C), b);
     unpack8(ld16(dout + base + 2 * w * C), c);
     unpack8(ld16(dout + base + 2 * w * C + C), d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) a[j] = (a[j] + b[j]) + (c[j] + d[j]);
-    st16(dlow + (size_t)i * 8, pack8(a));
+    const uint4 packed = pack8(a);
+    st16(dlow + (size_t)i * 8, packed);
+    if (STATS) {
+      float dd[8], yy[8];
+      unpack8(packed, dd);
+      unpack8(yv, yy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[0][j] += dd[j]; acc[1][j] += dd[j] * yy[j]; }
+    }
+  }
+  if (STATS) {
+    const int C = G * 8;
+    float* dst[2] = {bsums, bsums + C};
+    block_channel_flush<2>(acc, s_acc, dst, C, threadIdx.x % G, C);
   }
 }
 
@@ -397,42 +480,22 @@ int upsample_add_fwd(const bf16* skip, const bf16* low, bf16* out, int N, int h,
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
-int upsample_add_bwd(const bf16* dout, bf16* dlow, int N, int h, int w, int C, cudaStream_t st) {
+int upsample_add_bwd(const bf16* dout, bf16* dlow, int N, int h, int w, int C, cudaStream_t st, const bf16* ybn, float* bsums) {
   HGB_CHECK_ARG(C % 8 == 0, "upsample_add: C %% 8");
   const int64_t total = (int64_t)N * h * w * (C / 8);
   if (total == 0) return HGB_OK;
-  launch_pdl(upsample_add_bwd_kernel, dim3(flat_blocks(total)), dim3(256), 0, st, dout, dlow, total, h, w, C / 8);
+  if (ybn) {
+    HGB_CHECK_ARG(256 % (C / 8) == 0 && C <= 2048, "upsample_add_bwd: statistics need a channel count that divides 2048 (got %d)", C);
+    launch_pdl(upsample_add_bwd_kernel<true>, dim3(flat_blocks(total)), dim3(256), 2 * 2048 * sizeof(float), st, dout, dlow, total, h,
+               w, C / 8, ybn, bsums);
+  } else {
+    launch_pdl(upsample_add_bwd_kernel<false>, dim3(flat_blocks(total)), dim3(256), 0, st, dout, dlow, total, h, w, C / 8, ybn, bsums);
+  }
   HGB_LAUNCH_CHECK();
   return HGB_OK;
 }
 
 // ---------------------------------------------------------------------------------- BN backward
-// Block-level combine of per-thread 8-channel partials: every thread parks its partial sums in shared memory
-// ([row group][stat][channel], 2048 floats per statistic for any C), one thread per channel adds the row groups up and
-// issues one global reduction.  (Shared-memory float atomicAdd compiles to a compare-and-swap spin loop: with R
-// threads contending per address it cost several microseconds per block.)
-template <int NSTAT>
-__device__ __forceinline__ void block_channel_flush(float (&acc)[NSTAT][8], float* s_acc /*[R*NSTAT*C]*/, float* const* dst,
-                                                    int C, int g, int c_valid, float* dst2 = nullptr) {
-  const int G = C >> 3, R = 256 / G, r0 = threadIdx.x / G;
-#pragma unroll
-  for (int s = 0; s < NSTAT; ++s) {
-    float4* d = reinterpret_cast<float4*>(s_acc + ((size_t)r0 * NSTAT + s) * C + g * 8);
-    d[0] = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
-    d[1] = make_float4(acc[s][4], acc[s][5], acc[s][6], acc[s][7]);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < NSTAT * C; i += blockDim.x) {
-    const int s = i / C, c = i - s * C;
-    if (dst[s] && c < c_valid) {
-      float t = 0.f;
-      for (int r = 0; r < R; ++r) t += s_acc[(size_t)r * NSTAT * C + i];
-      atomicAdd(dst[s] + c, t);
-      if (dst2) atomicAdd(dst2 + c, t);      // a second consumer of the same column sums (statistic 0 only callers)
-    }
-  }
-}
-
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y,
                                                             float* __restrict__ bsums, int M, int C) {
   pdl_trigger();

@@ -23,12 +23,17 @@ int bn_apply_fwd(const bf16* y, const bf16* res, bf16* out, const float* sums, f
 // MaxPool2D 2x2/2 (hourglass.py:63,135,171-177) on [N][2h][2w][C] -> [N][h][w][C], and its gradient
 // (routed to the first maximum of each window in row-major order; accumulate=1 adds into dx).
 int maxpool_fwd(const bf16* x, bf16* out, int N, int h, int w, int C, cudaStream_t st);
-int maxpool_bwd(const bf16* x, const bf16* dy, bf16* dx, int N, int h, int w, int C, int accumulate, cudaStream_t st);
+// ybn != null: dx is the dz of a BatchNorm with pre-normalisation input ybn (same shape as dx): bsums[0:C] += sum dz,
+// bsums[C:2C] += sum dz * ybn over the values as stored -- the bn_bwd_reduce pass over the tensor disappears.
+int maxpool_bwd(const bf16* x, const bf16* dy, bf16* dx, int N, int h, int w, int C, int accumulate, cudaStream_t st,
+                const bf16* ybn = nullptr, float* bsums = nullptr);
 
 // UpSampling2D (nearest 2x) + Add (hourglass.py:152-154): out[N][2h][2w][C] = skip + up(low); gradient wrt low
 // = sum over each 2x2 block of dout (the gradient wrt skip is dout itself).
 int upsample_add_fwd(const bf16* skip, const bf16* low, bf16* out, int N, int h, int w, int C, cudaStream_t st);
-int upsample_add_bwd(const bf16* dout, bf16* dlow, int N, int h, int w, int C, cudaStream_t st);
+// (ybn / bsums: as in maxpool_bwd, for the BatchNorm whose dz is dlow)
+int upsample_add_bwd(const bf16* dout, bf16* dlow, int N, int h, int w, int C, cudaStream_t st, const bf16* ybn = nullptr,
+                     float* bsums = nullptr);
 
 // BatchNorm backward, pass 1: bsums[0:C] += sum_rows dz, bsums[C:2C] += sum_rows dz*y
 int bn_bwd_reduce(const bf16* dz, const bf16* y, float* bsums, int M, int C, cudaStream_t st);

@@ -716,6 +716,14 @@ int build(hgb_model* m) {
             out[w].flag = o.a1 + 1;   // y act (+1 so that 0 means none)
             continue;                 // the stand-alone reduction disappears
           }
+          // the gradient of a max-pool / of an upsample-add merge: those kernels accumulate the statistics of what they
+          // store (y act in a3 / a2), and the reduction's read of dz goes away with its launch.  hgb_debug_set(44, 1) keeps
+          // the stand-alone reduction.
+          const int cbn = m->bns[o.bn].c;
+          if (w >= 0 && !hgb::g_debug[44] && out[w].bn < 0 && out[w].lane == o.lane && 256 % (cbn / 8) == 0 && cbn <= 2048) {
+            if (out[w].type == B_POOL && out[w].a2 == o.a0) { out[w].bn = o.bn; out[w].a3 = o.a1; continue; }
+            if (out[w].type == B_UPADD && out[w].a1 == o.a0) { out[w].bn = o.bn; out[w].a2 = o.a1; continue; }
+          }
         }
         out.push_back(o);
       }
@@ -842,8 +850,14 @@ void op_access(const hgb_model* m, const Op& o, std::vector<Range>& r, std::vect
       add_act(m, r, o.a0); add_grad(w, m->convs[o.conv].b_off, m->convs[o.conv].cout);
       if (o.a1 >= 0) add_grad(w, m->convs[o.a1].b_off, m->convs[o.a1].cout);   // a1: a second convolution with the same gradient
       break;
-    case B_POOL: add_act(m, r, o.a0); add_act(m, r, o.a1); if (o.flag) add_act(m, r, o.a2); add_act(m, w, o.a2); break;
-    case B_UPADD: add_act(m, r, o.a0); add_act(m, w, o.a1); break;
+    case B_POOL:
+      add_act(m, r, o.a0); add_act(m, r, o.a1); if (o.flag) add_act(m, r, o.a2); add_act(m, w, o.a2);
+      if (o.bn >= 0) { add_act(m, r, o.a3); add_arena(w, m->bns[o.bn].bsums_off, 2 * (size_t)m->bns[o.bn].c * 4); }   // fused BatchNorm-backward reduction
+      break;
+    case B_UPADD:
+      add_act(m, r, o.a0); add_act(m, w, o.a1);
+      if (o.bn >= 0) { add_act(m, r, o.a2); add_arena(w, m->bns[o.bn].bsums_off, 2 * (size_t)m->bns[o.bn].c * 4); }
+      break;
     case B_HEAD:
       add_act(m, r, o.a0); add_act(m, w, o.a1);
       add_arena(r, m->heat_off[o.flag], hm_bytes);
@@ -1165,12 +1179,14 @@ int run_op_impl(hgb_model* m, const Op& o, const float* images, int training, cu
     }
     case B_POOL: {
       const Act& gy = m->acts[o.a1];
-      rc = maxpool_bwd(act_ptr(m, o.a0), act_ptr(m, o.a1), act_ptr(m, o.a2), gy.n, gy.h, gy.w, gy.c, o.flag, st);
+      rc = maxpool_bwd(act_ptr(m, o.a0), act_ptr(m, o.a1), act_ptr(m, o.a2), gy.n, gy.h, gy.w, gy.c, o.flag, st,
+                       o.bn >= 0 ? act_ptr(m, o.a3) : nullptr, o.bn >= 0 ? arena_f(m, m->bns[o.bn].bsums_off) : nullptr);
       break;
     }
     case B_UPADD: {
       const Act& lo = m->acts[o.a1];
-      rc = upsample_add_bwd(act_ptr(m, o.a0), act_ptr(m, o.a1), lo.n, lo.h, lo.w, lo.c, st);
+      rc = upsample_add_bwd(act_ptr(m, o.a0), act_ptr(m, o.a1), lo.n, lo.h, lo.w, lo.c, st,
+                            o.bn >= 0 ? act_ptr(m, o.a2) : nullptr, o.bn >= 0 ? arena_f(m, m->bns[o.bn].bsums_off) : nullptr);
       break;
     }
     case B_HEAD: {

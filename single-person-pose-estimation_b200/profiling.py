@@ -75,10 +75,10 @@ class PlanInfo:
             byt = 2.0 * 3 * el(a0)
         elif ty == 11:
             byt = 2.0 * el(a0)
-        elif ty == 12:   # x, dy, dx (+ the accumulate read of dx)
-            byt = 2.0 * (el(a0) + el(a1) + el(a2) * (2 if flag else 1))
-        elif ty == 13:
-            byt = 2.0 * (el(a0) + el(a1))
+        elif ty == 12:   # x, dy, dx (+ the accumulate read of dx) (+ the y of a folded BatchNorm-backward reduction: a3)
+            byt = 2.0 * (el(a0) + el(a1) + el(a2) * (2 if flag else 1) + (el(a3) if bn >= 0 else 0))
+        elif ty == 13:   # (+ the y of a folded BatchNorm-backward reduction: a2)
+            byt = 2.0 * (el(a0) + el(a1) + (el(a2) if bn >= 0 else 0))
         elif ty in (15, 16, 17):   # mobile variant, depthwise stencil: tensor in, tensor out (+ residuals) / two tensors in
             byt = 2.0 * (el(a0) + el(a1) + (el(a2) + el(a3) if ty == 16 else 0))
         else:            # B_HEAD: loss gradient + heat map (fp32), re-injection gradient in, logits gradient out
@@ -88,6 +88,8 @@ class PlanInfo:
         key = f"{name} C{cc} @{hh}"
         if ty == 2 and a3 >= 0:
             key += " +pool" if flag & 1 else " +upadd"
+        if ty in (12, 13) and bn >= 0:
+            key += " +bnstats"
         return key, 0.0, byt, (ty, 0, 0, cc, hh)
 
 

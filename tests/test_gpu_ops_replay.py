@@ -277,9 +277,25 @@ def test_replay_every_op(S, B, mobile):
     fused_reduces = [0]
     fused_applies = [0]
     shared_colsums = [0]
+    folded_reduces = [0]
+    standalone_reduces = [0]
+
+    def check_folded_reduce(bi, s0, dz_t, y_t):
+        b = R.bn(bi)
+        Cc = b["c"]
+        assert dz_t.shape == y_t.shape and dz_t.shape[-1] == Cc
+        dz, y = dz_t.float().reshape(-1, Cc), y_t.float().reshape(-1, Cc)
+        s1 = R.arena_f32(b["bsums"], 2 * Cc) - s0
+        sc = max(dz.abs().sum(0).max().item(), 1e-20)
+        assert (s1[:Cc] - dz.sum(0)).abs().max().item() <= 2e-3 * sc
+        sc = max((dz * y).abs().sum(0).max().item(), 1e-20)
+        assert (s1[Cc:] - (dz * y).sum(0)).abs().max().item() <= 2e-3 * sc
+        folded_reduces[0] += 1
+
     for seg in range(S, -1, -1):
         for i, (ty, ci, bi, a0, a1, a2, a3, flag) in R.ops(seg, 1):
             if ty == B_BN_REDUCE:
+                standalone_reduces[0] += 1
                 b = R.bn(bi)
                 Cc = b["c"]
                 s0 = R.arena_f32(b["bsums"], 2 * Cc).clone()
@@ -447,17 +463,23 @@ def test_replay_every_op(S, B, mobile):
             elif ty == B_POOL:
                 x, gy = R.act(a0).float(), R.act(a1).float()
                 old = R.act(a2).float().clone()
+                s0 = R.arena_f32(R.bn(bi)["bsums"], 2 * R.bn(bi)["c"]).clone() if bi >= 0 else None
                 R.run(seg, 1, i)
                 N, H, W, Cc = x.shape
                 mask = _first_max_mask(torch, _windows(x))
                 routed = _unwindows((mask * gy.unsqueeze(-2)).reshape(N, H // 2, W // 2, 4 * Cc), N, H, W, Cc)
                 ref = (routed + old) if flag else routed
                 assert torch.equal(R.act(a2), ref.to(bf))
+                if bi >= 0:       # BatchNorm-backward statistics of the gradient just written (y = act a3), folded into this kernel
+                    check_folded_reduce(bi, s0, R.act(a2), R.act(a3))
             elif ty == B_UPADD:
+                s0 = R.arena_f32(R.bn(bi)["bsums"], 2 * R.bn(bi)["c"]).clone() if bi >= 0 else None
                 R.run(seg, 1, i)
                 wv = _windows(R.act(a0).float())
                 ref = (wv[..., 0, :] + wv[..., 1, :]) + (wv[..., 2, :] + wv[..., 3, :])
                 assert torch.equal(R.act(a1), ref.to(bf))
+                if bi >= 0:       # (y = act a2)
+                    check_folded_reduce(bi, s0, R.act(a1), R.act(a2))
             elif ty == B_HEAD:
                 offs = (C.c_int64 * 2)()
                 chk(lib.hgb_model_head_buffers(R.h, flag, C.byref(offs)))
@@ -484,6 +506,9 @@ def test_replay_every_op(S, B, mobile):
     print("convolutions / weight gradients with a deferred input BatchNorm:", deferred[0], "statistic writers:", writers[0],
           " upsample-add merges folded into a BatchNorm:", fused_upadds[0])
     print("max-pools folded into the BatchNorm in front of them:", fused_pools[0])
+    print("BatchNorm-backward reductions folded into pool / upsample-add gradients:", folded_reduces[0], " stand-alone:", standalone_reduces[0])
+    if not mobile:    # every pool gradient (4 per stack + the front module's) and every upsample-add gradient feeds a closing BatchNorm
+        assert folded_reduces[0] == 1 + 8 * S
     assert fused_pools[0] == 1 + 4 * S         # the front module's pool + four per stack (hourglass.py:63,135,171-177)
     assert fused_upadds[0] == (4 * S if B > 48 else 0)      # every level of every stack (hourglass.py:143-157), large batches only
     if mobile:      # every pointwise GEMM is a 1x1: all three BatchNorm-backward applies of a bottleneck fuse; only the head BN defers
