@@ -69,6 +69,24 @@ class History:
         self.epoch = []
 
 
+class _PendingLosses:
+    """Per-output losses of a step that has been enqueued but not waited for: the device->host copy into a pinned
+    buffer is already on the stream, result() blocks on its event only.  Lets a training loop enqueue step i+1 before it
+    reads step i's numbers, so the device never waits for the host between steps (what Keras' fit does)."""
+
+    def __init__(self, host, event, allreduce_on_host):
+        self._host, self._event, self._ar, self._value = host, event, allreduce_on_host, None
+
+    def result(self):
+        if self._value is None:
+            self._event.synchronize()
+            per = self._host.numpy().copy()
+            if self._ar is not None:
+                per = self._ar.sum_host(per)
+            self._value = [float(per.sum())] + [float(v) for v in per]
+        return self._value
+
+
 class _Plan:
     """One execution plan (fixed batch, training or inference) = one C handle + its arena."""
 
@@ -521,17 +539,36 @@ class HourglassModel:
             t = torch.as_tensor(np.ascontiguousarray(np.asarray(y, dtype=np.float32))).to("cuda", non_blocking=True)
         return t.contiguous()
 
-    def train_on_batch(self, x, y):
+    def _read_losses_deferred(self, losses, ar):
+        """Enqueue the (all-reduced) read-back of a step's loss tensor; returns a _PendingLosses."""
+        torch = _lib.require_cuda()
+        if getattr(self, "_loss_slots", None) is None:
+            self._loss_slots = [(torch.empty(self.num_stacks, dtype=torch.float64).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+            self._loss_slot = 0
+        host, ev = self._loss_slots[self._loss_slot]
+        self._loss_slot = (self._loss_slot + 1) % len(self._loss_slots)
+        on_host = None
+        if ar:       # per-shard losses carry 1/global_batch: the global loss is their sum (on the device when the group is NCCL)
+            if ar.dist.get_backend(ar.group) == "nccl":
+                ar.dist.all_reduce(losses, op=ar.dist.ReduceOp.SUM, group=ar.group)
+            else:
+                on_host = ar
+        host.copy_(losses, non_blocking=True)
+        ev.record(torch.cuda.current_stream())
+        return _PendingLosses(host, ev, on_host)
+
+    def train_on_batch_deferred(self, x, y):
+        """train_on_batch without the wait: the step is enqueued, the returned handle's result() gives what
+        train_on_batch would have returned.  At most three handles may be outstanding (four pinned read-back slots)."""
         from ..parallel import current_allreduce
         ar = current_allreduce()
         x = self._to_device_images(x.numpy() if hasattr(x, "numpy") and not isinstance(x, np.ndarray) and not hasattr(x, "is_cuda") else x)
         y = self._to_device_targets(y)
         gb = x.shape[0] * (ar.world_size if ar else 1)
-        losses = self.train_step_device(x, y, global_batch=gb, allreduce=ar)
-        per = losses.cpu().numpy()
-        if ar:
-            per = ar.sum_host(per)
-        return [float(per.sum())] + [float(v) for v in per]
+        return self._read_losses_deferred(self.train_step_device(x, y, global_batch=gb, allreduce=ar), ar)
+
+    def train_on_batch(self, x, y):
+        return self.train_on_batch_deferred(x, y).result()
 
     def train_on_keypoints(self, images, kps_x, kps_y, kps_v):
         """One optimizer step from (images, keypoints): the Gaussian targets are rendered on the device
@@ -567,8 +604,7 @@ class HourglassModel:
         if getattr(self, "_h2d_stream", None) is None:
             self._h2d_stream = torch.cuda.Stream(priority=-1)
         copy = self._h2d_stream
-        slots = [dict(bufs=None, uploaded=torch.cuda.Event(), consumed=None, loss_ready=torch.cuda.Event(),
-                      host_loss=torch.empty(self.num_stacks, dtype=torch.float64).pin_memory()) for _ in range(2)]
+        slots = [dict(bufs=None, uploaded=torch.cuda.Event(), consumed=None) for _ in range(2)]
 
         def as_host(a, dtype):
             if isinstance(a, torch.Tensor):
@@ -593,14 +629,6 @@ class HourglassModel:
                 sl["uploaded"].record(copy)
             sl["src"] = src      # keeps the host tensors alive until the copy has run
 
-        def finish(s):
-            sl = slots[s]
-            sl["loss_ready"].synchronize()
-            per = sl["host_loss"].numpy().copy()
-            if ar and sl["reduce_on_host"]:
-                per = ar.sum_host(per)
-            return [float(per.sum())] + [float(v) for v in per]
-
         it = iter(batches)
         try:
             upload(next(it), 0)
@@ -621,19 +649,12 @@ class HourglassModel:
             losses = self.train_step_device(x, y, global_batch=gb, allreduce=ar)
             sl["consumed"] = torch.cuda.Event()
             sl["consumed"].record(compute)
-            sl["reduce_on_host"] = False
-            if ar:       # per-shard losses carry 1/global_batch: the global loss is their sum (device-side when the group is NCCL)
-                if ar.dist.get_backend(ar.group) == "nccl":
-                    ar.dist.all_reduce(losses, op=ar.dist.ReduceOp.SUM, group=ar.group)
-                else:
-                    sl["reduce_on_host"] = True
-            sl["host_loss"].copy_(losses, non_blocking=True)
-            sl["loss_ready"].record(compute)
+            nxt = self._read_losses_deferred(losses, ar)
             if pending is not None:
-                yield finish(pending)
-            pending = s
+                yield pending.result()
+            pending = nxt
             i += 1
-        yield finish(pending)
+        yield pending.result()
 
     def test_on_batch(self, x, y):
         from .. import ops
@@ -697,9 +718,14 @@ class HourglassModel:
             if verbose:
                 print(f"Epoch {epoch + 1}/{epochs}")
             tot = np.zeros(1 + self.num_stacks)
+            pending = None       # step i's losses are read after step i+1 has been enqueued: no host round trip between steps
             for _step in range(steps_per_epoch):
                 x, y = next(it)
-                tot += np.array(self.train_on_batch(x, y))
+                nxt = self.train_on_batch_deferred(x, y)
+                if pending is not None:
+                    tot += np.array(pending.result())
+                pending = nxt
+            tot += np.array(pending.result())
             logs = dict(zip(names, (tot / steps_per_epoch).tolist()))
             if validation_data is not None and validation_steps:
                 # Keras creates a fresh validation iterator every epoch: the same first `validation_steps` batches are

@@ -58,6 +58,22 @@ def main():
         torch.cuda.synchronize()
         return a.batch * a.steps / (time.perf_counter() - t0)
 
+    def run_fit_loop(next_batch):
+        """the loop HourglassModel.fit runs: step i's losses are read after step i+1 has been enqueued"""
+        for _ in range(2):
+            model.train_on_batch(*next_batch())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pending = None
+        for _ in range(a.steps):
+            nxt = model.train_on_batch_deferred(*next_batch())
+            if pending is not None:
+                pending.result()
+            pending = nxt
+        pending.result()
+        torch.cuda.synchronize()
+        return a.batch * a.steps / (time.perf_counter() - t0)
+
     out = {}
     ds0 = hgb200.dataset_builder.DatasetBuilder(cfg, seed=0, prefetch=0).build_datasets()[0]
     resident = next(ds0)
@@ -65,9 +81,11 @@ def main():
     out["from TFRecords, prefetch=0"] = run(lambda: next(ds0))
     ds2 = hgb200.dataset_builder.DatasetBuilder(cfg, seed=0, prefetch=2).build_datasets()[0]
     out["from TFRecords, prefetch=2"] = run(lambda: next(ds2))
+    out["resident batch, fit loop (deferred loss reads)"] = run_fit_loop(lambda: resident)
+    out["from TFRecords, prefetch=2, fit loop"] = run_fit_loop(lambda: next(ds2))
     ds2.close()
     for k, v in out.items():
-        print(f"{k:32s} {v:9.1f} img/s   ({a.stacks}-stack, batch {a.batch}, {a.steps} timed steps)")
+        print(f"{k:50s} {v:9.1f} img/s   ({a.stacks}-stack, batch {a.batch}, {a.steps} timed steps)")
 
 
 if __name__ == "__main__":
