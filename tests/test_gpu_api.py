@@ -178,35 +178,67 @@ def test_tf_checkpoint_round_trip_keeps_training_state(hgb, tmp_path):
     assert np.isfinite(lb[0]) and abs(la[0] - lb[0]) <= 5e-2 * abs(la[0]), (la, lb)
 
 
-def test_train_on_keypoints_stream_equals_per_batch_calls(hgb):
-    """The pipelined generator (copy of batch i+1 under step i, losses read one step late) returns, in order, what
-    train_on_keypoints returns for the same batches on an identically initialised model (same kernels in the same order).
-    The tolerance is measured, not chosen: two synchronous runs differ by the fp32 reduction order of the statistics /
-    weight-gradient atomics, and the pipelined run must stay within a small multiple of that spread.  The batches differ
-    strongly in their visible-keypoint count, so a slot mix-up would show as a loss from the wrong batch."""
+def _keypoint_batches(sizes, visible, seed):
     import torch
-    rng = np.random.default_rng(5)
-    batches = []
-    for i, b in enumerate((4, 4, 4, 2, 4)):        # a shape change in the middle re-allocates a slot
+    rng = np.random.default_rng(seed)
+    out = []
+    for b, nv in zip(sizes, visible):
         kv = np.zeros((b, 17), np.int32)
-        kv[:, :3 * i + 1] = 2                       # 1, 4, 7, 10, 13 visible joints: the weighted loss scales with them
-        batches.append((torch.from_numpy(rng.random((b, 256, 256, 3), dtype=np.float32)).pin_memory(),
-                        rng.uniform(4, 60, (b, 17)).astype(np.float32), rng.uniform(4, 60, (b, 17)).astype(np.float32), kv))
+        kv[:, :nv] = 2                               # visible joints per batch: the weighted loss scales with them
+        out.append((torch.from_numpy(rng.random((b, 256, 256, 3), dtype=np.float32)).pin_memory(),
+                    rng.uniform(4, 60, (b, 17)).astype(np.float32), rng.uniform(4, 60, (b, 17)).astype(np.float32), kv))
+    return out
+
+
+def test_train_on_keypoints_stream_plumbing_is_exact(hgb):
+    """The pipelined generator's own machinery -- two device slots filled on a copy stream, events both ways, losses read one
+    step late through pinned buffers -- checked bit-exactly: the training step is replaced by a deterministic function of the
+    device batch it is handed (image sum, target sum), so the generator must return exactly what per-batch calls return, in
+    order, including across batch-size changes (slot re-allocation) and for a single-batch stream."""
+    import torch
+    model = hgb.HourglassModel(17, 2, 256, (256, 256, 3), "sigmoid", seed=3)
+    model.compile(optimizer=hgb.Adam(1e-3), loss=hgb.loss.weighted_mse)
+
+    def fake_step(x, y, global_batch=None, allreduce=None):
+        filler = torch.empty(64 << 20, dtype=torch.uint8, device="cuda").zero_()      # keeps the compute stream busy for a while
+        return torch.stack([x.double().sum() + filler[0], y.double().sum() + float(global_batch)])
+    model.train_step_device = fake_step
+    batches = _keypoint_batches((8, 8, 4, 8, 2, 2, 8, 8, 8), (1, 9, 17, 4, 12, 2, 15, 6, 10), seed=7)
+    sync = np.array([model.train_on_keypoints(*b) for b in batches])
+    stream = np.array(list(model.train_on_keypoints_stream(iter(batches))))
+    assert stream.shape == sync.shape == (len(batches), 3)
+    assert len(np.unique(sync[:, 1])) == len(batches) and len(np.unique(sync[:, 2])) == len(batches)
+    np.testing.assert_array_equal(stream, sync)
+    np.testing.assert_array_equal(np.array(list(model.train_on_keypoints_stream(iter(batches[:1])))), sync[:1])
+    assert list(model.train_on_keypoints_stream(iter([]))) == []
+    pend = [model.train_on_batch_deferred(b[0], np.zeros((b[0].shape[0], 64, 64, 17), np.float32)) for b in batches[:3]]
+    got = np.array([p.result() for p in pend])                     # three handles outstanding: each keeps its own numbers
+    np.testing.assert_array_equal(got[:, 1], sync[:3, 1])
+
+
+def test_train_on_keypoints_stream_equals_per_batch_calls(hgb):
+    """The same generator around the real training step.  Two runs of the CUDA path differ by the fp32 reduction order of
+    the statistics / weight-gradient atomics, and a training-mode hourglass amplifies that within a few steps (measured on
+    B200, 1 stack, batch 8: <= 2e-3 on the first step, up to 3e-2 by the fifth), so equality is gated at 1e-2 on the first
+    step and at 8e-2 afterwards -- while the batches' visible-joint counts put consecutive losses, and the losses of the
+    steps that share a device slot, more than 20 % apart: a stale slot or a loss read from the wrong step cannot pass."""
+    batches = _keypoint_batches((8, 8, 8, 4, 8), (0, 17, 8, 0, 17), seed=5)      # three loss levels, any three consecutive steps distinct
     outs = []
-    for mode in ("sync", "sync", "stream"):
-        model = hgb.HourglassModel(17, 2, 256, (256, 256, 3), "sigmoid", seed=3)
-        model.compile(optimizer=hgb.Adam(1e-3), loss=hgb.loss.weighted_mse)
+    for mode in ("sync", "stream"):
+        model = hgb.HourglassModel(17, 1, 256, (256, 256, 3), "sigmoid", seed=3)
+        model.compile(optimizer=hgb.Adam(1e-4), loss=hgb.loss.weighted_mse)
         if mode == "sync":
             outs.append(np.array([model.train_on_keypoints(*b) for b in batches]))
         else:
             outs.append(np.array(list(model.train_on_keypoints_stream(iter(batches)))))
-            assert list(model.train_on_keypoints_stream(iter([]))) == []
         assert model.optimizer.iterations == len(batches)
-    a, b, c = outs
-    assert c.shape == (len(batches), 3)
-    floor = np.abs(a - b) / np.abs(a)
+    a, c = outs
+    assert c.shape == (len(batches), 2)
     err = np.abs(c - a) / np.abs(a)
-    print("sync vs sync:", floor.max(axis=1), " stream vs sync:", err.max(axis=1), " losses:", a[:, 0])
-    assert np.all(np.abs(np.diff(a[:, 0])) / a[:-1, 0] > 0.05), "batches must be told apart by their loss"
-    assert err[0].max() <= max(10 * floor[0].max(), 1e-5)                # same weights, same batch
-    assert np.all(err.max(axis=1) <= np.maximum(10 * floor.max(axis=1), 2e-3))      # trajectories stay together
+    print("stream vs sync:", err.max(axis=1), " losses:", a[:, 0])
+    la = a[:, 0]
+    for i in range(len(la)):
+        for j in range(i):
+            if i - j <= 2:        # neighbours and slot mates
+                assert abs(la[i] - la[j]) / min(la[i], la[j]) > 0.2, "batches must be told apart by their loss"
+    assert err[0].max() <= 1e-2 and err.max() <= 8e-2
