@@ -18,6 +18,7 @@ REPORTS = {   # op class (hgb200/profiling.py naming) -> report
     "F_CONV k1 128->256 @64": "r02_fconv_k1_128to256_bn_stats.ncu-rep",
     "F_CONV k1 128->256 @64 (plain: no input BatchNorm, no statistics; round-2 start)": "r02_fconv_k1_128to256.ncu-rep",
     "B_DGRAD k1 256->128 @64 +bnapply +bnstats +res": "r02_dgrad_k1_256to128_bnb.ncu-rep",
+    "B_DGRAD k1 128->256 @64 +bnapply +bnstats": "r02_dgrad_k1_128to256_bnb.ncu-rep",
     "decode_v2 f32 64x64 batch 1024": "r02_decode_f32_b1024_final.ncu-rep",
 }
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0, "msecond": 1e3, "nsecond": 1e-3}
