@@ -295,11 +295,14 @@ class DatasetBuilder:
     costs a handful of launches instead of one Python callback per example (the reference's tf.numpy_function path).
     Yields CUDA float32 tensors: (images (B,256,256,3), heatmaps (B,64,64,17))."""
 
-    def __init__(self, config, ratio=1, seed=None, shard=None, prefetch=0):
-        """`prefetch` > 0 prepares that many batches ahead on a side stream in a background thread.  It is OFF by default:
-        measured on B200 (tools_pipeline_bench.py, profiles/r01_pipeline_bench.txt) the side stream is starved while an
-        8-stack training step owns the GPU (49.8 img/s against 1245 img/s synchronous) -- the step's lanes run at the
-        highest stream priority with dependent CTAs parked on every SM; see DESIGN.md section 7.
+    def __init__(self, config, ratio=1, seed=None, shard=None, prefetch=2):
+        """`prefetch` > 0 prepares that many batches ahead on a side stream in a background thread -- the reference ends its
+        pipelines with `.prefetch(AUTOTUNE)` (dataset_builder.py:46,54,65), so it is ON by default (2 batches); 0 runs the
+        input path synchronously on the caller's stream.  Measured on B200 (tools_pipeline_bench.py,
+        profiles/r02_pipeline_bench.txt; 8-stack training at batch 128 from JPEG TFRecords): 1682 img/s with the prefetcher,
+        1445 synchronous, 1710 from a resident batch.  (Round 1 measured 49.8 img/s: nvJPEG's per-image host synchronisation
+        sat on a default-priority stream behind the step's persistent CTAs; the worker's and the decoder's streams now run at
+        the highest priority)
         `shard=(rank, world_size)` keeps every world_size-th record starting at `rank` (tf.data's `shard`), so each data-
         parallel process reads a disjoint slice with no exchange; default: the active hgb200.parallel context, else no sharding.
         `num_*_examples` stay GLOBAL counts (steps per epoch = n // BATCH_SIZE with BATCH_SIZE the per-process batch means a
