@@ -369,7 +369,10 @@ struct hgb_model {
     // pooled tensor next to its output (F_BN flag bit 0: a3 is the pooled OUTPUT) and the pool kernel's re-read of a whole
     // 256-channel tensor disappears, together with one launch on the main chain.  hgb_debug_set(43, 1) keeps the pool kernel.
     Op* last = fwd_ops[cur_seg].empty() ? nullptr : &fwd_ops[cur_seg].back();
-    if (!hgb::g_debug[43] && last && last->type == F_BN && last->a2 == x && last->a3 < 0 && last->lane == cur_lane &&
+    // Training plans only: in inference the BatchNorm runs inside the preceding convolution's epilogue (fuse_inference_bn) and
+    // the pre-BatchNorm tensor is never stored -- folding the pool into a BatchNorm op would bring that tensor back (batch 128,
+    // 8 stacks: 21.3 vs 21.7 ms; hgb_debug_set(43, 2) folds there too).
+    if ((cfg.training || hgb::g_debug[43] == 2) && hgb::g_debug[43] != 1 && last && last->type == F_BN && last->a2 == x && last->a3 < 0 && last->lane == cur_lane &&
         (a.h & (a.h - 1)) == 0 && (a.w & (a.w - 1)) == 0 && a.h >= 2 && a.w >= 2) {
       last->a3 = o;
       last->flag |= 1;
@@ -546,7 +549,9 @@ int build(hgb_model* m) {
       // (batch 256: 147.9 -> 146.5 ms per step.  At batch 32 the step is latency-bound and the folded kernel sits on the critical
       //  path behind the deep levels, where the stand-alone merge was shorter: 24.97 vs 25.13 ms -- so only above batch 48;
       //  hgb_debug_set(42, 2) forces it)
-      const bool fold_upadd = hgb::g_debug[42] == 2 || (hgb::g_debug[42] == 0 && cfg.batch > 48);
+      // Inference keeps the stand-alone merge: there the closing BatchNorm runs inside conv_1x1_3's epilogue (fuse_inference_bn),
+      // which a BatchNorm op with a folded merge would block (batch 128, 8 stacks: 21.1 vs 21.5 ms)
+      const bool fold_upadd = hgb::g_debug[42] == 2 || (hgb::g_debug[42] == 0 && cfg.batch > 48 && cfg.training);
       if (fold_upadd && last && last->type == F_BN && last->a2 == r.shortb[u].out && last->a1 >= 0 && last->a3 < 0) {
         // UpSampling2D + Add (hourglass.py:152-154) folded into the skip bottleneck's closing BatchNorm: that kernel already
         // reads y3 and the skip and writes the block output -- it now adds the upsampled lower level too and writes the MERGE
