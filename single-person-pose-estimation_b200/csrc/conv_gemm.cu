@@ -254,7 +254,10 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
   static_assert(EPI == 8 || EPI == 16, "two or four epilogue warps per TMEM lane quarter");
   static_assert(kAccStages * TILES * BLOCK_N <= 512, "TMEM columns");
   constexpr int kOutBytes = (BLOCK_N / 64) * kABytes;
-  constexpr int kASlots = TILES + 1, kBSlots = 6;             // HALO: strip boxes | two sets of three weight boxes
+  // HALO: strip boxes | two sets of three weight boxes.  A strip needs the rows of its TILES tiles plus one above and one below:
+  // TILES + 1 boxes when a box holds at least two image rows, TILES + 2 when a box is a single row (W = 128: the 64-channel
+  // front-module layers, the only ones that get the extra slot -- the 128-channel ring has no room for it and never needs it)
+  constexpr int kASlots = TILES + (BLOCK_N == 64 ? 2 : 1), kBSlots = 6;
   constexpr int kRingBytes = HALO ? kASlots * kABytes + kBSlots * kBBytes : STAGES * kStageBytes;
   // full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | residual
   // HALO: fullA[T+1] | emptyA[T+1] | fullB[6] | emptyB[6] | tmem_full[T] | tmem_empty[T] | residual
@@ -349,6 +352,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
   const uint32_t fullA = bar0, emptyA = bar0 + 8 * kASlots, fullB = bar0 + 16 * kASlots, emptyB = fullB + 8 * kBSlots;
   const uint32_t ringB = base + kASlots * kABytes;
   const int rpt = kBlockM / p.W;   // image rows per tile
+  const int nsl = (kASlots > TILES + 1 && rpt == 1) ? TILES + 2 : TILES + 1;   // HALO: strip boxes in use
 
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
   // Register re-partitioning (8 epilogue warps: 384 threads x 168 registers at launch).  The epilogue is the only
@@ -388,6 +392,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
           }
 #pragma unroll
           for (int j = 0; j < kASlots; ++j) {   // strip rows y0 - 1 ... y0 + TILES * rpt (+ slack), shifted by dx
+            if (j >= nsl) break;                // (the extra slot of the 64-channel ring is used by one-row boxes only)
             mbar_wait(emptyA + 8 * j, aph ^ 1);
             if (CTA2) {
               if (rank == 0) mbar_expect_tx(fullA + 8 * j, 2 * kABytes);
@@ -416,7 +421,8 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
           mbar_wait(fullA, aph);
 #pragma unroll
           for (int t = 0; t < TILES; ++t) {
-            mbar_wait(fullA + 8 * (t + 1), aph);      // tile t reads strip boxes t and t + 1
+            mbar_wait(fullA + 8 * (t + 1), aph);      // tile t reads strip boxes t and t + 1 (+ t + 2 when a box is one row)
+            if (kASlots > TILES + 1 && nsl > TILES + 1) mbar_wait(fullA + 8 * (t + 2), aph);
             if (st == 0) mbar_wait(tempty0 + 8 * t, (lt & 1) ^ 1);   // the epilogue has drained this accumulator
             tc_fence_after();
 #pragma unroll
@@ -434,6 +440,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1) conv_gemm_kernel(const _
             commit(emptyA + 8 * t);              // later tiles start at box t + 1
             if (t == TILES - 1) {
               commit(emptyA + 8 * TILES);
+              if (kASlots > TILES + 1 && nsl > TILES + 1) commit(emptyA + 8 * (TILES + 1));
 #pragma unroll
               for (int dyi = 0; dyi < 3; ++dyi) commit(emptyB + 8 * (set * 3 + dyi));
             }
@@ -1355,9 +1362,10 @@ template <int BLOCK_N, int STAGES, int TILES, int OUT_BUFS, bool HALO = false, i
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                          const CUtensorMap& tmY, const GemmKernelParams& kp, int tiles_m, int max_ctas, cudaStream_t st,
                          const CUtensorMap* tmZ = nullptr, const CUtensorMap* tmDP = nullptr) {
-  constexpr int ring = HALO ? (TILES + 1) * kABytes + 6 * (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 128
+  constexpr int aslots = TILES + (BLOCK_N == 64 ? 2 : 1);      // (kASlots of the kernel)
+  constexpr int ring = HALO ? aslots * kABytes + 6 * (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 128
                             : STAGES * (TILES * kABytes + BLOCK_N * 128 + (BNB ? kABytes : 0));
-  constexpr int nbars = HALO ? 2 * (TILES + 1) + 12 + 2 * TILES + 1 : 3 * STAGES + 5;
+  constexpr int nbars = HALO ? 2 * aslots + 12 + 2 * TILES + 1 : 3 * STAGES + 5;
   constexpr int smem = ring + OUT_BUFS * (BLOCK_N / 64) * kABytes + (nbars * 8 + 15) / 16 * 16 + 16 + BLOCK_N * 4 +
                        (TILES == 1 ? 4 * 256 * 4 : 0) + (BNB ? 8 * 4 * 64 * 4 : 0) + 1024;   // BatchNorm scale+shift tables only for the 1x1 variants
   static_assert(ring >= (EPI == 16 ? 32 : 16) * 1024, "stats scratch (16 / 32 KB) aliases the pipeline stages");
@@ -1445,6 +1453,10 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   const int halo_min = g_debug[15] > 0 ? g_debug[15] : 4 * g_num_sms;
   const bool halo = kp.tap3 && !g_debug[5] && tiles_m >= halo_min && !g_debug[12] && a.W <= 64 && rpt >= 2 &&
                     a.H % (4 * rpt) == 0 && a.Cout == 128;
+  // the 64-channel 3x3 layers of the front module (128x128: one image row per box, three-box windows; 64x64): the per-tap ring
+  // fetched every input pixel nine times from L2 and ran at a third of the tensor peak.  hgb_debug_set(45, 1) = per-tap ring.
+  const bool halo64 = kp.tap3 && !g_debug[5] && !g_debug[12] && !g_debug[45] && tiles_m >= halo_min && a.Cout == 64 && a.W <= 128 &&
+                      a.H % (4 * rpt) == 0 && !a.bn_bwd.gamma;
   if (a.bn_bwd.gamma) {   // 1x1 dgrad with the BatchNorm backward fused in
     if (a.Cout == 128) return launch_gemm_t<128, 3, 1, 2, false, 8, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st, tmZ, tmDP);
     // 16 epilogue warps when the epilogue also carries the next BatchNorm's statistics (569 -> 525 us at batch 256);
@@ -1462,6 +1474,7 @@ int launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     return launch_gemm_t<128, 1, 4, 1, true, 8, false, true>(tmA, *tmB64, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
   // (16 epilogue warps measured slower in the strip kernel: forward 277 vs 257 us, dgrad 308 vs 294 us)
   if (halo) return launch_gemm_t<128, 1, 4, 1, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
+  if (halo64) return launch_gemm_t<64, 1, 4, 1, true>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
   switch (conv_gemm_block_n(a.Cout)) {
     case 64: return ws ? launch_gemm_t<64, 2, 4, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st)
                        : launch_gemm_t<64, 6, 1, 2>(tmA, tmB, tmC, tmRr, tmYr, kp, tiles_m, a.max_ctas, st);
