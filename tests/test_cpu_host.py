@@ -390,3 +390,47 @@ def test_demo_reads_yolov5_style_detector_results():
     assert _boxes_from_detector_result(result, 1e-6) == [(10.0, 20.0, 100.0, 200.0), (200.0, 100.0, 60.0, 200.0)]
     assert _boxes_from_detector_result(np.array([[1.0, 2.0, 4.0, 8.0]]), 0.5) == [(1.0, 2.0, 3.0, 6.0)]
     assert _boxes_from_detector_result(np.zeros((0, 4)), 0.5) == []
+
+
+def _plan_ops(stacks, batch, training):
+    import ctypes as C
+    from hgb200._lib import lib, check, ModelConfig
+    cfg = ModelConfig(17, stacks, 256, 256, 256, 1, batch, int(training))
+    h = C.c_void_p()
+    check(lib.hgb_model_create(C.byref(cfg), 0, C.byref(h)))
+    try:
+        info = (C.c_int * 8)()
+        out = {0: [], 1: []}
+        for backward in ((0, 1) if training else (0,)):
+            for seg in range(stacks + 1):
+                for i in range(lib.hgb_model_num_ops(h, seg, backward)):
+                    check(lib.hgb_model_op_info(h, seg, backward, i, info))
+                    out[backward].append(tuple(info))
+        return out
+    finally:
+        lib.hgb_model_destroy(h)
+
+
+@pytest.mark.parametrize("stacks,batch", [(1, 8), (2, 64), (8, 256)])
+def test_plan_folds_data_movement_into_batchnorm_kernels(stacks, batch):
+    """Plan-level folds (host metadata, no GPU): a TRAINING plan has no stand-alone max-pool -- every MaxPool2D
+    (hourglass.py:63,135,171-177: one in the front module, four per stack) is written by the BatchNorm in front of it -- folds
+    the UpSampling2D + Add merges (:152-154) into the skip bottleneck's closing BatchNorm above batch 48, and lets the pool /
+    merge gradient kernels carry the BatchNorm-backward reductions.  An INFERENCE plan keeps the stand-alone kernels: there the
+    BatchNorm runs inside the preceding convolution's epilogue and a BatchNorm op with a fold would block that fusion."""
+    F_BN, F_POOL, F_UPADD, B_BN_REDUCE, B_POOL, B_UPADD = 2, 3, 4, 6, 12, 13
+    tr = _plan_ops(stacks, batch, True)
+    n_pool, n_merge = 1 + 4 * stacks, 4 * stacks
+    fwd = tr[0]
+    assert sum(o[0] == F_POOL for o in fwd) == 0
+    assert sum(o[0] == F_BN and o[6] >= 0 and (o[7] & 1) for o in fwd) == n_pool
+    folded_merges = sum(o[0] == F_BN and o[6] >= 0 and not (o[7] & 1) for o in fwd)
+    assert folded_merges == (n_merge if batch > 48 else 0)
+    assert sum(o[0] == F_UPADD for o in fwd) == n_merge - folded_merges
+    bwd = tr[1]
+    assert sum(o[0] == B_POOL and o[2] >= 0 for o in bwd) == n_pool          # bn index set: statistics accumulated by the kernel
+    assert sum(o[0] == B_UPADD and o[2] >= 0 for o in bwd) == n_merge
+    assert sum(o[0] == B_BN_REDUCE for o in bwd) <= 1                         # what is left: the head of the last stack at most
+    inf = _plan_ops(stacks, batch, False)[0]
+    assert sum(o[0] == F_POOL for o in inf) == n_pool and sum(o[0] == F_UPADD for o in inf) == n_merge
+    assert not any(o[0] == F_BN and o[6] >= 0 for o in inf)
