@@ -401,6 +401,12 @@ def run_ours(args):
                         f"sum of op times {op_ms:.1f} ms vs {total_ms / args.steps:.1f} ms for the real multi-lane step",
         "tensor_pipe_util_pct": {k: v.get("tensor_pipe_pct") for k, v in ncu.items() if v.get("tensor_pipe_pct") is not None},
         "model_flops_utilization": 3 * fwd_gflop * value / 1e3 / world / peak_tf,
+        # the whole step against the memory roofline: algorithmic bytes of EVERY op of one step (each operand tensor moved once,
+        # hgb200/profiling.py) over the real multi-lane step time -- what the op-by-op design achieves as a whole
+        "step_hbm": {"algorithmic_gb_per_step": sum(r["bytes"] for r in agg.values()) / 1e9,
+                     "achieved_gbps": sum(r["bytes"] for r in agg.values()) / 1e9 / (total_ms / args.steps * 1e-3),
+                     "frac_of_peak": sum(r["bytes"] for r in agg.values()) / 1e9 / (total_ms / args.steps * 1e-3) / peak_bw,
+                     "peak_gbps": peak_bw},
     }
     del model, plan, images, targets
     torch.cuda.empty_cache()
